@@ -1,0 +1,15 @@
+"""B200-native GP log-marginal-likelihood hot path of AutoGP.jl (Gram build -> Cholesky ->
+solve -> logdet), behind the reference's own operator names.  CUDA only; see DESIGN.md."""
+from . import _lib  # noqa: F401
+from .gp import (  # noqa: F401
+    BinaryOpNode, ChangePoint, Constant, Engine, GammaExponential, LeafNode, Linear, Node, Periodic, Plus,
+    SquaredExponential, Times, WhiteNoise, compute_cov_matrix, compute_cov_matrix_vectorized, default_engine,
+    depth, encode_program, eval_cov, size, unroll,
+)
+from .model import (  # noqa: F401
+    JITTER, PosDefException, log_marginal_likelihoods, log_marginal_likelihoods_info, mvnormal_logpdf,
+    transform_param, untransform_param,
+)
+from . import smc  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,431 @@
+// C-ABI of the engine (include/agp_b200.h): handle, workspaces, program upload, launches.
+// No torch types, no global mutable state; every entry point selects the handle's device
+// first because the reference calls this path from migrating Julia threads
+// (src/inference_smc_anneal_data.jl:133, 240).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/agp_b200.h"
+#include "agp_kernels.cuh"
+#include "agp_program.h"
+
+using agp::BatchView;
+using agp::TB;
+
+struct agp_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // resident batch
+    bool uploaded = false;
+    int P = 0, n_full = 0, n_active = 0, ld = 0;
+    BatchView view{};
+
+    // device workspaces (grow-only)
+    double* d_L = nullptr;       size_t cap_L = 0;       // bytes
+    unsigned char* d_in = nullptr;   size_t cap_in = 0;  // packed inputs arena
+    unsigned char* d_work = nullptr; size_t cap_work = 0;  // y, z, logdet, zz, dinv
+    unsigned char* d_res = nullptr;  size_t cap_res = 0;   // lml[P] + info[P]
+    unsigned char* h_in = nullptr;   size_t cap_hin = 0;   // pinned staging
+    unsigned char* h_res = nullptr;  size_t cap_hres = 0;  // pinned results
+    // gram scratch (separate from the resident LML batch so the two paths do not disturb each other)
+    double* d_K = nullptr;       size_t cap_K = 0;
+    unsigned char* d_gin = nullptr;  size_t cap_gin = 0;
+    unsigned char* h_gin = nullptr;  size_t cap_hgin = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int fail(agp_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define AGP_CUDA(h, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            return fail(h, (e__ == cudaErrorMemoryAllocation) ? AGP_ERR_NOMEM : AGP_ERR_CUDA,    \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                    \
+        }                                                                                        \
+    } while (0)
+
+template <typename T>
+int grow_device(agp_handle* h, T** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return AGP_OK;
+    if (*ptr) {
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        AGP_CUDA(h, cudaFree(*ptr));
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return fail(h, AGP_ERR_NOMEM, "device allocation of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    *cap = bytes;
+    return AGP_OK;
+}
+
+int grow_pinned(agp_handle* h, unsigned char** ptr, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return AGP_OK;
+    if (*ptr) {
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        AGP_CUDA(h, cudaFreeHost(*ptr));
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    AGP_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(ptr), bytes));
+    *cap = bytes;
+    return AGP_OK;
+}
+
+int check_launch(agp_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, AGP_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return AGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* agp_version(void) { return "0.1.0+sm_100a"; }
+
+int agp_create(int device, agp_handle** out) {
+    if (!out) return AGP_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return (e != cudaSuccess) ? AGP_ERR_CUDA : AGP_ERR_ARG;
+    }
+    agp_handle* h = new agp_handle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_kernels() != cudaSuccess) {
+        cudaGetLastError();
+        delete h;
+        return AGP_ERR_CUDA;
+    }
+    *out = h;
+    return AGP_OK;
+}
+
+void agp_destroy(agp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_L);
+    cudaFree(h->d_in);
+    cudaFree(h->d_work);
+    cudaFree(h->d_res);
+    cudaFree(h->d_K);
+    cudaFree(h->d_gin);
+    cudaFreeHost(h->h_gin);
+    cudaFreeHost(h->h_in);
+    cudaFreeHost(h->h_res);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* agp_last_error(const agp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+void* agp_stream(agp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int agp_synchronize(agp_handle* h) {
+    if (!h) return AGP_ERR_ARG;
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AGP_OK;
+}
+
+int64_t agp_launch_count(const agp_handle* h) { return h ? h->launches : 0; }
+
+// ---- Gram ---------------------------------------------------------------------------------
+
+static int gram_impl(agp_handle* h, const int32_t* ops, const int32_t* param_off, int32_t m, const double* params, int32_t n_params,
+                     const double* ts, int32_t n, double noise, int32_t form, double* K_dev) {
+    std::vector<AgpInstr> instr;
+    int need = 1;
+    std::string err;
+    int rc = agp_compile_program(ops, param_off, m, params, n_params, instr, &need, err);
+    if (rc != AGP_OK) return fail(h, rc, err);
+    size_t prog_bytes = instr.size() * sizeof(AgpInstr);
+    size_t ts_off = align_up(prog_bytes, 16);
+    size_t total = ts_off + (size_t)n * 8;
+    if ((rc = grow_pinned(h, &h->h_gin, &h->cap_hgin, total)) != AGP_OK) return rc;
+    if ((rc = grow_device(h, &h->d_gin, &h->cap_gin, total)) != AGP_OK) return rc;
+    if (!K_dev && (rc = grow_device(h, &h->d_K, &h->cap_K, (size_t)n * n * 8)) != AGP_OK) return rc;
+    // staging may still be in flight from a previous async call on this handle
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->h_gin, instr.data(), prog_bytes);
+    memcpy(h->h_gin + ts_off, ts, (size_t)n * 8);
+    unsigned char* d_args = h->d_gin;
+    AGP_CUDA(h, cudaMemcpyAsync(d_args, h->h_gin, total, cudaMemcpyHostToDevice, h->stream));
+    double* K_target = K_dev ? K_dev : h->d_K;
+    agp::launch_gram(reinterpret_cast<const AgpInstr*>(d_args), (int)instr.size(), need, reinterpret_cast<const double*>(d_args + ts_off), n, noise,
+                     form, K_target, h->stream);
+    h->launches += 1;
+    return check_launch(h, "gram");
+}
+
+int agp_gram(agp_handle* h, const int32_t* ops, const int32_t* param_off, int32_t m, const double* params, int32_t n_params, const double* ts,
+             int32_t n, double noise, int32_t form, double* K_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (!ops || !param_off || (!params && n_params > 0) || n < 0 || (n > 0 && (!ts || !K_out)) || (form != 0 && form != 1))
+        return fail(h, AGP_ERR_ARG, "agp_gram: bad argument");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    if (n == 0) {
+        // still validate the program, like the reference would construct the Node
+        std::vector<AgpInstr> instr; int need; std::string err;
+        int rc = agp_compile_program(ops, param_off, m, params, n_params, instr, &need, err);
+        return rc == AGP_OK ? AGP_OK : fail(h, rc, err);
+    }
+    int rc = gram_impl(h, ops, param_off, m, params, n_params, ts, n, noise, form, nullptr);
+    if (rc != AGP_OK) return rc;
+    AGP_CUDA(h, cudaMemcpyAsync(K_out, h->d_K, (size_t)n * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AGP_OK;
+}
+
+int agp_gram_device(agp_handle* h, const int32_t* ops, const int32_t* param_off, int32_t m, const double* params, int32_t n_params,
+                    const double* ts, int32_t n, double noise, int32_t form, double* K_out_dev) {
+    if (!h) return AGP_ERR_ARG;
+    if (!ops || !param_off || (!params && n_params > 0) || n <= 0 || !ts || !K_out_dev || (form != 0 && form != 1))
+        return fail(h, AGP_ERR_ARG, "agp_gram_device: bad argument");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    return gram_impl(h, ops, param_off, m, params, n_params, ts, n, noise, form, K_out_dev);
+}
+
+// ---- LML batch ------------------------------------------------------------------------------
+
+int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                   const double* params, const double* noise, const double* ts, const double* xs, int32_t n) {
+    if (!h) return AGP_ERR_ARG;
+    h->uploaded = false;
+    if (P < 0 || n < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)))
+        return fail(h, AGP_ERR_ARG, "agp_lml_upload: bad argument");
+    if (P > 65535) return fail(h, AGP_ERR_ARG, "agp_lml_upload: at most 65535 particles per batch");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+
+    // compile programs
+    std::vector<AgpInstr> instr;
+    std::vector<int32_t> poff(P + 1, 0), pneed(P > 0 ? P : 1, 1);
+    {
+        size_t o = 0, po = 0;
+        std::string err;
+        for (int p = 0; p < P; ++p) {
+            if (prog_len[p] <= 0 || n_params[p] < 0) return fail(h, AGP_ERR_PROGRAM, "particle " + std::to_string(p) + ": empty program");
+            poff[p] = (int32_t)instr.size();
+            int need = 1;
+            int rc = agp_compile_program(ops + o, param_off + o, prog_len[p], params ? params + po : nullptr, n_params[p], instr, &need, err);
+            if (rc != AGP_OK) return fail(h, rc, "particle " + std::to_string(p) + ": " + err);
+            pneed[p] = need;
+            o += prog_len[p];
+            po += n_params[p];
+        }
+        poff[P] = (int32_t)instr.size();
+    }
+
+    const int ld = (int)align_up((size_t)(n > 0 ? n : 1), TB);
+    // packed input arena: ts[ld] xs[ld] noise[P] prog_off[P+1] prog_need[P] instr[]
+    size_t off_ts = 0;
+    size_t off_xs = off_ts + (size_t)ld * 8;
+    size_t off_noise = off_xs + (size_t)ld * 8;
+    size_t off_poff = align_up(off_noise + (size_t)P * 8, 16);
+    size_t off_need = align_up(off_poff + (size_t)(P + 1) * 4, 16);
+    size_t off_instr = align_up(off_need + (size_t)P * 4, 32);
+    size_t in_bytes = off_instr + instr.size() * sizeof(AgpInstr);
+    int rc;
+    if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
+    if ((rc = grow_device(h, &h->d_in, &h->cap_in, in_bytes)) != AGP_OK) return rc;
+    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] dinv[P][4096]
+    size_t off_y = 0;
+    size_t off_z = off_y + (size_t)P * ld * 8;
+    size_t off_ld = off_z + (size_t)P * ld * 8;
+    size_t off_zz = off_ld + (size_t)P * 8;
+    size_t off_dinv = align_up(off_zz + (size_t)P * 8, 256);
+    size_t work_bytes = off_dinv + (size_t)P * 4096 * 8;
+    if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
+    size_t res_bytes = align_up((size_t)P * 8, 16) + (size_t)P * 4;
+    if ((rc = grow_device(h, &h->d_res, &h->cap_res, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
+    if ((rc = grow_pinned(h, &h->h_res, &h->cap_hres, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
+    size_t L_bytes = (size_t)P * ld * ld * 8;
+    if ((rc = grow_device(h, &h->d_L, &h->cap_L, L_bytes > 0 ? L_bytes : 16)) != AGP_OK) return rc;
+
+    // the pinned staging buffer may still be the source of an in-flight copy
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    memset(h->h_in, 0, off_noise);
+    if (n > 0) {
+        memcpy(h->h_in + off_ts, ts, (size_t)n * 8);
+        memcpy(h->h_in + off_xs, xs, (size_t)n * 8);
+    }
+    if (P > 0) {
+        memcpy(h->h_in + off_noise, noise, (size_t)P * 8);
+        memcpy(h->h_in + off_need, pneed.data(), (size_t)P * 4);
+    }
+    memcpy(h->h_in + off_poff, poff.data(), (size_t)(P + 1) * 4);
+    if (!instr.empty()) memcpy(h->h_in + off_instr, instr.data(), instr.size() * sizeof(AgpInstr));
+    AGP_CUDA(h, cudaMemcpyAsync(h->d_in, h->h_in, in_bytes, cudaMemcpyHostToDevice, h->stream));
+
+    BatchView& v = h->view;
+    v.L = h->d_L;
+    v.mat_stride = (long long)ld * ld;
+    v.ld = ld;
+    v.n = n;
+    v.nt = (n + TB - 1) / TB;
+    v.ts = reinterpret_cast<const double*>(h->d_in + off_ts);
+    v.xs = reinterpret_cast<const double*>(h->d_in + off_xs);
+    v.noise = reinterpret_cast<const double*>(h->d_in + off_noise);
+    v.prog_off = reinterpret_cast<const int*>(h->d_in + off_poff);
+    v.prog_need = reinterpret_cast<const int*>(h->d_in + off_need);
+    v.prog = reinterpret_cast<const AgpInstr*>(h->d_in + off_instr);
+    v.y = reinterpret_cast<double*>(h->d_work + off_y);
+    v.z = reinterpret_cast<double*>(h->d_work + off_z);
+    v.logdet_half = reinterpret_cast<double*>(h->d_work + off_ld);
+    v.zz = reinterpret_cast<double*>(h->d_work + off_zz);
+    v.dinv = reinterpret_cast<double*>(h->d_work + off_dinv);
+    v.lml = reinterpret_cast<double*>(h->d_res);
+    v.info = reinterpret_cast<int*>(h->d_res + align_up((size_t)P * 8, 16));
+    h->P = P;
+    h->n_full = n;
+    h->n_active = n;
+    h->ld = ld;
+    h->uploaded = true;
+    return AGP_OK;
+}
+
+int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
+    if (!h) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_set_prefix: no resident batch");
+    if (n_prefix < 0 || n_prefix > h->n_full) return fail(h, AGP_ERR_ARG, "agp_lml_set_prefix: prefix out of range");
+    h->n_active = n_prefix;
+    h->view.n = n_prefix;
+    h->view.nt = (n_prefix + TB - 1) / TB;
+    return AGP_OK;
+}
+
+static int run_impl(agp_handle* h, float* stage_ms) {
+    const BatchView& v = h->view;
+    const int P = h->P;
+    if (P == 0) return AGP_OK;
+    if (v.n == 0) {
+        // empty mvnormal: logpdf of a 0-vector is 0 (initial SMC state, inference_smc_anneal_data.jl:185-189)
+        size_t lml_bytes = (size_t)P * 8, res_bytes = (lml_bytes + 15) / 16 * 16 + (size_t)P * 4;
+        AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, res_bytes, h->stream));
+        return AGP_OK;
+    }
+    for (int k = 0; k < v.nt; ++k) {
+        if (stage_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        agp::launch_update(v, P, k, h->stream);
+        if (stage_ms) {
+            float ms;
+            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            stage_ms[0] += ms;
+            AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        }
+        agp::launch_potf2(v, P, k, h->stream);
+        if (stage_ms) {
+            float ms;
+            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            stage_ms[1] += ms;
+            AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        }
+        agp::launch_trsm(v, P, k, h->stream);
+        if (stage_ms) {
+            float ms;
+            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            stage_ms[2] += ms;
+        }
+        h->launches += (k < v.nt - 1) ? 3 : 2;
+    }
+    return check_launch(h, "lml");
+}
+
+int agp_lml_run(agp_handle* h) {
+    if (!h) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_run: no resident batch (call agp_lml_upload first)");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    return run_impl(h, nullptr);
+}
+
+int agp_lml_stage_times(agp_handle* h, float* stage_ms) {
+    if (!h || !stage_ms) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_stage_times: no resident batch");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.f;
+    return run_impl(h, stage_ms);
+}
+
+int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out) {
+    if (!h || !ms_out || reps <= 0) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_time: no resident batch");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    for (int r = 0; r < reps; ++r) {
+        int rc = run_impl(h, nullptr);
+        if (rc != AGP_OK) return rc;
+    }
+    AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+    AGP_CUDA(h, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    return AGP_OK;
+}
+
+int agp_lml_fetch(agp_handle* h, double* lml_out, int32_t* info_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_fetch: no resident batch");
+    const int P = h->P;
+    if (P == 0) return AGP_OK;
+    if (!lml_out || !info_out) return fail(h, AGP_ERR_ARG, "agp_lml_fetch: null output");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    size_t info_off = align_up((size_t)P * 8, 16);
+    size_t res_bytes = info_off + (size_t)P * 4;
+    AGP_CUDA(h, cudaMemcpyAsync(h->h_res, h->d_res, res_bytes, cudaMemcpyDeviceToHost, h->stream));
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(lml_out, h->h_res, (size_t)P * 8);
+    memcpy(info_out, h->h_res + info_off, (size_t)P * 4);
+    return AGP_OK;
+}
+
+int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev) {
+    if (!h || !lml_dev || !info_dev) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_device_results: no resident batch");
+    *lml_dev = h->view.lml;
+    *info_dev = h->view.info;
+    return AGP_OK;
+}
+
+int agp_lml_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                  const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
+                  int32_t* info_out) {
+    int rc = agp_lml_upload(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n);
+    if (rc != AGP_OK) return rc;
+    rc = agp_lml_run(h);
+    if (rc != AGP_OK) return rc;
+    return agp_lml_fetch(h, lml_out, info_out);
+}
+
+}  // extern "C"

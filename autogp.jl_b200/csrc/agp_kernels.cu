@@ -1,0 +1,563 @@
+// sm_100a kernels of the fused GP log-marginal-likelihood path.
+//
+//   update : tile (i,k) of block column k  <-  K(ts_i, ts_k) [+ noise I]  -  sum_{j<k} L_ij L_kj^T
+//            The Gram tile is generated on the fly from the kernel-tree program (K is never
+//            written to HBM on this path); the contraction runs on FP64 tensor cores
+//            (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind) fed by a
+//            3-stage cp.async pipeline; ts slices arrive by 1-D TMA bulk copies.
+//   potf2  : 128x128 diagonal tile Cholesky in shared memory, augmented with the observation
+//            row so z_k = L_kk^{-1} y_k falls out of the same sweep; accumulates log det and
+//            z'z; LAPACK-style info; inverts the four 32x32 diagonal blocks for trsm.
+//   trsm   : L_ik = C_ik L_kk^{-T} by blocked substitution on DMMA, then y_i -= L_ik z_k
+//            (the forward solve rides along the factorisation sweep).
+//   gram   : stand-alone K(ts,ts) + noise I, column-major, both triangles (HBM-write bound).
+//
+// Reference semantics: src/GP.jl:137-503, 666-684; src/Model.jl:134-136; Distributions'
+// MvNormal logpdf = -(n log 2pi + logdet)/2 - |U^{-T} x|^2 / 2 with K = U'U (upper Cholesky).
+// Our row-major lower factor L is bit-for-bit the column-major upper factor U = L'.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "agp_eval.cuh"
+#include "agp_kernels.cuh"
+
+namespace agp {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// D(8x8) += A(8x4,row) * B(4x8,col), FP64 tensor core
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// update kernel
+// ------------------------------------------------------------------------------------------
+constexpr int KC = 32;             // K-chunk per pipeline stage (doubles)
+constexpr int NSTAGE = 3;
+constexpr int UPD_THREADS = 512;   // 16 warps: 4 (m) x 4 (n), warp tile 32x32
+constexpr int CS_STRIDE = 136;     // accumulator staging row stride (doubles)
+constexpr int PROG_SMEM = 64;      // instructions cached in shared memory
+constexpr int STAGE_DOUBLES = 2 * TB * KC;
+constexpr int UPD_SMEM_STAGES = NSTAGE * STAGE_DOUBLES * 8;                      // 196608
+constexpr int UPD_SMEM_BYTES = UPD_SMEM_STAGES + 2 * TB * 8 + PROG_SMEM * 32 + 64;  // + ts_r, ts_c, program, mbarrier
+
+static_assert(TB * CS_STRIDE * 8 <= UPD_SMEM_STAGES, "accumulator staging must fit in the pipeline buffers");
+
+// element (row, kcol) of a [TB][KC] operand tile; 16-byte chunks swizzled so that the
+// LDS.128 fragment loads of two adjacent rows hit disjoint bank halves (no padding needed)
+__device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
+
+__global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v, int k) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    double* ts_r = reinterpret_cast<double*>(smem_raw + UPD_SMEM_STAGES);
+    double* ts_c = ts_r + TB;
+    AgpInstr* prog_s = reinterpret_cast<AgpInstr*>(ts_c + TB);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(prog_s + PROG_SMEM);
+
+    const int tid = threadIdx.x;
+    const int p = blockIdx.y;
+    const int it = k + blockIdx.x;  // tile row
+    const bool diag = (it == k);
+    const int row0 = it * TB, col0 = k * TB;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    const int ld = v.ld;
+
+    // --- stage ts slices with TMA bulk copies; program into shared memory -----------------
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * TB * 8);
+        tma_bulk_g2s(ts_r, v.ts + row0, TB * 8, bar);
+        tma_bulk_g2s(ts_c, v.ts + col0, TB * 8, bar);
+    }
+    const int poff = v.prog_off[p];
+    const int pm = v.prog_off[p + 1] - poff;
+    const AgpInstr* prog = v.prog + poff;
+    if (pm <= PROG_SMEM) {
+        // 32-byte instructions = 4 x 8-byte words
+        const double* src = reinterpret_cast<const double*>(prog);
+        double* dst = reinterpret_cast<double*>(prog_s);
+        for (int q = tid; q < pm * 4; q += UPD_THREADS) dst[q] = src[q];
+        prog = prog_s;
+    }
+    if (k == 0) {
+        // first touch of this batch: reset the forward-solve vector and the accumulators
+        double* yp = v.y + (long long)p * ld;
+        for (int r = tid; r < TB; r += UPD_THREADS) yp[row0 + r] = (row0 + r < v.n) ? v.xs[row0 + r] : 0.0;
+        if (it == 0 && tid == 0) {
+            v.logdet_half[p] = 0.0;
+            v.zz[p] = 0.0;
+            v.info[p] = 0;
+        }
+    }
+
+    // --- contraction: acc = sum_{j<k} L_ij L_kj^T over K = k*TB --------------------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, c4 = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+    const int nchunk = (k * TB) / KC;
+    const double* __restrict__ Ag = Lp + (long long)row0 * ld;
+    const double* __restrict__ Bg = Lp + (long long)col0 * ld;
+
+    auto load_stage = [&](int s, int chunk) {
+        double* As = stages + s * STAGE_DOUBLES;
+        double* Bs = As + TB * KC;
+        const int kk0 = chunk * KC;
+#pragma unroll
+        for (int e = 0; e < (TB * KC / 2) / UPD_THREADS; ++e) {
+            int q = tid + e * UPD_THREADS;
+            int row = q >> 4, ch = q & 15;
+            cp_async16(As + swz(row, ch), Ag + (long long)row * ld + kk0 + ch * 2);
+            if (!diag) cp_async16(Bs + swz(row, ch), Bg + (long long)row * ld + kk0 + ch * 2);
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < nchunk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        {
+            int nxt = ch + NSTAGE - 1;
+            if (nxt < nchunk) load_stage(nxt % NSTAGE, nxt);
+            cp_async_commit();
+        }
+        const double* As = stages + (ch % NSTAGE) * STAGE_DOUBLES;
+        const double* Bs = diag ? As : As + TB * KC;
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz(wm * 32 + mb * 8 + g, ks * 4 + c4));
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz(wn * 32 + nb * 8 + g, ks * 4 + c4));
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
+                    dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // --- epilogue: stage accumulators, then out = K(ts_r, ts_c) - acc, coalesced ----------
+    double* Cs = stages;
+    if (k > 0) {
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
+                *reinterpret_cast<double2*>(Cs + r * CS_STRIDE + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const int need = v.prog_need[p];
+    const double noise = v.noise[p];
+    const int n = v.n;
+    for (int idx = tid; idx < TB * TB; idx += UPD_THREADS) {
+        const int r = idx >> 7, c = idx & (TB - 1);
+        if (diag && c > r) continue;  // strictly-upper part of a diagonal tile is never read
+        const int gr = row0 + r, gc = col0 + c;
+        double val;
+        if (gr < n) {  // gc <= gr < n
+            val = eval_entry(prog, pm, need, ts_c[c], ts_r[r], 0);
+            if (gr == gc) val = val + noise;  // + noise*I, src/GP.jl:667
+        } else {
+            val = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+        }
+        if (k > 0) val = val - Cs[r * CS_STRIDE + c];
+        Lp[(long long)gr * ld + gc] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// potf2 kernel: one CTA per particle, diagonal tile k (+ observation row)
+// ------------------------------------------------------------------------------------------
+constexpr int PF_THREADS = 512;
+constexpr int SA = TB + 1;  // 129: odd stride, column walks are conflict free; row TB = y
+constexpr int PF_SMEM_BYTES = (TB + 1) * SA * 8 + TB * 8 * 2 + 64;
+
+__global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, int k) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);  // [TB+1][SA]
+    double* Ld = As + (TB + 1) * SA;                   // diag of L
+    double* Ri = Ld + TB;                              // 1 / diag
+    double* red = Ri + TB;                             // reduction scratch (8 doubles)
+
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x;
+    const int ld = v.ld;
+    const int o = k * TB;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    double* yp = v.y + (long long)p * ld;
+
+    for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
+        int r = idx >> 7, c = idx & (TB - 1);
+        if (c <= r) As[r * SA + c] = Lp[(long long)(o + r) * ld + o + c];
+    }
+    for (int c = tid; c < TB; c += PF_THREADS) As[TB * SA + c] = yp[o + c];
+    __syncthreads();
+
+    // right-looking Cholesky, one barrier per column.  Column j (scaled) is parked in the
+    // unused upper triangle As[j][i]; the working lower triangle keeps unscaled columns.
+    const int ti = tid >> 4, tc = tid & 15;
+    int bad = 0;
+    for (int j = 0; j < TB; ++j) {
+        double d = As[j * SA + j];
+        if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
+            if (bad == 0) bad = o + j + 1;
+            d = 1.0;
+        }
+        const double ljj = sqrt(d);
+        const double inv = 1.0 / ljj;
+        const int a0 = (j < ti) ? 0 : ((j - ti) >> 5) + 1;
+        const int b0 = (j < tc) ? 0 : ((j - tc) >> 4) + 1;
+        for (int a = a0; a < 5; ++a) {
+            const int i = ti + (a << 5);
+            if (i > TB) break;
+            const double li = As[i * SA + j] * inv;
+            if (tc == 0) As[j * SA + i] = li;
+            const int cmax = i < TB ? i : TB - 1;
+            double* __restrict__ rowi = As + i * SA;
+            for (int b = b0;; ++b) {
+                const int c = tc + (b << 4);
+                if (c > cmax) break;
+                const double lc = As[c * SA + j] * inv;
+                rowi[c] = fma(-li, lc, rowi[c]);
+            }
+        }
+        if (tid == 0) {
+            Ld[j] = ljj;
+            Ri[j] = inv;
+        }
+        __syncthreads();
+    }
+
+    // write L_kk (lower, row-major; strictly-upper zeroed so the tile is a clean factor)
+    for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
+        int r = idx >> 7, c = idx & (TB - 1);
+        double val = (c < r) ? As[c * SA + r] : (c == r ? Ld[r] : 0.0);
+        Lp[(long long)(o + r) * ld + o + c] = val;
+    }
+    // z_k, sum z^2, sum log L_jj
+    double part_ld = 0.0, part_zz = 0.0;
+    if (tid < TB) {
+        double zj = As[tid * SA + TB];
+        v.z[(long long)p * ld + o + tid] = zj;
+        part_zz = zj * zj;
+        part_ld = log(Ld[tid]);
+    }
+    if (tid < TB) {
+        part_ld = warp_sum(part_ld);
+        part_zz = warp_sum(part_zz);
+        if ((tid & 31) == 0) {
+            red[(tid >> 5) * 2] = part_ld;
+            red[(tid >> 5) * 2 + 1] = part_zz;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sl = ((red[0] + red[2]) + red[4]) + red[6];
+        double sz = ((red[1] + red[3]) + red[5]) + red[7];
+        double tot_l = v.logdet_half[p] + sl;
+        double tot_z = v.zz[p] + sz;
+        v.logdet_half[p] = tot_l;
+        v.zz[p] = tot_z;
+        int info = v.info[p];
+        if (info == 0 && bad != 0) {
+            info = bad;
+            v.info[p] = bad;
+        }
+        if (k == v.nt - 1) {
+            // -(n log 2pi + logdet)/2 - z'z/2, logdet = 2 sum log L_ii
+            const double log2pi = 1.8378770664093453;
+            double lml = -0.5 * ((double)v.n * log2pi + 2.0 * tot_l) - 0.5 * tot_z;
+            v.lml[p] = (info == 0) ? lml : __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+    // inverses of the four 32x32 diagonal blocks (warp b, lane = column of the inverse)
+    if (tid < 128 && k < v.nt - 1) {
+        const int b = tid >> 5, cc = tid & 31;
+        double x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < r; ++m) s = fma(As[(b * 32 + m) * SA + b * 32 + r], x[m], s);  // L(r,m), broadcast
+            double rhs = (r == cc) ? 1.0 : 0.0;
+            x[r] = (r < cc) ? 0.0 : (rhs - s) * Ri[b * 32 + r];
+        }
+        double* out = v.dinv + ((long long)p * 4 + b) * 1024;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) out[r * 32 + cc] = x[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// trsm kernel: 64 rows of tile (i,k) per CTA
+// ------------------------------------------------------------------------------------------
+constexpr int TR_THREADS = 256;
+constexpr int TR_ROWS = 64;
+constexpr int XS = 132;  // stride = 4 mod 16 doubles: DMMA fragment LDS.64 conflict free
+constexpr int TR_SMEM_BYTES = (TR_ROWS * XS + TB * XS + TB) * 8;
+
+__global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, int k) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Xs = reinterpret_cast<double*>(smem_raw);  // [64][XS]   C tile rows -> X
+    double* Ls = Xs + TR_ROWS * XS;                    // [128][XS]  L_kk (diag 32x32 blocks replaced by their inverses)
+    double* zs = Ls + TB * XS;                         // [128]
+
+    const int tid = threadIdx.x;
+    const int p = blockIdx.y;
+    const int it = k + 1 + (blockIdx.x >> 1);
+    const int r0 = it * TB + (blockIdx.x & 1) * TR_ROWS;
+    const int o = k * TB;
+    const int ld = v.ld;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+
+    // C rows: 64 x 128 doubles = 64 x 64 16-byte chunks
+    for (int q = tid; q < TR_ROWS * 64; q += TR_THREADS) {
+        int r = q >> 6, ch = q & 63;
+        cp_async16(Xs + r * XS + ch * 2, Lp + (long long)(r0 + r) * ld + o + ch * 2);
+    }
+    // L_kk strictly-lower 32x32 blocks; diagonal blocks come from dinv
+    const double* dinv = v.dinv + (long long)p * 4096;
+    for (int q = tid; q < TB * 64; q += TR_THREADS) {
+        int r = q >> 6, ch = q & 63;
+        int rb = r >> 5, cb = ch >> 4;
+        if (cb < rb) cp_async16(Ls + r * XS + ch * 2, Lp + (long long)(o + r) * ld + o + ch * 2);
+        else if (cb == rb) cp_async16(Ls + r * XS + ch * 2, dinv + rb * 1024 + (r & 31) * 32 + (ch & 15) * 2);
+    }
+    if (tid < TB) zs[tid] = v.z[(long long)p * ld + o + tid];
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, c4 = lane & 3;
+    double* xrow = Xs + (warp * 8 + g) * XS;  // this lane's row (fragment row g of the warp's 8 rows)
+
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+        double acc[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+        // S = sum_{m<jb} X_m L[jb,m]^T
+        for (int kk = 0; kk < jb * 32; kk += 4) {
+            double a = xrow[kk + c4];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                double b = Ls[(jb * 32 + nb * 8 + g) * XS + kk + c4];
+                dmma884(acc[nb][0], acc[nb][1], a, b);
+            }
+        }
+        // T = C_jb - S  (own rows only: warp-local dependency)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            double2* ptr = reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4);
+            double2 t = *ptr;
+            t.x -= acc[nb][0];
+            t.y -= acc[nb][1];
+            *ptr = t;
+            acc[nb][0] = acc[nb][1] = 0.0;
+        }
+        __syncwarp();
+        // X_jb = T inv(L_jb,jb)^T
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+            double a = xrow[jb * 32 + kk + c4];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                double b = Ls[(jb * 32 + nb * 8 + g) * XS + jb * 32 + kk + c4];
+                dmma884(acc[nb][0], acc[nb][1], a, b);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+            *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) = make_double2(acc[nb][0], acc[nb][1]);
+        __syncwarp();
+    }
+
+    // store L_ik rows (coalesced) and fold the forward solve: y_i -= L_ik z_k
+    double* yp = v.y + (long long)p * ld;
+#pragma unroll 1
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = warp * 8 + rr;
+        const double* xr = Xs + r * XS;
+        double s = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int c = lane + e * 32;
+            double x = xr[c];
+            Lp[(long long)(r0 + r) * ld + o + c] = x;
+            s = fma(x, zs[c], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) yp[r0 + r] -= s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone Gram kernel: column-major K, both triangles; 64x64 tile pairs mirrored via smem
+// ------------------------------------------------------------------------------------------
+constexpr int GT = 64;
+constexpr int GR_THREADS = 256;
+
+__global__ void __launch_bounds__(GR_THREADS) agp_gram_kernel(const AgpInstr* __restrict__ prog_g, int m, int need, const double* __restrict__ ts,
+                                                             int n, double noise, int form, double* __restrict__ K) {
+    __shared__ double tile[GT][GT + 1];
+    __shared__ double tsi[GT], tsj[GT];
+    __shared__ AgpInstr prog_s[PROG_SMEM];
+    // linear block id -> upper-triangular tile pair (bi <= bj)
+    const int ntile = (n + GT - 1) / GT;
+    int bj = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+    while ((long long)(bj + 1) * (bj + 2) / 2 <= (long long)blockIdx.x) ++bj;
+    while ((long long)bj * (bj + 1) / 2 > (long long)blockIdx.x) --bj;
+    const int bi = blockIdx.x - bj * (bj + 1) / 2;
+    (void)ntile;
+    const int tid = threadIdx.x;
+    const int i0 = bi * GT, j0 = bj * GT;
+    if (tid < GT) {
+        tsi[tid] = (i0 + tid < n) ? ts[i0 + tid] : 0.0;
+        tsj[tid] = (j0 + tid < n) ? ts[j0 + tid] : 0.0;
+    }
+    const AgpInstr* prog = prog_g;
+    if (m <= PROG_SMEM) {
+        const double* src = reinterpret_cast<const double*>(prog_g);
+        double* dst = reinterpret_cast<double*>(prog_s);
+        for (int q = tid; q < m * 4; q += GR_THREADS) dst[q] = src[q];
+        prog = prog_s;
+    }
+    __syncthreads();
+    const int il = tid & (GT - 1);
+#pragma unroll 1
+    for (int e = 0; e < GT / 4; ++e) {
+        const int jl = (tid >> 6) + e * 4;
+        const int gi = i0 + il, gj = j0 + jl;
+        double val = 0.0;
+        if (gi < n && gj < n) {
+            // Symmetric(K): entry (i,j) takes the upper-triangle element (min,max)
+            const bool up = gi <= gj;
+            const double t1 = up ? tsi[il] : tsj[jl];
+            const double t2 = up ? tsj[jl] : tsi[il];
+            val = eval_entry(prog, m, need, t1, t2, form);
+            if (gi == gj) val = val + noise;
+            K[(long long)gj * n + gi] = val;  // column j, rows contiguous
+        }
+        tile[jl][il] = val;
+    }
+    if (bi != bj) {
+        __syncthreads();
+        // mirrored block: rows j0.., columns i0..  (element (gj, gi) = value(gi, gj))
+        const int jl2 = tid & (GT - 1);
+#pragma unroll 1
+        for (int e = 0; e < GT / 4; ++e) {
+            const int il2 = (tid >> 6) + e * 4;
+            const int gi = i0 + il2, gj = j0 + jl2;
+            if (gi < n && gj < n) K[(long long)gi * n + gj] = tile[jl2][il2];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(agp_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(agp_potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(agp_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES);
+    return e;
+}
+
+void launch_update(const BatchView& v, int P, int k, cudaStream_t s) {
+    dim3 grid(v.nt - k, P);
+    agp_update_kernel<<<grid, UPD_THREADS, UPD_SMEM_BYTES, s>>>(v, k);
+}
+
+void launch_potf2(const BatchView& v, int P, int k, cudaStream_t s) {
+    agp_potf2_kernel<<<P, PF_THREADS, PF_SMEM_BYTES, s>>>(v, k);
+}
+
+void launch_trsm(const BatchView& v, int P, int k, cudaStream_t s) {
+    if (v.nt - k - 1 <= 0) return;
+    dim3 grid(2 * (v.nt - k - 1), P);
+    agp_trsm_kernel<<<grid, TR_THREADS, TR_SMEM_BYTES, s>>>(v, k);
+}
+
+void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n, double noise, int form, double* K, cudaStream_t s) {
+    if (n <= 0) return;
+    int nt = (n + GT - 1) / GT;
+    int blocks = nt * (nt + 1) / 2;
+    agp_gram_kernel<<<blocks, GR_THREADS, 0, s>>>(prog, m, need, ts, n, noise, form, K);
+}
+
+}  // namespace agp

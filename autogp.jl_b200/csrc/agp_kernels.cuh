@@ -1,0 +1,46 @@
+// Kernel launch interface shared by agp_kernels.cu and agp_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agp_program.h"
+
+namespace agp {
+
+constexpr int TB = 128;  // tile edge = Cholesky block-column width
+
+// Device view of one resident batch of particles (all pointers are device pointers).
+struct BatchView {
+    double* L;               // [P][ld][ld] row-major; lower-triangle tiles hold K, then L (== column-major U)
+    long long mat_stride;    // ld*ld
+    int ld;                  // row stride (allocated npad)
+    int n;                   // active number of observations (data prefix)
+    int nt;                  // active tiles = ceil(n / TB)
+    const double* ts;        // [ld]   time points, zero padded
+    const double* xs;        // [ld]   observations, zero padded
+    double* y;               // [P][ld] forward-substitution work vector
+    double* z;               // [P][ld] z = L^{-1} xs
+    const AgpInstr* prog;    // concatenated device programs
+    const int* prog_off;     // [P+1]
+    const int* prog_need;    // [P] register-stack depth
+    const double* noise;     // [P]
+    double* logdet_half;     // [P] sum log L_ii
+    double* zz;              // [P] sum z_i^2
+    double* lml;             // [P]
+    int* info;               // [P]
+    double* dinv;            // [P][4][32][32] inverses of the diagonal 32x32 blocks of L_kk
+};
+
+// Left-looking block column k:  tiles (i,k), i>=k  <-  K(ts_i, ts_k) - sum_{j<k} L_ij L_kj^T
+void launch_update(const BatchView& v, int P, int k, cudaStream_t s);
+// Diagonal tile: Cholesky, z_k, logdet, info, 32x32 diagonal-block inverses; last column writes lml
+void launch_potf2(const BatchView& v, int P, int k, cudaStream_t s);
+// Panel below the diagonal: L_ik = C_ik L_kk^{-T};  y_i -= L_ik z_k
+void launch_trsm(const BatchView& v, int P, int k, cudaStream_t s);
+// Stand-alone Gram matrix (drop-in for compute_cov_matrix[_vectorized]): column-major, both triangles
+void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n, double noise, int form,
+                 double* K, cudaStream_t s);
+// one-time: opt in to >48 KB dynamic shared memory
+cudaError_t configure_kernels();
+
+}  // namespace agp

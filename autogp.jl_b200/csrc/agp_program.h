@@ -1,0 +1,42 @@
+// Kernel-tree programs: wire format (include/agp_b200.h) -> device instruction stream.
+//
+// The wire format is the reference's postfix `unroll` order (src/GP.jl:111-113).  The device
+// interpreter (agp_eval.cuh) keeps its operand stack in registers, so the host re-orders the
+// evaluation of each binary node (deeper subtree first, Sethi-Ullman) to bound the stack at
+// AGP_MAX_STACK.  Plus and Times commute bit-for-bit in IEEE-754; ChangePoint gets a
+// "swapped" opcode so left/right keep their meaning.  Per-node scalars that the reference
+// computes once outside its broadcasts (lengthscale^2, pi/period, -2/lengthscale^2:
+// src/GP.jl:243, 332, 334) are computed here once in host FP64, exactly as Julia does.
+#pragma once
+#include <stdint.h>
+
+#define AGP_MAX_STACK 8
+
+enum AgpDevOp : int32_t {
+    AGP_I_CONST = 0,   // a = value
+    AGP_I_LINEAR = 1,  // a = intercept, b = bias, c = amplitude
+    AGP_I_SE = 2,      // a = lengthscale^2, b = amplitude
+    AGP_I_GE = 3,      // a = lengthscale, b = gamma, c = amplitude
+    AGP_I_PER = 4,     // a = pi/period, b = -2/lengthscale^2, c = amplitude
+    AGP_I_WN = 5,      // a = value
+    AGP_I_PLUS = 6,
+    AGP_I_TIMES = 7,
+    AGP_I_CP = 8,      // a = location, b = scale; stack: s1 = left, s0 = right
+    AGP_I_CP_SWAP = 9  // same, stack: s1 = right, s0 = left
+};
+
+struct __attribute__((aligned(16))) AgpInstr {
+    int32_t op;
+    int32_t pad;
+    double a, b, c;
+};
+
+#ifdef __cplusplus
+#include <string>
+#include <vector>
+
+// Compile one program.  Appends to `out`; returns 0 or an AGP_ERR_* code (message in `err`).
+// `need` receives the register-stack depth the program needs (1..AGP_MAX_STACK).
+int agp_compile_program(const int32_t* ops, const int32_t* param_off, int32_t m, const double* params,
+                        int32_t n_params, std::vector<AgpInstr>& out, int* need, std::string& err);
+#endif

@@ -1,0 +1,335 @@
+"""Host-side mirror of the reference's GP operator API for the hot path (src/GP.jl).
+
+Same names, argument meaning and error behaviour as the Julia functions they stand in for;
+all arithmetic runs in ``libagp_b200.so`` on the GPU (no CPU fallback):
+
+  ===========================================  =========================================
+  reference (src/GP.jl)                         here
+  ===========================================  =========================================
+  ``WhiteNoise … ChangePoint`` structs :131-479  dataclasses below (same field order)
+  ``unroll(node)``                    :111-113  :func:`unroll` (postfix; the wire order)
+  ``size`` / ``depth``                :93-104   :func:`size` / :func:`depth`
+  ``eval_cov(node, ts)``              :61       :func:`eval_cov`
+  ``compute_cov_matrix_vectorized``   :666-668  :func:`compute_cov_matrix_vectorized`
+  ``compute_cov_matrix``              :674-684  :func:`compute_cov_matrix`
+  ``GPConfig`` node codes             :1101-1108  ``OP_*`` constants
+  ===========================================  =========================================
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+
+OP_CONSTANT, OP_LINEAR, OP_SQUARED_EXPONENTIAL, OP_GAMMA_EXPONENTIAL, OP_PERIODIC = 1, 2, 3, 4, 5
+OP_PLUS, OP_TIMES, OP_CHANGEPOINT, OP_WHITE_NOISE = 6, 7, 8, 9
+FORM_VECTORIZED, FORM_SCALAR = 0, 1
+
+
+class Node:
+    """``abstract type Node`` (src/GP.jl:39)."""
+
+    def __add__(self, other: "Node") -> "Plus":  # Base.:+ (GP.jl:379)
+        return Plus(self, other)
+
+    def __mul__(self, other: "Node") -> "Times":  # Base.:* (GP.jl:380)
+        return Times(self, other)
+
+
+class LeafNode(Node):
+    pass
+
+
+class BinaryOpNode(Node):
+    pass
+
+
+@dataclass(frozen=True)
+class WhiteNoise(LeafNode):
+    value: float
+
+
+@dataclass(frozen=True)
+class Constant(LeafNode):
+    value: float
+
+
+@dataclass(frozen=True)
+class Linear(LeafNode):
+    intercept: float
+    bias: float = 1.0
+    amplitude: float = 1.0
+
+
+@dataclass(frozen=True)
+class SquaredExponential(LeafNode):
+    lengthscale: float
+    amplitude: float = 1.0
+
+
+@dataclass(frozen=True)
+class GammaExponential(LeafNode):
+    lengthscale: float
+    gamma: float
+    amplitude: float = 1.0
+
+    def __post_init__(self):
+        # `@assert (0 < gamma <= 2)` in the Julia constructor (GP.jl:274)
+        if not (0 < self.gamma <= 2):
+            raise AssertionError("0 < gamma <= 2")
+
+
+@dataclass(frozen=True)
+class Periodic(LeafNode):
+    lengthscale: float
+    period: float
+    amplitude: float = 1.0
+
+
+@dataclass(frozen=True)
+class Plus(BinaryOpNode):
+    left: Node
+    right: Node
+
+
+@dataclass(frozen=True)
+class Times(BinaryOpNode):
+    left: Node
+    right: Node
+
+
+@dataclass(frozen=True)
+class ChangePoint(BinaryOpNode):
+    left: Node
+    right: Node
+    location: float
+    scale: float
+
+
+def size(node: Node) -> int:
+    return 1 if isinstance(node, LeafNode) else 1 + size(node.left) + size(node.right)
+
+
+def depth(node: Node) -> int:
+    return 1 if isinstance(node, LeafNode) else 1 + max(depth(node.left), depth(node.right))
+
+
+def unroll(node: Node) -> List[Node]:
+    """Flat postfix list of all sub-kernels (src/GP.jl:111-113)."""
+    out: List[Node] = []
+    stack = [(node, False)]
+    while stack:  # iterative: trees are unbounded a priori (max_depth = -1)
+        nd, seen = stack.pop()
+        if isinstance(nd, LeafNode) or seen:
+            out.append(nd)
+        else:
+            stack.append((nd, True))
+            stack.append((nd.right, False))
+            stack.append((nd.left, False))
+    return out
+
+
+_LEAF_FIELDS = {
+    WhiteNoise: (OP_WHITE_NOISE, ("value",)),
+    Constant: (OP_CONSTANT, ("value",)),
+    Linear: (OP_LINEAR, ("intercept", "bias", "amplitude")),
+    SquaredExponential: (OP_SQUARED_EXPONENTIAL, ("lengthscale", "amplitude")),
+    GammaExponential: (OP_GAMMA_EXPONENTIAL, ("lengthscale", "gamma", "amplitude")),
+    Periodic: (OP_PERIODIC, ("lengthscale", "period", "amplitude")),
+}
+
+
+def encode_program(node: Node) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Kernel tree -> wire format (ops, param_off, params) of include/agp_b200.h."""
+    ops, offs, params = [], [], []
+    for nd in unroll(node):
+        offs.append(len(params))
+        t = type(nd)
+        if t in _LEAF_FIELDS:
+            code, fields = _LEAF_FIELDS[t]
+            ops.append(code)
+            params.extend(float(getattr(nd, f)) for f in fields)
+        elif t is Plus:
+            ops.append(OP_PLUS)
+        elif t is Times:
+            ops.append(OP_TIMES)
+        elif t is ChangePoint:
+            ops.append(OP_CHANGEPOINT)
+            params.extend((float(nd.location), float(nd.scale)))
+        else:
+            raise TypeError(f"not a covariance kernel node: {nd!r}")
+    return (np.asarray(ops, dtype=np.int32), np.asarray(offs, dtype=np.int32),
+            np.asarray(params, dtype=np.float64))
+
+
+def _i32p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Engine:
+    """One ``agp_handle``: a CUDA stream plus its device workspaces on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.agp_create(int(device), C.byref(h))
+        if rc != 0:
+            raise _lib.AgpError(rc, f"agp_create(device={device}) failed (is a CUDA device visible?)")
+        self._h = h
+        self.device = int(device)
+        self._P = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.agp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _lib.AgpError(rc, self._lib.agp_last_error(self._h).decode())
+
+    # ---- site 1 -------------------------------------------------------------------------
+    def gram(self, node: Node, noise: float, ts, form: int = FORM_VECTORIZED) -> np.ndarray:
+        ops, offs, params = encode_program(node)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        n = ts.shape[0]
+        K = np.empty((n, n), dtype=np.float64, order="F")
+        self._check(self._lib.agp_gram(self._h, _i32p(ops), _i32p(offs), len(ops), _f64p(params), len(params),
+                                       _f64p(ts), n, float(noise), int(form), _f64p(K)))
+        return K
+
+    def gram_device(self, node: Node, noise: float, ts, out_ptr: int, form: int = FORM_VECTORIZED) -> None:
+        ops, offs, params = encode_program(node)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        self._check(self._lib.agp_gram_device(self._h, _i32p(ops), _i32p(offs), len(ops), _f64p(params), len(params),
+                                              _f64p(ts), ts.shape[0], float(noise), int(form), C.c_void_p(out_ptr)))
+
+    # ---- site 2 -------------------------------------------------------------------------
+    @staticmethod
+    def pack_batch(nodes: Sequence[Node], noises: Sequence[float]):
+        progs = [encode_program(nd) for nd in nodes]
+        prog_len = np.asarray([len(p[0]) for p in progs], dtype=np.int32)
+        n_params = np.asarray([len(p[2]) for p in progs], dtype=np.int32)
+        ops = np.concatenate([p[0] for p in progs]) if progs else np.zeros(0, np.int32)
+        offs = np.concatenate([p[1] for p in progs]) if progs else np.zeros(0, np.int32)
+        params = np.concatenate([p[2] for p in progs]) if progs else np.zeros(0, np.float64)
+        noise = np.ascontiguousarray(noises, dtype=np.float64)
+        if noise.shape[0] != len(progs):
+            raise ValueError("one noise value per particle")
+        return prog_len, np.ascontiguousarray(ops), np.ascontiguousarray(offs), n_params, np.ascontiguousarray(params), noise
+
+    def lml_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs) -> Tuple[np.ndarray, np.ndarray]:
+        """Host buffers in, host results out: one ``agp_lml_batch`` call."""
+        packed = self.pack_batch(nodes, noises)
+        return self.lml_batch_packed(packed, ts, xs)
+
+    def lml_batch_packed(self, packed, ts, xs) -> Tuple[np.ndarray, np.ndarray]:
+        prog_len, ops, offs, n_params, params, noise = packed
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        P = len(prog_len)
+        lml = np.empty(P, dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_lml_batch(self._h, P, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                            _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                            _f64p(lml), _i32p(info)))
+        self._P = P
+        return lml, info
+
+    def upload(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs) -> None:
+        self.upload_packed(self.pack_batch(nodes, noises), ts, xs)
+
+    def upload_packed(self, packed, ts, xs) -> None:
+        prog_len, ops, offs, n_params, params, noise = packed
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        self._check(self._lib.agp_lml_upload(self._h, len(prog_len), _i32p(prog_len), _i32p(ops), _i32p(offs),
+                                             _i32p(n_params), _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs),
+                                             ts.shape[0]))
+        self._P = len(prog_len)
+
+    def set_prefix(self, n_prefix: int) -> None:
+        self._check(self._lib.agp_lml_set_prefix(self._h, int(n_prefix)))
+
+    def run(self) -> None:
+        self._check(self._lib.agp_lml_run(self._h))
+
+    def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
+        lml = np.empty(self._P, dtype=np.float64)
+        info = np.empty(self._P, dtype=np.int32)
+        self._check(self._lib.agp_lml_fetch(self._h, _f64p(lml), _i32p(info)))
+        return lml, info
+
+    def device_results(self) -> Tuple[int, int]:
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.agp_lml_device_results(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def time_runs(self, reps: int) -> float:
+        ms = C.c_float()
+        self._check(self._lib.agp_lml_time(self._h, int(reps), C.byref(ms)))
+        return float(ms.value)
+
+    def stage_times(self) -> Tuple[float, float, float]:
+        arr = (C.c_float * 3)()
+        self._check(self._lib.agp_lml_stage_times(self._h, arr))
+        return float(arr[0]), float(arr[1]), float(arr[2])
+
+    def synchronize(self) -> None:
+        self._check(self._lib.agp_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.agp_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.agp_launch_count(self._h))
+
+
+_default_engines = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Per-(thread, device) engine, like one handle per Julia thread."""
+    key = (threading.get_ident(), int(device))
+    with _default_lock:
+        eng = _default_engines.get(key)
+        if eng is None:
+            eng = _default_engines[key] = Engine(device)
+        return eng
+
+
+def eval_cov(node: Node, ts, *, engine: Optional[Engine] = None) -> np.ndarray:
+    """``eval_cov(node, ts::Vector{Float64})`` (src/GP.jl:61): n×n covariance matrix."""
+    return (engine or default_engine()).gram(node, 0.0, ts, FORM_VECTORIZED)
+
+
+def compute_cov_matrix_vectorized(node: Node, noise: float, ts, *, engine: Optional[Engine] = None) -> np.ndarray:
+    """``GP.compute_cov_matrix_vectorized(node, noise, ts)`` (src/GP.jl:666-668)."""
+    return (engine or default_engine()).gram(node, noise, ts, FORM_VECTORIZED)
+
+
+def compute_cov_matrix(node: Node, noise: float, ts, *, engine: Optional[Engine] = None) -> np.ndarray:
+    """``GP.compute_cov_matrix(node, noise, ts)`` (src/GP.jl:674-684), scalar-form arithmetic."""
+    return (engine or default_engine()).gram(node, noise, ts, FORM_SCALAR)

@@ -1,0 +1,149 @@
+"""Host-side mirror of the SMC reweight / resample step around the hot path.
+
+Reference: ``smc_step!`` (src/inference_smc_anneal_data.jl:127-141), the weight consumers
+``compute_particle_weights`` / ``effective_sample_size`` (:22-31) and Gen's
+``maybe_resample!`` as called at :229-234.  Particles are independent between resampling
+barriers, so they shard across GPUs (one process per GPU); the only exchange is ONE
+all-gather of the per-particle log-weights, after which every rank resamples identically from
+a shared seed.  No other collective exists on this path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import gp
+
+
+def logsumexp(v: np.ndarray) -> float:
+    v = np.asarray(v, dtype=np.float64)
+    if v.size == 0:
+        return -math.inf
+    m = float(np.max(v))
+    if not math.isfinite(m):
+        return m
+    return m + math.log(float(np.sum(np.exp(v - m))))
+
+
+def normalize_weights(log_weights: np.ndarray):
+    """``Gen.normalize_weights``: (log_total_weight, log_normalized_weights)."""
+    lt = logsumexp(log_weights)
+    return lt, np.asarray(log_weights, dtype=np.float64) - lt
+
+
+def compute_particle_weights(log_weights: np.ndarray) -> np.ndarray:  # inference_smc_anneal_data.jl:22-25
+    return np.exp(normalize_weights(log_weights)[1])
+
+
+def effective_sample_size(log_weights: np.ndarray) -> float:  # inference_smc_anneal_data.jl:28-31
+    lnw = normalize_weights(log_weights)[1]
+    return math.exp(-logsumexp(2.0 * lnw))
+
+
+def shard_range(P: int, rank: int, world: int):
+    """Contiguous block of particles owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(P, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class ParticleState:
+    """The slice of ``Gen.ParticleFilterState`` this path needs: kernels, noises, weights."""
+    nodes: List[gp.Node]
+    noises: List[float]
+    log_weights: np.ndarray = None
+    scores: np.ndarray = None  # current LML of each particle (the trace score's likelihood part)
+    log_ml_est: float = 0.0
+
+    def __post_init__(self):
+        P = len(self.nodes)
+        if self.log_weights is None:
+            self.log_weights = np.zeros(P)
+        if self.scores is None:
+            self.scores = np.zeros(P)  # n = 0: empty mvnormal scores 0 (:185-189)
+
+
+def all_gather_log_weights(local: "np.ndarray | object", P: int, group=None, device_tensor=None) -> np.ndarray:
+    """The single collective of the path: gather every rank's log-weights.
+
+    With ``torch.distributed`` initialised this is one ``all_gather`` (NCCL over NVLink when the
+    tensors live on the GPU, gloo in the CPU tests); single-process it is the identity.
+    Shards may be ragged (P not divisible by the world size): shards are padded to the largest.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if device_tensor is not None:
+            return device_tensor.detach().cpu().numpy().copy()
+        return np.asarray(local, dtype=np.float64).copy()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    width = -(-P // world)
+    if device_tensor is not None:
+        src = device_tensor
+        buf = torch.full((width,), float("nan"), dtype=torch.float64, device=src.device)
+        buf[: src.numel()] = src
+    else:
+        buf = torch.full((width,), float("nan"), dtype=torch.float64)
+        loc = torch.as_tensor(np.asarray(local, dtype=np.float64))
+        buf[: loc.numel()] = loc
+    out = torch.empty((world * width,), dtype=torch.float64, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.cpu().numpy()
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_range(P, r, world)
+        pieces.append(out[r * width: r * width + (hi - lo)])
+    return np.concatenate(pieces)
+
+
+def resample_indices(log_weights: np.ndarray, seed: int) -> np.ndarray:
+    """Multinomial parent indices from normalised weights (Gen.maybe_resample! default),
+    drawn from a seed shared by all ranks so the result is replicated without communication."""
+    w = compute_particle_weights(log_weights)
+    rng = np.random.default_rng(seed)
+    return rng.choice(len(w), size=len(w), replace=True, p=w / w.sum())
+
+
+def maybe_resample(state: ParticleState, ess_threshold: float, seed: int) -> bool:
+    """``Gen.maybe_resample!(state, ess_threshold=...)`` on the replicated weight vector."""
+    P = len(state.nodes)
+    lt, lnw = normalize_weights(state.log_weights)
+    ess = math.exp(-logsumexp(2.0 * lnw))
+    if not (ess < ess_threshold):
+        return False
+    parents = resample_indices(state.log_weights, seed)
+    state.log_ml_est += lt - math.log(P)
+    state.nodes = [state.nodes[i] for i in parents]
+    state.noises = [state.noises[i] for i in parents]
+    state.scores = state.scores[parents].copy()
+    state.log_weights = np.zeros(P)
+    return True
+
+
+def smc_step(state: ParticleState, ts, xs, *, engine: Optional[gp.Engine] = None, group=None) -> np.ndarray:
+    """``smc_step!`` (:127-141): re-score every particle on the grown data prefix and add the
+    incremental weight ``LML_new - score_old``.  Each rank scores its shard on its own GPU;
+    the all-gather replicates the new scores so every rank holds the full weight vector."""
+    import torch.distributed as dist
+
+    P = len(state.nodes)
+    dist_on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if dist_on else 1
+    rank = dist.get_rank(group) if dist_on else 0
+    lo, hi = shard_range(P, rank, world)
+    eng = engine or gp.default_engine()
+    local, info = eng.lml_batch(state.nodes[lo:hi], state.noises[lo:hi], ts, xs)
+    if np.any(info != 0):
+        from .model import PosDefException
+        bad = int(np.nonzero(info)[0][0])
+        raise PosDefException(int(info[bad]), lo + bad)
+    new_scores = all_gather_log_weights(local, P, group=group)
+    state.log_weights = state.log_weights + (new_scores - state.scores)
+    state.scores = new_scores
+    return new_scores

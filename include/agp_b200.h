@@ -1,0 +1,147 @@
+/*
+ * agp_b200.h — C-ABI of the B200-native GP log-marginal-likelihood engine.
+ *
+ * Drop-in boundary for the ONE hot path of probsys/AutoGP.jl (reference @ 2ad372d):
+ *
+ *     noise      = transform_param(:noise, z) + JITTER                 src/Model.jl:134
+ *     cov_matrix = GP.compute_cov_matrix_vectorized(node, noise, ts)   src/Model.jl:135 -> src/GP.jl:666-668
+ *     xs ~ mvnormal(zeros(n), cov_matrix)                              src/Model.jl:136 (Gen -> Distributions -> PDMats -> dpotrf)
+ *
+ * The reference has no FFI layer; these are the entry points a Julia `ccall` (or Python
+ * ctypes) binding for that path would bind.  Plain pointers and sizes
+ * only.  Every function is re-entrant per handle; the library keeps no global mutable state.
+ * Return value: 0 = success, <0 = error (text via agp_last_error); never throws/aborts.
+ *
+ * Kernel programs ("wire format"): a kernel tree is sent in the reference's own postfix
+ * order, i.e. the order of `GP.unroll(node)` (src/GP.jl:111-113), as
+ *   ops[m]        int32  node-type code  (GPConfig codes, src/GP.jl:1101-1108, + 9 = WhiteNoise)
+ *   param_off[m]  int32  index of the node's first parameter in params[] (ignored for Plus/Times)
+ *   params[]      f64    leaf/ChangePoint parameters in Julia `fieldnames` order:
+ *       Constant(value) | Linear(intercept,bias,amplitude) | SquaredExponential(lengthscale,amplitude)
+ *       GammaExponential(lengthscale,gamma,amplitude) | Periodic(lengthscale,period,amplitude)
+ *       WhiteNoise(value) | ChangePoint(location,scale)          (src/GP.jl:131-133,157-159,185-192,
+ *                                                                  228-234,269-277,315-322,466-473)
+ */
+#ifndef AGP_B200_H
+#define AGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agp_handle agp_handle;
+
+/* node-type codes == GP.GPConfig defaults (src/GP.jl:1101-1108); WhiteNoise has no code there */
+enum {
+    AGP_OP_CONSTANT = 1,
+    AGP_OP_LINEAR = 2,
+    AGP_OP_SQUARED_EXPONENTIAL = 3,
+    AGP_OP_GAMMA_EXPONENTIAL = 4,
+    AGP_OP_PERIODIC = 5,
+    AGP_OP_PLUS = 6,
+    AGP_OP_TIMES = 7,
+    AGP_OP_CHANGEPOINT = 8,
+    AGP_OP_WHITE_NOISE = 9
+};
+
+/* error codes */
+enum {
+    AGP_OK = 0,
+    AGP_ERR_ARG = -1,      /* bad argument (null pointer, negative size, ...) */
+    AGP_ERR_PROGRAM = -2,  /* malformed kernel program (bad opcode, stack under/overflow, gamma range) */
+    AGP_ERR_CUDA = -3,     /* CUDA runtime error */
+    AGP_ERR_NOMEM = -4,    /* device workspace allocation failed */
+    AGP_ERR_STATE = -5     /* call sequence error (run before upload, ...) */
+};
+
+/* Gram evaluation form */
+enum {
+    AGP_FORM_VECTORIZED = 0, /* eval_cov(node, ts::Vector)  src/GP.jl:137-503, used by Model.model */
+    AGP_FORM_SCALAR = 1      /* eval_cov(node, t1, t2)      src/GP.jl:135-491, used by compute_cov_matrix */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* Create an engine bound to CUDA device `device`; owns one stream + its workspaces.
+ * Replaces nothing in the reference (it has no device state); one handle per Julia thread
+ * or one shared handle for the batched lock-step path. */
+int agp_create(int device, agp_handle** out);
+void agp_destroy(agp_handle* h);
+/* Text of the last error on this handle (valid until the next call on it). */
+const char* agp_last_error(const agp_handle* h);
+/* "major.minor.patch+sm_100a" */
+const char* agp_version(void);
+
+/* ---- site 1: Gram matrix ------------------------------------------------------------- */
+
+/* K_out (host, n*n doubles, column-major, BOTH triangles) = eval_cov(program, ts) + noise*I.
+ * Replaces GP.compute_cov_matrix_vectorized (src/GP.jl:666-668) with form = VECTORIZED,
+ * GP.compute_cov_matrix (src/GP.jl:674-684) with form = SCALAR, and eval_cov(node, ts)
+ * (src/GP.jl:61) with noise = 0.  `ts` is not modified; no pointer is retained. */
+int agp_gram(agp_handle* h, const int32_t* ops, const int32_t* param_off, int32_t m,
+             const double* params, int32_t n_params, const double* ts, int32_t n, double noise,
+             int32_t form, double* K_out);
+
+/* Same, but K_out is a DEVICE pointer (n*n doubles) and the call is asynchronous on the
+ * handle's stream: what bench.py times for the HBM-bound Gram stage. */
+int agp_gram_device(agp_handle* h, const int32_t* ops, const int32_t* param_off, int32_t m,
+                    const double* params, int32_t n_params, const double* ts, int32_t n,
+                    double noise, int32_t form, double* K_out_dev);
+
+/* ---- site 2: the log marginal likelihood, batched over particles ----------------------- */
+
+/* lml_out[p] = logpdf(mvnormal(zeros(n), eval_cov(program_p, ts) + noise[p]*I), xs)
+ * for p = 0..P-1 — the fused replacement of src/Model.jl:135-136 for P particles that share
+ * (ts, xs), as they always do inside one SMC round (src/inference_smc_anneal_data.jl:127-141,
+ * 212-217) and one MH/HMC sweep (src/inference_utils.jl:78-119).
+ *
+ *   prog_len[P]   nodes in particle p's program
+ *   ops, param_off  concatenated programs (sum(prog_len) entries); param_off is relative to
+ *                   the start of particle p's slice of params
+ *   n_params[P]   doubles in particle p's slice of params; params = concatenation
+ *   noise[P]      observation noise variance incl. JITTER (src/Model.jl:134)
+ *   ts[n], xs[n]  time points (any order, duplicates allowed) and observations
+ *   lml_out[P]    result; info_out[P]: 0 = ok, k>0 = leading minor k not positive definite
+ *                 (LAPACK dpotrf convention; the Julia glue raises PosDefException(k) as PDMats
+ *                 would) and lml_out[p] = NaN.
+ * All pointers are HOST pointers; copies in/out and the synchronisation are inside the call. */
+int agp_lml_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                  const int32_t* param_off, const int32_t* n_params, const double* params,
+                  const double* noise, const double* ts, const double* xs, int32_t n,
+                  double* lml_out, int32_t* info_out);
+
+/* The same call split in three so a caller can keep inputs resident on the device and
+ * overlap: upload (host -> device, compiles the programs), run (asynchronous on the handle's
+ * stream; may be repeated), fetch (device -> host + synchronise). */
+int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                   const int32_t* param_off, const int32_t* n_params, const double* params,
+                   const double* noise, const double* ts, const double* xs, int32_t n);
+int agp_lml_run(agp_handle* h);
+int agp_lml_fetch(agp_handle* h, double* lml_out, int32_t* info_out);
+/* Device pointers to the P results of the last run (valid until the next upload): lets the
+ * multi-GPU caller all-gather log-weights straight from HBM (NCCL). */
+int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev);
+/* Re-target the resident batch at a data prefix ts[0:n_prefix], xs[0:n_prefix] without a new
+ * upload — the data-annealing step of src/inference_smc_anneal_data.jl:212-217. */
+int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix);
+
+/* ---- plumbing -------------------------------------------------------------------------- */
+
+/* cudaStream_t of the handle (as void*), for event timing / stream ordering by the caller. */
+void* agp_stream(agp_handle* h);
+int agp_synchronize(agp_handle* h);
+/* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
+int64_t agp_launch_count(const agp_handle* h);
+/* Time `reps` back-to-back agp_lml_run() calls with CUDA events on the handle's stream;
+ * returns total milliseconds in *ms_out. */
+int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
+/* Per-stage device time of ONE run (ms): gram+update, potf2, trsm — serialised with events,
+ * for the roofline line in bench.py. stage_ms must hold 3 floats. */
+int agp_lml_stage_times(agp_handle* h, float* stage_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGP_B200_H */

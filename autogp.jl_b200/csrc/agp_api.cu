@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -40,6 +41,19 @@ struct agp_handle {
     unsigned char* d_gin = nullptr;  size_t cap_gin = 0;
     unsigned char* h_gin = nullptr;  size_t cap_hgin = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // particle groups: independent chains of (update, potf2, trsm) launches on side streams so
+    // that one group's latency-bound diagonal factorisation overlaps another group's GEMMs
+    static constexpr int kMaxGroups = 8;
+    int groups = 0;  // 0 = choose from P
+    cudaStream_t gstream[kMaxGroups] = {};
+    cudaEvent_t gfork = nullptr, gjoin[kMaxGroups] = {};
+    // cached CUDA graph of one full run
+    cudaGraphExec_t graph_exec = nullptr;
+    BatchView graph_view{};
+    int graph_P = -1, graph_groups = -1;
+    int64_t graph_kernels = 0;
+    bool use_graph = true;
 };
 
 namespace {
@@ -121,6 +135,17 @@ int agp_create(int device, agp_handle** out) {
         delete h;
         return AGP_ERR_CUDA;
     }
+    bool ok = cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming) == cudaSuccess;
+    for (int g = 0; ok && g < agp_handle::kMaxGroups; ++g)
+        ok = cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->gjoin[g], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        agp_destroy(h);
+        return AGP_ERR_CUDA;
+    }
+    if (const char* e = getenv("AGP_GROUPS")) h->groups = atoi(e);
+    if (const char* e = getenv("AGP_GRAPH")) h->use_graph = atoi(e) != 0;
     *out = h;
     return AGP_OK;
 }
@@ -140,6 +165,12 @@ void agp_destroy(agp_handle* h) {
     cudaFreeHost(h->h_res);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->gfork) cudaEventDestroy(h->gfork);
+    for (int g = 0; g < agp_handle::kMaxGroups; ++g) {
+        if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]);
+        if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -321,8 +352,46 @@ int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
     return AGP_OK;
 }
 
+static int pick_groups(const agp_handle* h) {
+    int g = h->groups;
+    if (g <= 0) g = h->P >= 32 ? 4 : (h->P >= 8 ? 2 : 1);
+    if (g > agp_handle::kMaxGroups) g = agp_handle::kMaxGroups;
+    if (g > h->P) g = h->P;
+    return g < 1 ? 1 : g;
+}
+
+// Enqueue one full factorisation sweep for particles [p0, p0+Pg) on stream s.
+static void enqueue_chain(const BatchView& view, int p0, int Pg, cudaStream_t s, int64_t* kernels) {
+    BatchView v = view;
+    v.p0 = p0;
+    for (int k = 0; k < v.nt; ++k) {
+        agp::launch_update(v, Pg, k, s);
+        agp::launch_potf2(v, Pg, k, s);
+        agp::launch_trsm(v, Pg, k, s);
+        *kernels += (k < v.nt - 1) ? 3 : 2;
+    }
+}
+
+// Fork the particle groups onto the side streams and join them back into the main stream.
+static int enqueue_groups(agp_handle* h, int G, int64_t* kernels) {
+    const int P = h->P;
+    if (G == 1) {
+        enqueue_chain(h->view, 0, P, h->stream, kernels);
+        return AGP_OK;
+    }
+    AGP_CUDA(h, cudaEventRecord(h->gfork, h->stream));
+    for (int g = 0; g < G; ++g) {
+        int lo = (int)((long long)P * g / G), hi = (int)((long long)P * (g + 1) / G);
+        AGP_CUDA(h, cudaStreamWaitEvent(h->gstream[g], h->gfork, 0));
+        enqueue_chain(h->view, lo, hi - lo, h->gstream[g], kernels);
+        AGP_CUDA(h, cudaEventRecord(h->gjoin[g], h->gstream[g]));
+        AGP_CUDA(h, cudaStreamWaitEvent(h->stream, h->gjoin[g], 0));
+    }
+    return AGP_OK;
+}
+
 static int run_impl(agp_handle* h, float* stage_ms) {
-    const BatchView& v = h->view;
+    BatchView& v = h->view;
     const int P = h->P;
     if (P == 0) return AGP_OK;
     if (v.n == 0) {
@@ -331,37 +400,65 @@ static int run_impl(agp_handle* h, float* stage_ms) {
         AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, res_bytes, h->stream));
         return AGP_OK;
     }
-    for (int k = 0; k < v.nt; ++k) {
-        if (stage_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        agp::launch_update(v, P, k, h->stream);
-        if (stage_ms) {
-            float ms;
-            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
-            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-            stage_ms[0] += ms;
-            AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    v.p0 = 0;
+    if (stage_ms) {
+        // serialised, one stream, events around every launch
+        for (int k = 0; k < v.nt; ++k) {
+            for (int st = 0; st < 3; ++st) {
+                if (st == 2 && k == v.nt - 1) break;
+                AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+                if (st == 0) agp::launch_update(v, P, k, h->stream);
+                else if (st == 1) agp::launch_potf2(v, P, k, h->stream);
+                else agp::launch_trsm(v, P, k, h->stream);
+                float ms;
+                AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+                AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+                AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+                stage_ms[st] += ms;
+                h->launches += 1;
+            }
         }
-        agp::launch_potf2(v, P, k, h->stream);
-        if (stage_ms) {
-            float ms;
-            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
-            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-            stage_ms[1] += ms;
-            AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        }
-        agp::launch_trsm(v, P, k, h->stream);
-        if (stage_ms) {
-            float ms;
-            AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-            AGP_CUDA(h, cudaEventSynchronize(h->ev1));
-            AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-            stage_ms[2] += ms;
-        }
-        h->launches += (k < v.nt - 1) ? 3 : 2;
+        return check_launch(h, "lml");
     }
-    return check_launch(h, "lml");
+    const int G = pick_groups(h);
+    if (!h->use_graph) {
+        int64_t kernels = 0;
+        int rc = enqueue_groups(h, G, &kernels);
+        if (rc != AGP_OK) return rc;
+        h->launches += kernels;
+        return check_launch(h, "lml");
+    }
+    const bool cached = h->graph_exec && h->graph_P == P && h->graph_groups == G && memcmp(&h->graph_view, &v, sizeof(BatchView)) == 0;
+    if (!cached) {
+        if (h->graph_exec) {
+            AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+            cudaGraphExecDestroy(h->graph_exec);
+            h->graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        int64_t kernels = 0;
+        AGP_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_groups(h, G, &kernels);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != AGP_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(h, AGP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            h->graph_exec = nullptr;
+            return fail(h, AGP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        }
+        h->graph_view = v;
+        h->graph_P = P;
+        h->graph_groups = G;
+        h->graph_kernels = kernels;
+    }
+    AGP_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->graph_kernels;
+    return AGP_OK;
 }
 
 int agp_lml_run(agp_handle* h) {

@@ -19,92 +19,137 @@ __device__ __forceinline__ double sigma_cp(double x, double location, double sca
     return 0.5 * (1.0 + tanh((location - x) / scale));
 }
 
-template <int D>
+// E independent entries are evaluated per interpreter pass (instruction-level parallelism hides
+// the latency of the FP64 transcendental chains and amortises the dispatch); the stack holds
+// E values per level.
+template <int D, int E>
 struct RegStack {
-    double s[D];
-    __device__ __forceinline__ void push(double v) {
+    double s[D][E];
+    __device__ __forceinline__ void push(const double (&v)[E]) {
 #pragma unroll
-        for (int i = D - 1; i > 0; --i) s[i] = s[i - 1];
-        s[0] = v;
+        for (int i = D - 1; i > 0; --i)
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[i][e] = s[i - 1][e];
+#pragma unroll
+        for (int e = 0; e < E; ++e) s[0][e] = v[e];
     }
     // replace the two top entries by r
-    __device__ __forceinline__ void reduce(double r) {
-        s[0] = r;
+    __device__ __forceinline__ void reduce(const double (&r)[E]) {
 #pragma unroll
-        for (int i = 1; i < D - 1; ++i) s[i] = s[i + 1];
+        for (int e = 0; e < E; ++e) s[0][e] = r[e];
+#pragma unroll
+        for (int i = 1; i < D - 1; ++i)
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[i][e] = s[i + 1][e];
     }
 };
 
-// (t1, t2) = (ts[row], ts[col]) of the UPPER-triangle element; lower-triangle entries are the
-// mirror image (Matrix(Symmetric(K)), src/GP.jl:501-502), so callers pass row <= col.
-template <int D>
-__device__ __forceinline__ double eval_program(const AgpInstr* __restrict__ prog, int m, double t1, double t2, int form) {
-    RegStack<D> st;
+// (t1[e], t2[e]) = (ts[row], ts[col]) of the UPPER-triangle element; lower-triangle entries are
+// the mirror image (Matrix(Symmetric(K)), src/GP.jl:501-502), so callers pass row <= col.
+template <int D, int E>
+__device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, int m, const double (&t1)[E], const double (&t2)[E], int form,
+                                             double (&out)[E]) {
+    RegStack<D, E> st;
 #pragma unroll
-    for (int i = 0; i < D; ++i) st.s[i] = 0.0;
-    const double dx = t1 - t2;
-    const double adx = fabs(dx);
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int e = 0; e < E; ++e) st.s[i][e] = 0.0;
+    double dx[E], adx[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        dx[e] = t1[e] - t2[e];
+        adx[e] = fabs(dx[e]);
+    }
     for (int q = 0; q < m; ++q) {
         const int op = prog[q].op;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        double v[E];
         switch (op) {
             case AGP_I_CONST:
-                st.push(a);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = a;
+                st.push(v);
                 break;
-            case AGP_I_LINEAR: {
-                double cc = (t1 - a) * (t2 - a);
-                st.push(b + c * cc);
+            case AGP_I_LINEAR:
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double cc = (t1[e] - a) * (t2[e] - a);
+                    v[e] = b + c * cc;
+                }
+                st.push(v);
                 break;
-            }
-            case AGP_I_SE: {
-                double e = exp(((-0.5 * dx) * dx) / a);
-                st.push(b * e);
+            case AGP_I_SE:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b * exp(((-0.5 * dx[e]) * dx[e]) / a);
+                st.push(v);
                 break;
-            }
-            case AGP_I_GE: {
-                double e = exp(-pow(adx / a, b));
-                st.push(c * e);
+            case AGP_I_GE:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * exp(-pow(adx[e] / a, b));
+                st.push(v);
                 break;
-            }
-            case AGP_I_PER: {
-                double sn = sin(a * adx);
-                double e = exp(b * (sn * sn));
-                st.push(c * e);
+            case AGP_I_PER:
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double sn = sin(a * adx[e]);
+                    v[e] = c * exp(b * (sn * sn));
+                }
+                st.push(v);
                 break;
-            }
             case AGP_I_WN:
-                st.push(t1 == t2 ? a : 0.0);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
+                st.push(v);
                 break;
             case AGP_I_PLUS:
-                st.reduce(st.s[1] + st.s[0]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = st.s[1][e] + st.s[0][e];
+                st.reduce(v);
                 break;
             case AGP_I_TIMES:
-                st.reduce(st.s[1] * st.s[0]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = st.s[1][e] * st.s[0][e];
+                st.reduce(v);
                 break;
             default: {  // AGP_I_CP / AGP_I_CP_SWAP
-                double kl = (op == AGP_I_CP) ? st.s[1] : st.s[0];
-                double kr = (op == AGP_I_CP) ? st.s[0] : st.s[1];
-                double g1 = sigma_cp(t1, a, b);
-                double g2 = sigma_cp(t2, a, b);
-                double r;
-                if (form == 0) {  // vectorised: sig_1 .* k_1 + sig_2 .* k_2   (GP.jl:494-501)
-                    double sig1 = g1 * g2;
-                    double sig2 = (1.0 - g1) * (1.0 - g2);
-                    r = sig1 * kl + sig2 * kr;
-                } else {  // scalar: s1*k_l*s2 + (1-s1)*k_r*(1-s2)            (GP.jl:485-491)
-                    r = (g1 * kl) * g2 + ((1.0 - g1) * kr) * (1.0 - g2);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double kl = (op == AGP_I_CP) ? st.s[1][e] : st.s[0][e];
+                    double kr = (op == AGP_I_CP) ? st.s[0][e] : st.s[1][e];
+                    double g1 = sigma_cp(t1[e], a, b);
+                    double g2 = sigma_cp(t2[e], a, b);
+                    if (form == 0) {  // vectorised: sig_1 .* k_1 + sig_2 .* k_2   (GP.jl:494-501)
+                        double sig1 = g1 * g2;
+                        double sig2 = (1.0 - g1) * (1.0 - g2);
+                        v[e] = sig1 * kl + sig2 * kr;
+                    } else {  // scalar: s1*k_l*s2 + (1-s1)*k_r*(1-s2)            (GP.jl:485-491)
+                        v[e] = (g1 * kl) * g2 + ((1.0 - g1) * kr) * (1.0 - g2);
+                    }
                 }
-                st.reduce(r);
+                st.reduce(v);
                 break;
             }
         }
     }
-    return st.s[0];
+#pragma unroll
+    for (int e = 0; e < E; ++e) out[e] = st.s[0][e];
 }
 
-__device__ __forceinline__ double eval_entry(const AgpInstr* __restrict__ prog, int m, int need, double t1, double t2, int form) {
-    if (need <= 4) return eval_program<4>(prog, m, t1, t2, form);
-    return eval_program<AGP_MAX_STACK>(prog, m, t1, t2, form);
+// E entries at once; deep trees (need > 4) fall back to pairs to bound register use.
+template <int E>
+__device__ __forceinline__ void eval_entries(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E], const double (&t2)[E],
+                                             int form, double (&out)[E]) {
+    if (need <= 4) {
+        eval_program<4, E>(prog, m, t1, t2, form, out);
+    } else {
+#pragma unroll
+        for (int h = 0; h < E; h += 2) {
+            double a1[2] = {t1[h], t1[h + 1]}, a2[2] = {t2[h], t2[h + 1]}, o2[2];
+            eval_program<AGP_MAX_STACK, 2>(prog, m, a1, a2, form, o2);
+            out[h] = o2[0];
+            out[h + 1] = o2[1];
+        }
+    }
 }
 
 }  // namespace agp

@@ -76,36 +76,40 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// update kernel
+// update kernel: one CTA = 128 rows x 64 columns of tile (i,k); two CTAs are resident per SM so
+// that one CTA's Gram/store epilogue (FP64 ALU + LSU) overlaps the other's DMMA main loop.
 // ------------------------------------------------------------------------------------------
-constexpr int KC = 32;             // K-chunk per pipeline stage (doubles)
-constexpr int NSTAGE = 3;
-constexpr int UPD_THREADS = 512;   // 16 warps: 4 (m) x 4 (n), warp tile 32x32
-constexpr int CS_STRIDE = 136;     // accumulator staging row stride (doubles)
+constexpr int TBN = 64;            // CTA tile columns
+constexpr int KC = 16;             // K-chunk per pipeline stage (doubles) = one 128-byte row
+constexpr int NSTAGE = 4;
+constexpr int UPD_THREADS = 256;   // 8 warps: 4 (m) x 2 (n), warp tile 32x32
+constexpr int CS_STRIDE = TBN + 8; // accumulator staging row stride (doubles): 72 = 8 mod 16
 constexpr int PROG_SMEM = 64;      // instructions cached in shared memory
-constexpr int STAGE_DOUBLES = 2 * TB * KC;
-constexpr int UPD_SMEM_STAGES = NSTAGE * STAGE_DOUBLES * 8;                      // 196608
-constexpr int UPD_SMEM_BYTES = UPD_SMEM_STAGES + 2 * TB * 8 + PROG_SMEM * 32 + 64;  // + ts_r, ts_c, program, mbarrier
+constexpr int STAGE_DOUBLES = (TB + TBN) * KC;
+constexpr int UPD_SMEM_STAGES = NSTAGE * STAGE_DOUBLES * 8;                                // 98304
+constexpr int UPD_SMEM_BYTES = UPD_SMEM_STAGES + (TB + TBN) * 8 + PROG_SMEM * 32 + 64;     // + ts_r, ts_c, program, mbarrier
 
 static_assert(TB * CS_STRIDE * 8 <= UPD_SMEM_STAGES, "accumulator staging must fit in the pipeline buffers");
+static_assert(2 * (UPD_SMEM_BYTES + 1024) <= 227 * 1024, "two CTAs per SM");
 
-// element (row, kcol) of a [TB][KC] operand tile; 16-byte chunks swizzled so that the
-// LDS.128 fragment loads of two adjacent rows hit disjoint bank halves (no padding needed)
+// element (row, chunk) of a [rows][KC] operand tile; the eight 16-byte chunks of a row are
+// swizzled so that the LDS.128 fragment loads of two adjacent rows hit disjoint bank halves
 __device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
 
-__global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v, int k) {
+__global__ void __launch_bounds__(UPD_THREADS, 2) agp_update_kernel(BatchView v, int k) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     double* ts_r = reinterpret_cast<double*>(smem_raw + UPD_SMEM_STAGES);
     double* ts_c = ts_r + TB;
-    AgpInstr* prog_s = reinterpret_cast<AgpInstr*>(ts_c + TB);
+    AgpInstr* prog_s = reinterpret_cast<AgpInstr*>(ts_c + TBN);
     uint64_t* bar = reinterpret_cast<uint64_t*>(prog_s + PROG_SMEM);
 
     const int tid = threadIdx.x;
-    const int p = blockIdx.y;
-    const int it = k + blockIdx.x;  // tile row
+    const int p = v.p0 + blockIdx.y;
+    const int it = k + (blockIdx.x >> 1);  // tile row
+    const int half = blockIdx.x & 1;       // column half of the tile
     const bool diag = (it == k);
-    const int row0 = it * TB, col0 = k * TB;
+    const int row0 = it * TB, col0 = k * TB + half * TBN;
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
     const int ld = v.ld;
 
@@ -116,9 +120,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, 2 * TB * 8);
+        mbar_expect_tx(bar, (TB + TBN) * 8);
         tma_bulk_g2s(ts_r, v.ts + row0, TB * 8, bar);
-        tma_bulk_g2s(ts_c, v.ts + col0, TB * 8, bar);
+        tma_bulk_g2s(ts_c, v.ts + col0, TBN * 8, bar);
     }
     const int poff = v.prog_off[p];
     const int pm = v.prog_off[p + 1] - poff;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
         for (int q = tid; q < pm * 4; q += UPD_THREADS) dst[q] = src[q];
         prog = prog_s;
     }
-    if (k == 0) {
+    if (k == 0 && half == 0) {
         // first touch of this batch: reset the forward-solve vector and the accumulators
         double* yp = v.y + (long long)p * ld;
         for (int r = tid; r < TB; r += UPD_THREADS) yp[row0 + r] = (row0 + r < v.n) ? v.xs[row0 + r] : 0.0;
@@ -143,8 +147,12 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
 
     // --- contraction: acc = sum_{j<k} L_ij L_kj^T over K = k*TB --------------------------
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp >> 1, wn = warp & 1;
     const int g = lane >> 2, c4 = lane & 3;
+    // warp tiles strictly above the diagonal of a diagonal tile are never read: skip their math.
+    // (warp w sits on scheduler w%4, so the active warps of a half-empty CTA still spread over
+    // all four schedulers and the co-resident CTA picks up the freed tensor-pipe time)
+    const bool active = !diag || (wm * 32 + 31 >= half * TBN + wn * 32);
     double acc[4][4][2];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb)
@@ -160,11 +168,18 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
         double* Bs = As + TB * KC;
         const int kk0 = chunk * KC;
 #pragma unroll
-        for (int e = 0; e < (TB * KC / 2) / UPD_THREADS; ++e) {
+        for (int e = 0; e < (TB * KC / 2) / UPD_THREADS; ++e) {  // 4
             int q = tid + e * UPD_THREADS;
-            int row = q >> 4, ch = q & 15;
+            int row = q >> 3, ch = q & 7;
             cp_async16(As + swz(row, ch), Ag + (long long)row * ld + kk0 + ch * 2);
-            if (!diag) cp_async16(Bs + swz(row, ch), Bg + (long long)row * ld + kk0 + ch * 2);
+        }
+        if (!diag) {
+#pragma unroll
+            for (int e = 0; e < (TBN * KC / 2) / UPD_THREADS; ++e) {  // 2
+                int q = tid + e * UPD_THREADS;
+                int row = q >> 3, ch = q & 7;
+                cp_async16(Bs + swz(row, ch), Bg + (long long)row * ld + kk0 + ch * 2);
+            }
         }
     };
 
@@ -181,22 +196,27 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
             if (nxt < nchunk) load_stage(nxt % NSTAGE, nxt);
             cp_async_commit();
         }
-        const double* As = stages + (ch % NSTAGE) * STAGE_DOUBLES;
-        const double* Bs = diag ? As : As + TB * KC;
+        if (active) {
+            const double* As = stages + (ch % NSTAGE) * STAGE_DOUBLES;
+            const double* Bs = diag ? As + half * TBN * KC : As + TB * KC;  // diagonal tile: B rows are a slice of A
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {
-            double2 a[4], b[4];
+            for (int ks = 0; ks < KC / 8; ++ks) {
+                double2 a[4], b[4];
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz(wm * 32 + mb * 8 + g, ks * 4 + c4));
+                for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz(wm * 32 + mb * 8 + g, ks * 4 + c4));
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz(wn * 32 + nb * 8 + g, ks * 4 + c4));
+                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz(wn * 32 + nb * 8 + g, ks * 4 + c4));
+                // two independent passes over the 16 accumulators: consecutive DMMAs never
+                // depend on each other (dependency distance = 16 instructions)
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb)
+                for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
-                    dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
-                }
+                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
+            }
         }
     }
     cp_async_wait<0>();
@@ -219,81 +239,183 @@ __global__ void __launch_bounds__(UPD_THREADS, 1) agp_update_kernel(BatchView v,
     const int need = v.prog_need[p];
     const double noise = v.noise[p];
     const int n = v.n;
-    for (int idx = tid; idx < TB * TB; idx += UPD_THREADS) {
-        const int r = idx >> 7, c = idx & (TB - 1);
-        if (diag && c > r) continue;  // strictly-upper part of a diagonal tile is never read
-        const int gr = row0 + r, gc = col0 + c;
-        double val;
-        if (gr < n) {  // gc <= gr < n
-            val = eval_entry(prog, pm, need, ts_c[c], ts_r[r], 0);
-            if (gr == gc) val = val + noise;  // + noise*I, src/GP.jl:667
-        } else {
-            val = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+    // thread -> column c, rows rbase + 4*e (e = 0..31), evaluated four entries at a time
+    const int c = tid & (TBN - 1), rbase = tid >> 6;
+    const int gc = col0 + c;
+    const int cdiag = half * TBN + c;  // column index inside the 128x128 tile
+    const double tcol = ts_c[c];
+#pragma unroll 1
+    for (int e4 = 0; e4 < 8; ++e4) {
+        const int rlast = rbase + 4 * (4 * e4 + 3);
+        if (diag && cdiag > rlast) continue;  // strictly-upper part of a diagonal tile is never read
+        double t1[4], t2[4], val[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            t1[j] = tcol;  // upper-triangle element (gc, gr): row index gc <= gr
+            t2[j] = ts_r[rbase + 4 * (4 * e4 + j)];
         }
-        if (k > 0) val = val - Cs[r * CS_STRIDE + c];
-        Lp[(long long)gr * ld + gc] = val;
+        eval_entries<4>(prog, pm, need, t1, t2, 0, val);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = rbase + 4 * (4 * e4 + j);
+            const int gr = row0 + r;
+            if (diag && cdiag > r) continue;
+            double out;
+            if (gr < n) {  // gc <= gr < n
+                out = val[j];
+                if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+            } else {
+                out = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+            }
+            if (k > 0) out = out - Cs[r * CS_STRIDE + c];
+            Lp[(long long)gr * ld + gc] = out;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // potf2 kernel: one CTA per particle, diagonal tile k (+ observation row)
+//
+// Blocked right-looking Cholesky of the 128x128 tile in shared memory, 32-wide panels:
+//   phase 1  warp 0 factors the 32x32 diagonal block in REGISTERS (lane = row, shuffles carry the
+//            pivot column) — the only inherently serial chain: 32 x (shfl, rsqrt, mul, fma)
+//   phase 2  one thread per sub-diagonal row (the observation vector y rides along as row 128,
+//            so z_k = L_kk^{-1} y_k needs no separate solve) substitutes against the block;
+//            meanwhile warp 1 inverts the diagonal block for the trsm kernel
+//   phase 3  rank-32 update of the trailing part of the tile on DMMA
 // ------------------------------------------------------------------------------------------
 constexpr int PF_THREADS = 512;
-constexpr int SA = TB + 1;  // 129: odd stride, column walks are conflict free; row TB = y
-constexpr int PF_SMEM_BYTES = (TB + 1) * SA * 8 + TB * 8 * 2 + 64;
+constexpr int SA = TB + 1;   // 129: odd stride, lane-per-row walks are conflict free; row TB = y
+constexpr int LPS = 36;      // panel staging stride (4 mod 16 doubles): DMMA fragment loads conflict free
+constexpr int PF_SMEM_BYTES = ((TB + 1) * SA + (TB - 32 + 1) * LPS + TB + 16) * 8;
 
 __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, int k) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);  // [TB+1][SA]
-    double* Ld = As + (TB + 1) * SA;                   // diag of L
-    double* Ri = Ld + TB;                              // 1 / diag
-    double* red = Ri + TB;                             // reduction scratch (8 doubles)
+    double* As = reinterpret_cast<double*>(smem_raw);  // [TB+1][SA] lower triangle + y row
+    double* Lpn = As + (TB + 1) * SA;                   // [97][LPS] current panel, rows below the diagonal block
+    double* Ri = Lpn + (TB - 32 + 1) * LPS;            // [TB] 1 / L_jj
+    double* red = Ri + TB;                             // reduction scratch
+    __shared__ int bad_s;
 
     const int tid = threadIdx.x;
-    const int p = blockIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int p = v.p0 + blockIdx.x;
     const int ld = v.ld;
     const int o = k * TB;
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
     double* yp = v.y + (long long)p * ld;
 
+    if (tid == 0) bad_s = 0;
     for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
         int r = idx >> 7, c = idx & (TB - 1);
-        if (c <= r) As[r * SA + c] = Lp[(long long)(o + r) * ld + o + c];
+        As[r * SA + c] = (c <= r) ? Lp[(long long)(o + r) * ld + o + c] : 0.0;
     }
     for (int c = tid; c < TB; c += PF_THREADS) As[TB * SA + c] = yp[o + c];
     __syncthreads();
 
-    // right-looking Cholesky, one barrier per column.  Column j (scaled) is parked in the
-    // unused upper triangle As[j][i]; the working lower triangle keeps unscaled columns.
-    const int ti = tid >> 4, tc = tid & 15;
-    int bad = 0;
-    for (int j = 0; j < TB; ++j) {
-        double d = As[j * SA + j];
-        if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
-            if (bad == 0) bad = o + j + 1;
-            d = 1.0;
-        }
-        const double ljj = sqrt(d);
-        const double inv = 1.0 / ljj;
-        const int a0 = (j < ti) ? 0 : ((j - ti) >> 5) + 1;
-        const int b0 = (j < tc) ? 0 : ((j - tc) >> 4) + 1;
-        for (int a = a0; a < 5; ++a) {
-            const int i = ti + (a << 5);
-            if (i > TB) break;
-            const double li = As[i * SA + j] * inv;
-            if (tc == 0) As[j * SA + i] = li;
-            const int cmax = i < TB ? i : TB - 1;
-            double* __restrict__ rowi = As + i * SA;
-            for (int b = b0;; ++b) {
-                const int c = tc + (b << 4);
-                if (c > cmax) break;
-                const double lc = As[c * SA + j] * inv;
-                rowi[c] = fma(-li, lc, rowi[c]);
+    const bool want_dinv = (k < v.nt - 1);
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+        const int j0 = jb * 32;
+        // ---- phase 1: diagonal block in registers (warp 0) -------------------------------
+        if (warp == 0) {
+            double a[32];
+            const double* rowp = As + (j0 + lane) * SA + j0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+            int bad = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double d = __shfl_sync(0xffffffffu, a[j], j);
+                if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
+                    if (bad == 0) bad = o + j0 + j + 1;
+                    d = 1.0;
+                }
+                const double inv = rsqrt(d);
+                const double l = (lane == j) ? d * inv : a[j] * inv;
+                a[j] = l;
+                if (lane == 0) Ri[j0 + j] = inv;
+#pragma unroll
+                for (int c = j + 1; c < 32; ++c) {
+                    const double lc = __shfl_sync(0xffffffffu, l, c);
+                    a[c] = fma(-l, lc, a[c]);
+                }
             }
+            double* roww = As + (j0 + lane) * SA + j0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                if (c <= lane) roww[c] = a[c];
+            if (lane == 0 && bad != 0 && bad_s == 0) bad_s = bad;
         }
-        if (tid == 0) {
-            Ld[j] = ljj;
-            Ri[j] = inv;
+        __syncthreads();
+        // ---- phase 2: rows below the block (threads 64..), block inverse (warp 1) ----------
+        const int R = TB + 1 - (j0 + 32);  // rows j0+32 .. 128 (row 128 = y)
+        if (tid >= 64 && tid - 64 < R) {
+            const int t = tid - 64;
+            const int i = j0 + 32 + t;
+            double a[32];
+            double* rowp = As + i * SA + j0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const double l = a[j] * Ri[j0 + j];
+                a[j] = l;
+#pragma unroll
+                for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, As[(j0 + c) * SA + j0 + j], a[c]);  // broadcast
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                rowp[c] = a[c];
+                Lpn[t * LPS + c] = a[c];
+            }
+        } else if (warp == 1 && want_dinv) {
+            // inverse of the diagonal block, lane = column of the inverse
+            double x[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int m = 0; m < r; ++m) sacc = fma(As[(j0 + r) * SA + j0 + m], x[m], sacc);  // L(r,m), broadcast
+                const double rhs = (r == lane) ? 1.0 : 0.0;
+                x[r] = (r < lane) ? 0.0 : (rhs - sacc) * Ri[j0 + r];
+            }
+            double* out = v.dinv + ((long long)p * 4 + jb) * 1024;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) out[r * 32 + lane] = x[r];
+        }
+        __syncthreads();
+        // ---- phase 3: trailing update  A[i][c] -= sum_m L[i][m] L[c][m]  (DMMA) -------------
+        const int T = TB - (j0 + 32);  // trailing rows/cols inside the tile
+        if (T > 0) {
+            const int nb8 = T >> 3;
+            const int nblk = nb8 * (nb8 + 1) / 2;
+            const int g = lane >> 2, c4 = lane & 3;
+            for (int blk = warp; blk < nblk; blk += PF_THREADS / 32) {
+                int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+                while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+                while (bi * (bi + 1) / 2 > blk) --bi;
+                const int bc = blk - bi * (bi + 1) / 2;
+                double c0 = 0.0, c1 = 0.0;
+                const double* ap = Lpn + (bi * 8 + g) * LPS + c4;
+                const double* bp = Lpn + (bc * 8 + g) * LPS + c4;
+#pragma unroll
+                for (int kk = 0; kk < 32; kk += 4) dmma884(c0, c1, ap[kk], bp[kk]);
+                double* cp = As + (j0 + 32 + bi * 8 + g) * SA + j0 + 32 + bc * 8 + 2 * c4;
+                cp[0] -= c0;
+                cp[1] -= c1;
+            }
+            // observation row (t = T): y[c] -= sum_m z_panel[m] L[c][m]
+            if (warp == PF_THREADS / 32 - 1) {
+                const double* zp = Lpn + T * LPS;
+                for (int cc = lane; cc < T; cc += 32) {
+                    const double* lp = Lpn + cc * LPS;
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) sacc = fma(zp[m], lp[m], sacc);
+                    As[TB * SA + j0 + 32 + cc] -= sacc;
+                }
+            }
         }
         __syncthreads();
     }
@@ -301,23 +423,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, i
     // write L_kk (lower, row-major; strictly-upper zeroed so the tile is a clean factor)
     for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
         int r = idx >> 7, c = idx & (TB - 1);
-        double val = (c < r) ? As[c * SA + r] : (c == r ? Ld[r] : 0.0);
-        Lp[(long long)(o + r) * ld + o + c] = val;
+        Lp[(long long)(o + r) * ld + o + c] = (c <= r) ? As[r * SA + c] : 0.0;
     }
     // z_k, sum z^2, sum log L_jj
     double part_ld = 0.0, part_zz = 0.0;
     if (tid < TB) {
-        double zj = As[tid * SA + TB];
+        double zj = As[TB * SA + tid];
         v.z[(long long)p * ld + o + tid] = zj;
         part_zz = zj * zj;
-        part_ld = log(Ld[tid]);
-    }
-    if (tid < TB) {
+        part_ld = log(As[tid * SA + tid]);
         part_ld = warp_sum(part_ld);
         part_zz = warp_sum(part_zz);
-        if ((tid & 31) == 0) {
-            red[(tid >> 5) * 2] = part_ld;
-            red[(tid >> 5) * 2 + 1] = part_zz;
+        if (lane == 0) {
+            red[warp * 2] = part_ld;
+            red[warp * 2 + 1] = part_zz;
         }
     }
     __syncthreads();
@@ -329,9 +448,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, i
         v.logdet_half[p] = tot_l;
         v.zz[p] = tot_z;
         int info = v.info[p];
-        if (info == 0 && bad != 0) {
-            info = bad;
-            v.info[p] = bad;
+        if (info == 0 && bad_s != 0) {
+            info = bad_s;
+            v.info[p] = info;
         }
         if (k == v.nt - 1) {
             // -(n log 2pi + logdet)/2 - z'z/2, logdet = 2 sum log L_ii
@@ -339,22 +458,6 @@ __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, i
             double lml = -0.5 * ((double)v.n * log2pi + 2.0 * tot_l) - 0.5 * tot_z;
             v.lml[p] = (info == 0) ? lml : __longlong_as_double(0x7ff8000000000000LL);
         }
-    }
-    // inverses of the four 32x32 diagonal blocks (warp b, lane = column of the inverse)
-    if (tid < 128 && k < v.nt - 1) {
-        const int b = tid >> 5, cc = tid & 31;
-        double x[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            double s = 0.0;
-#pragma unroll
-            for (int m = 0; m < r; ++m) s = fma(As[(b * 32 + m) * SA + b * 32 + r], x[m], s);  // L(r,m), broadcast
-            double rhs = (r == cc) ? 1.0 : 0.0;
-            x[r] = (r < cc) ? 0.0 : (rhs - s) * Ri[b * 32 + r];
-        }
-        double* out = v.dinv + ((long long)p * 4 + b) * 1024;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) out[r * 32 + cc] = x[r];
     }
 }
 
@@ -373,7 +476,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
     double* zs = Ls + TB * XS;                         // [128]
 
     const int tid = threadIdx.x;
-    const int p = blockIdx.y;
+    const int p = v.p0 + blockIdx.y;
     const int it = k + 1 + (blockIdx.x >> 1);
     const int r0 = it * TB + (blockIdx.x & 1) * TR_ROWS;
     const int o = k * TB;
@@ -496,21 +599,31 @@ __global__ void __launch_bounds__(GR_THREADS) agp_gram_kernel(const AgpInstr* __
     }
     __syncthreads();
     const int il = tid & (GT - 1);
+    const int gi = i0 + il;
 #pragma unroll 1
-    for (int e = 0; e < GT / 4; ++e) {
-        const int jl = (tid >> 6) + e * 4;
-        const int gi = i0 + il, gj = j0 + jl;
-        double val = 0.0;
-        if (gi < n && gj < n) {
+    for (int e4 = 0; e4 < GT / 16; ++e4) {
+        double t1[4], t2[4], val[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jl = (tid >> 6) + (e4 * 4 + j) * 4;
             // Symmetric(K): entry (i,j) takes the upper-triangle element (min,max)
-            const bool up = gi <= gj;
-            const double t1 = up ? tsi[il] : tsj[jl];
-            const double t2 = up ? tsj[jl] : tsi[il];
-            val = eval_entry(prog, m, need, t1, t2, form);
-            if (gi == gj) val = val + noise;
-            K[(long long)gj * n + gi] = val;  // column j, rows contiguous
+            const bool up = gi <= j0 + jl;
+            t1[j] = up ? tsi[il] : tsj[jl];
+            t2[j] = up ? tsj[jl] : tsi[il];
         }
-        tile[jl][il] = val;
+        eval_entries<4>(prog, m, need, t1, t2, form, val);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jl = (tid >> 6) + (e4 * 4 + j) * 4;
+            const int gj = j0 + jl;
+            double v = 0.0;
+            if (gi < n && gj < n) {
+                v = val[j];
+                if (gi == gj) v = v + noise;
+                K[(long long)gj * n + gi] = v;  // column j, rows contiguous
+            }
+            tile[jl][il] = v;
+        }
     }
     if (bi != bj) {
         __syncthreads();
@@ -539,7 +652,7 @@ cudaError_t configure_kernels() {
 }
 
 void launch_update(const BatchView& v, int P, int k, cudaStream_t s) {
-    dim3 grid(v.nt - k, P);
+    dim3 grid(2 * (v.nt - k), P);  // two 128x64 half tiles per tile
     agp_update_kernel<<<grid, UPD_THREADS, UPD_SMEM_BYTES, s>>>(v, k);
 }
 

@@ -29,6 +29,7 @@ struct BatchView {
     double* lml;             // [P]
     int* info;               // [P]
     double* dinv;            // [P][4][32][32] inverses of the diagonal 32x32 blocks of L_kk
+    int p0;                  // first particle of this launch (particle groups run on separate streams)
 };
 
 // Left-looking block column k:  tiles (i,k), i>=k  <-  K(ts_i, ts_k) - sum_{j<k} L_ij L_kj^T

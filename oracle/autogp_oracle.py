@@ -471,6 +471,8 @@ def synthetic_series(n: int) -> Tuple[np.ndarray, np.ndarray]:
     x = 0.3 * np.sin(2 * np.pi * 4 * t) + 0.5 * (t - 0.5) + 0.05 * eps
     # LinearTransform(data, width=1): mean 0, range 1 (Transforms.jl:71-81)
     a = float(x.max() - x.min())
+    if a == 0.0:  # n == 1: the reference's LinearTransform refuses (<2 values); keep the raw value
+        return t[perm].copy(), x[perm].copy()
     x = (1.0 / a) * x + (-(1.0 * float(x.mean())) / a)
     return t[perm].copy(), x[perm].copy()
 

@@ -1,0 +1,129 @@
+"""CPU suite, part 2: the C-ABI library and the host-side mirror (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import autogp_oracle as o
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "agp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(agp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    assert set(declared) == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None, name
+    assert b"sm_100a" in lib.agp_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    import autogp.jl_b200 as agp
+    from autogp.jl_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.AgpError):
+        agp.Engine(0)
+    with pytest.raises(_lib.AgpError):
+        agp.compute_cov_matrix_vectorized(agp.Constant(1.0), 0.1, np.linspace(0, 1, 4))
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "autogp.jl_b200")
+    pat = re.compile(r"^\s*(import|from|#include)\b.*oracle|CDLL\(.*oracle|liboracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), f
+
+
+def test_encode_program_matches_oracle_encoder_and_unroll_order():
+    import autogp.jl_b200 as agp
+
+    for k in H.fixture_kernels():
+        a = agp.encode_program(H.to_agp(k))
+        b = o.encode_program(k)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # postfix order of GP.unroll (src/GP.jl:111-113): left, right, node
+    t = agp.Plus(agp.Times(agp.SquaredExponential(1.0), agp.Periodic(1.0, 2.0)), agp.Linear(0.5))
+    names = [type(n).__name__ for n in agp.unroll(t)]
+    assert names == ["SquaredExponential", "Periodic", "Times", "Linear", "Plus"]
+    assert agp.size(t) == 5 and agp.depth(t) == 3
+    # GPConfig integer codes (src/GP.jl:1101-1108)
+    assert agp.encode_program(t)[0].tolist() == [3, 5, 7, 2, 6]
+
+
+def test_operator_overloads_and_defaults():
+    import autogp.jl_b200 as agp
+
+    a, b = agp.Linear(0.5), agp.Periodic(2.0, 1.0)
+    assert (a + b) == agp.Plus(a, b) and (a * b) == agp.Times(a, b)
+    assert agp.Linear(0.5).bias == 1.0 and agp.Linear(0.5).amplitude == 1.0  # GP.jl:189
+    assert agp.SquaredExponential(2.0).amplitude == 1.0
+    with pytest.raises(AssertionError):
+        agp.GammaExponential(1.0, 2.5)  # GP.jl:274
+
+
+def test_transforms_match_oracle():
+    import autogp.jl_b200 as agp
+
+    assert agp.JITTER == o.JITTER
+    for f in ("noise", "period", "gamma", "lengthscale"):
+        for z in (-2.0, 0.0, 0.7):
+            v = agp.transform_param(f, z)
+            assert v == o.transform_param(f, z)
+            assert agp.untransform_param(f, v) == pytest.approx(z, abs=1e-12)
+
+
+def test_program_compiler_rejects_malformed_programs():
+    """Error behaviour of the boundary: bad programs are rejected before any CUDA work."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    # agp_create fails without a GPU, but argument checks on a null handle must not crash
+    assert lib.agp_lml_run(None) == _lib.AGP_ERR_ARG
+    assert lib.agp_synchronize(None) == _lib.AGP_ERR_ARG
+    assert lib.agp_launch_count(None) == 0
+    assert lib.agp_last_error(None) == b"null handle"
+    h = C.c_void_p()
+    assert lib.agp_create(-1, C.byref(h)) != 0 and not h.value
+
+
+def test_shard_range_partitions():
+    from autogp.jl_b200 import smc
+
+    for P in (1, 7, 64, 512):
+        for w in (1, 2, 3, 8):
+            spans = [smc.shard_range(P, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == P
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_weight_consumers_match_oracle():
+    from autogp.jl_b200 import smc
+
+    rng = np.random.default_rng(3)
+    lw = rng.normal(size=32) * 5
+    assert smc.effective_sample_size(lw) == pytest.approx(o.effective_sample_size(o.normalize_weights(lw)[1]))
+    assert np.allclose(smc.compute_particle_weights(lw), np.exp(o.normalize_weights(lw)[1]))
+    assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))

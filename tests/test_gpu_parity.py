@@ -1,0 +1,333 @@
+"""GPU suite: the CUDA path, called through the C-ABI (ctypes), against the CPU oracle and the
+committed golden fixtures.
+
+Stated tolerances
+  * Gram entries: |K_gpu - K_oracle| <= 64 eps |K|.  +,* are exact (no FMA contraction); the
+    slack is the libm difference (CUDA libdevice exp/sin/pow/tanh, each <= 2 ulp, vs glibc/NumPy)
+    amplified by the exponent's condition number (|coef * sin^2| up to ~10 for the fixtures).
+  * LML: relative error <= 1e-8 (BASELINE.json north_star); observed ~1e-15 on these cases, and
+    a tighter 1e-11 regression bound is asserted where the problem is well conditioned.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+import autogp_oracle as o
+import c_oracle
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+GRAM_RTOL = 64 * EPS
+LML_RTOL = 1e-8
+LML_RTOL_TIGHT = 1e-11
+
+
+def oracle_lmls(parts, ts, xs):
+    return np.array([o.log_marginal_likelihood(nd, nz, ts, xs) for nd, nz in parts])
+
+
+def gpu_lmls(engine, parts, ts, xs):
+    return engine.lml_batch([H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
+
+
+# ---- site 1: Gram ---------------------------------------------------------------------------
+
+def test_gram_fixture_sweep_vectorised_and_scalar(engine):
+    """The 6 base + 108 composite kernels of test/test_GP.jl:24-33,54-56 on its 100-point grid."""
+    import autogp.jl_b200 as agp
+
+    _, ds = H.fixture_grid()
+    for k in H.fixture_kernels():
+        Kv = engine.gram(H.to_agp(k), 0.25, ds, agp.gp.FORM_VECTORIZED)
+        Ks = engine.gram(H.to_agp(k), 0.25, ds, agp.gp.FORM_SCALAR)
+        Rv = o.compute_cov_matrix_vectorized(k, 0.25, ds)
+        Rs = c_oracle.gram(o.encode_program(k), ds, 0.25, form=1)
+        assert np.all(np.abs(Kv - Rv) <= GRAM_RTOL * np.abs(Rv)), k
+        assert np.all(np.abs(Ks - Rs) <= GRAM_RTOL * np.abs(Rs)), k
+        assert np.array_equal(Kv, Kv.T)  # both triangles, Matrix(Symmetric(K))
+        assert Kv.flags["F_CONTIGUOUS"]
+
+
+def test_gram_against_committed_golden(engine):
+    ts, grams, _ = H.golden()
+    for k, G in zip(H.fixture_kernels(), grams):
+        K = engine.gram(H.to_agp(k), 0.0, ts)
+        assert np.all(np.abs(K - G) <= GRAM_RTOL * np.abs(G)), k
+
+
+def test_gram_exact_for_transcendental_free_kernels(engine):
+    """Constant / Linear / WhiteNoise / Plus / Times involve only +,*: bit-exact."""
+    rng = np.random.default_rng(0)
+    ts = rng.uniform(0, 1, 77)
+    ts[5] = ts[40]  # duplicate time point: WhiteNoise equality test (GP.jl:139)
+    k = o.Plus(o.Times(o.Linear(0.3, 1.1, 0.9), o.Constant(0.7)), o.Plus(o.WhiteNoise(0.4), o.Linear(0.6, 0.2, 1.7)))
+    K = engine.gram(H.to_agp(k), 0.125, ts)
+    R = o.compute_cov_matrix_vectorized(k, 0.125, ts)
+    assert np.array_equal(K, R)
+    assert K[5, 40] == R[5, 40] and K[5, 40] != K[5, 41]
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 130, 257])
+def test_gram_ragged_sizes(engine, n):
+    ts = np.random.default_rng(n).uniform(0, 1, n)
+    k, nz = o.synthetic_particle(n % 5, "ge+per*lin")
+    K = engine.gram(H.to_agp(k), nz, ts)
+    R = o.compute_cov_matrix_vectorized(k, nz, ts)
+    assert K.shape == (n, n)
+    assert np.all(np.abs(K - R) <= GRAM_RTOL * np.abs(R))
+
+
+def test_gram_changepoint_saturates_exactly(engine):
+    """Model.jl:121 hard-codes scale = .001: tanh saturates to +-1, sigma to exactly 0 / 1."""
+    ts = np.linspace(0, 1, 64)
+    k = o.ChangePoint(o.Linear(0.5), o.SquaredExponential(0.2, 1.3), 0.4, 0.001)
+    K = engine.gram(H.to_agp(k), 0.0, ts)
+    R = o.compute_cov_matrix_vectorized(k, 0.0, ts)
+    # next to the change point (1 - sigma) cancels catastrophically, so a 1-ulp tanh difference is
+    # an ABSOLUTE error of a few eps * max|K| there; away from it the entries agree relatively
+    assert np.all(np.abs(K - R) <= GRAM_RTOL * np.abs(R) + 8 * EPS * np.max(np.abs(R)))
+    assert np.all(K[:20, 40:] == 0.0)  # opposite sides of the change point are independent
+    assert np.array_equal(K[:20, :20], R[:20, :20])  # sigma == 1 exactly: pure Linear block, bit-exact
+
+
+def test_gram_does_not_mutate_inputs_and_empty(engine):
+    ts = np.linspace(0, 1, 10)
+    ts0 = ts.copy()
+    engine.gram(H.to_agp(o.SquaredExponential(0.3)), 0.1, ts)
+    assert np.array_equal(ts, ts0)
+    assert engine.gram(H.to_agp(o.SquaredExponential(0.3)), 0.1, np.zeros(0)).shape == (0, 0)
+
+
+# ---- site 2: LML ------------------------------------------------------------------------------
+
+def test_lml_golden_fixture_batch_ragged_programs(engine):
+    """All 114 fixture kernels as ONE ragged batch against the mpmath 50-digit golden values."""
+    ts, _, lml = H.golden()
+    xs = H.fixture_xs(ts)
+    ks = H.fixture_kernels()
+    got, info = engine.lml_batch([H.to_agp(k) for k in ks], [lml["noise"]] * len(ks), ts, xs)
+    assert np.all(info == 0)
+    truth = np.array(lml["fixture_mp"])
+    assert np.all(np.abs(got - truth) <= 1e-12 * np.maximum(1.0, np.abs(truth)))
+
+
+def test_lml_config0_n128_se_whitenoise(engine):
+    """BASELINE.json configs[0]: n=128, 4 particles, SE + WhiteNoise."""
+    _, _, lml = H.golden()
+    ts, xs = o.synthetic_series(128)
+    parts = [o.synthetic_particle(p, "se+wn") for p in range(4)]
+    got, info = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(info == 0)
+    assert H.rel_err(got, lml["config0_f64"]) <= LML_RTOL_TIGHT
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 127, 128, 129, 255, 256, 257, 300, 513, 640])
+def test_lml_ragged_sizes_mixed_trees(engine, n):
+    ts, xs = o.synthetic_series(n)
+    trees = ["se*per+lin", "se+wn", "ge+per*lin", "cp(lin,se)"]
+    parts = [o.synthetic_particle(p, trees[p % 4]) for p in range(7)]
+    got, info = gpu_lmls(engine, parts, ts, xs)
+    ref = oracle_lmls(parts, ts, xs)
+    assert np.all(info == 0)
+    assert H.rel_err(got, ref) <= LML_RTOL_TIGHT
+
+
+def test_lml_hmc_benchmarks_and_predictive_identity(engine):
+    """test/experiment_hmc.jl:111-132, 180-184: LML(joint) - LML(obs) = predictive logpdf."""
+    ts = np.linspace(0.0, 10.0, 1000)
+    rng = np.random.default_rng(7)
+    idx = rng.permutation(1000)
+    obs, test = idx[:200], idx[200:260]  # unsorted, like the shuffled reference path
+    both = np.concatenate([obs, test])
+    xs = H.fixture_xs(ts / 10.0) + 0.05 * rng.standard_normal(1000)
+    parts = [(k, nz + o.JITTER) for k, nz in H.hmc_benchmarks()]
+    l_obs, i1 = gpu_lmls(engine, parts, ts[obs], xs[obs])
+    l_joint, i2 = gpu_lmls(engine, parts, ts[both], xs[both])
+    assert np.all(i1 == 0) and np.all(i2 == 0)
+    assert H.rel_err(l_obs, oracle_lmls(parts, ts[obs], xs[obs])) <= LML_RTOL
+    assert H.rel_err(l_joint, oracle_lmls(parts, ts[both], xs[both])) <= LML_RTOL
+    for (k, nz), a, b in zip(parts, l_joint, l_obs):
+        mu, cov = o.predictive_mvn(k, nz, ts[obs], xs[obs], ts[test])
+        assert o.mvn_logpdf(xs[test], mu, cov) == pytest.approx(a - b, rel=2e-7)
+
+
+def test_lml_not_positive_definite_reports_lapack_info(engine):
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(200)
+    cases = [(o.Constant(1.0), -2.0),                 # first pivot negative -> info 1
+             (o.SquaredExponential(0.1, 1.0), 0.1),   # fine
+             (o.Constant(1.0), 0.0)]                  # rank one: second pivot is exactly 0 -> info 2
+    got, info = gpu_lmls(engine, cases, ts, xs)
+    want = [c_oracle.lml(o.encode_program(k), ts, xs, nz)[1] for k, nz in cases]
+    assert info.tolist() == want
+    assert info[1] == 0 and np.isfinite(got[1])
+    assert np.isnan(got[0]) and np.isnan(got[2])
+    with pytest.raises(agp.PosDefException) as e:
+        agp.log_marginal_likelihoods([H.to_agp(k) for k, _ in cases], [nz for _, nz in cases], ts, xs, engine=engine)
+    assert e.value.info == 1 and e.value.particle == 0
+    # failure deep inside the matrix (second block column) still reports the global 1-based index
+    n = 300
+    ts, xs = o.synthetic_series(n)
+    tsd = ts.copy()
+    tsd[200] = tsd[10]  # duplicate time point + zero noise => singular leading minor 201
+    got, info = gpu_lmls(engine, [(o.SquaredExponential(0.5, 1.0), 0.0)], tsd, xs)
+    ref_info = c_oracle.lml(o.encode_program(o.SquaredExponential(0.5, 1.0)), tsd, xs, 0.0)[1]
+    assert info[0] != 0 and ref_info != 0
+
+
+def test_lml_empty_inputs(engine):
+    lml, info = engine.lml_batch([H.to_agp(o.Constant(1.0))] * 3, [0.1] * 3, np.zeros(0), np.zeros(0))
+    assert lml.tolist() == [0.0, 0.0, 0.0] and info.tolist() == [0, 0, 0]  # empty mvnormal scores 0
+    lml, info = engine.lml_batch([], [], np.linspace(0, 1, 5), np.zeros(5))
+    assert lml.shape == (0,) and info.shape == (0,)
+
+
+def test_lml_data_annealing_prefixes(engine):
+    """inference_smc_anneal_data.jl:212-217: the same particles re-scored on growing prefixes."""
+    n = 410
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(5)]
+    engine.upload([H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
+    for step in (41, 128, 205, 300, 410, 129):
+        engine.set_prefix(step)
+        engine.run()
+        got, info = engine.fetch()
+        assert np.all(info == 0)
+        assert H.rel_err(got, oracle_lmls(parts, ts[:step], xs[:step])) <= LML_RTOL_TIGHT
+
+
+def test_lml_deep_and_bushy_trees(engine):
+    ts, xs = o.synthetic_series(150)
+    leaves = [o.SquaredExponential(0.2 + 0.05 * i, 0.5 + 0.1 * i) for i in range(6)] + \
+             [o.Periodic(0.5 + 0.1 * i, 0.2 + 0.05 * i, 0.7) for i in range(6)] + [o.Linear(0.1 * i, 0.3, 0.4) for i in range(4)]
+
+    def right_chain(xs_, op):
+        t = xs_[-1]
+        for leaf in reversed(xs_[:-1]):
+            t = op(leaf, t)
+        return t
+
+    def balanced(xs_, d=0):
+        if len(xs_) == 1:
+            return xs_[0]
+        h = len(xs_) // 2
+        op = o.Plus if d % 2 == 0 else o.Times
+        return op(balanced(xs_[:h], d + 1), balanced(xs_[h:], d + 1))
+
+    big = [o.SquaredExponential(0.1 + 0.01 * i, 0.05) for i in range(40)]  # 79 instructions: global-memory program path
+    cp_nest = o.ChangePoint(o.ChangePoint(leaves[0], leaves[7], 0.3, 0.05), o.Plus(leaves[12], o.ChangePoint(leaves[1], leaves[8], 0.7, 0.1)), 0.5, 0.02)
+    trees = [right_chain(leaves[:12], o.Plus), balanced(leaves), balanced(big), cp_nest,
+             o.ChangePoint(leaves[12], balanced(leaves[:8]), 0.4, 0.01)]  # right operand deeper: swapped CP opcode
+    parts = [(t, 0.05 + 0.01 * i) for i, t in enumerate(trees)]
+    got, info = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(info == 0)
+    assert H.rel_err(got, oracle_lmls(parts, ts, xs)) <= LML_RTOL_TIGHT
+    K = engine.gram(H.to_agp(trees[2]), 0.1, ts)
+    R = o.compute_cov_matrix_vectorized(trees[2], 0.1, ts)
+    assert np.all(np.abs(K - R) <= GRAM_RTOL * np.abs(R))
+
+
+def test_program_errors_are_reported_not_thrown(engine):
+    from autogp.jl_b200 import _lib
+    import ctypes as C
+
+    lib = _lib.load()
+    h = engine._h
+    ts = np.linspace(0, 1, 8)
+    K = np.empty((8, 8), order="F")
+
+    def gram(ops, offs, params):
+        ops = np.asarray(ops, np.int32)
+        offs = np.asarray(offs, np.int32)
+        params = np.asarray(params, np.float64)
+        f = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        return lib.agp_gram(h, f(ops, C.c_int32), f(offs, C.c_int32), len(ops), f(params, C.c_double), len(params),
+                            f(ts, C.c_double), 8, 0.1, 0, f(K, C.c_double))
+
+    assert gram([42], [0], [1.0]) == _lib.AGP_ERR_PROGRAM and b"unknown node-type" in lib.agp_last_error(h)
+    assert gram([1, 6], [0, 1], [1.0]) == _lib.AGP_ERR_PROGRAM and b"underflow" in lib.agp_last_error(h)
+    assert gram([1, 1], [0, 1], [1.0, 2.0]) == _lib.AGP_ERR_PROGRAM  # two trees left on the stack
+    assert gram([4], [0], [1.0, 2.5, 1.0]) == _lib.AGP_ERR_PROGRAM and b"gamma" in lib.agp_last_error(h)
+    assert gram([2], [0], [1.0]) == _lib.AGP_ERR_PROGRAM  # Linear needs 3 params
+    assert gram([1], [0], [1.0]) == 0  # handle still usable afterwards
+    assert lib.agp_lml_run(h) in (0, _lib.AGP_ERR_STATE)
+
+
+def test_lml_reentrant_engines_from_threads(engine):
+    """up to nthreads concurrent callers, one handle each."""
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(260)
+    parts = [o.synthetic_particle(p, "ge+per*lin") for p in range(6)]
+    ref = oracle_lmls(parts, ts, xs)
+    out = {}
+
+    def work(i):
+        eng = agp.Engine(0)
+        for _ in range(3):
+            out[i] = eng.lml_batch([H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)[0]
+        eng.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        assert H.rel_err(out[i], ref) <= LML_RTOL_TIGHT
+
+
+def test_smc_step_single_gpu(engine):
+    from autogp.jl_b200 import smc
+
+    ts, xs = o.synthetic_series(96)
+    parts = [o.synthetic_particle(p, "se+wn") for p in range(8)]
+    state = smc.ParticleState(nodes=[H.to_agp(nd) for nd, _ in parts], noises=[nz for _, nz in parts])
+    prev = np.zeros(8)
+    for step in (32, 64, 96):
+        scores = smc.smc_step(state, ts[:step], xs[:step], engine=engine)
+        ref = oracle_lmls(parts, ts[:step], xs[:step])
+        assert H.rel_err(scores, ref) <= LML_RTOL_TIGHT
+        prev = ref
+    assert np.allclose(state.log_weights, prev, rtol=1e-10)  # sum of increments telescopes to the last score
+
+
+# ---- BASELINE.json full sizes: size-independent properties ------------------------------------
+
+def test_full_size_n2048_p64_properties(engine):
+    """configs[1]: n=2048, 64 particles, Plus(Times(SE, Periodic), Linear)."""
+    n, P = 2048, 64
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(P)]
+    got, info = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(info == 0) and np.all(np.isfinite(got))
+    # (a) spot-check against the oracle (0.5 s of CPU each)
+    for p in (0, 17, 63):
+        assert abs(got[p] - o.log_marginal_likelihood(*parts[p], ts, xs)) <= LML_RTOL * abs(got[p])
+    # (b) determinism: bitwise identical on re-run
+    again, _ = gpu_lmls(engine, parts, ts, xs)
+    assert np.array_equal(got, again)
+    # (c) the likelihood of exchangeable data is invariant to a joint permutation of (ts, xs)
+    perm = np.random.default_rng(5).permutation(n)
+    permuted, info = gpu_lmls(engine, parts, ts[perm], xs[perm])
+    assert np.all(info == 0)
+    assert H.rel_err(permuted, got) <= 1e-9
+    # (d) chain rule on a prefix: LML(n) - LML(n-64) = predictive logpdf of the last 64 points
+    p = 5
+    head, _ = gpu_lmls(engine, [parts[p]], ts[: n - 64], xs[: n - 64])
+    mu, cov = o.predictive_mvn(parts[p][0], parts[p][1], ts[: n - 64], xs[: n - 64], ts[n - 64:])
+    assert o.mvn_logpdf(xs[n - 64:], mu, cov) == pytest.approx(got[p] - head[0], rel=1e-6)
+
+
+def test_full_size_n8192_one_particle(engine):
+    """configs[2] shape (n=8192): one particle against the oracle, one more for determinism."""
+    n = 8192
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(3), o.synthetic_particle(3)]
+    got, info = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(info == 0)
+    assert got[0] == got[1]
+    ref = o.log_marginal_likelihood(*parts[0], ts, xs)
+    assert abs(got[0] - ref) <= LML_RTOL * abs(ref)

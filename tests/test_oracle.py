@@ -1,0 +1,130 @@
+"""CPU suite, part 1: pin the oracle.
+
+The reference holds no golden values for this path, so the oracle is pinned by
+(a) the committed fixtures generated from the reference's own test kernels/grids,
+(b) three independent routes agreeing (vectorised NumPy, scalar C, mpmath 50 digits),
+(c) the identities the reference's tests assert (test/test_GP.jl:35-106,
+    test/experiment_hmc.jl:111-132).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import autogp_oracle as o
+import c_oracle
+import helpers as H
+
+
+def test_golden_gram_matches_oracle():
+    ts, grams, _ = H.golden()
+    for k, G in zip(H.fixture_kernels(), grams):
+        K = o.compute_cov_matrix_vectorized(k, 0.0, ts)
+        assert np.array_equal(K, G), k
+
+
+def test_golden_lml_mpmath_vs_f64_routes():
+    ts, _, lml = H.golden()
+    xs = H.fixture_xs(ts)
+    for i, k in enumerate(H.fixture_kernels()):
+        a = o.log_marginal_likelihood(k, lml["noise"], ts, xs)
+        b, info = c_oracle.lml(o.encode_program(k), ts, xs, lml["noise"])
+        c = o.log_marginal_likelihood_lu(k, lml["noise"], ts, xs)
+        assert info == 0
+        truth = lml["fixture_mp"][i]
+        # n = 15, well conditioned: FP64 routes agree with the 50-digit value to ~1e-13
+        for v in (a, b, c):
+            assert abs(v - truth) <= 1e-12 * max(1.0, abs(truth)), (k, v, truth)
+
+
+def test_scalar_and_vectorised_gram_agree():
+    _, ds = H.fixture_grid()
+    ts = ds[::3]
+    for k in H.fixture_kernels():
+        Kv = o.compute_cov_matrix_vectorized(k, 0.3, ts)
+        Ks = o.compute_cov_matrix(k, 0.3, ts)
+        Kc0 = c_oracle.gram(o.encode_program(k), ts, 0.3, form=0)
+        Kc1 = c_oracle.gram(o.encode_program(k), ts, 0.3, form=1)
+        assert np.allclose(Kv, Ks, rtol=1e-14, atol=1e-300)
+        # C (glibc scalar libm) vs NumPy (SIMD libm): identical formulas, <= 2 ulp transcendentals
+        assert np.allclose(Kv, Kc0, rtol=4e-15, atol=1e-300)
+        assert np.allclose(Ks, Kc1, rtol=4e-15, atol=1e-300)
+        assert np.array_equal(Kv, Kv.T)  # Matrix(Symmetric(K))
+
+
+def test_reparameterize_identity():
+    """test/test_GP.jl:35-68: eval_cov(k, ds) ≈ eval_cov(reparameterize(k, T), ds_raw)."""
+    ds_raw, ds = H.fixture_grid()
+    slope = 1.0 / 20.0
+    intercept = 0.5
+    for k in H.fixture_kernels():
+        M1 = o.eval_cov(k, ds)
+        M2 = o.eval_cov(H.reparameterize(k, slope, intercept), ds_raw)
+        # Julia's default isapprox: rtol = sqrt(eps)
+        assert np.all(np.abs(M1 - M2) <= math.sqrt(np.finfo(float).eps) * np.maximum(np.abs(M1), np.abs(M2))), k
+
+
+def test_rescale_identity():
+    """test/test_GP.jl:70-106: eval_cov(rescale(k, T^-1)) ≈ unapply_var(T, eval_cov(k)), atol 1e-8."""
+    ds = np.linspace(-10, 10, 50)
+    slope = 2.0 / 20.0  # LinearTransform(ys_raw, -1, 1)
+    inv_slope = 1.0 / slope
+    for k in H.fixture_kernels():
+        M1 = o.eval_cov(H.rescale(k, inv_slope), ds)
+        M2 = (1 / slope ** 2) * o.eval_cov(k, ds)
+        assert np.all(np.abs(M1 - M2) <= 1e-8), k
+
+
+def test_predictive_likelihood_identity():
+    """test/experiment_hmc.jl:111-132: logpdf(predictive MVN, xs_test) ≈ LML(joint) − LML(obs)."""
+    ts = np.linspace(0.0, 10.0, 1000)
+    rng = np.random.default_rng(7)
+    idx = rng.permutation(1000)
+    obs, test = np.sort(idx[:200]), np.sort(idx[200:260])
+    for k, nz in H.hmc_benchmarks():
+        noise = nz + o.JITTER
+        xs = H.fixture_xs(ts / 10.0) + 0.05 * rng.standard_normal(1000)
+        lml_obs = o.log_marginal_likelihood(k, noise, ts[obs], xs[obs])
+        both = np.concatenate([obs, test])
+        lml_joint = o.log_marginal_likelihood(k, noise, ts[both], xs[both])
+        mu, cov = o.predictive_mvn(k, noise, ts[obs], xs[obs], ts[test])
+        lp = o.mvn_logpdf(xs[test], mu, cov)
+        assert lp == pytest.approx(lml_joint - lml_obs, rel=2e-7), k
+
+
+def test_model_constants_and_transforms():
+    assert o.JITTER == 1e-5  # Model.jl:22
+    assert o.transform_param("noise", 0.0) == math.exp(-1.5)
+    assert o.transform_param("period", 1.0) == math.exp(-0.5)
+    assert o.transform_param("gamma", 0.0) == 1.0
+    assert 0 < o.transform_param("gamma", 5.0) <= 2
+
+
+def test_posdef_exception_info():
+    ts = np.linspace(0, 1, 10)
+    K = o.compute_cov_matrix_vectorized(o.Constant(1.0), -2.0, ts)
+    with pytest.raises(o.PosDefException) as e:
+        o.mvnormal_logpdf(np.zeros(10), K)
+    assert e.value.info == 1
+    _, info = c_oracle.lml(o.encode_program(o.Constant(1.0)), ts, np.zeros(10), -2.0)
+    assert info == 1
+
+
+def test_empty_mvnormal_scores_zero():
+    assert o.mvnormal_logpdf(np.zeros(0), np.zeros((0, 0))) == 0.0
+
+
+def test_linear_schedule_matches_reference_examples():
+    """src/Schedule.jl:24-39."""
+    assert o.linear_schedule(2048, 0.10) == [205, 410, 615, 820, 1025, 1230, 1435, 1640, 1845, 2048]
+    assert o.linear_schedule(10, 0.5) == [5, 10]
+    assert o.linear_schedule(100, 0.3)[-1] == 100
+
+
+def test_weights_and_ess():
+    lw = np.array([0.0, 0.0, 0.0, 0.0])
+    lt, lnw = o.normalize_weights(lw)
+    assert lt == pytest.approx(math.log(4))
+    assert o.effective_sample_size(lnw) == pytest.approx(4.0)
+    lw = np.array([0.0, -1e9, -1e9])
+    assert o.effective_sample_size(o.normalize_weights(lw)[1]) == pytest.approx(1.0)

@@ -32,6 +32,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+// named barrier among `count` threads (count multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -306,119 +311,145 @@ __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, i
     double* yp = v.y + (long long)p * ld;
 
     if (tid == 0) bad_s = 0;
+    // lower triangle + observation row, all loads in flight at once (8-byte cp.async: the odd
+    // row stride rules out 16-byte copies)
     for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
         int r = idx >> 7, c = idx & (TB - 1);
-        As[r * SA + c] = (c <= r) ? Lp[(long long)(o + r) * ld + o + c] : 0.0;
+        if (c <= r) cp_async8(As + r * SA + c, Lp + (long long)(o + r) * ld + o + c);
+        else As[r * SA + c] = 0.0;
     }
-    for (int c = tid; c < TB; c += PF_THREADS) As[TB * SA + c] = yp[o + c];
+    for (int c = tid; c < TB; c += PF_THREADS) cp_async8(As + TB * SA + c, yp + o + c);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
     const bool want_dinv = (k < v.nt - 1);
+    constexpr int NW = PF_THREADS / 32;      // 16 warps
+    constexpr int WORKERS = (NW - 1) * 32;   // warps 0..14 factor; warp 15 inverts diagonal blocks
+    // Barriers: id 1 = "diagonal block jb is final" (all 16 warps); ids 2, 3 = phase boundaries of
+    // the 15 factor warps.  The inverse warp only joins barrier 1, so inverting block jb overlaps
+    // phases 2, 3 of panel jb and phase 1 of panel jb+1 instead of sitting on the critical path.
+    if (warp == NW - 1) {
 #pragma unroll 1
-    for (int jb = 0; jb < 4; ++jb) {
-        const int j0 = jb * 32;
-        // ---- phase 1: diagonal block in registers (warp 0) -------------------------------
-        if (warp == 0) {
-            double a[32];
-            const double* rowp = As + (j0 + lane) * SA + j0;
+        for (int jb = 0; jb < 4; ++jb) {
+            const int j0 = jb * 32;
+            named_bar_sync(1, PF_THREADS);
+            if (want_dinv) {
+                // inverse of the diagonal block, lane = column of the inverse
+                double x[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = rowp[c];
-            int bad = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
-                    if (bad == 0) bad = o + j0 + j + 1;
-                    d = 1.0;
-                }
-                const double inv = rsqrt(d);
-                const double l = (lane == j) ? d * inv : a[j] * inv;
-                a[j] = l;
-                if (lane == 0) Ri[j0 + j] = inv;
-#pragma unroll
-                for (int c = j + 1; c < 32; ++c) {
-                    const double lc = __shfl_sync(0xffffffffu, l, c);
-                    a[c] = fma(-l, lc, a[c]);
-                }
-            }
-            double* roww = As + (j0 + lane) * SA + j0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                if (c <= lane) roww[c] = a[c];
-            if (lane == 0 && bad != 0 && bad_s == 0) bad_s = bad;
-        }
-        __syncthreads();
-        // ---- phase 2: rows below the block (threads 64..), block inverse (warp 1) ----------
-        const int R = TB + 1 - (j0 + 32);  // rows j0+32 .. 128 (row 128 = y)
-        if (tid >= 64 && tid - 64 < R) {
-            const int t = tid - 64;
-            const int i = j0 + 32 + t;
-            double a[32];
-            double* rowp = As + i * SA + j0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) a[c] = rowp[c];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const double l = a[j] * Ri[j0 + j];
-                a[j] = l;
-#pragma unroll
-                for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, As[(j0 + c) * SA + j0 + j], a[c]);  // broadcast
-            }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                rowp[c] = a[c];
-                Lpn[t * LPS + c] = a[c];
-            }
-        } else if (warp == 1 && want_dinv) {
-            // inverse of the diagonal block, lane = column of the inverse
-            double x[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int m = 0; m < r; ++m) sacc = fma(As[(j0 + r) * SA + j0 + m], x[m], sacc);  // L(r,m), broadcast
-                const double rhs = (r == lane) ? 1.0 : 0.0;
-                x[r] = (r < lane) ? 0.0 : (rhs - sacc) * Ri[j0 + r];
-            }
-            double* out = v.dinv + ((long long)p * 4 + jb) * 1024;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) out[r * 32 + lane] = x[r];
-        }
-        __syncthreads();
-        // ---- phase 3: trailing update  A[i][c] -= sum_m L[i][m] L[c][m]  (DMMA) -------------
-        const int T = TB - (j0 + 32);  // trailing rows/cols inside the tile
-        if (T > 0) {
-            const int nb8 = T >> 3;
-            const int nblk = nb8 * (nb8 + 1) / 2;
-            const int g = lane >> 2, c4 = lane & 3;
-            for (int blk = warp; blk < nblk; blk += PF_THREADS / 32) {
-                int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
-                while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
-                while (bi * (bi + 1) / 2 > blk) --bi;
-                const int bc = blk - bi * (bi + 1) / 2;
-                double c0 = 0.0, c1 = 0.0;
-                const double* ap = Lpn + (bi * 8 + g) * LPS + c4;
-                const double* bp = Lpn + (bc * 8 + g) * LPS + c4;
-#pragma unroll
-                for (int kk = 0; kk < 32; kk += 4) dmma884(c0, c1, ap[kk], bp[kk]);
-                double* cp = As + (j0 + 32 + bi * 8 + g) * SA + j0 + 32 + bc * 8 + 2 * c4;
-                cp[0] -= c0;
-                cp[1] -= c1;
-            }
-            // observation row (t = T): y[c] -= sum_m z_panel[m] L[c][m]
-            if (warp == PF_THREADS / 32 - 1) {
-                const double* zp = Lpn + T * LPS;
-                for (int cc = lane; cc < T; cc += 32) {
-                    const double* lp = Lpn + cc * LPS;
+                for (int r = 0; r < 32; ++r) {
                     double sacc = 0.0;
 #pragma unroll
-                    for (int m = 0; m < 32; ++m) sacc = fma(zp[m], lp[m], sacc);
-                    As[TB * SA + j0 + 32 + cc] -= sacc;
+                    for (int m = 0; m < r; ++m) sacc = fma(As[(j0 + r) * SA + j0 + m], x[m], sacc);  // L(r,m), broadcast
+                    const double rhs = (r == lane) ? 1.0 : 0.0;
+                    x[r] = (r < lane) ? 0.0 : (rhs - sacc) * Ri[j0 + r];
                 }
+                double* out = v.dinv + ((long long)p * 4 + jb) * 1024;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) out[r * 32 + lane] = x[r];
             }
         }
-        __syncthreads();
+    } else {
+#pragma unroll 1
+        for (int jb = 0; jb < 4; ++jb) {
+            const int j0 = jb * 32;
+            // ---- phase 1: diagonal block in registers (warp 0) ---------------------------
+            if (warp == 0) {
+                double a[32];
+                const double* rowp = As + (j0 + lane) * SA + j0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+                int bad = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    double d = __shfl_sync(0xffffffffu, a[j], j);
+                    if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
+                        if (bad == 0) bad = o + j0 + j + 1;
+                        d = 1.0;
+                    }
+                    const double inv = rsqrt(d);
+                    const double l = (lane == j) ? d * inv : a[j] * inv;
+                    a[j] = l;
+                    if (lane == 0) Ri[j0 + j] = inv;
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) {
+                        const double lc = __shfl_sync(0xffffffffu, l, c);
+                        a[c] = fma(-l, lc, a[c]);
+                    }
+                }
+                double* roww = As + (j0 + lane) * SA + j0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c <= lane) roww[c] = a[c];
+                if (lane == 0 && bad != 0 && bad_s == 0) bad_s = bad;
+            }
+            named_bar_sync(1, PF_THREADS);
+            // ---- phase 2: rows below the block, one thread per row (threads 32..) -----------
+            const int R = TB + 1 - (j0 + 32);  // rows j0+32 .. 128 (row 128 = y)
+            if (tid >= 32 && tid - 32 < R) {
+                const int t = tid - 32;
+                const int i = j0 + 32 + t;
+                double a[32];
+                double* rowp = As + i * SA + j0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double l = a[j] * Ri[j0 + j];
+                    a[j] = l;
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, As[(j0 + c) * SA + j0 + j], a[c]);  // broadcast
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    rowp[c] = a[c];
+                    Lpn[t * LPS + c] = a[c];
+                }
+            }
+            named_bar_sync(2, WORKERS);
+            // ---- phase 3: trailing update  A[i][c] -= sum_m L[i][m] L[c][m]  (DMMA) ---------
+            const int T = TB - (j0 + 32);  // trailing rows/cols inside the tile
+            if (T > 0) {
+                const int nb8 = T >> 3;
+                const int nblk = nb8 * (nb8 + 1) / 2;
+                const int g = lane >> 2, c4 = lane & 3;
+                for (int blk = warp; blk < nblk; blk += NW - 1) {
+                    int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+                    while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+                    while (bi * (bi + 1) / 2 > blk) --bi;
+                    const int bc = blk - bi * (bi + 1) / 2;
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                    const double* ap = Lpn + (bi * 8 + g) * LPS + c4;
+                    const double* bp = Lpn + (bc * 8 + g) * LPS + c4;
+#pragma unroll
+                    for (int kk = 0; kk < 32; kk += 8) {
+                        dmma884(c0, c1, ap[kk], bp[kk]);
+                        dmma884(d0, d1, ap[kk + 4], bp[kk + 4]);
+                    }
+                    double* cp = As + (j0 + 32 + bi * 8 + g) * SA + j0 + 32 + bc * 8 + 2 * c4;
+                    cp[0] -= c0 + d0;
+                    cp[1] -= c1 + d1;
+                }
+                // observation row (t = T): y[c] -= sum_m z_panel[m] L[c][m]
+                if (warp == NW - 2) {
+                    const double* zp = Lpn + T * LPS;
+                    for (int cc = lane; cc < T; cc += 32) {
+                        const double* lp = Lpn + cc * LPS;
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 32; m += 2) {
+                            s0 = fma(zp[m], lp[m], s0);
+                            s1 = fma(zp[m + 1], lp[m + 1], s1);
+                        }
+                        As[TB * SA + j0 + 32 + cc] -= s0 + s1;
+                    }
+                }
+            }
+            named_bar_sync(3, WORKERS);
+        }
     }
+    __syncthreads();
 
     // write L_kk (lower, row-major; strictly-upper zeroed so the tile is a clean factor)
     for (int idx = tid; idx < TB * TB; idx += PF_THREADS) {
@@ -462,11 +493,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) agp_potf2_kernel(BatchView v, i
 }
 
 // ------------------------------------------------------------------------------------------
-// trsm kernel: 64 rows of tile (i,k) per CTA
+// trsm kernel: 64 rows of tile (i,k) per CTA.  Blocked substitution over the four 32-column
+// blocks of L_kk:  X_jb = (C_jb - sum_{m<jb} X_m L[jb,m]^T) inv(L[jb,jb])^T, all on DMMA.
+// Each warp owns 8 rows for the whole sweep, so the block-to-block dependency is warp-local.
+// Operands arrive in four cp.async groups (one per column block) so the first block's math
+// starts while the rest of L_kk is still in flight.
 // ------------------------------------------------------------------------------------------
 constexpr int TR_THREADS = 256;
 constexpr int TR_ROWS = 64;
-constexpr int XS = 132;  // stride = 4 mod 16 doubles: DMMA fragment LDS.64 conflict free
+constexpr int XS = 136;  // stride = 8 mod 16 doubles: LDS.128 / STS.128 of two adjacent rows hit disjoint bank halves
 constexpr int TR_SMEM_BYTES = (TR_ROWS * XS + TB * XS + TB) * 8;
 
 __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, int k) {
@@ -482,41 +517,49 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
     const int o = k * TB;
     const int ld = v.ld;
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
-
-    // C rows: 64 x 128 doubles = 64 x 64 16-byte chunks
-    for (int q = tid; q < TR_ROWS * 64; q += TR_THREADS) {
-        int r = q >> 6, ch = q & 63;
-        cp_async16(Xs + r * XS + ch * 2, Lp + (long long)(r0 + r) * ld + o + ch * 2);
-    }
-    // L_kk strictly-lower 32x32 blocks; diagonal blocks come from dinv
     const double* dinv = v.dinv + (long long)p * 4096;
-    for (int q = tid; q < TB * 64; q += TR_THREADS) {
-        int r = q >> 6, ch = q & 63;
-        int rb = r >> 5, cb = ch >> 4;
-        if (cb < rb) cp_async16(Ls + r * XS + ch * 2, Lp + (long long)(o + r) * ld + o + ch * 2);
-        else if (cb == rb) cp_async16(Ls + r * XS + ch * 2, dinv + rb * 1024 + (r & 31) * 32 + (ch & 15) * 2);
+
+    // group jb: columns [32 jb, 32 jb + 32) of the C rows, and row panel jb of L_kk
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+        for (int q = tid; q < TR_ROWS * 16; q += TR_THREADS) {  // 64 rows x 16 chunks
+            int r = q >> 4, ch = jb * 16 + (q & 15);
+            cp_async16(Xs + r * XS + ch * 2, Lp + (long long)(r0 + r) * ld + o + ch * 2);
+        }
+        const int nch = (jb + 1) * 16;  // chunks per row of the panel (lower blocks + diagonal block)
+        for (int q = tid; q < 32 * nch; q += TR_THREADS) {
+            int r = jb * 32 + q / nch, ch = q % nch;
+            if (ch < jb * 16) cp_async16(Ls + r * XS + ch * 2, Lp + (long long)(o + r) * ld + o + ch * 2);
+            else cp_async16(Ls + r * XS + ch * 2, dinv + jb * 1024 + (r & 31) * 32 + (ch & 15) * 2);
+        }
+        cp_async_commit();
     }
     if (tid < TB) zs[tid] = v.z[(long long)p * ld + o + tid];
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c4 = lane & 3;
     double* xrow = Xs + (warp * 8 + g) * XS;  // this lane's row (fragment row g of the warp's 8 rows)
 
-#pragma unroll 1
-    for (int jb = 0; jb < 4; ++jb) {
-        double acc[4][2];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
-        // S = sum_{m<jb} X_m L[jb,m]^T
-        for (int kk = 0; kk < jb * 32; kk += 4) {
-            double a = xrow[kk + c4];
+    for (int jb = 0; jb < 4; ++jb) {
+        if (jb == 0) cp_async_wait<3>();
+        else if (jb == 1) cp_async_wait<2>();
+        else if (jb == 2) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        // two accumulator sets (even / odd k of each LDS.128 pair): 8 independent DMMA chains
+        double acc0[4][2], acc1[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
+        // S = sum_{m<jb} X_m L[jb,m]^T     (k runs over columns [0, 32 jb); thread c4 takes k = kk+2c4, kk+2c4+1)
+#pragma unroll 2
+        for (int kk = 0; kk < jb * 32; kk += 8) {
+            const double2 a = *reinterpret_cast<const double2*>(xrow + kk + 2 * c4);
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                double b = Ls[(jb * 32 + nb * 8 + g) * XS + kk + c4];
-                dmma884(acc[nb][0], acc[nb][1], a, b);
+                const double2 b = *reinterpret_cast<const double2*>(Ls + (jb * 32 + nb * 8 + g) * XS + kk + 2 * c4);
+                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
+                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
             }
         }
         // T = C_jb - S  (own rows only: warp-local dependency)
@@ -524,45 +567,47 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
         for (int nb = 0; nb < 4; ++nb) {
             double2* ptr = reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4);
             double2 t = *ptr;
-            t.x -= acc[nb][0];
-            t.y -= acc[nb][1];
+            t.x -= acc0[nb][0] + acc1[nb][0];
+            t.y -= acc0[nb][1] + acc1[nb][1];
             *ptr = t;
-            acc[nb][0] = acc[nb][1] = 0.0;
+            acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
         }
         __syncwarp();
         // X_jb = T inv(L_jb,jb)^T
 #pragma unroll
-        for (int kk = 0; kk < 32; kk += 4) {
-            double a = xrow[jb * 32 + kk + c4];
+        for (int kk = 0; kk < 32; kk += 8) {
+            const double2 a = *reinterpret_cast<const double2*>(xrow + jb * 32 + kk + 2 * c4);
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                double b = Ls[(jb * 32 + nb * 8 + g) * XS + jb * 32 + kk + c4];
-                dmma884(acc[nb][0], acc[nb][1], a, b);
+                const double2 b = *reinterpret_cast<const double2*>(Ls + (jb * 32 + nb * 8 + g) * XS + jb * 32 + kk + 2 * c4);
+                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
+                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
             }
         }
         __syncwarp();
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb)
-            *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) = make_double2(acc[nb][0], acc[nb][1]);
+            *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) =
+                make_double2(acc0[nb][0] + acc1[nb][0], acc0[nb][1] + acc1[nb][1]);
         __syncwarp();
     }
 
     // store L_ik rows (coalesced) and fold the forward solve: y_i -= L_ik z_k
     double* yp = v.y + (long long)p * ld;
-#pragma unroll 1
+#pragma unroll 2
     for (int rr = 0; rr < 8; ++rr) {
         const int r = warp * 8 + rr;
         const double* xr = Xs + r * XS;
-        double s = 0.0;
+        double sacc = 0.0;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             int c = lane + e * 32;
             double x = xr[c];
             Lp[(long long)(r0 + r) * ld + o + c] = x;
-            s = fma(x, zs[c], s);
+            sacc = fma(x, zs[c], sacc);
         }
-        s = warp_sum(s);
-        if (lane == 0) yp[r0 + r] -= s;
+        sacc = warp_sum(sacc);
+        if (lane == 0) yp[r0 + r] -= sacc;
     }
 }
 

@@ -539,6 +539,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, c4 = lane & 3;
     double* xrow = Xs + (warp * 8 + g) * XS;  // this lane's row (fragment row g of the warp's 8 rows)
+    // forward-solve vector entry of row warp*8 + lane (lanes 0..7): fetched now, consumed at the end
+    double* yp = v.y + (long long)p * ld;
+    const double y_old = (lane < 8) ? yp[r0 + warp * 8 + lane] : 0.0;
 
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
@@ -593,8 +596,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
     }
 
     // store L_ik rows (coalesced) and fold the forward solve: y_i -= L_ik z_k
-    double* yp = v.y + (long long)p * ld;
-#pragma unroll 2
+    double dot_mine = 0.0;
+#pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
         const int r = warp * 8 + rr;
         const double* xr = Xs + r * XS;
@@ -607,8 +610,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) agp_trsm_kernel(BatchView v, in
             sacc = fma(x, zs[c], sacc);
         }
         sacc = warp_sum(sacc);
-        if (lane == 0) yp[r0 + r] -= sacc;
+        if (lane == rr) dot_mine = sacc;
     }
+    if (lane < 8) yp[r0 + warp * 8 + lane] = y_old - dot_mine;
 }
 
 // ------------------------------------------------------------------------------------------

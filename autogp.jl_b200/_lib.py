@@ -19,6 +19,7 @@ EXPORTS = (
     "agp_lml_batch", "agp_lml_upload", "agp_lml_run", "agp_lml_fetch",
     "agp_lml_device_results", "agp_lml_set_prefix",
     "agp_stream", "agp_synchronize", "agp_launch_count", "agp_lml_time", "agp_lml_stage_times",
+    "agp_queue_build", "agp_lml_trace",
 )
 
 AGP_OK, AGP_ERR_ARG, AGP_ERR_PROGRAM, AGP_ERR_CUDA, AGP_ERR_NOMEM, AGP_ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -80,5 +81,9 @@ def load() -> C.CDLL:
     lib.agp_lml_time.restype = C.c_int
     lib.agp_lml_stage_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.agp_lml_stage_times.restype = C.c_int
+    lib.agp_queue_build.argtypes = [C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64]
+    lib.agp_queue_build.restype = C.c_int64
+    lib.agp_lml_trace.argtypes = [vp, C.POINTER(C.c_int64), C.c_int64]
+    lib.agp_lml_trace.restype = C.c_int64
     _lib = lib
     return lib

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -16,6 +17,7 @@
 #include "agp_program.h"
 
 using agp::BatchView;
+using agp::SchedView;
 using agp::TB;
 
 struct agp_handle {
@@ -54,6 +56,19 @@ struct agp_handle {
     int graph_P = -1, graph_groups = -1;
     int64_t graph_kernels = 0;
     bool use_graph = true;
+
+    // persistent dataflow path (default): work queues per (P, nt) shape + dependency counters
+    bool staged = false;  // AGP_PATH=staged selects the one-launch-per-stage path (A/B measurements)
+    int order = 1;        // queue order variant (AGP_ORDER)
+    int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
+    int num_sms = 0;
+    struct Queue {
+        int4* d_items = nullptr;
+        int n_items = 0;
+    };
+    std::map<std::pair<int, int>, Queue> queues;
+    int* d_sync = nullptr;   size_t cap_sync = 0;
+    int* h_sync = nullptr;   // pinned, 2 ints: queue head, error flag
 };
 
 namespace {
@@ -116,6 +131,8 @@ int check_launch(agp_handle* h, const char* what) {
 
 extern "C" {
 
+int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap);
+
 const char* agp_version(void) { return "0.1.0+sm_100a"; }
 
 int agp_create(int device, agp_handle** out) {
@@ -130,7 +147,9 @@ int agp_create(int device, agp_handle** out) {
     agp_handle* h = new agp_handle();
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_kernels() != cudaSuccess) {
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_kernels() != cudaSuccess || agp::configure_fused() != cudaSuccess ||
+        cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void**>(&h->h_sync), 2 * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         delete h;
         return AGP_ERR_CUDA;
@@ -146,6 +165,9 @@ int agp_create(int device, agp_handle** out) {
     }
     if (const char* e = getenv("AGP_GROUPS")) h->groups = atoi(e);
     if (const char* e = getenv("AGP_GRAPH")) h->use_graph = atoi(e) != 0;
+    if (const char* e = getenv("AGP_PATH")) h->staged = strcmp(e, "staged") == 0;
+    if (const char* e = getenv("AGP_ORDER")) h->order = atoi(e);
+    if (const char* e = getenv("AGP_CTAS_PER_SM")) h->ctas_per_sm = atoi(e) >= 1 ? atoi(e) : 1;
     *out = h;
     return AGP_OK;
 }
@@ -160,6 +182,9 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_res);
     cudaFree(h->d_K);
     cudaFree(h->d_gin);
+    cudaFree(h->d_sync);
+    for (auto& kv : h->queues) cudaFree(kv.second.d_items);
+    cudaFreeHost(h->h_sync);
     cudaFreeHost(h->h_gin);
     cudaFreeHost(h->h_in);
     cudaFreeHost(h->h_res);
@@ -352,6 +377,94 @@ int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
     return AGP_OK;
 }
 
+
+// ---- persistent dataflow path: the in-order work queue -------------------------------------
+//
+// Any order is valid as long as every item's producers come EARLIER (agp_fused.cu):
+//   DIAG(p,k,h)    <- PANEL(p,j,k,*) for all j < k
+//   POTF2(p,k)     <- DIAG(p,k,0), DIAG(p,k,1)
+//   PANEL(p,k,i,h) <- PANEL(p,j,i,*), PANEL(p,j,k,*) for all j < k;  POTF2(p,k)
+// order 0: block column by block column:  DIAG | POTF2 | PANEL.
+// order 1: look-ahead: within block column k the panels of tile row k+1 go first, and the
+//          diagonal tile of column k+1 (DIAG, POTF2) is interleaved into the bulk of column k's
+//          panels, so neither the diagonal factorisation nor its producers are ever waited for.
+static void build_queue(int P, int nt, int order, std::vector<int4>& items) {
+    auto push = [&](int type, int h, int p, int k, int i) { items.push_back(make_int4(type | (h << 8), p, k, i)); };
+    items.clear();
+    if (order == 0 || nt == 1) {
+        for (int k = 0; k < nt; ++k) {
+            for (int p = 0; p < P; ++p)
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k, k);
+            for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, k, k);
+            for (int p = 0; p < P; ++p)
+                for (int i = k + 1; i < nt; ++i)
+                    for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, i);
+        }
+        return;
+    }
+    for (int p = 0; p < P; ++p)
+        for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, 0, 0);
+    for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, 0, 0);
+    for (int k = 0; k < nt - 1; ++k) {
+        // panels of tile row k+1 first: they feed the next diagonal tile
+        for (int p = 0; p < P; ++p)
+            for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, k + 1);
+        // bulk of column k, with DIAG(k+1) after the first third and POTF2(k+1) after the second
+        std::vector<int4> bulk;
+        for (int p = 0; p < P; ++p)
+            for (int i = k + 2; i < nt; ++i)
+                for (int h = 0; h < 2; ++h) bulk.push_back(make_int4(agp::ITEM_PANEL | (h << 8), p, k, i));
+        size_t c1 = bulk.size() / 3, c2 = 2 * bulk.size() / 3;
+        items.insert(items.end(), bulk.begin(), bulk.begin() + c1);
+        for (int p = 0; p < P; ++p)
+            for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k + 1, k + 1);
+        items.insert(items.end(), bulk.begin() + c1, bulk.begin() + c2);
+        for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, k + 1, k + 1);
+        items.insert(items.end(), bulk.begin() + c2, bulk.end());
+    }
+}
+
+static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
+    const BatchView& v = h->view;
+    const int P = h->P, nt = v.nt;
+    const int nt_stride = h->ld / TB;
+    auto key = std::make_pair(P, nt);
+    auto it = h->queues.find(key);
+    if (it == h->queues.end()) {
+        std::vector<int4> items;
+        build_queue(P, nt, h->order, items);
+        agp_handle::Queue qu;
+        qu.n_items = (int)items.size();
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, AGP_ERR_NOMEM, std::string("work queue allocation failed: ") + cudaGetErrorString(e));
+        }
+        // pageable source: the copy is staged before the call returns, so `items` may go out of scope
+        AGP_CUDA(h, cudaMemcpyAsync(qu.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        it = h->queues.emplace(key, qu).first;
+    }
+    // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], fdone[P]
+    const size_t n_sync = 32 + (size_t)2 * P * nt_stride + P;
+    int rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int));
+    if (rc != AGP_OK) return rc;
+    AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
+    SchedView q;
+    q.items = it->second.d_items;
+    q.n_items = it->second.n_items;
+    q.head = h->d_sync;
+    q.err = h->d_sync + 1;
+    q.rowdone = h->d_sync + 32;
+    q.diagu = q.rowdone + (size_t)P * nt_stride;
+    q.fdone = q.diagu + (size_t)P * nt_stride;
+    q.nt_stride = nt_stride;
+    q.trace = d_trace;
+    agp::launch_chol(v, q, h->ctas_per_sm * h->num_sms, h->stream);
+    h->launches += 1;
+    return check_launch(h, "chol");
+}
+
 static int pick_groups(const agp_handle* h) {
     int g = h->groups;
     if (g <= 0) g = h->P >= 32 ? 4 : (h->P >= 8 ? 2 : 1);
@@ -401,6 +514,7 @@ static int run_impl(agp_handle* h, float* stage_ms) {
         return AGP_OK;
     }
     v.p0 = 0;
+    if (!stage_ms && !h->staged) return run_fused(h);
     if (stage_ms) {
         // serialised, one stream, events around every launch
         for (int k = 0; k < v.nt; ++k) {
@@ -501,7 +615,10 @@ int agp_lml_fetch(agp_handle* h, double* lml_out, int32_t* info_out) {
     size_t info_off = align_up((size_t)P * 8, 16);
     size_t res_bytes = info_off + (size_t)P * 4;
     AGP_CUDA(h, cudaMemcpyAsync(h->h_res, h->d_res, res_bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->h_sync[0] = h->h_sync[1] = 0;
+    if (h->d_sync) AGP_CUDA(h, cudaMemcpyAsync(h->h_sync, h->d_sync, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_sync[1] != 0) return fail(h, AGP_ERR_CUDA, "agp_lml_fetch: the work-queue scheduler reported a dependency time-out");
     memcpy(lml_out, h->h_res, (size_t)P * 8);
     memcpy(info_out, h->h_res + info_off, (size_t)P * 4);
     return AGP_OK;
@@ -513,6 +630,44 @@ int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev) 
     *lml_dev = h->view.lml;
     *info_dev = h->view.info;
     return AGP_OK;
+}
+
+int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
+    if (!h) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_trace: no resident batch");
+    if (h->P == 0 || h->view.n == 0) return 0;
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0);
+    if (!trace_out) return n_items;
+    long long* d_trace = nullptr;
+    AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_trace), (size_t)n_items * 8 * sizeof(long long)));
+    cudaMemsetAsync(d_trace, 0, (size_t)n_items * 8 * sizeof(long long), h->stream);
+    int rc = run_fused(h, d_trace);
+    if (rc == AGP_OK) {
+        int64_t m = n_items < cap_items ? n_items : cap_items;
+        cudaError_t e = cudaMemcpyAsync(trace_out, d_trace, (size_t)m * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, AGP_ERR_CUDA, std::string("agp_lml_trace: ") + cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_trace);
+    return rc == AGP_OK ? n_items : rc;
+}
+
+int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
+    if (P < 0 || nt < 0) return AGP_ERR_ARG;
+    std::vector<int4> items;
+    build_queue(P, nt, order, items);
+    if (items_out) {
+        int64_t m = (int64_t)items.size() < cap ? (int64_t)items.size() : cap;
+        for (int64_t q = 0; q < m; ++q) {
+            items_out[4 * q + 0] = items[q].x;
+            items_out[4 * q + 1] = items[q].y;
+            items_out[4 * q + 2] = items[q].z;
+            items_out[4 * q + 3] = items[q].w;
+        }
+    }
+    return (int64_t)items.size();
 }
 
 int agp_lml_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,

@@ -1,0 +1,650 @@
+// Persistent dataflow kernel of the fused GP log-marginal-likelihood path (sm_100a).
+//
+// One launch factorises every particle's K + noise*I (blocked left-looking Cholesky, block
+// column width 128) and finishes the LML.  CTAs (two per SM) pop work items from an in-order
+// queue; every item's producers sit EARLIER in the queue, so a consumer that spins on a
+// dependency counter always waits for a CTA that is already running: no deadlock, no
+// co-residency requirement, no tail waves between the stages of a block column, and the two
+// CTAs of an SM drift apart so one CTA's Gram/solve epilogue (issue-bound FP64 ALU work) fills
+// the gaps of the other's DMMA main loop.
+//
+//   ITEM_DIAG  (p,k,h)    64 rows of the diagonal tile:  K(ts_k,ts_k) + noise I - sum_j L_kj L_kj^T
+//   ITEM_POTF2 (p,k)      Cholesky of the 128x128 diagonal tile (+ observation row): L_kk, z_k,
+//                         log det, z'z, LAPACK info, inverses of the 32x32 diagonal blocks
+//   ITEM_PANEL (p,k,i,h)  64 rows of tile (i,k): Gram - contraction on FP64 tensor cores, then the
+//                         triangular solve against L_kk IN SHARED MEMORY (the unfactored tile never
+//                         touches HBM), then y_i -= L_ik z_k (forward solve folded in)
+//
+// Reference semantics: src/GP.jl:137-503, 666-668 (Gram), src/Model.jl:134-136 (noise, mvnormal),
+// Distributions' MvNormal logpdf = -(n log 2pi + logdet)/2 - |U^{-T} x|^2/2 with K = U'U.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "agp_eval.cuh"
+#include "agp_kernels.cuh"
+#include "agp_ptx.cuh"
+
+namespace agp {
+
+namespace {
+
+constexpr int FT = 256;   // threads per CTA: 8 warps
+constexpr int UM = 64;    // item rows
+constexpr int UN = TB;    // item columns (one block column)
+constexpr int KC = 16;    // K-chunk per pipeline stage (doubles) = one 128-byte row
+constexpr int NSTAGE = 4;
+constexpr int STAGE_D = (UM + UN) * KC;  // doubles per stage
+constexpr int XS = 136;                  // X / L_kk-panel row stride: 8 mod 16 doubles -> conflict-free LDS.128
+constexpr int BS = 33;                   // potf2 32x32 block row stride (odd: lane-per-row walks conflict free)
+constexpr int BLK = 32 * BS;
+constexpr int REGION_D = UM * XS + 32 * XS;  // X rows + one 32-row panel of L_kk
+constexpr int PROG_SMEM = 64;
+// tail of the shared-memory image (doubles): ts_r[UM] ts_c[UN] zs[TB] ys[TB] Ri[TB] red[16]
+constexpr int TAIL_D = UM + UN + 3 * TB + 16;
+constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + PROG_SMEM * 32 + 64;
+
+static_assert(NSTAGE * STAGE_D <= REGION_D, "pipeline stages must fit in the region");
+static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region");
+static_assert(2 * (FUSED_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+
+__device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+
+// thread 0 only: wait until *flag >= need.  A wait that exceeds ~2 s raises the scheduler error
+// flag so every CTA drains instead of hanging the device.
+__device__ bool wait_ge(const int* flag, int need, int* err) {
+    if (ld_acquire_gpu(flag) >= need) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    for (;;) {
+        __nanosleep(64);
+        if (ld_acquire_gpu(flag) >= need) return true;
+        if ((++spins & 255u) == 0) {
+            if (ld_relaxed_gpu(err) != 0) return false;
+            if (globaltimer_ns() - t0 > 2000000000ull) {
+                atomicExch(err, 1);
+                return false;
+            }
+        }
+    }
+}
+
+// diagnostics: thread 0 stamps phase boundaries of item `idx` when tracing is on
+__device__ __forceinline__ void stamp(const SchedView& q, int idx, int slot) {
+    if (q.trace != nullptr && threadIdx.x == 0) q.trace[(long long)idx * 8 + slot] = (long long)globaltimer_ns();
+}
+
+// all threads: release this item's global writes, then bump the counter
+__device__ __forceinline__ void signal_done(int* counter) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1);
+    }
+}
+
+struct Smem {
+    double* region;
+    double* ts_r;
+    double* ts_c;
+    double* zs;
+    double* ys;
+    double* Ri;
+    double* red;
+    AgpInstr* prog_s;
+    uint64_t* bar;
+    int* ctl;  // [0] item index, [1] wait result, [2] potf2 info
+};
+
+// ------------------------------------------------------------------------------------------
+// ITEM_DIAG / ITEM_PANEL
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, const Smem& s, int idx, int p, int k, int i, int h, bool diag,
+                                       uint32_t& tma_parity) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int row0 = i * TB + h * UM, col0 = k * TB;
+    const int ld = v.ld;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    double* stages = s.region;
+
+    // inputs that no other CTA writes: ts slices (TMA bulk), program
+    if (tid == 0) {
+        mbar_expect_tx(s.bar, (UM + UN) * 8);
+        tma_bulk_g2s(s.ts_r, v.ts + row0, UM * 8, s.bar);
+        tma_bulk_g2s(s.ts_c, v.ts + col0, UN * 8, s.bar);
+    }
+    const int poff = v.prog_off[p];
+    const int pm = v.prog_off[p + 1] - poff;
+    const AgpInstr* prog = v.prog + poff;
+    if (pm <= PROG_SMEM) {
+        const double* src = reinterpret_cast<const double*>(prog);
+        double* dst = reinterpret_cast<double*>(s.prog_s);
+        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];
+        prog = s.prog_s;
+    }
+
+    // rows i and k of L must be final for all block columns < k
+    if (k > 0) {
+        if (tid == 0) {
+            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * k, q.err);
+            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * k, q.err);
+            s.ctl[1] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s.ctl[1]) return false;
+    }
+    stamp(q, idx, 1);
+
+    // --- contraction: acc = sum_{j<k} L_ij L_kj^T -----------------------------------------
+    const int wm = warp >> 2, wn = warp & 3;  // 2 (m) x 4 (n) warps, warp tile 32x32
+    const int g = lane >> 2, c4 = lane & 3;
+    // warp tiles strictly above the diagonal of a diagonal tile are never read
+    const bool active = !diag || (wn * 32 <= h * UM + wm * 32 + 31);
+    double acc[4][4][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+    const int nchunk = (k * TB) / KC;
+    const double* __restrict__ Ag = Lp + (long long)row0 * ld;
+    const double* __restrict__ Bg = Lp + (long long)col0 * ld;
+
+    auto load_stage = [&](int st, int chunk) {
+        double* Bs = stages + st * STAGE_D;  // [UN][KC]
+        double* As = Bs + UN * KC;           // [UM][KC]
+        const int kk0 = chunk * KC;
+#pragma unroll
+        for (int e = 0; e < (UN * KC / 2) / FT; ++e) {  // 4
+            int w = tid + e * FT;
+            int row = w >> 3, ch = w & 7;
+            cp_async16(Bs + swz(row, ch), Bg + (long long)row * ld + kk0 + ch * 2);
+        }
+        if (!diag) {
+#pragma unroll
+            for (int e = 0; e < (UM * KC / 2) / FT; ++e) {  // 2
+                int w = tid + e * FT;
+                int row = w >> 3, ch = w & 7;
+                cp_async16(As + swz(row, ch), Ag + (long long)row * ld + kk0 + ch * 2);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int st = 0; st < NSTAGE - 1; ++st) {
+        if (st < nchunk) load_stage(st, st);
+        cp_async_commit();
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        const double* Bs = stages + (ch % NSTAGE) * STAGE_D;
+        const double* As = diag ? Bs + h * UM * KC : Bs + UN * KC;  // diagonal tile: A rows are a slice of B
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {
+            if (active) {
+                double2 a[4], b[4];
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz(wm * 32 + mb * 8 + g, ks * 4 + c4));
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz(wn * 32 + nb * 8 + g, ks * 4 + c4));
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
+            }
+            if (ks == 0) {
+                // refill behind the first half of the chunk's math so the copy instructions issue
+                // while the tensor pipe is busy
+                int nxt = ch + NSTAGE - 1;
+                if (nxt < nchunk) load_stage(nxt % NSTAGE, nxt);
+                cp_async_commit();
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    stamp(q, idx, 2);
+
+    // --- Gram tile on the fly:  X = K(ts_r, ts_c) [+ noise I] - acc ------------------------
+    double* Xs = s.region;            // [UM][XS]
+    double* Ls = s.region + UM * XS;  // [32][XS]
+    if (k > 0 && active) {
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
+                *reinterpret_cast<double2*>(Xs + r * XS + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+            }
+    }
+    mbar_wait(s.bar, tma_parity);
+    tma_parity ^= 1u;
+    __syncthreads();
+
+    const int need = v.prog_need[p];
+    const double noise = v.noise[p];
+    const int n = v.n;
+    {
+        // thread -> column c, rows rbase + 2*e (e = 0..31), four entries per interpreter pass
+        const int c = tid & (UN - 1), rbase = tid >> 7;
+        const int gc = col0 + c;
+        const double tcol = s.ts_c[c];
+#pragma unroll 1
+        for (int e4 = 0; e4 < 8; ++e4) {
+            const int rlast = rbase + 2 * (4 * e4 + 3);
+            if (diag && c > rlast + h * UM) continue;  // strictly-upper part of a diagonal tile is never read
+            double t1[4], t2[4], val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
+                t2[j] = s.ts_r[rbase + 2 * (4 * e4 + j)];
+            }
+            eval_entries<4>(prog, pm, need, t1, t2, 0, val);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 2 * (4 * e4 + j);
+                const int gr = row0 + r;
+                if (diag && c > r + h * UM) continue;
+                double out;
+                if (gr < n) {  // gc <= gr < n
+                    out = val[j];
+                    if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+                } else {
+                    out = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+                }
+                if (k > 0) out = out - Xs[r * XS + c];
+                if (diag) Lp[(long long)gr * ld + gc] = out;
+                else Xs[r * XS + c] = out;
+            }
+        }
+    }
+
+    double* yp = v.y + (long long)p * ld;
+    if (diag) {
+        if (k == 0 && tid < UM) yp[row0 + tid] = (row0 + tid < n) ? v.xs[row0 + tid] : 0.0;
+        signal_done(q.diagu + p * q.nt_stride + k);
+        return true;
+    }
+
+    // --- triangular solve against L_kk in shared memory ------------------------------------
+    stamp(q, idx, 3);
+    if (tid == 0) s.ctl[1] = wait_ge(q.fdone + p, k + 1, q.err) ? 1 : 0;
+    __syncthreads();  // also publishes X
+    if (!s.ctl[1]) return false;
+    stamp(q, idx, 4);
+
+    const int o = col0;
+    const double* dinv = v.dinv + (long long)p * 4096;
+    if (tid < TB) s.zs[tid] = __ldcg(v.z + (long long)p * ld + o + tid);
+    double* xrow = Xs + (warp * 8 + g) * XS;  // this lane's row (fragment row g of the warp's 8 rows)
+    double y_old = 0.0;
+    if (lane < 8) {
+        const int gr = row0 + warp * 8 + lane;
+        y_old = (k == 0) ? ((gr < n) ? v.xs[gr] : 0.0) : __ldcg(yp + gr);
+    }
+
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+        // panel jb of L_kk: rows [32 jb, 32 jb + 32), columns [0, 32 jb) from L, diagonal block from dinv
+        const int nch = (jb + 1) * 16;
+        for (int w = tid; w < 32 * nch; w += FT) {
+            int r = w / nch, ch = w - r * nch;
+            if (ch < jb * 16) cp_async16(Ls + r * XS + ch * 2, Lp + (long long)(o + jb * 32 + r) * ld + o + ch * 2);
+            else cp_async16(Ls + r * XS + ch * 2, dinv + jb * 1024 + r * 32 + (ch - jb * 16) * 2);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // two accumulator sets (even / odd k of each LDS.128 pair): 8 independent DMMA chains
+        double acc0[4][2], acc1[4][2];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
+        // S = sum_{m<jb} X_m L[jb,m]^T
+#pragma unroll 2
+        for (int kk = 0; kk < jb * 32; kk += 8) {
+            const double2 a = *reinterpret_cast<const double2*>(xrow + kk + 2 * c4);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const double2 b = *reinterpret_cast<const double2*>(Ls + (nb * 8 + g) * XS + kk + 2 * c4);
+                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
+                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
+            }
+        }
+        // T = C_jb - S  (own rows only: warp-local dependency)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            double2* ptr = reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4);
+            double2 t = *ptr;
+            t.x -= acc0[nb][0] + acc1[nb][0];
+            t.y -= acc0[nb][1] + acc1[nb][1];
+            *ptr = t;
+            acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
+        }
+        __syncwarp();
+        // X_jb = T inv(L_jb,jb)^T
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 8) {
+            const double2 a = *reinterpret_cast<const double2*>(xrow + jb * 32 + kk + 2 * c4);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const double2 b = *reinterpret_cast<const double2*>(Ls + (nb * 8 + g) * XS + jb * 32 + kk + 2 * c4);
+                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
+                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+            *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) =
+                make_double2(acc0[nb][0] + acc1[nb][0], acc0[nb][1] + acc1[nb][1]);
+        __syncthreads();  // panel buffer is reused by the next block
+    }
+
+    // store L_ik rows (coalesced) and fold the forward solve: y_i -= L_ik z_k
+    double dot_mine = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        const int r = warp * 8 + rr;
+        const double* xr = Xs + r * XS;
+        double sacc = 0.0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int c = lane + e * 32;
+            double x = xr[c];
+            Lp[(long long)(row0 + r) * ld + o + c] = x;
+            sacc = fma(x, s.zs[c], sacc);
+        }
+        sacc = warp_sum(sacc);
+        if (lane == rr) dot_mine = sacc;
+    }
+    if (lane < 8) yp[row0 + warp * 8 + lane] = y_old - dot_mine;
+    signal_done(q.rowdone + p * q.nt_stride + i);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// ITEM_POTF2: blocked right-looking Cholesky of the diagonal tile, stored as packed 32x32 blocks
+//   phase 1  warp 0 factors the 32x32 diagonal block in REGISTERS (lane = row, shuffles carry the
+//            pivot column)
+//   phase 2  one thread per sub-diagonal row (the observation vector rides along as row 128, so
+//            z_k = L_kk^{-1} y_k needs no separate solve) substitutes against the block
+//   phase 3  rank-32 update of the trailing part of the tile on DMMA
+// Warp 7 inverts the diagonal blocks for the panel solves behind a named barrier, off the
+// critical path.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int blk_off(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * BLK; }
+
+__device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, const Smem& s, int idx, int p, int k) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ld = v.ld;
+    const int o = k * TB;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    double* yp = v.y + (long long)p * ld;
+    double* Ab = s.region;
+    double* ys = s.ys;
+    double* Ri = s.Ri;
+
+    if (tid == 0) {
+        s.ctl[1] = wait_ge(q.diagu + p * q.nt_stride + k, 2, q.err) ? 1 : 0;
+        s.ctl[2] = 0;
+    }
+    __syncthreads();
+    if (!s.ctl[1]) return false;
+    stamp(q, idx, 1);
+
+    // lower triangle -> packed blocks (L2 loads: the tile was written by other CTAs of this launch)
+#pragma unroll 1
+    for (int base = 0; base < TB * TB; base += FT * 8) {
+        double tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int idx = base + u * FT + tid;
+            int r = idx >> 7, c = idx & (TB - 1);
+            tmp[u] = (c <= r) ? __ldcg(Lp + (long long)(o + r) * ld + o + c) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int idx = base + u * FT + tid;
+            int r = idx >> 7, c = idx & (TB - 1);
+            if ((c >> 5) <= (r >> 5)) Ab[blk_off(r >> 5, c >> 5) + (r & 31) * BS + (c & 31)] = tmp[u];
+        }
+    }
+    if (tid < TB) ys[tid] = __ldcg(yp + o + tid);
+    __syncthreads();
+
+    const bool want_dinv = (k < v.nt - 1);
+    constexpr int NW = FT / 32;             // 8 warps
+    constexpr int WORKERS = (NW - 1) * 32;  // warps 0..6 factor; warp 7 inverts diagonal blocks
+    if (warp == NW - 1) {
+#pragma unroll 1
+        for (int jb = 0; jb < 4; ++jb) {
+            const int j0 = jb * 32;
+            const double* Dg = Ab + blk_off(jb, jb);
+            named_bar_sync(1, FT);  // diagonal block jb is final
+            if (want_dinv) {
+                // inverse of the diagonal block, lane = column of the inverse
+                double x[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < r; ++m) sacc = fma(Dg[r * BS + m], x[m], sacc);  // L(r,m), broadcast
+                    const double rhs = (r == lane) ? 1.0 : 0.0;
+                    x[r] = (r < lane) ? 0.0 : (rhs - sacc) * Ri[j0 + r];
+                }
+                double* out = v.dinv + ((long long)p * 4 + jb) * 1024;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) out[r * 32 + lane] = x[r];
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int jb = 0; jb < 4; ++jb) {
+            const int j0 = jb * 32;
+            double* Dg = Ab + blk_off(jb, jb);
+            // ---- phase 1: diagonal block in registers (warp 0) ---------------------------
+            if (warp == 0) {
+                double a[32];
+                const double* rowp = Dg + lane * BS;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+                int bad = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    double d = __shfl_sync(0xffffffffu, a[j], j);
+                    if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
+                        if (bad == 0) bad = o + j0 + j + 1;
+                        d = 1.0;
+                    }
+                    const double inv = rsqrt(d);
+                    const double l = (lane == j) ? d * inv : a[j] * inv;
+                    a[j] = l;
+                    if (lane == 0) Ri[j0 + j] = inv;
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) {
+                        const double lc = __shfl_sync(0xffffffffu, l, c);
+                        a[c] = fma(-l, lc, a[c]);
+                    }
+                }
+                double* roww = Dg + lane * BS;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c <= lane) roww[c] = a[c];
+                if (lane == 0 && bad != 0 && s.ctl[2] == 0) s.ctl[2] = bad;
+            }
+            named_bar_sync(1, FT);
+            // ---- phase 2: rows below the block, one thread per row (threads 32..) -----------
+            const int R = TB + 1 - (j0 + 32);  // rows j0+32 .. 128 (row 128 = y)
+            if (tid >= 32 && tid - 32 < R) {
+                const int i = j0 + 32 + (tid - 32);
+                double* rowp = (i < TB) ? Ab + blk_off(i >> 5, jb) + (i & 31) * BS : ys + j0;
+                double a[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] = rowp[c];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double l = a[j] * Ri[j0 + j];
+                    a[j] = l;
+#pragma unroll
+                    for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, Dg[c * BS + j], a[c]);  // broadcast
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) rowp[c] = a[c];
+            }
+            named_bar_sync(2, WORKERS);
+            // ---- phase 3: trailing update  A[i][c] -= sum_m L[i][m] L[c][m]  (DMMA) ---------
+            const int T = TB - (j0 + 32);  // trailing rows/cols inside the tile
+            if (T > 0) {
+                const int nb8 = T >> 3;
+                const int nblk = nb8 * (nb8 + 1) / 2;
+                const int g = lane >> 2, c4 = lane & 3;
+                for (int blk = warp; blk < nblk; blk += NW - 1) {
+                    int bi = (int)((sqrtf(8.0f * (float)blk + 1.0f) - 1.0f) * 0.5f);
+                    while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+                    while (bi * (bi + 1) / 2 > blk) --bi;
+                    const int bc = blk - bi * (bi + 1) / 2;
+                    const int ri = j0 + 32 + bi * 8 + g;  // row of the A fragment / of C
+                    const int rc = j0 + 32 + bc * 8 + g;  // row of the B fragment
+                    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+                    const double* ap = Ab + blk_off(ri >> 5, jb) + (ri & 31) * BS + c4;
+                    const double* bp = Ab + blk_off(rc >> 5, jb) + (rc & 31) * BS + c4;
+#pragma unroll
+                    for (int kk = 0; kk < 32; kk += 8) {
+                        dmma884(c0, c1, ap[kk], bp[kk]);
+                        dmma884(d0, d1, ap[kk + 4], bp[kk + 4]);
+                    }
+                    const int cc = j0 + 32 + bc * 8 + 2 * c4;  // column of C
+                    double* cp = Ab + blk_off(ri >> 5, cc >> 5) + (ri & 31) * BS + (cc & 31);
+                    cp[0] -= c0 + d0;
+                    cp[1] -= c1 + d1;
+                }
+                // observation row: y[c] -= sum_m z_panel[m] L[c][m]
+                if (warp == NW - 2) {
+                    const double* zp = ys + j0;
+                    for (int cc = lane; cc < T; cc += 32) {
+                        const int rc = j0 + 32 + cc;
+                        const double* lp = Ab + blk_off(rc >> 5, jb) + (rc & 31) * BS;
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 32; m += 2) {
+                            s0 = fma(zp[m], lp[m], s0);
+                            s1 = fma(zp[m + 1], lp[m + 1], s1);
+                        }
+                        ys[rc] -= s0 + s1;
+                    }
+                }
+            }
+            named_bar_sync(3, WORKERS);
+        }
+    }
+    __syncthreads();
+
+    // write L_kk (lower, row-major; strictly-upper zeroed so the tile is a clean factor)
+    for (int idx = tid; idx < TB * TB; idx += FT) {
+        int r = idx >> 7, c = idx & (TB - 1);
+        Lp[(long long)(o + r) * ld + o + c] = (c <= r) ? Ab[blk_off(r >> 5, c >> 5) + (r & 31) * BS + (c & 31)] : 0.0;
+    }
+    // z_k, sum z^2, sum log L_jj
+    if (tid < TB) {
+        double zj = ys[tid];
+        v.z[(long long)p * ld + o + tid] = zj;
+        double part_zz = zj * zj;
+        double part_ld = log(Ab[blk_off(tid >> 5, tid >> 5) + (tid & 31) * BS + (tid & 31)]);
+        part_ld = warp_sum(part_ld);
+        part_zz = warp_sum(part_zz);
+        if (lane == 0) {
+            s.red[warp * 2] = part_ld;
+            s.red[warp * 2 + 1] = part_zz;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double sl = ((s.red[0] + s.red[2]) + s.red[4]) + s.red[6];
+        double sz = ((s.red[1] + s.red[3]) + s.red[5]) + s.red[7];
+        // block column 0 starts the accumulators; later columns of this particle run strictly after it
+        double tot_l = (k == 0 ? 0.0 : __ldcg(v.logdet_half + p)) + sl;
+        double tot_z = (k == 0 ? 0.0 : __ldcg(v.zz + p)) + sz;
+        v.logdet_half[p] = tot_l;
+        v.zz[p] = tot_z;
+        int info = (k == 0) ? 0 : __ldcg(v.info + p);
+        if (info == 0 && s.ctl[2] != 0) info = s.ctl[2];
+        v.info[p] = info;
+        if (k == v.nt - 1) {
+            // -(n log 2pi + logdet)/2 - z'z/2, logdet = 2 sum log L_ii
+            const double log2pi = 1.8378770664093453;
+            double lml = -0.5 * ((double)v.n * log2pi + 2.0 * tot_l) - 0.5 * tot_z;
+            v.lml[p] = (info == 0) ? lml : __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+    signal_done(q.fdone + p);
+    return true;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem s;
+    s.region = reinterpret_cast<double*>(smem_raw);
+    s.ts_r = s.region + REGION_D;
+    s.ts_c = s.ts_r + UM;
+    s.zs = s.ts_c + UN;
+    s.ys = s.zs + TB;
+    s.Ri = s.ys + TB;
+    s.red = s.Ri + TB;
+    s.prog_s = reinterpret_cast<AgpInstr*>(s.red + 16);
+    s.bar = reinterpret_cast<uint64_t*>(s.prog_s + PROG_SMEM);
+    s.ctl = reinterpret_cast<int*>(s.bar + 1);
+
+    if (threadIdx.x == 0) {
+        mbar_init(s.bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t tma_parity = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s.ctl[0] = atomicAdd(q.head, 1);
+        __syncthreads();
+        const int idx = s.ctl[0];
+        if (idx >= q.n_items) break;
+        const int4 it = __ldg(q.items + idx);
+        const int type = it.x & 0xff, h = it.x >> 8;
+        bool ok;
+        stamp(q, idx, 0);
+        if (type == ITEM_POTF2) ok = do_potf2(v, q, s, idx, it.y, it.z);
+        else ok = do_update(v, q, s, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, tma_parity);
+        if (!ok) break;
+        stamp(q, idx, 5);
+        if (q.trace != nullptr && threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            q.trace[(long long)idx * 8 + 6] = (long long)smid;
+            q.trace[(long long)idx * 8 + 7] = (long long)blockIdx.x;
+        }
+    }
+}
+
+cudaError_t configure_fused() {
+    return cudaFuncSetAttribute(agp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+}
+
+void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {
+    if (q.n_items <= 0) return;
+    if (ctas > q.n_items) ctas = q.n_items;
+    agp_chol_kernel<<<ctas, FT, FUSED_SMEM, s>>>(v, q);
+}
+
+}  // namespace agp

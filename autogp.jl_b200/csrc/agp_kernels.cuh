@@ -32,6 +32,27 @@ struct BatchView {
     int p0;                  // first particle of this launch (particle groups run on separate streams)
 };
 
+// ---- persistent dataflow scheduler (agp_fused.cu) ------------------------------------------
+// Work items, packed as int4 {type | h << 8, particle, block column k, tile row i}.
+enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2 };
+
+struct SchedView {
+    const int4* items;  // in-order queue: every item's producers sit earlier in the list
+    int n_items;
+    int* head;          // queue head (atomic ticket)
+    int* err;           // set when a dependency wait timed out (never in a valid schedule)
+    int* rowdone;       // [P][nt_stride] finished 64-row panel items of tile row i (2 per block column)
+    int* diagu;         // [P][nt_stride] finished halves of diagonal tile k
+    int* fdone;         // [P] factored diagonal tiles
+    int nt_stride;
+    long long* trace;   // optional [n_items][8] globaltimer stamps (diagnostics; nullptr = off)
+};
+
+// One launch = the whole batch: Gram + Cholesky + solve + logdet for every particle.
+void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s);
+cudaError_t configure_fused();
+
+// ---- staged path (one launch per stage and block column; kept for A/B measurements) ----------
 // Left-looking block column k:  tiles (i,k), i>=k  <-  K(ts_i, ts_k) - sum_{j<k} L_ij L_kj^T
 void launch_update(const BatchView& v, int P, int k, cudaStream_t s);
 // Diagonal tile: Cholesky, z_k, logdet, info, 32x32 diagonal-block inverses; last column writes lml

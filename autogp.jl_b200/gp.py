@@ -294,6 +294,18 @@ class Engine:
         self._check(self._lib.agp_lml_stage_times(self._h, arr))
         return float(arr[0]), float(arr[1]), float(arr[2])
 
+    def trace(self) -> np.ndarray:
+        """Diagnostics: one traced run of the resident batch -> (items[n,4], stamps[n,8]) in queue
+        order (see agp_lml_trace / agp_queue_build in include/agp_b200.h)."""
+        n_items = int(self._lib.agp_lml_trace(self._h, None, 0))
+        if n_items < 0:
+            self._check(n_items)
+        stamps = np.zeros((n_items, 8), dtype=np.int64)
+        rc = int(self._lib.agp_lml_trace(self._h, stamps.ctypes.data_as(C.POINTER(C.c_int64)), n_items))
+        if rc < 0:
+            self._check(rc)
+        return stamps
+
     def synchronize(self) -> None:
         self._check(self._lib.agp_synchronize(self._h))
 

@@ -278,32 +278,38 @@ def main():
     h2d = 2 * ld * 8 + P * 8 + (P + 1) * 4 + P * 4 + n_instr * 32
     d2h = P * 8 + P * 4
 
-    # ---- roofline of the dominant kernel (agp_update_kernel), timed live with CUDA events ----------
-    st_upd, st_pf, st_tr = [], [], []
-    for _ in range(3):
-        a, b, c = eng.stage_times()
-        st_upd.append(a), st_pf.append(b), st_tr.append(c)
-    upd_ms, pf_ms, tr_ms = float(np.median(st_upd)), float(np.median(st_pf)), float(np.median(st_tr))
-    nt = -(-n // 128)
-    upd_flops = P * update_stage_flops(n)
-    achieved = upd_flops / (upd_ms * 1e-3) * 1e-12
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
+    # One step = ONE launch of agp_chol_kernel (persistent dataflow kernel: Gram tiles, DMMA
+    # contraction, diagonal Cholesky, panel solves, forward solve, log det).  Algorithmic work per
+    # launch = P * n^3 / 3 flops.
+    staged = os.environ.get("AGP_PATH", "") == "staged"
+    reps = 20
+    eng.run()
+    eng.synchronize()
+    kern_ms = eng.time_runs(reps) / reps
+    flops = P * n ** 3 / 3.0
+    achieved = flops / (kern_ms * 1e-3) * 1e-12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "chol_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("n") == n and tj.get("particles") == P:
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {
-        "bound": "tensor", "kernel": "agp_update_kernel (FP64 DMMA trailing update + fused Gram tile)",
+        "bound": "tensor",
+        "kernel": "agp_chol_kernel (persistent: Gram tile + FP64 DMMA contraction + potf2 + panel solve)" if not staged
+                  else "staged path: update/potf2/trsm launches of one step",
         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
         "traffic": traffic,
         "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "
                        "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.2",
-        "launches_per_step": nt, "avg_launch_ms": upd_ms / nt,
-        "stage_ms_serialised": {"update": upd_ms, "potf2": pf_ms, "trsm": tr_ms},
-        "whole_step": {"flops": world * P * n ** 3 / 3.0, "achieved": world * P * n ** 3 / 3.0 / (ms_per_step * 1e-3) * 1e-12 / world,
-                       "frac": P * n ** 3 / 3.0 / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
+        "launches_per_step": 1 if not staged else 3 * (-(-n // 128)) - 1, "avg_launch_ms": kern_ms,
+        "algorithmic_flops_per_launch": flops,
+        "whole_step": {"flops": world * flops, "achieved": flops / (ms_per_step * 1e-3) * 1e-12,
+                       "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
     }
 
     line = {

@@ -141,6 +141,19 @@ int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
  * for the roofline line in bench.py. stage_ms must hold 3 floats. */
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 
+/* The in-order work queue the persistent kernel executes for P particles x nt block columns
+ * (host-only, no GPU needed): items_out receives up to `cap` items as 4 int32 each
+ * {type | half << 8, particle, block column k, tile row i}, type 0 = DIAG, 1 = POTF2, 2 = PANEL;
+ * returns the total item count.  Every item's producers precede it (tests/test_abi_host.py
+ * checks the order is topological — the scheduler's deadlock-freedom argument). */
+int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap);
+
+/* Diagnostics: one traced run of the resident batch.  trace_out receives 8 int64 per work item
+ * (queue order): globaltimer ns at {pop, producers ready, contraction done, Gram done, L_kk
+ * ready, item done}, then SM id and CTA id.  Returns the item count (trace_out may be NULL to
+ * query it).  tools/trace_report.py turns this into per-phase / per-SM utilisation. */
+int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items);
+
 #ifdef __cplusplus
 }
 #endif

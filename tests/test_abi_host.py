@@ -127,3 +127,37 @@ def test_weight_consumers_match_oracle():
     assert smc.effective_sample_size(lw) == pytest.approx(o.effective_sample_size(o.normalize_weights(lw)[1]))
     assert np.allclose(smc.compute_particle_weights(lw), np.exp(o.normalize_weights(lw)[1]))
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
+
+
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16)])
+def test_work_queue_is_complete_and_topological(P, nt, order):
+    """Deadlock-freedom of the persistent kernel (agp_fused.cu): a CTA only ever waits for items
+    that were popped before its own, so every producer must precede its consumers in the queue."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build(P, nt, order, None, 0)
+    assert n_items == P * sum(2 * (nt - k) + 1 for k in range(nt))
+    buf = np.zeros((n_items, 4), dtype=np.int32)
+    assert lib.agp_queue_build(P, nt, order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
+    DIAG, POTF2, PANEL = 0, 1, 2
+    done = set()
+    for x, p, k, i in buf.tolist():
+        t, h = x & 0xFF, x >> 8
+        assert 0 <= p < P and 0 <= k < nt and h in (0, 1)
+        if t == DIAG:
+            assert i == k
+            need = [(PANEL, p, j, k, hh) for j in range(k) for hh in (0, 1)]
+        elif t == POTF2:
+            assert h == 0
+            need = [(DIAG, p, k, k, 0), (DIAG, p, k, k, 1)]
+        else:
+            assert t == PANEL and k < i < nt
+            need = [(PANEL, p, j, r, hh) for j in range(k) for r in (i, k) for hh in (0, 1)] + [(POTF2, p, k, k, 0)]
+        for d in need:
+            assert d in done, (t, p, k, i, h, d)
+        key = (t, p, k, i, h)
+        assert key not in done
+        done.add(key)
+    assert len(done) == n_items

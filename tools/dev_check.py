@@ -62,9 +62,8 @@ def main():
         eng.run()
         eng.synchronize()
         ms = eng.time_runs(5) / 5
-        st = eng.stage_times()
         fl = P * n ** 3 / 3
-        print(f"n={n} P={P}: {ms:.3f} ms/run  {P/ms*1e3:.0f} LML/s  {fl/ms*1e-9:.2f} TFLOP/s  stages(update,potf2,trsm)={st}")
+        print(f"n={n} P={P}: {ms:.3f} ms/run  {P/ms*1e3:.0f} LML/s  {fl/ms*1e-9:.2f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,92 @@
+"""Per-phase / per-slot utilisation of one traced run of the persistent kernel (GPU box)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import autogp_oracle as o  # noqa: E402  (workload definition only)
+import autogp.jl_b200 as agp  # noqa: E402
+from autogp.jl_b200 import _lib  # noqa: E402
+
+
+def to_agp(nd):
+    cls = getattr(agp, type(nd).__name__)
+    if isinstance(nd, o.LEAVES):
+        return cls(**nd.__dict__)
+    if isinstance(nd, o.ChangePoint):
+        return cls(to_agp(nd.left), to_agp(nd.right), nd.location, nd.scale)
+    return cls(to_agp(nd.left), to_agp(nd.right))
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    order = int(os.environ.get("AGP_ORDER", "1"))
+    eng = agp.Engine(0)
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(P)]
+    eng.upload([to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
+    for _ in range(3):
+        eng.run()
+    eng.synchronize()
+    ms = eng.time_runs(10) / 10
+    st = eng.trace()
+    nt = -(-n // 128)
+    lib = _lib.load()
+    items = np.zeros((st.shape[0], 4), dtype=np.int32)
+    lib.agp_queue_build(P, nt, order, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0])
+    typ = items[:, 0] & 0xFF
+    t0 = st[:, 0].min()
+    t_end = st[:, 5].max()
+    span = (t_end - t0) * 1e-3
+    print(f"n={n} P={P} order={order}: untraced {ms*1e3:.0f} us/run, traced span {span:.0f} us, items {len(st)}")
+    names = {0: "DIAG", 1: "POTF2", 2: "PANEL"}
+    slots = len(np.unique(st[:, 7]))
+    busy_total = 0.0
+    for t in (0, 1, 2):
+        m = typ == t
+        s = st[m].astype(np.float64) * 1e-3
+        tot = s[:, 5] - s[:, 0]
+        busy_total += tot.sum()
+        line = f"{names[t]:6s} items {m.sum():6d}  total {tot.sum()/1e3:9.1f} ms*cta  mean {tot.mean():7.1f} us"
+        if t == 1:
+            w = s[:, 1] - s[:, 0]
+            line += f" | wait {w.mean():6.1f}  work {(s[:,5]-s[:,1]).mean():6.1f}"
+        else:
+            w1 = s[:, 1] - s[:, 0]
+            mm = s[:, 2] - s[:, 1]
+            if t == 2:
+                gr = s[:, 3] - s[:, 2]
+                w2 = s[:, 4] - s[:, 3]
+                tr = s[:, 5] - s[:, 4]
+                line += f" | wait1 {w1.mean():6.1f} mma {mm.mean():6.1f} gram {gr.mean():6.1f} waitF {w2.mean():6.1f} trsm {tr.mean():6.1f}"
+                line += f" | sums(ms*cta): wait1 {w1.sum()/1e3:.1f} mma {mm.sum()/1e3:.1f} gram {gr.sum()/1e3:.1f} waitF {w2.sum()/1e3:.1f} trsm {tr.sum()/1e3:.1f}"
+            else:
+                rest = s[:, 5] - s[:, 2]
+                line += f" | wait1 {w1.mean():6.1f} mma {mm.mean():6.1f} gram+store {rest.mean():6.1f}"
+        print(line)
+    print(f"slots {slots}  busy {busy_total/1e3:.1f} ms*cta  capacity {slots*span/1e3:.1f} ms*cta  occupancy {busy_total/(slots*span):.3f}")
+    # per-block-column view of the panels
+    print("per block column k: panel items mean us (wait1, mma, gram, waitF, trsm) and the wall-clock window of the column")
+    for k in range(nt):
+        m = (typ == 2) & (items[:, 2] == k)
+        if not m.any():
+            continue
+        s = st[m].astype(np.float64) * 1e-3
+        print(f"  k={k:2d} n={m.sum():5d} wait1 {np.mean(s[:,1]-s[:,0]):6.1f} mma {np.mean(s[:,2]-s[:,1]):6.1f} gram {np.mean(s[:,3]-s[:,2]):6.1f} "
+              f"waitF {np.mean(s[:,4]-s[:,3]):6.1f} trsm {np.mean(s[:,5]-s[:,4]):6.1f}  window [{(s[:,0].min()-t0*1e-3):8.0f}, {(s[:,5].max()-t0*1e-3):8.0f}] us")
+    m = typ == 1
+    s = st[m].astype(np.float64) * 1e-3
+    for k in range(nt):
+        mk = items[m, 2] == k
+        print(f"  potf2 k={k:2d} wait {np.mean(s[mk,1]-s[mk,0]):6.1f} work {np.mean(s[mk,5]-s[mk,1]):6.1f} window [{(s[mk,0].min()-t0*1e-3):8.0f}, {(s[mk,5].max()-t0*1e-3):8.0f}]")
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", f"trace_n{n}_P{P}_o{order}.npz"), items=items, stamps=st)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,7 @@ struct agp_handle {
     bool staged = false;  // AGP_PATH=staged selects the one-launch-per-stage path (A/B measurements)
     int order = 1;        // queue order variant (AGP_ORDER)
     int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
+    unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
     int num_sms = 0;
     struct Queue {
         int4* d_items = nullptr;
@@ -167,6 +168,7 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_GRAPH")) h->use_graph = atoi(e) != 0;
     if (const char* e = getenv("AGP_PATH")) h->staged = strcmp(e, "staged") == 0;
     if (const char* e = getenv("AGP_ORDER")) h->order = atoi(e);
+    if (const char* e = getenv("AGP_WAIT_TIMEOUT_MS")) h->wait_timeout_ns = 1000000ull * (unsigned long long)atoll(e);
     if (const char* e = getenv("AGP_CTAS_PER_SM")) h->ctas_per_sm = atoi(e) >= 1 ? atoi(e) : 1;
     *out = h;
     return AGP_OK;
@@ -460,8 +462,10 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
     q.fdone = q.diagu + (size_t)P * nt_stride;
     q.nt_stride = nt_stride;
     q.trace = d_trace;
+    q.wait_timeout_ns = h->wait_timeout_ns;
+    agp::launch_gramfill(v, P, h->stream);
     agp::launch_chol(v, q, h->ctas_per_sm * h->num_sms, h->stream);
-    h->launches += 1;
+    h->launches += 2;
     return check_launch(h, "chol");
 }
 

@@ -10,13 +10,14 @@
 // The operand stack lives in D registers (shift on push/pop) — D = 4 covers every tree with
 // fewer than 16 leaves, D = 8 the rest (host guarantees need <= AGP_MAX_STACK).
 #pragma once
+#include "agp_math.cuh"
 #include "agp_program.h"
 
 namespace agp {
 
-__device__ __forceinline__ double sigma_cp(double x, double location, double scale) {
+__device__ __forceinline__ double sigma_cp(double x, double location, double scale, double rscale, bool fast) {
     // src/GP.jl:481-483
-    return 0.5 * (1.0 + tanh((location - x) / scale));
+    return 0.5 * (1.0 + tanh(div_const(location - x, scale, rscale, fast)));
 }
 
 // E independent entries are evaluated per interpreter pass (instruction-level parallelism hides
@@ -62,6 +63,7 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     }
     for (int q = 0; q < m; ++q) {
         const int op = prog[q].op;
+        const bool fast = (prog[q].pad & 1) != 0;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
         double v[E];
         switch (op) {
@@ -78,24 +80,34 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 }
                 st.push(v);
                 break;
-            case AGP_I_SE:
+            case AGP_I_SE: {  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245
+                double w[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = b * exp(((-0.5 * dx[e]) * dx[e]) / a);
+                for (int e = 0; e < E; ++e) w[e] = div_const((-0.5 * dx[e]) * dx[e], a, c, fast);
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b * v[e];
                 st.push(v);
                 break;
+            }
             case AGP_I_GE:
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = c * exp(-pow(adx[e] / a, b));
                 st.push(v);
                 break;
-            case AGP_I_PER:
+            case AGP_I_PER: {  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
+                double w[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    double sn = sin(a * adx[e]);
-                    v[e] = c * exp(b * (sn * sn));
-                }
+                for (int e = 0; e < E; ++e) w[e] = a * adx[e];
+                sin_abs_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = b * (v[e] * v[e]);
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * v[e];
                 st.push(v);
                 break;
+            }
             case AGP_I_WN:
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
@@ -116,8 +128,8 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 for (int e = 0; e < E; ++e) {
                     double kl = (op == AGP_I_CP) ? st.s[1][e] : st.s[0][e];
                     double kr = (op == AGP_I_CP) ? st.s[0][e] : st.s[1][e];
-                    double g1 = sigma_cp(t1[e], a, b);
-                    double g2 = sigma_cp(t2[e], a, b);
+                    double g1 = sigma_cp(t1[e], a, b, c, fast);
+                    double g2 = sigma_cp(t2[e], a, b, c, fast);
                     if (form == 0) {  // vectorised: sig_1 .* k_1 + sig_2 .* k_2   (GP.jl:494-501)
                         double sig1 = g1 * g2;
                         double sig2 = (1.0 - g1) * (1.0 - g2);
@@ -133,6 +145,32 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     }
 #pragma unroll
     for (int e = 0; e < E; ++e) out[e] = st.s[0][e];
+}
+
+// Eight entries at once for shallow programs (register stack of 2 covers e.g. Plus(Times(SE,
+// Periodic),Linear) after Sethi-Ullman ordering): twice the independent FP64 chains per thread
+// for the latency-bound epilogue of the persistent kernel.  Deeper programs run as 2 x 4 or 4 x 2.
+__device__ __forceinline__ void eval_entries8(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[8], const double (&t2)[8],
+                                              int form, double (&out)[8]) {
+    if (need <= 2) {
+        eval_program<2, 8>(prog, m, t1, t2, form, out);
+    } else if (need <= 4) {
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            double a1[4] = {t1[h], t1[h + 1], t1[h + 2], t1[h + 3]}, a2[4] = {t2[h], t2[h + 1], t2[h + 2], t2[h + 3]}, o4[4];
+            eval_program<4, 4>(prog, m, a1, a2, form, o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[h + e] = o4[e];
+        }
+    } else {
+#pragma unroll 1
+        for (int h = 0; h < 8; h += 2) {
+            double a1[2] = {t1[h], t1[h + 1]}, a2[2] = {t2[h], t2[h + 1]}, o2[2];
+            eval_program<AGP_MAX_STACK, 2>(prog, m, a1, a2, form, o2);
+            out[h] = o2[0];
+            out[h + 1] = o2[1];
+        }
+    }
 }
 
 // E entries at once; deep trees (need > 4) fall back to pairs to bound register use.

@@ -8,10 +8,15 @@
 // CTAs of an SM drift apart so one CTA's Gram/solve epilogue (issue-bound FP64 ALU work) fills
 // the gaps of the other's DMMA main loop.
 //
+// agp_gramfill_kernel runs first: it evaluates every particle's kernel-tree program over the lower
+// 128x128 tiles and leaves K(ts,ts) + noise*I in L (ts slices staged by 1-D TMA bulk copies, all
+// warps of the SM in the FP64-ALU-bound interpreter at once).  The persistent kernel then starts
+// each tile's accumulators from -K, so the Gram work never sits between two DMMA main loops.
+//
 //   ITEM_DIAG  (p,k,h)    64 rows of the diagonal tile:  K(ts_k,ts_k) + noise I - sum_j L_kj L_kj^T
 //   ITEM_POTF2 (p,k)      Cholesky of the 128x128 diagonal tile (+ observation row): L_kk, z_k,
 //                         log det, z'z, LAPACK info, inverses of the 32x32 diagonal blocks
-//   ITEM_PANEL (p,k,i,h)  64 rows of tile (i,k): Gram - contraction on FP64 tensor cores, then the
+//   ITEM_PANEL (p,k,i,h)  64 rows of tile (i,k): K - contraction on FP64 tensor cores, then the
 //                         triangular solve against L_kk IN SHARED MEMORY (the unfactored tile never
 //                         touches HBM), then y_i -= L_ik z_k (forward solve folded in)
 //
@@ -40,9 +45,9 @@ constexpr int BS = 33;                   // potf2 32x32 block row stride (odd: l
 constexpr int BLK = 32 * BS;
 constexpr int REGION_D = UM * XS + 32 * XS;  // X rows + one 32-row panel of L_kk
 constexpr int PROG_SMEM = 64;
-// tail of the shared-memory image (doubles): ts_r[UM] ts_c[UN] zs[TB] ys[TB] Ri[TB] red[16]
-constexpr int TAIL_D = UM + UN + 3 * TB + 16;
-constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + PROG_SMEM * 32 + 64;
+// tail of the shared-memory image (doubles): zs[TB] ys[TB] Ri[TB] red[16]
+constexpr int TAIL_D = 3 * TB + 16;
+constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + 64;
 
 static_assert(NSTAGE * STAGE_D <= REGION_D, "pipeline stages must fit in the region");
 static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region");
@@ -56,9 +61,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// thread 0 only: wait until *flag >= need.  A wait that exceeds ~2 s raises the scheduler error
+// thread 0 only: wait until *flag >= need.  A wait that exceeds the limit (2 s by default) raises the scheduler error
 // flag so every CTA drains instead of hanging the device.
-__device__ bool wait_ge(const int* flag, int need, int* err) {
+__device__ bool wait_ge(const int* flag, int need, int* err, unsigned long long limit_ns) {
     if (ld_acquire_gpu(flag) >= need) return true;
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
@@ -67,7 +72,7 @@ __device__ bool wait_ge(const int* flag, int need, int* err) {
         if (ld_acquire_gpu(flag) >= need) return true;
         if ((++spins & 255u) == 0) {
             if (ld_relaxed_gpu(err) != 0) return false;
-            if (globaltimer_ns() - t0 > 2000000000ull) {
+            if (globaltimer_ns() - t0 > limit_ns) {
                 atomicExch(err, 1);
                 return false;
             }
@@ -89,24 +94,35 @@ __device__ __forceinline__ void signal_done(int* counter) {
     }
 }
 
+// Shared-memory image of one CTA.  Every device function rebuilds this view from the extern
+// array itself (never through a pointer argument) so the compiler keeps the shared address
+// space and emits LDS/STS instead of generic loads.
 struct Smem {
     double* region;
-    double* ts_r;
-    double* ts_c;
     double* zs;
     double* ys;
     double* Ri;
     double* red;
-    AgpInstr* prog_s;
-    uint64_t* bar;
     int* ctl;  // [0] item index, [1] wait result, [2] potf2 info
 };
+
+__device__ __forceinline__ Smem smem_view() {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem s;
+    s.region = reinterpret_cast<double*>(smem_raw);
+    s.zs = s.region + REGION_D;
+    s.ys = s.zs + TB;
+    s.Ri = s.ys + TB;
+    s.red = s.Ri + TB;
+    s.ctl = reinterpret_cast<int*>(s.red + 16);
+    return s;
+}
 
 // ------------------------------------------------------------------------------------------
 // ITEM_DIAG / ITEM_PANEL
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, const Smem& s, int idx, int p, int k, int i, int h, bool diag,
-                                       uint32_t& tma_parity) {
+__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag) {
+    const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int row0 = i * TB + h * UM, col0 = k * TB;
@@ -114,27 +130,11 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
     double* stages = s.region;
 
-    // inputs that no other CTA writes: ts slices (TMA bulk), program
-    if (tid == 0) {
-        mbar_expect_tx(s.bar, (UM + UN) * 8);
-        tma_bulk_g2s(s.ts_r, v.ts + row0, UM * 8, s.bar);
-        tma_bulk_g2s(s.ts_c, v.ts + col0, UN * 8, s.bar);
-    }
-    const int poff = v.prog_off[p];
-    const int pm = v.prog_off[p + 1] - poff;
-    const AgpInstr* prog = v.prog + poff;
-    if (pm <= PROG_SMEM) {
-        const double* src = reinterpret_cast<const double*>(prog);
-        double* dst = reinterpret_cast<double*>(s.prog_s);
-        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];
-        prog = s.prog_s;
-    }
-
     // rows i and k of L must be final for all block columns < k
     if (k > 0) {
         if (tid == 0) {
-            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * k, q.err);
-            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * k, q.err);
+            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * k, q.err, q.wait_timeout_ns);
+            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * k, q.err, q.wait_timeout_ns);
             s.ctl[1] = ok ? 1 : 0;
         }
         __syncthreads();
@@ -147,11 +147,25 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
     const int g = lane >> 2, c4 = lane & 3;
     // warp tiles strictly above the diagonal of a diagonal tile are never read
     const bool active = !diag || (wn * 32 <= h * UM + wm * 32 + 31);
+    // The Gram tile K(ts_i, ts_k) [+ noise I] was written into L by agp_gramfill_kernel.  Block
+    // column 0 needs no contraction: the diagonal tile is already in place and a panel goes
+    // straight to shared memory.  Otherwise the accumulators start from -K, so that after the
+    // contraction  acc = -(K - sum_j L_ij L_kj^T).
+    if (k == 0 && diag) {
+        if (tid < UM) v.y[(long long)p * ld + row0 + tid] = (row0 + tid < v.n) ? v.xs[row0 + tid] : 0.0;
+        signal_done(q.diagu + p * q.nt_stride + k);
+        return true;
+    }
     double acc[4][4][2];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+        for (int nb = 0; nb < 4; ++nb) {
+            const int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
+            const double2 kv = __ldcg(reinterpret_cast<const double2*>(Lp + (long long)(row0 + r) * ld + col0 + c));
+            acc[mb][nb][0] = -kv.x;
+            acc[mb][nb][1] = -kv.y;
+        }
 
     const int nchunk = (k * TB) / KC;
     const double* __restrict__ Ag = Lp + (long long)row0 * ld;
@@ -217,70 +231,36 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
     __syncthreads();
     stamp(q, idx, 2);
 
-    // --- Gram tile on the fly:  X = K(ts_r, ts_c) [+ noise I] - acc ------------------------
+    // --- X = -acc:  the diagonal tile goes back to L (lower part), a panel stays in shared memory ----
     double* Xs = s.region;            // [UM][XS]
     double* Ls = s.region + UM * XS;  // [32][XS]
-    if (k > 0 && active) {
+    if (active) {
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
-                *reinterpret_cast<double2*>(Xs + r * XS + c) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-            }
-    }
-    mbar_wait(s.bar, tma_parity);
-    tma_parity ^= 1u;
-    __syncthreads();
-
-    const int need = v.prog_need[p];
-    const double noise = v.noise[p];
-    const int n = v.n;
-    {
-        // thread -> column c, rows rbase + 2*e (e = 0..31), four entries per interpreter pass
-        const int c = tid & (UN - 1), rbase = tid >> 7;
-        const int gc = col0 + c;
-        const double tcol = s.ts_c[c];
-#pragma unroll 1
-        for (int e4 = 0; e4 < 8; ++e4) {
-            const int rlast = rbase + 2 * (4 * e4 + 3);
-            if (diag && c > rlast + h * UM) continue;  // strictly-upper part of a diagonal tile is never read
-            double t1[4], t2[4], val[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
-                t2[j] = s.ts_r[rbase + 2 * (4 * e4 + j)];
-            }
-            eval_entries<4>(prog, pm, need, t1, t2, 0, val);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rbase + 2 * (4 * e4 + j);
-                const int gr = row0 + r;
-                if (diag && c > r + h * UM) continue;
-                double out;
-                if (gr < n) {  // gc <= gr < n
-                    out = val[j];
-                    if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+                const int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
+                const double2 x2 = make_double2(-acc[mb][nb][0], -acc[mb][nb][1]);
+                if (!diag) {
+                    *reinterpret_cast<double2*>(Xs + r * XS + c) = x2;
                 } else {
-                    out = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+                    const int rd = h * UM + r;  // row inside the 128x128 tile
+                    double* dst = Lp + (long long)(row0 + r) * ld + col0 + c;
+                    if (c + 1 <= rd) *reinterpret_cast<double2*>(dst) = x2;
+                    else if (c <= rd) dst[0] = x2.x;
                 }
-                if (k > 0) out = out - Xs[r * XS + c];
-                if (diag) Lp[(long long)gr * ld + gc] = out;
-                else Xs[r * XS + c] = out;
             }
-        }
     }
-
-    double* yp = v.y + (long long)p * ld;
     if (diag) {
-        if (k == 0 && tid < UM) yp[row0 + tid] = (row0 + tid < n) ? v.xs[row0 + tid] : 0.0;
         signal_done(q.diagu + p * q.nt_stride + k);
         return true;
     }
+    double* yp = v.y + (long long)p * ld;
+    const int n = v.n;
 
     // --- triangular solve against L_kk in shared memory ------------------------------------
     stamp(q, idx, 3);
-    if (tid == 0) s.ctl[1] = wait_ge(q.fdone + p, k + 1, q.err) ? 1 : 0;
+    if (tid == 0) s.ctl[1] = wait_ge(q.fdone + p, k + 1, q.err, q.wait_timeout_ns) ? 1 : 0;
     __syncthreads();  // also publishes X
     if (!s.ctl[1]) return false;
     stamp(q, idx, 4);
@@ -386,7 +366,8 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_off(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * BLK; }
 
-__device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, const Smem& s, int idx, int p, int k) {
+__device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, int idx, int p, int k) {
+    const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ld = v.ld;
@@ -398,7 +379,7 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, co
     double* Ri = s.Ri;
 
     if (tid == 0) {
-        s.ctl[1] = wait_ge(q.diagu + p * q.nt_stride + k, 2, q.err) ? 1 : 0;
+        s.ctl[1] = wait_ge(q.diagu + p * q.nt_stride + k, 2, q.err, q.wait_timeout_ns) ? 1 : 0;
         s.ctl[2] = 0;
     }
     __syncthreads();
@@ -596,25 +577,8 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, co
 }  // namespace
 
 __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView q) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem s;
-    s.region = reinterpret_cast<double*>(smem_raw);
-    s.ts_r = s.region + REGION_D;
-    s.ts_c = s.ts_r + UM;
-    s.zs = s.ts_c + UN;
-    s.ys = s.zs + TB;
-    s.Ri = s.ys + TB;
-    s.red = s.Ri + TB;
-    s.prog_s = reinterpret_cast<AgpInstr*>(s.red + 16);
-    s.bar = reinterpret_cast<uint64_t*>(s.prog_s + PROG_SMEM);
-    s.ctl = reinterpret_cast<int*>(s.bar + 1);
+    const Smem s = smem_view();
 
-    if (threadIdx.x == 0) {
-        mbar_init(s.bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    uint32_t tma_parity = 0;
     for (;;) {
         if (threadIdx.x == 0) s.ctl[0] = atomicAdd(q.head, 1);
         __syncthreads();
@@ -624,8 +588,8 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
         const int type = it.x & 0xff, h = it.x >> 8;
         bool ok;
         stamp(q, idx, 0);
-        if (type == ITEM_POTF2) ok = do_potf2(v, q, s, idx, it.y, it.z);
-        else ok = do_update(v, q, s, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, tma_parity);
+        if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z);
+        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG);
         if (!ok) break;
         stamp(q, idx, 5);
         if (q.trace != nullptr && threadIdx.x == 0) {
@@ -637,8 +601,97 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Gram fill: L tile (i,k), i >= k  <-  K(ts_i, ts_k) [+ noise I]; identity in the padding rows.
+// grid (2 * nt(nt+1)/2, P): one CTA = 64 rows x 128 columns; thread -> column, 32 rows, eight
+// entries per interpreter pass; rows are written as coalesced 1 KB segments.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT, 2) agp_gramfill_kernel(BatchView v) {
+    __shared__ __align__(128) double ts_r[UM];
+    __shared__ __align__(128) double ts_c[UN];
+    __shared__ AgpInstr prog_s[PROG_SMEM];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int p = blockIdx.y;
+    // linear id -> lower-triangular tile (i >= k) and row half
+    const int t = blockIdx.x >> 1, h = blockIdx.x & 1;
+    int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    const int k = t - i * (i + 1) / 2;
+    const bool diag = (i == k);
+    const int row0 = i * TB + h * UM, col0 = k * TB;
+    const int ld = v.ld;
+    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, (UM + UN) * 8);
+        tma_bulk_g2s(ts_r, v.ts + row0, UM * 8, &bar);
+        tma_bulk_g2s(ts_c, v.ts + col0, UN * 8, &bar);
+    }
+    const int poff = v.prog_off[p];
+    const int pm = v.prog_off[p + 1] - poff;
+    const AgpInstr* prog = v.prog + poff;
+    if (pm <= PROG_SMEM) {
+        const double* src = reinterpret_cast<const double*>(prog);
+        double* dst = reinterpret_cast<double*>(prog_s);
+        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];
+        prog = prog_s;
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    const int need = v.prog_need[p];
+    const double noise = v.noise[p];
+    const int n = v.n;
+    const int c = tid & (UN - 1), rbase = tid >> 7;
+    const int gc = col0 + c;
+    const double tcol = ts_c[c];
+#pragma unroll 1
+    for (int e8 = 0; e8 < 4; ++e8) {
+        double t1[8], t2[8], val[8];
+        const int rlast = rbase + 2 * (8 * e8 + 7);
+        const bool skip = diag && c > rlast + h * UM;  // strictly-upper part of a diagonal tile: zeros
+        if (!skip) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
+                t2[j] = ts_r[rbase + 2 * (8 * e8 + j)];
+            }
+            eval_entries8(prog, pm, need, t1, t2, 0, val);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = rbase + 2 * (8 * e8 + j);
+            const int gr = row0 + r;
+            double out = 0.0;
+            if (!(diag && c > r + h * UM)) {
+                if (gr < n) {  // gc <= gr < n
+                    out = val[j];
+                    if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+                } else {
+                    out = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+                }
+            }
+            Lp[(long long)gr * ld + gc] = out;
+        }
+    }
+}
+
 cudaError_t configure_fused() {
     return cudaFuncSetAttribute(agp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
+}
+
+void launch_gramfill(const BatchView& v, int P, cudaStream_t s) {
+    if (P <= 0 || v.nt <= 0) return;
+    dim3 grid(v.nt * (v.nt + 1), P);  // 2 halves x nt(nt+1)/2 lower tiles
+    agp_gramfill_kernel<<<grid, FT, 0, s>>>(v);
 }
 
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {

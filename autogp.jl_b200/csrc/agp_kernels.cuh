@@ -45,10 +45,13 @@ struct SchedView {
     int* diagu;         // [P][nt_stride] finished halves of diagonal tile k
     int* fdone;         // [P] factored diagonal tiles
     int nt_stride;
+    unsigned long long wait_timeout_ns;  // dependency wait limit before the error flag is raised
     long long* trace;   // optional [n_items][8] globaltimer stamps (diagnostics; nullptr = off)
 };
 
-// One launch = the whole batch: Gram + Cholesky + solve + logdet for every particle.
+// Gram fill: every lower tile of every particle  <-  K(ts,ts) + noise*I  (runs before launch_chol)
+void launch_gramfill(const BatchView& v, int P, cudaStream_t s);
+// One launch = the whole batch: Cholesky + solve + logdet for every particle.
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s);
 cudaError_t configure_fused();
 

@@ -26,11 +26,10 @@ eng.upload([to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
 eng.run(); eng.run(); eng.synchronize()
 ms = eng.time_runs(a.reps) / a.reps
 lml, info = eng.fetch()
-st = eng.stage_times()
 msg = ""
 for p in range(min(a.check, a.P)):
     ref = o.log_marginal_likelihood(*parts[p], ts, xs)
     msg += f" relerr[{p}]={abs(lml[p]-ref)/abs(ref):.1e}"
 fl = a.P * a.n ** 3 / 3
 print(f"groups={os.environ.get('AGP_GROUPS','auto')} graph={os.environ.get('AGP_GRAPH','1')} n={a.n} P={a.P}: {ms:.3f} ms/run {a.P/ms*1e3:.0f} LML/s "
-      f"{fl/ms*1e-9:.2f} TF/s stages(upd,potf2,trsm)=({st[0]:.3f},{st[1]:.3f},{st[2]:.3f}) info_ok={bool(np.all(info==0))}{msg}", flush=True)
+      f"{fl/ms*1e-9:.2f} TF/s info_ok={bool(np.all(info==0))}{msg}", flush=True)

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagp_b200.so")
+LIB_PATH = os.environ.get("AGP_LIB") or os.path.join(_HERE, "libagp_b200.so")  # AGP_LIB: developer A/B builds
 
 # every symbol include/agp_b200.h declares
 EXPORTS = (

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/agp_b200.h"
@@ -59,7 +60,7 @@ struct agp_handle {
 
     // persistent dataflow path (default): work queues per (P, nt) shape + dependency counters
     bool staged = false;  // AGP_PATH=staged selects the one-launch-per-stage path (A/B measurements)
-    int order = 1;        // queue order variant (AGP_ORDER)
+    int order = 2;        // queue order variant (AGP_ORDER)
     int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
     unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
     int num_sms = 0;
@@ -67,7 +68,7 @@ struct agp_handle {
         int4* d_items = nullptr;
         int n_items = 0;
     };
-    std::map<std::pair<int, int>, Queue> queues;
+    std::map<std::tuple<int, int, int>, Queue> queues;
     int* d_sync = nullptr;   size_t cap_sync = 0;
     int* h_sync = nullptr;   // pinned, 2 ints: queue head, error flag
 };
@@ -313,13 +314,15 @@ int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int3
     int rc;
     if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
     if ((rc = grow_device(h, &h->d_in, &h->cap_in, in_bytes)) != AGP_OK) return rc;
-    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] dinv[P][4096]
+    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] dinv[P][ld/128][4096] (one set of diagonal-block
+    // inverses per block column: the persistent kernel factors column k+1 while column k is still
+    // being solved; the staged path only uses the first set of each particle's slice)
     size_t off_y = 0;
     size_t off_z = off_y + (size_t)P * ld * 8;
     size_t off_ld = off_z + (size_t)P * ld * 8;
     size_t off_zz = off_ld + (size_t)P * 8;
     size_t off_dinv = align_up(off_zz + (size_t)P * 8, 256);
-    size_t work_bytes = off_dinv + (size_t)P * 4096 * 8;
+    size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * 4096 * 8;
     if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
     size_t res_bytes = align_up((size_t)P * 8, 16) + (size_t)P * 4;
     if ((rc = grow_device(h, &h->d_res, &h->cap_res, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
@@ -382,46 +385,89 @@ int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
 
 // ---- persistent dataflow path: the in-order work queue -------------------------------------
 //
-// Any order is valid as long as every item's producers come EARLIER (agp_fused.cu):
-//   DIAG(p,k,h)    <- PANEL(p,j,k,*) for all j < k
-//   POTF2(p,k)     <- DIAG(p,k,0), DIAG(p,k,1)
-//   PANEL(p,k,i,h) <- PANEL(p,j,i,*), PANEL(p,j,k,*) for all j < k;  POTF2(p,k)
+// Any order is valid as long as every item's producers come EARLIER (agp_fused.cu); with
+// PANEL(p,k,i,h)[j0,j1) / DIAG(p,k,h)[j0,j1) contracting block columns j0 <= j < j1:
+//   any item [j0,j1)     <- final PANEL(p,j,i,*) and PANEL(p,j,k,*) for all j < j1
+//   continuation j0 > 0  <- the partial item [0,j0) of the same tile (both halves)
+//   POTF2(p,k)           <- every DIAG item of tile (k,k)
+//   final PANEL(p,k,i,h) <- POTF2(p,k)
 // order 0: block column by block column:  DIAG | POTF2 | PANEL.
-// order 1: look-ahead: within block column k the panels of tile row k+1 go first, and the
-//          diagonal tile of column k+1 (DIAG, POTF2) is interleaved into the bulk of column k's
-//          panels, so neither the diagonal factorisation nor its producers are ever waited for.
-static void build_queue(int P, int nt, int order, std::vector<int4>& items) {
-    auto push = [&](int type, int h, int p, int k, int i) { items.push_back(make_int4(type | (h << 8), p, k, i)); };
+// order 1: look-ahead: the panels of tile row k+1 go first in block column k, and DIAG(k+1),
+//          POTF2(k+1) are interleaved into the bulk of column k's panels.
+// order 2: order 1 + split contractions: the next diagonal tile (k+1,k+1) and the panel below it
+//          (k+2,k+1) get a PARTIAL item over [0,k) one block column early, so only the last 128
+//          columns of their contraction remain on the per-particle critical path
+//          POTF2(k) -> PANEL(k,k+1) -> DIAG(k+1) -> POTF2(k+1).
+struct QueueLayout {
+    int P, nt, nt_stride;
+    int flag_diagu(int p, int k) const { return 32 + P * nt_stride + p * nt_stride + k; }
+    int flag_ppre(int p, int i) const { return 32 + 2 * P * nt_stride + p * nt_stride + i; }
+};
+
+static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int4>& items) {
+    const QueueLayout lay{P, nt, nt_stride};
+    const int split_from = 3;  // block columns below this are too short to be worth splitting
+    auto split = [&](int k) { return order >= 2 && k >= split_from && k < nt; };  // tile (k,k) and (k+1,k) are split
+    auto push = [&](int type, int h, int p, int k, int i, int j0, int j1, int flag, int need) {
+        items.push_back(make_int4(type | (h << 8), p, k, i));
+        items.push_back(make_int4(j0, j1, flag, need));
+    };
+    auto diag_full = [&](int p, int k) {
+        for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k, k, 0, k, -1, 0);
+    };
+    auto potf2 = [&](int p, int k) { push(agp::ITEM_POTF2, 0, p, k, k, 0, 0, -1, split(k) ? 4 : 2); };
+    auto panel_full = [&](int p, int k, int i) {
+        for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, i, 0, k, -1, 0);
+    };
     items.clear();
     if (order == 0 || nt == 1) {
         for (int k = 0; k < nt; ++k) {
+            for (int p = 0; p < P; ++p) diag_full(p, k);
+            for (int p = 0; p < P; ++p) potf2(p, k);
             for (int p = 0; p < P; ++p)
-                for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k, k);
-            for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, k, k);
-            for (int p = 0; p < P; ++p)
-                for (int i = k + 1; i < nt; ++i)
-                    for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, i);
+                for (int i = k + 1; i < nt; ++i) panel_full(p, k, i);
         }
         return;
     }
-    for (int p = 0; p < P; ++p)
-        for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, 0, 0);
-    for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, 0, 0);
+    for (int p = 0; p < P; ++p) diag_full(p, 0);
+    for (int p = 0; p < P; ++p) potf2(p, 0);
     for (int k = 0; k < nt - 1; ++k) {
         // panels of tile row k+1 first: they feed the next diagonal tile
-        for (int p = 0; p < P; ++p)
-            for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, k + 1);
+        for (int p = 0; p < P; ++p) {
+            if (split(k)) {
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k, k + 1, k - 1, k, lay.flag_ppre(p, k + 1), 2);
+            } else {
+                panel_full(p, k, k + 1);
+            }
+        }
+        // look-ahead partials of block column k+1 (need block columns < k only)
+        if (split(k + 1)) {
+            for (int p = 0; p < P; ++p) {
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k + 1, k + 1, 0, k, -1, 0);
+                if (k + 2 < nt)
+                    for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, p, k + 1, k + 2, 0, k, -1, 0);
+            }
+        }
         // bulk of column k, with DIAG(k+1) after the first third and POTF2(k+1) after the second
         std::vector<int4> bulk;
         for (int p = 0; p < P; ++p)
             for (int i = k + 2; i < nt; ++i)
-                for (int h = 0; h < 2; ++h) bulk.push_back(make_int4(agp::ITEM_PANEL | (h << 8), p, k, i));
-        size_t c1 = bulk.size() / 3, c2 = 2 * bulk.size() / 3;
+                for (int h = 0; h < 2; ++h) {
+                    bulk.push_back(make_int4(agp::ITEM_PANEL | (h << 8), p, k, i));
+                    bulk.push_back(make_int4(0, k, -1, 0));
+                }
+        size_t n_bulk = bulk.size() / 2;
+        size_t c1 = 2 * (n_bulk / 3), c2 = 2 * (2 * n_bulk / 3);
         items.insert(items.end(), bulk.begin(), bulk.begin() + c1);
-        for (int p = 0; p < P; ++p)
-            for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k + 1, k + 1);
+        for (int p = 0; p < P; ++p) {
+            if (split(k + 1)) {
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k + 1, k + 1, k, k + 1, lay.flag_diagu(p, k + 1), 2);
+            } else {
+                diag_full(p, k + 1);
+            }
+        }
         items.insert(items.end(), bulk.begin() + c1, bulk.begin() + c2);
-        for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, p, k + 1, k + 1);
+        for (int p = 0; p < P; ++p) potf2(p, k + 1);
         items.insert(items.end(), bulk.begin() + c2, bulk.end());
     }
 }
@@ -430,13 +476,13 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
-    auto key = std::make_pair(P, nt);
+    auto key = std::make_tuple(P, nt, nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
-        build_queue(P, nt, h->order, items);
+        build_queue(P, nt, nt_stride, h->order, items);
         agp_handle::Queue qu;
-        qu.n_items = (int)items.size();
+        qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -447,8 +493,8 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
         it = h->queues.emplace(key, qu).first;
     }
-    // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], fdone[P]
-    const size_t n_sync = 32 + (size_t)2 * P * nt_stride + P;
+    // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], ppre[P][nt_stride], fdone[P]
+    const size_t n_sync = 32 + (size_t)3 * P * nt_stride + P;
     int rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int));
     if (rc != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
@@ -459,7 +505,8 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
     q.err = h->d_sync + 1;
     q.rowdone = h->d_sync + 32;
     q.diagu = q.rowdone + (size_t)P * nt_stride;
-    q.fdone = q.diagu + (size_t)P * nt_stride;
+    q.ppre = q.diagu + (size_t)P * nt_stride;
+    q.fdone = q.ppre + (size_t)P * nt_stride;
     q.nt_stride = nt_stride;
     q.trace = d_trace;
     q.wait_timeout_ns = h->wait_timeout_ns;
@@ -661,17 +708,18 @@ int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
     if (P < 0 || nt < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
-    build_queue(P, nt, order, items);
+    build_queue(P, nt, nt, order, items);
+    const int64_t n_items = (int64_t)items.size() / 2;
     if (items_out) {
-        int64_t m = (int64_t)items.size() < cap ? (int64_t)items.size() : cap;
-        for (int64_t q = 0; q < m; ++q) {
+        int64_t m = n_items < cap ? n_items : cap;
+        for (int64_t q = 0; q < 2 * m; ++q) {
             items_out[4 * q + 0] = items[q].x;
             items_out[4 * q + 1] = items[q].y;
             items_out[4 * q + 2] = items[q].z;
             items_out[4 * q + 3] = items[q].w;
         }
     }
-    return (int64_t)items.size();
+    return n_items;
 }
 
 int agp_lml_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,

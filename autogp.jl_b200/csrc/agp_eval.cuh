@@ -10,14 +10,14 @@
 // The operand stack lives in D registers (shift on push/pop) — D = 4 covers every tree with
 // fewer than 16 leaves, D = 8 the rest (host guarantees need <= AGP_MAX_STACK).
 #pragma once
-#include "agp_math.cuh"
 #include "agp_program.h"
 
 namespace agp {
 
-__device__ __forceinline__ double sigma_cp(double x, double location, double scale, double rscale, bool fast) {
+
+__device__ __forceinline__ double sigma_cp(double x, double location, double scale) {
     // src/GP.jl:481-483
-    return 0.5 * (1.0 + tanh(div_const(location - x, scale, rscale, fast)));
+    return 0.5 * (1.0 + tanh((location - x) / scale));
 }
 
 // E independent entries are evaluated per interpreter pass (instruction-level parallelism hides
@@ -63,7 +63,6 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     }
     for (int q = 0; q < m; ++q) {
         const int op = prog[q].op;
-        const bool fast = (prog[q].pad & 1) != 0;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
         double v[E];
         switch (op) {
@@ -80,34 +79,24 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 }
                 st.push(v);
                 break;
-            case AGP_I_SE: {  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245
-                double w[E];
+            case AGP_I_SE:  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245
 #pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = div_const((-0.5 * dx[e]) * dx[e], a, c, fast);
-                exp_v<E>(w, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = b * v[e];
+                for (int e = 0; e < E; ++e) v[e] = b * exp(((-0.5 * dx[e]) * dx[e]) / a);
                 st.push(v);
                 break;
-            }
             case AGP_I_GE:
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = c * exp(-pow(adx[e] / a, b));
                 st.push(v);
                 break;
-            case AGP_I_PER: {  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
-                double w[E];
+            case AGP_I_PER:  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
 #pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = a * adx[e];
-                sin_abs_v<E>(w, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = b * (v[e] * v[e]);
-                exp_v<E>(w, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = c * v[e];
+                for (int e = 0; e < E; ++e) {
+                    double sn = sin(a * adx[e]);
+                    v[e] = c * exp(b * (sn * sn));
+                }
                 st.push(v);
                 break;
-            }
             case AGP_I_WN:
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
@@ -128,8 +117,8 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 for (int e = 0; e < E; ++e) {
                     double kl = (op == AGP_I_CP) ? st.s[1][e] : st.s[0][e];
                     double kr = (op == AGP_I_CP) ? st.s[0][e] : st.s[1][e];
-                    double g1 = sigma_cp(t1[e], a, b, c, fast);
-                    double g2 = sigma_cp(t2[e], a, b, c, fast);
+                    double g1 = sigma_cp(t1[e], a, b);
+                    double g2 = sigma_cp(t2[e], a, b);
                     if (form == 0) {  // vectorised: sig_1 .* k_1 + sig_2 .* k_2   (GP.jl:494-501)
                         double sig1 = g1 * g2;
                         double sig2 = (1.0 - g1) * (1.0 - g2);

@@ -121,7 +121,13 @@ __device__ __forceinline__ Smem smem_view() {
 // ------------------------------------------------------------------------------------------
 // ITEM_DIAG / ITEM_PANEL
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag) {
+// Contraction range [j0, j1) in block columns.  j1 == k: the item finishes the tile (diagonal tile
+// -> L for potf2; panel -> triangular solve).  j1 < k: look-ahead PARTIAL item, the tile in L
+// receives K - sum_{j<j1} and a later item with j0 = j1 picks it up from there (the accumulators
+// always start from minus the tile), which takes the long early part of the contraction of the
+// next diagonal tile and of the panel below it off the per-particle critical path.
+__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag, int j0, int j1,
+                                       int extra_flag, int extra_need) {
     const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -130,11 +136,14 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
     double* stages = s.region;
 
-    // rows i and k of L must be final for all block columns < k
-    if (k > 0) {
+    // rows i and k of L must be final for all block columns < j1; a continuation item also needs
+    // the partial tile of its predecessor (extra_flag)
+    const bool partial = j1 < k;
+    if (j1 > 0) {
         if (tid == 0) {
-            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * k, q.err, q.wait_timeout_ns);
-            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * k, q.err, q.wait_timeout_ns);
+            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * j1, q.err, q.wait_timeout_ns);
+            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * j1, q.err, q.wait_timeout_ns);
+            if (ok && extra_flag >= 0) ok = wait_ge(q.head + extra_flag, extra_need, q.err, q.wait_timeout_ns);
             s.ctl[1] = ok ? 1 : 0;
         }
         __syncthreads();
@@ -167,9 +176,9 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
             acc[mb][nb][1] = -kv.y;
         }
 
-    const int nchunk = (k * TB) / KC;
-    const double* __restrict__ Ag = Lp + (long long)row0 * ld;
-    const double* __restrict__ Bg = Lp + (long long)col0 * ld;
+    const int nchunk = ((j1 - j0) * TB) / KC;
+    const double* __restrict__ Ag = Lp + (long long)row0 * ld + j0 * TB;
+    const double* __restrict__ Bg = Lp + (long long)col0 * ld + j0 * TB;
 
     auto load_stage = [&](int st, int chunk) {
         double* Bs = stages + st * STAGE_D;  // [UN][KC]
@@ -241,10 +250,10 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
             for (int nb = 0; nb < 4; ++nb) {
                 const int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
                 const double2 x2 = make_double2(-acc[mb][nb][0], -acc[mb][nb][1]);
-                if (!diag) {
+                if (!diag && !partial) {
                     *reinterpret_cast<double2*>(Xs + r * XS + c) = x2;
                 } else {
-                    const int rd = h * UM + r;  // row inside the 128x128 tile
+                    const int rd = diag ? h * UM + r : TB;  // row inside a diagonal tile: only c <= rd is kept
                     double* dst = Lp + (long long)(row0 + r) * ld + col0 + c;
                     if (c + 1 <= rd) *reinterpret_cast<double2*>(dst) = x2;
                     else if (c <= rd) dst[0] = x2.x;
@@ -253,6 +262,10 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
     }
     if (diag) {
         signal_done(q.diagu + p * q.nt_stride + k);
+        return true;
+    }
+    if (partial) {
+        signal_done(q.ppre + p * q.nt_stride + i);
         return true;
     }
     double* yp = v.y + (long long)p * ld;
@@ -266,7 +279,7 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
     stamp(q, idx, 4);
 
     const int o = col0;
-    const double* dinv = v.dinv + (long long)p * 4096;
+    const double* dinv = v.dinv + ((long long)p * q.nt_stride + k) * 4096;  // per block column: POTF2(k+1) may run while column k is still being solved
     if (tid < TB) s.zs[tid] = __ldcg(v.z + (long long)p * ld + o + tid);
     double* xrow = Xs + (warp * 8 + g) * XS;  // this lane's row (fragment row g of the warp's 8 rows)
     double y_old = 0.0;
@@ -366,7 +379,7 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_off(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * BLK; }
 
-__device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, int idx, int p, int k) {
+__device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, int idx, int p, int k, int need_diag) {
     const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -379,7 +392,7 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
     double* Ri = s.Ri;
 
     if (tid == 0) {
-        s.ctl[1] = wait_ge(q.diagu + p * q.nt_stride + k, 2, q.err, q.wait_timeout_ns) ? 1 : 0;
+        s.ctl[1] = wait_ge(q.diagu + p * q.nt_stride + k, need_diag, q.err, q.wait_timeout_ns) ? 1 : 0;
         s.ctl[2] = 0;
     }
     __syncthreads();
@@ -426,7 +439,7 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
                     const double rhs = (r == lane) ? 1.0 : 0.0;
                     x[r] = (r < lane) ? 0.0 : (rhs - sacc) * Ri[j0 + r];
                 }
-                double* out = v.dinv + ((long long)p * 4 + jb) * 1024;
+                double* out = v.dinv + (((long long)p * q.nt_stride + k) * 4 + jb) * 1024;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) out[r * 32 + lane] = x[r];
             }
@@ -584,12 +597,12 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
         __syncthreads();
         const int idx = s.ctl[0];
         if (idx >= q.n_items) break;
-        const int4 it = __ldg(q.items + idx);
+        const int4 it = __ldg(q.items + 2 * idx), dep = __ldg(q.items + 2 * idx + 1);
         const int type = it.x & 0xff, h = it.x >> 8;
         bool ok;
         stamp(q, idx, 0);
-        if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z);
-        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG);
+        if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z, dep.w);
+        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, dep.x, dep.y, dep.z, dep.w);
         if (!ok) break;
         stamp(q, idx, 5);
         if (q.trace != nullptr && threadIdx.x == 0) {
@@ -606,7 +619,8 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
 // grid (2 * nt(nt+1)/2, P): one CTA = 64 rows x 128 columns; thread -> column, 32 rows, eight
 // entries per interpreter pass; rows are written as coalesced 1 KB segments.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FT, 2) agp_gramfill_kernel(BatchView v) {
+template <int E, int MINB>
+__global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v) {
     __shared__ __align__(128) double ts_r[UM];
     __shared__ __align__(128) double ts_c[UN];
     __shared__ AgpInstr prog_s[PROG_SMEM];
@@ -654,21 +668,22 @@ __global__ void __launch_bounds__(FT, 2) agp_gramfill_kernel(BatchView v) {
     const int gc = col0 + c;
     const double tcol = ts_c[c];
 #pragma unroll 1
-    for (int e8 = 0; e8 < 4; ++e8) {
-        double t1[8], t2[8], val[8];
-        const int rlast = rbase + 2 * (8 * e8 + 7);
+    for (int eb = 0; eb < 32 / E; ++eb) {
+        double t1[E], t2[E], val[E];
+        const int rlast = rbase + 2 * (E * eb + E - 1);
         const bool skip = diag && c > rlast + h * UM;  // strictly-upper part of a diagonal tile: zeros
         if (!skip) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < E; ++j) {
                 t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
-                t2[j] = ts_r[rbase + 2 * (8 * e8 + j)];
+                t2[j] = ts_r[rbase + 2 * (E * eb + j)];
             }
-            eval_entries8(prog, pm, need, t1, t2, 0, val);
+            if constexpr (E == 8) eval_entries8(prog, pm, need, t1, t2, 0, val);
+            else eval_entries<E>(prog, pm, need, t1, t2, 0, val);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = rbase + 2 * (8 * e8 + j);
+        for (int j = 0; j < E; ++j) {
+            const int r = rbase + 2 * (E * eb + j);
             const int gr = row0 + r;
             double out = 0.0;
             if (!(diag && c > r + h * UM)) {
@@ -691,7 +706,9 @@ cudaError_t configure_fused() {
 void launch_gramfill(const BatchView& v, int P, cudaStream_t s) {
     if (P <= 0 || v.nt <= 0) return;
     dim3 grid(v.nt * (v.nt + 1), P);  // 2 halves x nt(nt+1)/2 lower tiles
-    agp_gramfill_kernel<<<grid, FT, 0, s>>>(v);
+    // eight entries per interpreter pass, two CTAs per SM: measured equal (within 3 %) to 4 entries x
+    // 2-3 CTAs and 2 entries x 4 CTAs — the kernel is bound by FP64 issue, not by latency
+    agp_gramfill_kernel<8, 2><<<grid, FT, 0, s>>>(v);
 }
 
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {

@@ -28,21 +28,26 @@ struct BatchView {
     double* zz;              // [P] sum z_i^2
     double* lml;             // [P]
     int* info;               // [P]
-    double* dinv;            // [P][4][32][32] inverses of the diagonal 32x32 blocks of L_kk
+    double* dinv;            // [P][ld/128][4][32][32] inverses of the diagonal 32x32 blocks of every L_kk
     int p0;                  // first particle of this launch (particle groups run on separate streams)
 };
 
 // ---- persistent dataflow scheduler (agp_fused.cu) ------------------------------------------
-// Work items, packed as int4 {type | h << 8, particle, block column k, tile row i}.
+// Work items: two int4 each,
+//   {type | h << 8, particle, block column k, tile row i}
+//   {j0, j1, extra_flag, extra_need}: contraction range [j0, j1) in block columns; for a continuation
+//   item, the index (relative to SchedView::head) and value of the counter its predecessor bumps;
+//   POTF2 carries in extra_need how many DIAG items finish its tile.
 enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2 };
 
 struct SchedView {
-    const int4* items;  // in-order queue: every item's producers sit earlier in the list
+    const int4* items;  // in-order queue (2 x int4 per item): every item's producers sit earlier in the list
     int n_items;
     int* head;          // queue head (atomic ticket)
     int* err;           // set when a dependency wait timed out (never in a valid schedule)
     int* rowdone;       // [P][nt_stride] finished 64-row panel items of tile row i (2 per block column)
-    int* diagu;         // [P][nt_stride] finished halves of diagonal tile k
+    int* diagu;         // [P][nt_stride] finished DIAG items of diagonal tile k
+    int* ppre;          // [P][nt_stride] finished PARTIAL panel items of tile row i (look-ahead)
     int* fdone;         // [P] factored diagonal tiles
     int nt_stride;
     unsigned long long wait_timeout_ns;  // dependency wait limit before the error flag is raised

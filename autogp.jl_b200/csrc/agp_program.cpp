@@ -30,14 +30,6 @@ int n_node_params(int32_t op) {
     }
 }
 
-// Reciprocal fast path of agp_math.cuh::div_const: valid when the divisor is a normal number of
-// moderate magnitude (then quotient and remainders of in-window dividends cannot under/overflow).
-void set_reciprocal(AgpInstr& in, double divisor) {
-    const double m = std::fabs(divisor);
-    in.c = 1.0 / divisor;
-    in.pad = (std::isfinite(divisor) && m >= 0x1p-400 && m <= 0x1p400) ? 1 : 0;
-}
-
 void emit(const std::vector<TNode>& t, int id, const double* params, std::vector<AgpInstr>& out) {
     // explicit stack instead of recursion: trees can be deep (max_depth = -1, src/GP.jl:1127)
     struct Frame { int id; int state; bool swapped; };
@@ -52,7 +44,7 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
             switch (nd.op) {
                 case AGP_OP_CONSTANT: in.op = AGP_I_CONST; in.a = p[0]; break;
                 case AGP_OP_LINEAR: in.op = AGP_I_LINEAR; in.a = p[0]; in.b = p[1]; in.c = p[2]; break;
-                case AGP_OP_SQUARED_EXPONENTIAL: in.op = AGP_I_SE; in.a = p[0] * p[0]; in.b = p[1]; set_reciprocal(in, in.a); break;
+                case AGP_OP_SQUARED_EXPONENTIAL: in.op = AGP_I_SE; in.a = p[0] * p[0]; in.b = p[1]; break;
                 case AGP_OP_GAMMA_EXPONENTIAL: in.op = AGP_I_GE; in.a = p[0]; in.b = p[1]; in.c = p[2]; break;
                 case AGP_OP_PERIODIC:
                     in.op = AGP_I_PER;
@@ -78,7 +70,7 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
         } else {
             if (nd.op == AGP_OP_PLUS) in.op = AGP_I_PLUS;
             else if (nd.op == AGP_OP_TIMES) in.op = AGP_I_TIMES;
-            else { in.op = f.swapped ? AGP_I_CP_SWAP : AGP_I_CP; in.a = p[0]; in.b = p[1]; set_reciprocal(in, in.b); }
+            else { in.op = f.swapped ? AGP_I_CP_SWAP : AGP_I_CP; in.a = p[0]; in.b = p[1]; }
             out.push_back(in);
             st.pop_back();
         }

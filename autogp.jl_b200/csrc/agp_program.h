@@ -15,19 +15,19 @@
 enum AgpDevOp : int32_t {
     AGP_I_CONST = 0,   // a = value
     AGP_I_LINEAR = 1,  // a = intercept, b = bias, c = amplitude
-    AGP_I_SE = 2,      // a = lengthscale^2, b = amplitude, c = 1/a (pad bit 0: reciprocal fast path valid)
+    AGP_I_SE = 2,      // a = lengthscale^2, b = amplitude
     AGP_I_GE = 3,      // a = lengthscale, b = gamma, c = amplitude
     AGP_I_PER = 4,     // a = pi/period, b = -2/lengthscale^2, c = amplitude
     AGP_I_WN = 5,      // a = value
     AGP_I_PLUS = 6,
     AGP_I_TIMES = 7,
-    AGP_I_CP = 8,      // a = location, b = scale, c = 1/scale (pad bit 0); stack: s1 = left, s0 = right
+    AGP_I_CP = 8,      // a = location, b = scale; stack: s1 = left, s0 = right
     AGP_I_CP_SWAP = 9  // same, stack: s1 = right, s0 = left
 };
 
 struct __attribute__((aligned(16))) AgpInstr {
     int32_t op;
-    int32_t pad;  // flags: bit 0 = c holds the correctly rounded reciprocal of the node's divisor
+    int32_t pad;
     double a, b, c;
 };
 

@@ -142,10 +142,13 @@ int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 
 /* The in-order work queue the persistent kernel executes for P particles x nt block columns
- * (host-only, no GPU needed): items_out receives up to `cap` items as 4 int32 each
- * {type | half << 8, particle, block column k, tile row i}, type 0 = DIAG, 1 = POTF2, 2 = PANEL;
- * returns the total item count.  Every item's producers precede it (tests/test_abi_host.py
- * checks the order is topological — the scheduler's deadlock-freedom argument). */
+ * (host-only, no GPU needed): items_out receives up to `cap` items as 8 int32 each
+ * {type | half << 8, particle, block column k, tile row i, j0, j1, extra_flag, extra_need},
+ * type 0 = DIAG, 1 = POTF2, 2 = PANEL; [j0, j1) = contraction range in block columns; extra_flag
+ * (index into the counter array laid out for nt_stride = nt) / extra_need = the counter a
+ * continuation item waits for; POTF2: extra_need = number of DIAG items of its tile.  Returns the
+ * total item count.  tests/test_abi_host.py replays the queue against the kernel's wait rules and
+ * checks that no item ever waits for a later one (the scheduler's deadlock-freedom argument). */
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap);
 
 /* Diagnostics: one traced run of the resident batch.  trace_out receives 8 int64 per work item

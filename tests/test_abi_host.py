@@ -129,35 +129,60 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-@pytest.mark.parametrize("order", [0, 1])
-@pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16)])
-def test_work_queue_is_complete_and_topological(P, nt, order):
-    """Deadlock-freedom of the persistent kernel (agp_fused.cu): a CTA only ever waits for items
-    that were popped before its own, so every producer must precede its consumers in the queue."""
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16), (2, 23)])
+def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
+    """Deadlock-freedom of the persistent kernel (agp_fused.cu): CTAs pop items in queue order and a
+    CTA only ever spins on counters, so replaying the queue sequentially with the kernel's own wait
+    rules must find every wait already satisfied.  Also checks that the contraction ranges of
+    every tile tile [0, k) exactly and that each tile is finished once per half."""
     from autogp.jl_b200 import _lib
 
     lib = _lib.load()
     n_items = lib.agp_queue_build(P, nt, order, None, 0)
-    assert n_items == P * sum(2 * (nt - k) + 1 for k in range(nt))
-    buf = np.zeros((n_items, 4), dtype=np.int32)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
     assert lib.agp_queue_build(P, nt, order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
     DIAG, POTF2, PANEL = 0, 1, 2
-    done = set()
-    for x, p, k, i in buf.tolist():
+    nts = nt  # agp_queue_build lays the counters out for nt_stride = nt
+    counters = np.zeros(32 + 3 * P * nts + P, dtype=np.int64)
+    rowdone = lambda p, i: 32 + p * nts + i
+    diagu = lambda p, k: 32 + P * nts + p * nts + k
+    ppre = lambda p, i: 32 + 2 * P * nts + p * nts + i
+    fdone = lambda p: 32 + 3 * P * nts + p
+    covered = {}   # (p, i, k, h) -> next block column to contract
+    n_diag = {}
+    for x, p, k, i, j0, j1, flag, need in buf.tolist():
         t, h = x & 0xFF, x >> 8
         assert 0 <= p < P and 0 <= k < nt and h in (0, 1)
+        if t == POTF2:
+            assert counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
+            assert counters[fdone(p)] == k          # block columns are factored in order
+            counters[fdone(p)] += 1
+            continue
+        assert (t == DIAG and i == k) or (t == PANEL and k < i < nt)
+        assert 0 <= j0 <= j1 <= k
+        assert covered.get((p, i, k, h), 0) == j0, "contraction ranges must be contiguous"
+        covered[(p, i, k, h)] = j1 if j1 < k else -1   # -1: finished
+        if j1 > 0:
+            assert counters[rowdone(p, k)] >= 2 * j1
+            if t == PANEL:
+                assert counters[rowdone(p, i)] >= 2 * j1
+            if flag >= 0:
+                assert flag == (diagu(p, k) if t == DIAG else ppre(p, i))
+                assert counters[flag] >= need
+        assert (flag >= 0) == (j0 > 0)
         if t == DIAG:
-            assert i == k
-            need = [(PANEL, p, j, k, hh) for j in range(k) for hh in (0, 1)]
-        elif t == POTF2:
-            assert h == 0
-            need = [(DIAG, p, k, k, 0), (DIAG, p, k, k, 1)]
+            counters[diagu(p, k)] += 1
+            n_diag[(p, k)] = n_diag.get((p, k), 0) + 1
+        elif j1 < k:
+            counters[ppre(p, i)] += 1
         else:
-            assert t == PANEL and k < i < nt
-            need = [(PANEL, p, j, r, hh) for j in range(k) for r in (i, k) for hh in (0, 1)] + [(POTF2, p, k, k, 0)]
-        for d in need:
-            assert d in done, (t, p, k, i, h, d)
-        key = (t, p, k, i, h)
-        assert key not in done
-        done.add(key)
-    assert len(done) == n_items
+            assert counters[fdone(p)] >= k + 1      # L_kk ready for the triangular solve
+            counters[rowdone(p, i)] += 1
+    for p in range(P):
+        assert counters[fdone(p)] == nt
+        for i in range(nt):
+            assert counters[rowdone(p, i)] == 2 * i
+            for k in range(i + 1):
+                for h in (0, 1):
+                    assert covered[(p, i, k, h)] == -1 or k == 0

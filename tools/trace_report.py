@@ -26,7 +26,7 @@ def to_agp(nd):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    order = int(os.environ.get("AGP_ORDER", "1"))
+    order = int(os.environ.get("AGP_ORDER", "2"))
     eng = agp.Engine(0)
     ts, xs = o.synthetic_series(n)
     parts = [o.synthetic_particle(p) for p in range(P)]
@@ -38,7 +38,7 @@ def main():
     st = eng.trace()
     nt = -(-n // 128)
     lib = _lib.load()
-    items = np.zeros((st.shape[0], 4), dtype=np.int32)
+    items = np.zeros((st.shape[0], 8), dtype=np.int32)
     lib.agp_queue_build(P, nt, order, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0])
     typ = items[:, 0] & 0xFF
     t0 = st[:, 0].min()
@@ -64,21 +64,22 @@ def main():
                 gr = s[:, 3] - s[:, 2]
                 w2 = s[:, 4] - s[:, 3]
                 tr = s[:, 5] - s[:, 4]
-                line += f" | wait1 {w1.mean():6.1f} mma {mm.mean():6.1f} gram {gr.mean():6.1f} waitF {w2.mean():6.1f} trsm {tr.mean():6.1f}"
-                line += f" | sums(ms*cta): wait1 {w1.sum()/1e3:.1f} mma {mm.sum()/1e3:.1f} gram {gr.sum()/1e3:.1f} waitF {w2.sum()/1e3:.1f} trsm {tr.sum()/1e3:.1f}"
+                line += f" | wait1 {w1.mean():6.1f} mma {mm.mean():6.1f} xst {gr.mean():6.1f} waitF {w2.mean():6.1f} trsm {tr.mean():6.1f}"
+                line += f" | sums(ms*cta): wait1 {w1.sum()/1e3:.1f} mma {mm.sum()/1e3:.1f} xst {gr.sum()/1e3:.1f} waitF {w2.sum()/1e3:.1f} trsm {tr.sum()/1e3:.1f}"
             else:
                 rest = s[:, 5] - s[:, 2]
-                line += f" | wait1 {w1.mean():6.1f} mma {mm.mean():6.1f} gram+store {rest.mean():6.1f}"
+                kk = items[m, 2] > 0
+                line += f" | (k>0) wait1 {w1[kk].mean():6.1f} mma {mm[kk].mean():6.1f} store {rest[kk].mean():6.1f}"
         print(line)
     print(f"slots {slots}  busy {busy_total/1e3:.1f} ms*cta  capacity {slots*span/1e3:.1f} ms*cta  occupancy {busy_total/(slots*span):.3f}")
     # per-block-column view of the panels
     print("per block column k: panel items mean us (wait1, mma, gram, waitF, trsm) and the wall-clock window of the column")
     for k in range(nt):
-        m = (typ == 2) & (items[:, 2] == k)
+        m = (typ == 2) & (items[:, 2] == k) & (items[:, 5] == k)   # final panel items
         if not m.any():
             continue
         s = st[m].astype(np.float64) * 1e-3
-        print(f"  k={k:2d} n={m.sum():5d} wait1 {np.mean(s[:,1]-s[:,0]):6.1f} mma {np.mean(s[:,2]-s[:,1]):6.1f} gram {np.mean(s[:,3]-s[:,2]):6.1f} "
+        print(f"  k={k:2d} n={m.sum():5d} wait1 {np.mean(s[:,1]-s[:,0]):6.1f} mma {np.mean(s[:,2]-s[:,1]):6.1f} xst {np.mean(s[:,3]-s[:,2]):6.1f} "
               f"waitF {np.mean(s[:,4]-s[:,3]):6.1f} trsm {np.mean(s[:,5]-s[:,4]):6.1f}  window [{(s[:,0].min()-t0*1e-3):8.0f}, {(s[:,5].max()-t0*1e-3):8.0f}] us")
     m = typ == 1
     s = st[m].astype(np.float64) * 1e-3

@@ -30,6 +30,10 @@ struct agp_handle {
     // resident batch
     bool uploaded = false;
     int P = 0, n_full = 0, n_active = 0, ld = 0;
+    int n_pred = 0;          // prediction points appended to the resident batch (agp_predict_batch)
+    int n_factored = -1;     // observations covered by the factor resident in d_L (-1: none), for agp_lml_run_append
+    bool factor_clean = false;  // the last fetch saw info == 0 for every particle
+    double* d_pred = nullptr; size_t cap_pred = 0;  // predictive means + covariances
     BatchView view{};
 
     // device workspaces (grow-only)
@@ -68,7 +72,7 @@ struct agp_handle {
         int4* d_items = nullptr;
         int n_items = 0;
     };
-    std::map<std::tuple<int, int, int>, Queue> queues;
+    std::map<std::tuple<int, int, int, int, int>, Queue> queues;  // (P, nt, nt_total, first row tile, nt_stride)
     int* d_sync = nullptr;   size_t cap_sync = 0;
     int* h_sync = nullptr;   // pinned, 2 ints: queue head, error flag
 };
@@ -186,6 +190,7 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_K);
     cudaFree(h->d_gin);
     cudaFree(h->d_sync);
+    cudaFree(h->d_pred);
     for (auto& kv : h->queues) cudaFree(kv.second.d_items);
     cudaFreeHost(h->h_sync);
     cudaFreeHost(h->h_gin);
@@ -274,11 +279,16 @@ int agp_gram_device(agp_handle* h, const int32_t* ops, const int32_t* param_off,
 
 // ---- LML batch ------------------------------------------------------------------------------
 
-int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
-                   const double* params, const double* noise, const double* ts, const double* xs, int32_t n) {
+// Upload of a batch; with m > 0 the prediction points ts_pred are appended as extra rows that start
+// at the next tile boundary after the observations (agp_predict_batch).
+static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                       const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred, int32_t m,
+                       const double* noise_pred) {
     if (!h) return AGP_ERR_ARG;
     h->uploaded = false;
-    if (P < 0 || n < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)))
+    h->n_factored = -1;
+    h->factor_clean = false;
+    if (P < 0 || n < 0 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)) || (m > 0 && !ts_pred))
         return fail(h, AGP_ERR_ARG, "agp_lml_upload: bad argument");
     if (P > 65535) return fail(h, AGP_ERR_ARG, "agp_lml_upload: at most 65535 particles per batch");
     AGP_CUDA(h, cudaSetDevice(h->device));
@@ -302,26 +312,29 @@ int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int3
         poff[P] = (int32_t)instr.size();
     }
 
-    const int ld = (int)align_up((size_t)(n > 0 ? n : 1), TB);
-    // packed input arena: ts[ld] xs[ld] noise[P] prog_off[P+1] prog_need[P] instr[]
+    const int ld_obs = (int)align_up((size_t)(n > 0 ? n : (m > 0 ? 0 : 1)), TB);
+    const int ld = ld_obs + (int)align_up((size_t)m, TB);
+    // packed input arena: ts[ld] xs[ld] noise[P] noise_pred[P] prog_off[P+1] prog_need[P] instr[]
     size_t off_ts = 0;
     size_t off_xs = off_ts + (size_t)ld * 8;
     size_t off_noise = off_xs + (size_t)ld * 8;
-    size_t off_poff = align_up(off_noise + (size_t)P * 8, 16);
+    size_t off_npred = off_noise + (size_t)P * 8;
+    size_t off_poff = align_up(off_npred + (size_t)P * 8, 16);
     size_t off_need = align_up(off_poff + (size_t)(P + 1) * 4, 16);
     size_t off_instr = align_up(off_need + (size_t)P * 4, 32);
     size_t in_bytes = off_instr + instr.size() * sizeof(AgpInstr);
     int rc;
     if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
     if ((rc = grow_device(h, &h->d_in, &h->cap_in, in_bytes)) != AGP_OK) return rc;
-    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] dinv[P][ld/128][4096] (one set of diagonal-block
-    // inverses per block column: the persistent kernel factors column k+1 while column k is still
-    // being solved; the staged path only uses the first set of each particle's slice)
+    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] cum[P][ld/128][2] dinv[P][ld/128][4096] (one set of
+    // diagonal-block inverses per block column: the persistent kernel factors column k+1 while
+    // column k is still being solved)
     size_t off_y = 0;
     size_t off_z = off_y + (size_t)P * ld * 8;
     size_t off_ld = off_z + (size_t)P * ld * 8;
     size_t off_zz = off_ld + (size_t)P * 8;
-    size_t off_dinv = align_up(off_zz + (size_t)P * 8, 256);
+    size_t off_cum = off_zz + (size_t)P * 8;
+    size_t off_dinv = align_up(off_cum + (size_t)P * (ld / TB) * 2 * 8, 256);
     size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * 4096 * 8;
     if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
     size_t res_bytes = align_up((size_t)P * 8, 16) + (size_t)P * 4;
@@ -337,8 +350,10 @@ int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int3
         memcpy(h->h_in + off_ts, ts, (size_t)n * 8);
         memcpy(h->h_in + off_xs, xs, (size_t)n * 8);
     }
+    if (m > 0) memcpy(h->h_in + off_ts + (size_t)ld_obs * 8, ts_pred, (size_t)m * 8);
     if (P > 0) {
         memcpy(h->h_in + off_noise, noise, (size_t)P * 8);
+        memcpy(h->h_in + off_npred, noise_pred ? noise_pred : noise, (size_t)P * 8);  // default: noise_pred = noise (src/GP.jl:738)
         memcpy(h->h_in + off_need, pneed.data(), (size_t)P * 4);
     }
     memcpy(h->h_in + off_poff, poff.data(), (size_t)(P + 1) * 4);
@@ -351,6 +366,8 @@ int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int3
     v.ld = ld;
     v.n = n;
     v.nt = (n + TB - 1) / TB;
+    v.n_pred = m;
+    v.nt_total = v.nt + (m + TB - 1) / TB;
     v.ts = reinterpret_cast<const double*>(h->d_in + off_ts);
     v.xs = reinterpret_cast<const double*>(h->d_in + off_xs);
     v.noise = reinterpret_cast<const double*>(h->d_in + off_noise);
@@ -361,24 +378,33 @@ int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int3
     v.z = reinterpret_cast<double*>(h->d_work + off_z);
     v.logdet_half = reinterpret_cast<double*>(h->d_work + off_ld);
     v.zz = reinterpret_cast<double*>(h->d_work + off_zz);
+    v.cum = reinterpret_cast<double*>(h->d_work + off_cum);
     v.dinv = reinterpret_cast<double*>(h->d_work + off_dinv);
     v.lml = reinterpret_cast<double*>(h->d_res);
     v.info = reinterpret_cast<int*>(h->d_res + align_up((size_t)P * 8, 16));
     h->P = P;
     h->n_full = n;
     h->n_active = n;
+    h->n_pred = m;
     h->ld = ld;
     h->uploaded = true;
     return AGP_OK;
 }
 
+int agp_lml_upload(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                   const double* params, const double* noise, const double* ts, const double* xs, int32_t n) {
+    return upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, nullptr, 0, nullptr);
+}
+
 int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
     if (!h) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_set_prefix: no resident batch");
+    if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_set_prefix: the resident batch carries prediction points");
     if (n_prefix < 0 || n_prefix > h->n_full) return fail(h, AGP_ERR_ARG, "agp_lml_set_prefix: prefix out of range");
     h->n_active = n_prefix;
     h->view.n = n_prefix;
     h->view.nt = (n_prefix + TB - 1) / TB;
+    h->view.nt_total = h->view.nt;
     return AGP_OK;
 }
 
@@ -409,7 +435,8 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
     const int split_from = 3;  // block columns below this are too short to be worth splitting
     auto split = [&](int k) { return order >= 2 && k >= split_from && k < nt; };  // tile (k,k) and (k+1,k) are split
     auto push = [&](int type, int h, int p, int k, int i, int j0, int j1, int flag, int need) {
-        items.push_back(make_int4(type | (h << 8), p, k, i));
+        const int partial = (type != agp::ITEM_POTF2 && j1 < k) ? agp::ITEM_PARTIAL : 0;
+        items.push_back(make_int4(type | (h << 8) | partial, p, k, i));
         items.push_back(make_int4(j0, j1, flag, need));
     };
     auto diag_full = [&](int p, int k) {
@@ -472,15 +499,46 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
     }
 }
 
-static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
+// General schedule (simple block-column order) for the two continuations of a factorisation:
+//   first_row > 0        only tile rows >= first_row are (re)computed: the data prefix grew and rows
+//                        above keep their factor (agp_lml_run_append)
+//   nt_total > nt        tile rows >= nt hold prediction points: they are solved against every L_kk
+//                        (PANEL) and their mutual tiles receive the Schur complement
+//                        K_22 - L_21 L_21^T as store-only items over [0, nt) (agp_predict_batch)
+static void build_queue_general(int P, int nt, int nt_total, int first_row, std::vector<int4>& items) {
+    auto push = [&](int type, int h, int partial, int p, int k, int i, int j0, int j1, int need) {
+        items.push_back(make_int4(type | (h << 8) | (partial ? agp::ITEM_PARTIAL : 0), p, k, i));
+        items.push_back(make_int4(j0, j1, -1, need));
+    };
+    items.clear();
+    for (int k = 0; k < nt; ++k) {
+        if (k >= first_row) {
+            for (int p = 0; p < P; ++p)
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, 0, p, k, k, 0, k, 0);
+            for (int p = 0; p < P; ++p) push(agp::ITEM_POTF2, 0, 0, p, k, k, 0, 0, 2);
+        }
+        const int i0 = (k + 1 > first_row) ? k + 1 : first_row;
+        for (int p = 0; p < P; ++p)
+            for (int i = i0; i < nt_total; ++i)
+                for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, 0, p, k, i, 0, k, 0);
+    }
+    for (int p = 0; p < P; ++p)
+        for (int i = nt; i < nt_total; ++i)
+            for (int k = nt; k <= i; ++k)
+                for (int h = 0; h < 2; ++h) push(i == k ? agp::ITEM_DIAG : agp::ITEM_PANEL, h, 1, p, k, i, 0, nt, 0);
+}
+
+static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_ms = nullptr, int first_row = 0) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
-    auto key = std::make_tuple(P, nt, nt_stride);
+    const int nt_total = v.nt_total;
+    auto key = std::make_tuple(P, nt, nt_total, first_row, nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
-        build_queue(P, nt, nt_stride, h->order, items);
+        if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
+        else build_queue_general(P, nt, nt_total, first_row, items);
         agp_handle::Queue qu;
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
@@ -498,6 +556,17 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
     int rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int));
     if (rc != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
+    if (first_row > 0) {
+        // continuation: tile rows above first_row are final for every block column, and the first
+        // first_row diagonal tiles are factored
+        std::vector<int> init(n_sync, 0);
+        for (int p = 0; p < P; ++p) {
+            for (int i = 0; i < first_row; ++i) init[32 + (size_t)p * nt_stride + i] = 2 * i;
+            init[32 + (size_t)3 * P * nt_stride + p] = first_row;
+        }
+        AGP_CUDA(h, cudaMemcpyAsync(h->d_sync, init.data(), n_sync * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));  // `init` is pageable and goes out of scope
+    }
     SchedView q;
     q.items = it->second.d_items;
     q.n_items = it->second.n_items;
@@ -510,9 +579,23 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr) {
     q.nt_stride = nt_stride;
     q.trace = d_trace;
     q.wait_timeout_ns = h->wait_timeout_ns;
-    agp::launch_gramfill(v, P, h->stream);
+    if (kernel_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    agp::launch_gramfill(v, P, first_row, h->stream);
+    if (kernel_ms) {
+        AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+        AGP_CUDA(h, cudaEventElapsedTime(&kernel_ms[0], h->ev0, h->ev1));
+        AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    }
     agp::launch_chol(v, q, h->ctas_per_sm * h->num_sms, h->stream);
+    if (kernel_ms) {
+        AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+        AGP_CUDA(h, cudaEventElapsedTime(&kernel_ms[1], h->ev0, h->ev1));
+    }
     h->launches += 2;
+    h->n_factored = v.n;
+    h->factor_clean = false;
     return check_launch(h, "chol");
 }
 
@@ -565,7 +648,7 @@ static int run_impl(agp_handle* h, float* stage_ms) {
         return AGP_OK;
     }
     v.p0 = 0;
-    if (!stage_ms && !h->staged) return run_fused(h);
+    if (!h->staged) return run_fused(h, nullptr, stage_ms);
     if (stage_ms) {
         // serialised, one stream, events around every launch
         for (int k = 0; k < v.nt; ++k) {
@@ -672,6 +755,8 @@ int agp_lml_fetch(agp_handle* h, double* lml_out, int32_t* info_out) {
     if (h->h_sync[1] != 0) return fail(h, AGP_ERR_CUDA, "agp_lml_fetch: the work-queue scheduler reported a dependency time-out");
     memcpy(lml_out, h->h_res, (size_t)P * 8);
     memcpy(info_out, h->h_res + info_off, (size_t)P * 4);
+    h->factor_clean = true;
+    for (int p = 0; p < P; ++p) h->factor_clean = h->factor_clean && info_out[p] == 0;
     return AGP_OK;
 }
 
@@ -683,10 +768,57 @@ int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev) 
     return AGP_OK;
 }
 
+int agp_lml_run_append(agp_handle* h) {
+    if (!h) return AGP_ERR_ARG;
+    if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no resident batch");
+    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: not available with AGP_PATH=staged");
+    if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the resident batch carries prediction points");
+    if (h->n_factored < 0 || !h->factor_clean)
+        return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no clean factor resident (run + fetch with info == 0 for every particle first)");
+    if (h->view.n < h->n_factored) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the data prefix shrank; use agp_lml_run");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    if (h->P == 0 || h->view.n == 0) return run_impl(h, nullptr);
+    // tile rows that were complete (all 128 rows observed) keep their factor, z and running sums
+    const int first_row = h->n_factored / TB;
+    if (first_row >= h->view.nt) return AGP_OK;  // nothing new: the resident results stand
+    return run_fused(h, nullptr, nullptr, first_row);
+}
+
+int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                      const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred,
+                      int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_predict_batch: not available with AGP_PATH=staged");
+    if (m < 0 || (P > 0 && m > 0 && (!mean_out || !cov_out)) || (P > 0 && !info_out)) return fail(h, AGP_ERR_ARG, "agp_predict_batch: bad argument");
+    int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, ts_pred, m, noise_pred);
+    if (rc != AGP_OK) return rc;
+    if (P == 0) return AGP_OK;
+    const size_t mean_bytes = (size_t)P * m * 8, cov_bytes = (size_t)P * m * m * 8;
+    if ((rc = grow_device(h, &h->d_pred, &h->cap_pred, mean_bytes + cov_bytes + 16)) != AGP_OK) return rc;
+    AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, align_up((size_t)P * 8, 16) + (size_t)P * 4, h->stream));  // info = 0 when nothing is factored
+    if ((rc = run_fused(h)) != AGP_OK) return rc;
+    h->n_factored = -1;  // the resident factor belongs to an augmented matrix
+    if (m > 0) {
+        const double* d_npred = h->view.noise + P;  // noise_pred[P] follows noise[P] in the input arena
+        double* d_mean = h->d_pred;
+        double* d_cov = h->d_pred + (size_t)P * m;
+        agp::launch_predict_extract(h->view, P, d_npred, d_mean, d_cov, h->stream);
+        h->launches += 1;
+        if ((rc = check_launch(h, "predict_extract")) != AGP_OK) return rc;
+        AGP_CUDA(h, cudaMemcpyAsync(mean_out, d_mean, mean_bytes, cudaMemcpyDeviceToHost, h->stream));
+        AGP_CUDA(h, cudaMemcpyAsync(cov_out, d_cov, cov_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    std::vector<double> lml(P);
+    rc = agp_lml_fetch(h, lml.data(), info_out);  // synchronises; info: LAPACK code of the training block
+    h->factor_clean = false;
+    return rc;
+}
+
 int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     if (!h) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_trace: no resident batch");
     if (h->P == 0 || h->view.n == 0) return 0;
+    if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_trace: plain LML batches only");
     AGP_CUDA(h, cudaSetDevice(h->device));
     const int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0);
     if (!trace_out) return n_items;
@@ -705,10 +837,23 @@ int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     return rc == AGP_OK ? n_items : rc;
 }
 
+static int64_t export_queue(const std::vector<int4>& items, int32_t* items_out, int64_t cap);
+
+int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t first_row, int32_t* items_out, int64_t cap) {
+    if (P < 0 || nt < 0 || nt_total < nt || first_row < 0) return AGP_ERR_ARG;
+    std::vector<int4> items;
+    build_queue_general(P, nt, nt_total, first_row, items);
+    return export_queue(items, items_out, cap);
+}
+
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
     if (P < 0 || nt < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
     build_queue(P, nt, nt, order, items);
+    return export_queue(items, items_out, cap);
+}
+
+static int64_t export_queue(const std::vector<int4>& items, int32_t* items_out, int64_t cap) {
     const int64_t n_items = (int64_t)items.size() / 2;
     if (items_out) {
         int64_t m = n_items < cap ? n_items : cap;

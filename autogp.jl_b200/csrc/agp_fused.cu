@@ -121,13 +121,13 @@ __device__ __forceinline__ Smem smem_view() {
 // ------------------------------------------------------------------------------------------
 // ITEM_DIAG / ITEM_PANEL
 // ------------------------------------------------------------------------------------------
-// Contraction range [j0, j1) in block columns.  j1 == k: the item finishes the tile (diagonal tile
-// -> L for potf2; panel -> triangular solve).  j1 < k: look-ahead PARTIAL item, the tile in L
-// receives K - sum_{j<j1} and a later item with j0 = j1 picks it up from there (the accumulators
+// Contraction range [j0, j1) in block columns.  A finishing item (j1 == k) hands the diagonal tile to
+// potf2 or takes a panel through the triangular solve.  A PARTIAL item only stores: the tile in L
+// receives K - sum_{j<j1}; either a later item with j0 = j1 picks it up from there (the accumulators
 // always start from minus the tile), which takes the long early part of the contraction of the
 // next diagonal tile and of the panel below it off the per-particle critical path.
-__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag, int j0, int j1,
-                                       int extra_flag, int extra_need) {
+__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag, bool partial,
+                                       int j0, int j1, int extra_flag, int extra_need) {
     const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -138,7 +138,6 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
 
     // rows i and k of L must be final for all block columns < j1; a continuation item also needs
     // the partial tile of its predecessor (extra_flag)
-    const bool partial = j1 < k;
     if (j1 > 0) {
         if (tid == 0) {
             bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * j1, q.err, q.wait_timeout_ns);
@@ -419,7 +418,7 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
     if (tid < TB) ys[tid] = __ldcg(yp + o + tid);
     __syncthreads();
 
-    const bool want_dinv = (k < v.nt - 1);
+    const bool want_dinv = true;  // also for the last block column: a later agp_lml_run_append solves new tile rows against it
     constexpr int NW = FT / 32;             // 8 warps
     constexpr int WORKERS = (NW - 1) * 32;  // warps 0..6 factor; warp 7 inverts diagonal blocks
     if (warp == NW - 1) {
@@ -568,11 +567,12 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
     if (tid == 0) {
         double sl = ((s.red[0] + s.red[2]) + s.red[4]) + s.red[6];
         double sz = ((s.red[1] + s.red[3]) + s.red[5]) + s.red[7];
-        // block column 0 starts the accumulators; later columns of this particle run strictly after it
-        double tot_l = (k == 0 ? 0.0 : __ldcg(v.logdet_half + p)) + sl;
-        double tot_z = (k == 0 ? 0.0 : __ldcg(v.zz + p)) + sz;
-        v.logdet_half[p] = tot_l;
-        v.zz[p] = tot_z;
+        // running sums per block column (a later call may continue the factorisation from any column)
+        double* cum = v.cum + ((long long)p * q.nt_stride + k) * 2;
+        double tot_l = (k == 0 ? 0.0 : __ldcg(cum - 2)) + sl;
+        double tot_z = (k == 0 ? 0.0 : __ldcg(cum - 1)) + sz;
+        cum[0] = tot_l;
+        cum[1] = tot_z;
         int info = (k == 0) ? 0 : __ldcg(v.info + p);
         if (info == 0 && s.ctl[2] != 0) info = s.ctl[2];
         v.info[p] = info;
@@ -598,11 +598,11 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
         const int idx = s.ctl[0];
         if (idx >= q.n_items) break;
         const int4 it = __ldg(q.items + 2 * idx), dep = __ldg(q.items + 2 * idx + 1);
-        const int type = it.x & 0xff, h = it.x >> 8;
+        const int type = it.x & 0xff, h = (it.x >> 8) & 1;
         bool ok;
         stamp(q, idx, 0);
         if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z, dep.w);
-        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, dep.x, dep.y, dep.z, dep.w);
+        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, (it.x & ITEM_PARTIAL) != 0, dep.x, dep.y, dep.z, dep.w);
         if (!ok) break;
         stamp(q, idx, 5);
         if (q.trace != nullptr && threadIdx.x == 0) {
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
 // entries per interpreter pass; rows are written as coalesced 1 KB segments.
 // ------------------------------------------------------------------------------------------
 template <int E, int MINB>
-__global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v) {
+__global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int tile_id0) {
     __shared__ __align__(128) double ts_r[UM];
     __shared__ __align__(128) double ts_c[UN];
     __shared__ AgpInstr prog_s[PROG_SMEM];
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v) {
     const int tid = threadIdx.x;
     const int p = blockIdx.y;
     // linear id -> lower-triangular tile (i >= k) and row half
-    const int t = blockIdx.x >> 1, h = blockIdx.x & 1;
+    const int t = tile_id0 + (blockIdx.x >> 1), h = blockIdx.x & 1;
     int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
@@ -685,13 +685,19 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v) {
         for (int j = 0; j < E; ++j) {
             const int r = rbase + 2 * (E * eb + j);
             const int gr = row0 + r;
+            // rows/columns: [0, n) observations | [n, nt*TB) padding | [nt*TB, nt*TB + n_pred) appended
+            // prediction points | padding.  Padding rows are independent unit-variance dummies
+            // (identity block: log 1 = 0 in the log det, 0 in the quadratic form).
             double out = 0.0;
             if (!(diag && c > r + h * UM)) {
+                const int lt = v.nt * TB;
                 if (gr < n) {  // gc <= gr < n
                     out = val[j];
                     if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+                } else if (gr >= lt && gr < lt + v.n_pred && (gc < n || gc >= lt)) {
+                    out = val[j];  // K(t, t*) and K(t*, t*), no noise (src/GP.jl:743-747)
                 } else {
-                    out = (gr == gc) ? 1.0 : 0.0;  // padding: identity block, contributes log 1 = 0
+                    out = (gr == gc) ? 1.0 : 0.0;
                 }
             }
             Lp[(long long)gr * ld + gc] = out;
@@ -699,16 +705,51 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Predictive distribution out of the augmented factorisation (src/GP.jl:731-758): with the m
+// prediction points appended as extra rows, the panel solves leave L_21 = K_21 L_11^{-T}, the
+// forward solve leaves y_2 = 0 - L_21 z = -K_21 K_11^{-1} xs, and the partial items leave the Schur
+// complement K_22 - L_21 L_21^T in the trailing lower tiles.
+//   mean[p][a]   = -y[nt*TB + a]
+//   cov[p][a][b] = S[max(a,b)][min(a,b)] + noise_pred[p] * (a == b)      (symmetric by construction)
+// ------------------------------------------------------------------------------------------
+__global__ void agp_predict_extract_kernel(BatchView v, const double* __restrict__ noise_pred, double* __restrict__ mean_out,
+                                           double* __restrict__ cov_out) {
+    const int p = blockIdx.y;
+    const int m = v.n_pred, o = v.nt * TB, ld = v.ld;
+    const double* Lp = v.L + (long long)p * v.mat_stride;
+    const double np_ = noise_pred[p];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)m * m; e += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(e / m), b = (int)(e % m);
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        double s = Lp[(long long)(o + hi) * ld + o + lo];
+        if (a == b) s = s + np_;
+        cov_out[(long long)p * m * m + e] = s;
+    }
+    if (blockIdx.x == 0)
+        for (int a = threadIdx.x; a < m; a += blockDim.x) mean_out[(long long)p * m + a] = -v.y[(long long)p * ld + o + a];
+}
+
+void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s) {
+    if (P <= 0 || v.n_pred <= 0) return;
+    long long e = (long long)v.n_pred * v.n_pred;
+    int bx = (int)((e + 255) / 256);
+    if (bx > 1024) bx = 1024;
+    agp_predict_extract_kernel<<<dim3(bx, P), 256, 0, s>>>(v, noise_pred, mean_out, cov_out);
+}
+
 cudaError_t configure_fused() {
     return cudaFuncSetAttribute(agp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM);
 }
 
-void launch_gramfill(const BatchView& v, int P, cudaStream_t s) {
-    if (P <= 0 || v.nt <= 0) return;
-    dim3 grid(v.nt * (v.nt + 1), P);  // 2 halves x nt(nt+1)/2 lower tiles
+void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s) {
+    if (P <= 0 || v.nt_total <= row_tile0) return;
+    const int tile_id0 = row_tile0 * (row_tile0 + 1) / 2;  // lower tiles are numbered row by row
+    const int tiles = v.nt_total * (v.nt_total + 1) / 2 - tile_id0;
+    dim3 grid(2 * tiles, P);  // 2 row halves per tile
     // eight entries per interpreter pass, two CTAs per SM: measured equal (within 3 %) to 4 entries x
     // 2-3 CTAs and 2 entries x 4 CTAs — the kernel is bound by FP64 issue, not by latency
-    agp_gramfill_kernel<8, 2><<<grid, FT, 0, s>>>(v);
+    agp_gramfill_kernel<8, 2><<<grid, FT, 0, s>>>(v, tile_id0);
 }
 
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {

@@ -30,15 +30,22 @@ struct BatchView {
     int* info;               // [P]
     double* dinv;            // [P][ld/128][4][32][32] inverses of the diagonal 32x32 blocks of every L_kk
     int p0;                  // first particle of this launch (particle groups run on separate streams)
+    // persistent path: rows beyond the factored block (prediction points appended at a tile
+    // boundary, see agp_predict_batch) and per-block-column running sums (so a factorisation can be
+    // continued from any block column, see agp_lml_run_append)
+    int nt_total;            // tile rows in the matrix: nt + ceil(n_pred / TB)
+    int n_pred;              // appended time points (0 for a plain LML batch)
+    double* cum;             // [P][ld/TB][2] running (sum log L_ii, sum z_i^2) after each block column
 };
 
 // ---- persistent dataflow scheduler (agp_fused.cu) ------------------------------------------
 // Work items: two int4 each,
-//   {type | h << 8, particle, block column k, tile row i}
+//   {type | h << 8 | ITEM_PARTIAL?, particle, block column k, tile row i}   ITEM_PARTIAL: store-only item,
+//                          the tile in L receives K - sum_{j0<=j<j1} (no solve, no factorisation follows from it)
 //   {j0, j1, extra_flag, extra_need}: contraction range [j0, j1) in block columns; for a continuation
 //   item, the index (relative to SchedView::head) and value of the counter its predecessor bumps;
 //   POTF2 carries in extra_need how many DIAG items finish its tile.
-enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2 };
+enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_PARTIAL = 1 << 9 };
 
 struct SchedView {
     const int4* items;  // in-order queue (2 x int4 per item): every item's producers sit earlier in the list
@@ -54,8 +61,11 @@ struct SchedView {
     long long* trace;   // optional [n_items][8] globaltimer stamps (diagnostics; nullptr = off)
 };
 
-// Gram fill: every lower tile of every particle  <-  K(ts,ts) + noise*I  (runs before launch_chol)
-void launch_gramfill(const BatchView& v, int P, cudaStream_t s);
+// Gram fill: lower tiles of tile rows [row_tile0, nt_total) of every particle  <-  K(ts,ts) + noise*I
+// (runs before launch_chol)
+void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s);
+// Predictive mean / covariance out of an augmented factorisation (agp_predict_batch)
+void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
 // One launch = the whole batch: Cholesky + solve + logdet for every particle.
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s);
 cudaError_t configure_fused();

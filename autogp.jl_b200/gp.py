@@ -273,6 +273,37 @@ class Engine:
     def run(self) -> None:
         self._check(self._lib.agp_lml_run(self._h))
 
+    def run_append(self) -> None:
+        """Continue the resident factorisation after ``set_prefix`` grew the data (block-append:
+        only the new tile rows are computed).  Raises AgpError(AGP_ERR_STATE) when no clean factor
+        is resident — the caller then falls back to :meth:`run`."""
+        self._check(self._lib.agp_lml_run_append(self._h))
+
+    # ---- site 3 -------------------------------------------------------------------------
+    def predict_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs, ts_pred,
+                      noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Conditional MVN of every particle at ``ts_pred`` (``Distributions.MvNormal(node, noise, ts, xs,
+        ts_pred; noise_pred)``, src/GP.jl:731-758): returns (mean[P, m], cov[P, m, m], info[P])."""
+        prog_len, ops, offs, n_params, params, noise = self.pack_batch(nodes, noises)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        tp = np.ascontiguousarray(ts_pred, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        P, m = len(prog_len), tp.shape[0]
+        npred = None if noise_pred is None else np.ascontiguousarray(noise_pred, dtype=np.float64)
+        if npred is not None and npred.shape[0] != P:
+            raise ValueError("one noise_pred value per particle")
+        mean = np.empty((P, m), dtype=np.float64)
+        cov = np.empty((P, m, m), dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_predict_batch(self._h, P, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                                _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                                _f64p(tp), m, None if npred is None else _f64p(npred),
+                                                _f64p(mean), _f64p(cov), _i32p(info)))
+        self._P = P
+        return mean, cov, info
+
     def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
         lml = np.empty(self._P, dtype=np.float64)
         info = np.empty(self._P, dtype=np.int32)
@@ -340,6 +371,19 @@ def eval_cov(node: Node, ts, *, engine: Optional[Engine] = None) -> np.ndarray:
 def compute_cov_matrix_vectorized(node: Node, noise: float, ts, *, engine: Optional[Engine] = None) -> np.ndarray:
     """``GP.compute_cov_matrix_vectorized(node, noise, ts)`` (src/GP.jl:666-668)."""
     return (engine or default_engine()).gram(node, noise, ts, FORM_VECTORIZED)
+
+
+def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, *, noise_pred: Optional[float] = None,
+                   engine: Optional[Engine] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """``Distributions.MvNormal(node, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:731-758): the mean
+    vector and covariance matrix of X(ts_pred) | X(ts) = xs.  Raises ``PosDefException`` when the
+    training covariance is not positive definite (as the reference's ``\\`` would)."""
+    eng = engine or default_engine()
+    mean, cov, info = eng.predict_batch([node], [noise], ts, xs, ts_pred, None if noise_pred is None else [noise_pred])
+    if info[0] != 0:
+        from .model import PosDefException
+        raise PosDefException(int(info[0]), 0)
+    return mean[0], cov[0]
 
 
 def compute_cov_matrix(node: Node, noise: float, ts, *, engine: Optional[Engine] = None) -> np.ndarray:

@@ -279,16 +279,18 @@ def main():
     d2h = P * 8 + P * 4
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
-    # One step = ONE launch of agp_chol_kernel (persistent dataflow kernel: Gram tiles, DMMA
-    # contraction, diagonal Cholesky, panel solves, forward solve, log det).  Algorithmic work per
-    # launch = P * n^3 / 3 flops.
+    # One step = agp_gramfill_kernel (kernel-tree interpreter -> K tiles in HBM, FP64-issue bound)
+    # followed by ONE launch of agp_chol_kernel (persistent dataflow kernel: FP64 DMMA contraction,
+    # diagonal Cholesky, panel solves, forward solve, log det), which dominates.  Algorithmic work of
+    # that launch = P * n^3 / 3 flops.
     staged = os.environ.get("AGP_PATH", "") == "staged"
-    reps = 20
-    eng.run()
-    eng.synchronize()
-    kern_ms = eng.time_runs(reps) / reps
+    gram_ms, chol_ms = [], []
+    for _ in range(7):
+        a, b, _c = eng.stage_times()
+        gram_ms.append(a), chol_ms.append(b)
+    gram_ms, chol_ms = float(np.median(gram_ms)), float(np.median(chol_ms))
     flops = P * n ** 3 / 3.0
-    achieved = flops / (kern_ms * 1e-3) * 1e-12
+    achieved = flops / (chol_ms * 1e-3) * 1e-12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "chol_kernel_traffic.json")
     if os.path.exists(tpath):
@@ -298,16 +300,20 @@ def main():
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    n_entries = P * (n * (n + 1) / 2.0)
     roofline = {
         "bound": "tensor",
-        "kernel": "agp_chol_kernel (persistent: Gram tile + FP64 DMMA contraction + potf2 + panel solve)" if not staged
-                  else "staged path: update/potf2/trsm launches of one step",
+        "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)" if not staged
+                  else "staged path: update launches of one step",
         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
         "traffic": traffic,
         "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "
                        "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.2",
-        "launches_per_step": 1 if not staged else 3 * (-(-n // 128)) - 1, "avg_launch_ms": kern_ms,
+        "launches_per_step": 1, "avg_launch_ms": chol_ms,
         "algorithmic_flops_per_launch": flops,
+        "gramfill_kernel": {"avg_launch_ms": gram_ms, "entries_per_s": n_entries / (gram_ms * 1e-3),
+                            "hbm_write_GBps": 8.0 * n_entries / (gram_ms * 1e-3) * 1e-9,
+                            "bound": "FP64 issue (2 exp + 1 sin + 1 div per entry), not HBM"},
         "whole_step": {"flops": world * flops, "achieved": flops / (ms_per_step * 1e-3) * 1e-12,
                        "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
     }

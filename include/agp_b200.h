@@ -127,6 +127,34 @@ int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev);
  * upload — the data-annealing step of src/inference_smc_anneal_data.jl:212-217. */
 int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix);
 
+/* Continue the factorisation of the resident batch after the data prefix GREW (agp_lml_set_prefix
+ * with a larger n), keeping every tile row of L, z and the running log-det / quadratic-form sums
+ * that the previous run completed: only tile rows >= floor(n_old / 128) are recomputed, O(n^2 k)
+ * instead of O(n^3) — the block-append path of BASELINE.json configs[4].  The reference has no
+ * counterpart: it re-scores from scratch on every prefix (src/inference_smc_anneal_data.jl:
+ * 127-141, src/api.jl:426-443); results are bitwise those of agp_lml_run on the same prefix.
+ * Requires: same resident batch (no upload in between), the previous run fetched with info == 0
+ * for every particle; otherwise AGP_ERR_STATE and the caller falls back to agp_lml_run. */
+int agp_lml_run_append(agp_handle* h);
+
+/* ---- site 3: predictive distribution ---------------------------------------------------------- */
+
+/* For each particle p: the conditional multivariate normal  X(ts_pred) | X(ts) = xs  of
+ * Distributions.MvNormal(node, noise, ts, xs, ts_pred; noise_pred) (src/GP.jl:731-758, zero mean
+ * function), used by predict / predict_mvn / predict_proba (src/api.jl:497-522, 633-699):
+ *   mean_out[p*m + a]        = K_21 K_11^{-1} xs
+ *   cov_out[p*m*m + a*m + b] = K_22 - K_21 K_11^{-1} K_12 + noise_pred[p] * (a == b)   (symmetric)
+ * noise_pred may be NULL (= noise, the reference's default).  One factorisation serves both
+ * solves (the reference factorises twice, src/GP.jl:753-754): the prediction points are appended
+ * to the matrix as extra tile rows, the panel solves leave L_21 = K_21 L_11^{-T}, the forward solve
+ * leaves -mean, and the trailing tiles receive the Schur complement.  info_out[p]: LAPACK code of
+ * the training block (0 = ok).  Replaces the resident LML batch of the handle. */
+int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                      const int32_t* param_off, const int32_t* n_params, const double* params,
+                      const double* noise, const double* ts, const double* xs, int32_t n,
+                      const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out,
+                      double* cov_out, int32_t* info_out);
+
 /* ---- plumbing -------------------------------------------------------------------------- */
 
 /* cudaStream_t of the handle (as void*), for event timing / stream ordering by the caller. */
@@ -137,19 +165,25 @@ int64_t agp_launch_count(const agp_handle* h);
 /* Time `reps` back-to-back agp_lml_run() calls with CUDA events on the handle's stream;
  * returns total milliseconds in *ms_out. */
 int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
-/* Per-stage device time of ONE run (ms): gram+update, potf2, trsm — serialised with events,
- * for the roofline line in bench.py. stage_ms must hold 3 floats. */
+/* Per-kernel device time of ONE run (ms), CUDA events on the handle's stream around each launch:
+ * {agp_gramfill_kernel, agp_chol_kernel, 0} — for the roofline line in bench.py.  (With
+ * AGP_PATH=staged: the serialised sums of the update / potf2 / trsm launches.)  stage_ms must
+ * hold 3 floats. */
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 
 /* The in-order work queue the persistent kernel executes for P particles x nt block columns
  * (host-only, no GPU needed): items_out receives up to `cap` items as 8 int32 each
- * {type | half << 8, particle, block column k, tile row i, j0, j1, extra_flag, extra_need},
- * type 0 = DIAG, 1 = POTF2, 2 = PANEL; [j0, j1) = contraction range in block columns; extra_flag
+ * {type | half << 8 | store_only << 9, particle, block column k, tile row i, j0, j1, extra_flag,
+ * extra_need}, type 0 = DIAG, 1 = POTF2, 2 = PANEL; [j0, j1) = contraction range in block columns; extra_flag
  * (index into the counter array laid out for nt_stride = nt) / extra_need = the counter a
  * continuation item waits for; POTF2: extra_need = number of DIAG items of its tile.  Returns the
  * total item count.  tests/test_abi_host.py replays the queue against the kernel's wait rules and
  * checks that no item ever waits for a later one (the scheduler's deadlock-freedom argument). */
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap);
+/* Same for the continuation schedules: tile rows >= first_row only (agp_lml_run_append) and
+ * nt_total - nt tile rows of prediction points below the factored block (agp_predict_batch). */
+int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t first_row,
+                                int32_t* items_out, int64_t cap);
 
 /* Diagnostics: one traced run of the resident batch.  trace_out receives 8 int64 per work item
  * (queue order): globaltimer ns at {pop, producers ready, contraction done, Gram done, L_kk

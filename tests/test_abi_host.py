@@ -129,60 +129,90 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
+def _replay_queue(buf, P, nt, nt_total, first_row):
+    """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu): every wait
+    must already be satisfied by EARLIER items, and the items must tile every contraction exactly."""
+    DIAG, POTF2, PANEL, PARTIAL = 0, 1, 2, 1 << 9
+    nts = nt_total  # the builders lay the counters out for nt_stride = nt_total
+    counters = np.zeros(32 + 3 * P * nts + P, dtype=np.int64)
+    rowdone = lambda p, i: 32 + p * nts + i
+    diagu = lambda p, k: 32 + P * nts + p * nts + k
+    ppre = lambda p, i: 32 + 2 * P * nts + p * nts + i
+    fdone = lambda p: 32 + 3 * P * nts + p
+    for p in range(P):  # continuation: rows above first_row are final, first_row diagonal tiles factored
+        for i in range(first_row):
+            counters[rowdone(p, i)] = 2 * i
+        counters[fdone(p)] = first_row
+    covered, n_diag, stored = {}, {}, set()
+    for x, p, k, i, j0, j1, flag, need in buf.tolist():
+        t, h, partial = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL)
+        assert 0 <= p < P and 0 <= k < nt_total
+        if t == POTF2:
+            assert k < nt and counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
+            assert counters[fdone(p)] == k          # block columns are factored in order
+            counters[fdone(p)] += 1
+            continue
+        assert (t == DIAG and i == k) or (t == PANEL and k < i < nt_total)
+        assert i >= first_row and 0 <= j0 <= j1 <= min(k, nt)
+        assert covered.get((p, i, k, h), 0) == j0, "contraction ranges must be contiguous"
+        covered[(p, i, k, h)] = j1
+        if j1 > 0:
+            assert counters[rowdone(p, k)] >= 2 * j1
+            if t == PANEL:
+                assert counters[rowdone(p, i)] >= 2 * j1
+            if flag >= 0:
+                assert flag == (diagu(p, k) if t == DIAG else ppre(p, i)) and counters[flag] >= need
+        assert (flag >= 0) == (j0 > 0)
+        if t == DIAG:
+            counters[diagu(p, k)] += 1
+            n_diag[(p, k)] = n_diag.get((p, k), 0) + 1
+            if partial and k >= nt:
+                stored.add((p, i, k, h))
+        elif partial:
+            counters[ppre(p, i)] += 1
+            if k >= nt:
+                stored.add((p, i, k, h))
+        else:
+            assert k < nt and j1 == k
+            assert counters[fdone(p)] >= k + 1      # L_kk ready for the triangular solve
+            counters[rowdone(p, i)] += 1
+    for p in range(P):
+        assert counters[fdone(p)] == nt
+        for i in range(first_row, nt_total):
+            assert counters[rowdone(p, i)] == 2 * min(i, nt)
+            for k in range(i + 1):
+                for h in (0, 1):
+                    if k < nt:
+                        assert covered[(p, i, k, h)] == k         # finished: contraction over all of [0, k)
+                    else:
+                        assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # Schur complement tile
+
+
 @pytest.mark.parametrize("order", [0, 1, 2])
 @pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16), (2, 23)])
 def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     """Deadlock-freedom of the persistent kernel (agp_fused.cu): CTAs pop items in queue order and a
     CTA only ever spins on counters, so replaying the queue sequentially with the kernel's own wait
-    rules must find every wait already satisfied.  Also checks that the contraction ranges of
-    every tile tile [0, k) exactly and that each tile is finished once per half."""
+    rules must find every wait already satisfied."""
     from autogp.jl_b200 import _lib
 
     lib = _lib.load()
     n_items = lib.agp_queue_build(P, nt, order, None, 0)
     buf = np.zeros((n_items, 8), dtype=np.int32)
     assert lib.agp_queue_build(P, nt, order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
-    DIAG, POTF2, PANEL = 0, 1, 2
-    nts = nt  # agp_queue_build lays the counters out for nt_stride = nt
-    counters = np.zeros(32 + 3 * P * nts + P, dtype=np.int64)
-    rowdone = lambda p, i: 32 + p * nts + i
-    diagu = lambda p, k: 32 + P * nts + p * nts + k
-    ppre = lambda p, i: 32 + 2 * P * nts + p * nts + i
-    fdone = lambda p: 32 + 3 * P * nts + p
-    covered = {}   # (p, i, k, h) -> next block column to contract
-    n_diag = {}
-    for x, p, k, i, j0, j1, flag, need in buf.tolist():
-        t, h = x & 0xFF, x >> 8
-        assert 0 <= p < P and 0 <= k < nt and h in (0, 1)
-        if t == POTF2:
-            assert counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
-            assert counters[fdone(p)] == k          # block columns are factored in order
-            counters[fdone(p)] += 1
-            continue
-        assert (t == DIAG and i == k) or (t == PANEL and k < i < nt)
-        assert 0 <= j0 <= j1 <= k
-        assert covered.get((p, i, k, h), 0) == j0, "contraction ranges must be contiguous"
-        covered[(p, i, k, h)] = j1 if j1 < k else -1   # -1: finished
-        if j1 > 0:
-            assert counters[rowdone(p, k)] >= 2 * j1
-            if t == PANEL:
-                assert counters[rowdone(p, i)] >= 2 * j1
-            if flag >= 0:
-                assert flag == (diagu(p, k) if t == DIAG else ppre(p, i))
-                assert counters[flag] >= need
-        assert (flag >= 0) == (j0 > 0)
-        if t == DIAG:
-            counters[diagu(p, k)] += 1
-            n_diag[(p, k)] = n_diag.get((p, k), 0) + 1
-        elif j1 < k:
-            counters[ppre(p, i)] += 1
-        else:
-            assert counters[fdone(p)] >= k + 1      # L_kk ready for the triangular solve
-            counters[rowdone(p, i)] += 1
-    for p in range(P):
-        assert counters[fdone(p)] == nt
-        for i in range(nt):
-            assert counters[rowdone(p, i)] == 2 * i
-            for k in range(i + 1):
-                for h in (0, 1):
-                    assert covered[(p, i, k, h)] == -1 or k == 0
+    _replay_queue(buf, P, nt, nt, 0)
+
+
+@pytest.mark.parametrize("P,nt,nt_total,first_row", [(2, 4, 4, 2), (3, 6, 6, 5), (1, 3, 3, 0), (2, 4, 6, 0), (1, 1, 2, 0),
+                                                     (2, 0, 2, 0), (3, 5, 6, 0)])
+def test_continuation_queues_replay(P, nt, nt_total, first_row):
+    """Block-append (tile rows >= first_row only) and predictive (extra tile rows below the factored
+    block) schedules obey the same rules."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build_general(P, nt, nt_total, first_row, None, 0)
+    assert n_items > 0
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    lib.agp_queue_build_general(P, nt, nt_total, first_row, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
+    _replay_queue(buf, P, nt, nt_total, first_row)

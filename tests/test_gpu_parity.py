@@ -331,3 +331,125 @@ def test_full_size_n8192_one_particle(engine):
     assert got[0] == got[1]
     ref = o.log_marginal_likelihood(*parts[0], ts, xs)
     assert abs(got[0] - ref) <= LML_RTOL * abs(ref)
+
+
+def test_scheduler_stress_repeated_runs_are_bitwise_stable(engine):
+    """The persistent kernel resolves dependencies with spin-waits on counters; a missing
+    dependency (like the diagonal-block inverses being overwritten by the next block column while
+    the current one is still being solved) shows up as run-to-run differences.  Batch shapes that
+    exercise the look-ahead split items (nt >= 4) with few and many particles, 6 runs each."""
+    for n, P in ((640, 3), (1100, 7), (2048, 4), (2048, 16), (2300, 5)):
+        ts, xs = o.synthetic_series(n)
+        parts = [o.synthetic_particle(p) for p in range(P)]
+        first, info = gpu_lmls(engine, parts, ts, xs)
+        assert np.all(info == 0)
+        ref = oracle_lmls(parts[:2], ts, xs)
+        assert H.rel_err(first[:2], ref) <= LML_RTOL_TIGHT
+        for _ in range(5):
+            again, _ = gpu_lmls(engine, parts, ts, xs)
+            assert np.array_equal(first, again), (n, P)
+    # all particles identical => all results identical, whatever the interleaving of their items
+    ts, xs = o.synthetic_series(1500)
+    parts = [o.synthetic_particle(11)] * 24
+    got, _ = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(got == got[0])
+
+
+# ---- §8 f-2: block-append continuation of the factorisation ------------------------------------
+
+def test_lml_block_append_is_bitwise_the_full_recompute(engine):
+    """agp_lml_run_append keeps the tile rows the previous prefix completed and computes only the new
+    ones; the arithmetic per tile is the same, so the result must equal a from-scratch run on the
+    same prefix bit for bit (and the oracle to the usual tolerance)."""
+    import autogp.jl_b200 as agp
+    from autogp.jl_b200 import _lib
+
+    n_full, P = 1500, 6
+    ts, xs = o.synthetic_series(n_full)
+    parts = [o.synthetic_particle(p, t) for p, t in zip(range(P), ["se*per+lin", "se+wn", "ge+per*lin", "se*per+lin", "cp(lin,se)", "se*per+lin"])]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    fresh = agp.Engine(0)
+    engine.upload(nodes, noises, ts, xs)
+    with pytest.raises(_lib.AgpError):   # nothing factored yet
+        engine.run_append()
+    engine.set_prefix(200)
+    engine.run()
+    got, info = engine.fetch()
+    assert np.all(info == 0)
+    for n in (200, 456, 512, 513, 900, 1279, 1500):   # same size, inside a tile, tile-aligned, across tiles
+        engine.set_prefix(n)
+        engine.run_append()
+        got, info = engine.fetch()
+        ref, info_ref = fresh.lml_batch(nodes, noises, ts[:n], xs[:n])
+        assert np.all(info == 0) and np.all(info_ref == 0)
+        assert np.array_equal(got, ref), n
+        assert H.rel_err(got[:2], oracle_lmls(parts[:2], ts[:n], xs[:n])) <= LML_RTOL_TIGHT
+    # a shrinking prefix, or a failed factorisation, must be refused (caller falls back to run())
+    engine.set_prefix(700)
+    with pytest.raises(_lib.AgpError):
+        engine.run_append()
+    engine.upload([agp.Constant(1.0)], [-2.0], ts[:300], xs[:300])
+    engine.set_prefix(150)
+    engine.run()
+    _, info = engine.fetch()
+    assert info[0] != 0
+    engine.set_prefix(300)
+    with pytest.raises(_lib.AgpError):
+        engine.run_append()
+    fresh.close()
+
+
+# ---- §8 f-3: predictive conditional MVN -----------------------------------------------------------
+
+@pytest.mark.parametrize("n,m", [(200, 50), (128, 128), (333, 1), (700, 300), (50, 260)])
+def test_predictive_mvn_matches_oracle(engine, n, m):
+    """Distributions.MvNormal(node, noise, ts, xs, ts_pred) (src/GP.jl:731-758) for a ragged batch of
+    kernels: mean and covariance against the oracle's dense restatement."""
+    rng = np.random.default_rng(n * 1000 + m)
+    ts, xs = o.synthetic_series(n)
+    ts_pred = np.sort(rng.uniform(-0.1, 1.3, size=m))
+    trees = ["se*per+lin", "se+wn", "ge+per*lin", "cp(lin,se)"]
+    parts = [o.synthetic_particle(7 + p, t) for p, t in enumerate(trees)]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    noise_pred = [0.0, 0.3, noises[2], 1e-3]
+    mean, cov, info = engine.predict_batch(nodes, noises, ts, xs, ts_pred, noise_pred)
+    assert np.all(info == 0)
+    for p, (nd, nz) in enumerate(parts):
+        mu_ref, cov_ref = o.predictive_mvn(nd, nz, ts, xs, ts_pred, noise_pred=noise_pred[p])
+        scale = max(1.0, float(np.max(np.abs(cov_ref))))
+        assert np.max(np.abs(mean[p] - mu_ref)) <= 1e-8 * max(1.0, float(np.max(np.abs(mu_ref)))), p
+        assert np.max(np.abs(cov[p] - cov_ref)) <= 1e-8 * scale, p
+        assert np.array_equal(cov[p], cov[p].T)
+    # default noise_pred = noise (src/GP.jl:738)
+    mean2, cov2, _ = engine.predict_batch(nodes[:1], noises[:1], ts, xs, ts_pred)
+    mu_ref, cov_ref = o.predictive_mvn(parts[0][0], parts[0][1], ts, xs, ts_pred)
+    assert np.max(np.abs(cov2[0] - cov_ref)) <= 1e-8 * max(1.0, float(np.max(np.abs(cov_ref))))
+    assert np.array_equal(mean2[0], mean[0])
+
+
+def test_predictive_likelihood_identity_of_the_reference(engine):
+    """test/experiment_hmc.jl:111-132: logpdf(MvNormal(node, noise, ts_obs, xs_obs, ts_test), xs_test)
+    == LML(ts_all) - LML(ts_obs), on its three benchmark kernels (:180-184) — here with BOTH sides from
+    the GPU path (predictive MVN from agp_predict_batch, LMLs from agp_lml_batch)."""
+    import autogp.jl_b200 as agp
+
+    ts_all = np.linspace(0, 10, 1000)
+    rng = np.random.default_rng(42)
+    xs_all = np.sin(ts_all) + 0.1 * rng.normal(size=ts_all.size)
+    n_obs = 200
+    cases = [(agp.SquaredExponential(2.0), 0.01), (agp.Plus(agp.Linear(0.5), agp.Periodic(2.0, 1.0)), 0.05),
+             (agp.ChangePoint(agp.Linear(0.5), agp.Linear(1.5), 1.0, 0.001), 0.001)]
+    for node, noise in cases:
+        mean, cov = agp.predictive_mvn(node, noise, ts_all[:n_obs], xs_all[:n_obs], ts_all[n_obs:], engine=engine)
+        lhs = o.mvn_logpdf(xs_all[n_obs:], mean, cov)
+        lml_all = agp.mvnormal_logpdf(node, noise, ts_all, xs_all, engine=engine)
+        lml_obs = agp.mvnormal_logpdf(node, noise, ts_all[:n_obs], xs_all[:n_obs], engine=engine)
+        assert lhs == pytest.approx(lml_all - lml_obs, rel=1.5e-8)
+
+
+def test_predictive_not_positive_definite_raises(engine):
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(150)
+    with pytest.raises(agp.PosDefException):
+        agp.predictive_mvn(agp.Constant(1.0), -2.0, ts, xs, np.linspace(0, 1, 5), engine=engine)

@@ -34,6 +34,9 @@ struct agp_handle {
     int n_factored = -1;     // observations covered by the factor resident in d_L (-1: none), for agp_lml_run_append
     bool factor_clean = false;  // the last fetch saw info == 0 for every particle
     double* d_pred = nullptr; size_t cap_pred = 0;  // predictive means + covariances
+    bool aug_identity = false;  // the resident batch is identity-augmented (agp_lml_grad_batch)
+    double* d_grad = nullptr; size_t cap_grad = 0;  // per-CTA partial sums + gradients
+    const int* d_param_prefix = nullptr;            // [P+1] prefix sums of n_params (inside the input arena)
     BatchView view{};
 
     // device workspaces (grow-only)
@@ -191,6 +194,7 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_gin);
     cudaFree(h->d_sync);
     cudaFree(h->d_pred);
+    cudaFree(h->d_grad);
     for (auto& kv : h->queues) cudaFree(kv.second.d_items);
     cudaFreeHost(h->h_sync);
     cudaFreeHost(h->h_gin);
@@ -283,12 +287,12 @@ int agp_gram_device(agp_handle* h, const int32_t* ops, const int32_t* param_off,
 // at the next tile boundary after the observations (agp_predict_batch).
 static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
                        const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred, int32_t m,
-                       const double* noise_pred) {
+                       const double* noise_pred, bool aug_identity = false) {
     if (!h) return AGP_ERR_ARG;
     h->uploaded = false;
     h->n_factored = -1;
     h->factor_clean = false;
-    if (P < 0 || n < 0 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)) || (m > 0 && !ts_pred))
+    if (P < 0 || n < 0 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)) || (m > 0 && !ts_pred && !aug_identity))
         return fail(h, AGP_ERR_ARG, "agp_lml_upload: bad argument");
     if (P > 65535) return fail(h, AGP_ERR_ARG, "agp_lml_upload: at most 65535 particles per batch");
     AGP_CUDA(h, cudaSetDevice(h->device));
@@ -313,6 +317,7 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     }
 
     const int ld_obs = (int)align_up((size_t)(n > 0 ? n : (m > 0 ? 0 : 1)), TB);
+    if (aug_identity) m = ld_obs;  // one appended row per (padded) observation, carrying [I 0]
     const int ld = ld_obs + (int)align_up((size_t)m, TB);
     // packed input arena: ts[ld] xs[ld] noise[P] noise_pred[P] prog_off[P+1] prog_need[P] instr[]
     size_t off_ts = 0;
@@ -321,7 +326,8 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     size_t off_npred = off_noise + (size_t)P * 8;
     size_t off_poff = align_up(off_npred + (size_t)P * 8, 16);
     size_t off_need = align_up(off_poff + (size_t)(P + 1) * 4, 16);
-    size_t off_instr = align_up(off_need + (size_t)P * 4, 32);
+    size_t off_pprefix = align_up(off_need + (size_t)P * 4, 16);
+    size_t off_instr = align_up(off_pprefix + (size_t)(P + 1) * 4, 32);
     size_t in_bytes = off_instr + instr.size() * sizeof(AgpInstr);
     int rc;
     if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
@@ -350,7 +356,12 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
         memcpy(h->h_in + off_ts, ts, (size_t)n * 8);
         memcpy(h->h_in + off_xs, xs, (size_t)n * 8);
     }
-    if (m > 0) memcpy(h->h_in + off_ts + (size_t)ld_obs * 8, ts_pred, (size_t)m * 8);
+    if (m > 0 && ts_pred) memcpy(h->h_in + off_ts + (size_t)ld_obs * 8, ts_pred, (size_t)m * 8);
+    {
+        int32_t* pp = reinterpret_cast<int32_t*>(h->h_in + off_pprefix);
+        pp[0] = 0;
+        for (int p = 0; p < P; ++p) pp[p + 1] = pp[p] + n_params[p];
+    }
     if (P > 0) {
         memcpy(h->h_in + off_noise, noise, (size_t)P * 8);
         memcpy(h->h_in + off_npred, noise_pred ? noise_pred : noise, (size_t)P * 8);  // default: noise_pred = noise (src/GP.jl:738)
@@ -378,6 +389,9 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     v.z = reinterpret_cast<double*>(h->d_work + off_z);
     v.logdet_half = reinterpret_cast<double*>(h->d_work + off_ld);
     v.zz = reinterpret_cast<double*>(h->d_work + off_zz);
+    v.aug_identity = aug_identity ? 1 : 0;
+    h->aug_identity = aug_identity;
+    h->d_param_prefix = reinterpret_cast<const int*>(h->d_in + off_pprefix);
     v.cum = reinterpret_cast<double*>(h->d_work + off_cum);
     v.dinv = reinterpret_cast<double*>(h->d_work + off_dinv);
     v.lml = reinterpret_cast<double*>(h->d_res);
@@ -424,6 +438,11 @@ int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix) {
 //          (k+2,k+1) get a PARTIAL item over [0,k) one block column early, so only the last 128
 //          columns of their contraction remain on the per-particle critical path
 //          POTF2(k) -> PANEL(k,k+1) -> DIAG(k+1) -> POTF2(k+1).
+// second int4 of a work item (agp_kernels.cuh)
+static int4 pack_dep(int j0, int j1, int need_k, int need_i, int flag, int need) {
+    return make_int4(j0 | (j1 << 16), need_k | (need_i << 16), flag, need);
+}
+
 struct QueueLayout {
     int P, nt, nt_stride;
     int flag_diagu(int p, int k) const { return 32 + P * nt_stride + p * nt_stride + k; }
@@ -435,9 +454,10 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
     const int split_from = 3;  // block columns below this are too short to be worth splitting
     auto split = [&](int k) { return order >= 2 && k >= split_from && k < nt; };  // tile (k,k) and (k+1,k) are split
     auto push = [&](int type, int h, int p, int k, int i, int j0, int j1, int flag, int need) {
-        const int partial = (type != agp::ITEM_POTF2 && j1 < k) ? agp::ITEM_PARTIAL : 0;
-        items.push_back(make_int4(type | (h << 8) | partial, p, k, i));
-        items.push_back(make_int4(j0, j1, flag, need));
+        int flags = (type != agp::ITEM_POTF2 && j1 < k) ? agp::ITEM_PARTIAL : 0;
+        if (type == agp::ITEM_PANEL && k == 0) flags |= agp::ITEM_YINIT;
+        items.push_back(make_int4(type | (h << 8) | flags, p, k, i));
+        items.push_back(pack_dep(j0, j1, type == agp::ITEM_POTF2 ? 0 : 2 * j1, type == agp::ITEM_PANEL ? 2 * j1 : 0, flag, need));
     };
     auto diag_full = [&](int p, int k) {
         for (int h = 0; h < 2; ++h) push(agp::ITEM_DIAG, h, p, k, k, 0, k, -1, 0);
@@ -480,8 +500,8 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
         for (int p = 0; p < P; ++p)
             for (int i = k + 2; i < nt; ++i)
                 for (int h = 0; h < 2; ++h) {
-                    bulk.push_back(make_int4(agp::ITEM_PANEL | (h << 8), p, k, i));
-                    bulk.push_back(make_int4(0, k, -1, 0));
+                    bulk.push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (k == 0 ? agp::ITEM_YINIT : 0), p, k, i));
+                    bulk.push_back(pack_dep(0, k, 2 * k, 2 * k, -1, 0));
                 }
         size_t n_bulk = bulk.size() / 2;
         size_t c1 = 2 * (n_bulk / 3), c2 = 2 * (2 * n_bulk / 3);
@@ -507,8 +527,10 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
 //                        K_22 - L_21 L_21^T as store-only items over [0, nt) (agp_predict_batch)
 static void build_queue_general(int P, int nt, int nt_total, int first_row, std::vector<int4>& items) {
     auto push = [&](int type, int h, int partial, int p, int k, int i, int j0, int j1, int need) {
-        items.push_back(make_int4(type | (h << 8) | (partial ? agp::ITEM_PARTIAL : 0), p, k, i));
-        items.push_back(make_int4(j0, j1, -1, need));
+        int flags = partial ? agp::ITEM_PARTIAL : 0;
+        if (type == agp::ITEM_PANEL && k == 0) flags |= agp::ITEM_YINIT;
+        items.push_back(make_int4(type | (h << 8) | flags, p, k, i));
+        items.push_back(pack_dep(j0, j1, type == agp::ITEM_POTF2 ? 0 : 2 * j1, type == agp::ITEM_PANEL ? 2 * j1 : 0, -1, need));
     };
     items.clear();
     for (int k = 0; k < nt; ++k) {
@@ -528,16 +550,41 @@ static void build_queue_general(int P, int nt, int nt_total, int first_row, std:
                 for (int h = 0; h < 2; ++h) push(i == k ? agp::ITEM_DIAG : agp::ITEM_PANEL, h, 1, p, k, i, 0, nt, 0);
 }
 
+// Schedule of the identity-augmented factorisation (agp_lml_grad_batch): the matrix [[K, I], [I, 0]] is
+// factored over its first nt tile rows; tile row nt + a then solves to block row a of L^{-T}
+// (non-zero from block column a on: PANEL items over [a, k), k >= a, i.e. a blocked trtri at n^3/3 flops),
+// and the trailing tile (nt + a, nt + b), b <= a, receives the Schur complement
+// 0 - sum_{j >= a} L^{-T}[a][j] L^{-T}[b][j]^T = -K^{-1}[a][b] as a store-only item over [a, nt) (a blocked
+// lauum at n^3/3 flops).  The forward-solve entries of the appended rows end as 0 - L^{-T} z = -alpha.
+static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::vector<int4>& items) {
+    build_queue(P, nt, nt_stride, order, items);
+    for (int k = 0; k < nt; ++k)
+        for (int p = 0; p < P; ++p)
+            for (int a = 0; a <= k; ++a)
+                for (int h = 0; h < 2; ++h) {
+                    items.push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (k == a ? agp::ITEM_YINIT : 0), p, k, nt + a));
+                    items.push_back(pack_dep(a, k, 2 * k, 2 * (k - a), -1, 0));
+                }
+    for (int p = 0; p < P; ++p)
+        for (int a = 0; a < nt; ++a)
+            for (int b = 0; b <= a; ++b)
+                for (int h = 0; h < 2; ++h) {
+                    items.push_back(make_int4((a == b ? agp::ITEM_DIAG : agp::ITEM_PANEL) | (h << 8) | agp::ITEM_PARTIAL, p, nt + b, nt + a));
+                    items.push_back(pack_dep(a, nt, 2 * (nt - b), a == b ? 0 : 2 * (nt - a), -1, 0));
+                }
+}
+
 static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_ms = nullptr, int first_row = 0) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
     const int nt_total = v.nt_total;
-    auto key = std::make_tuple(P, nt, nt_total, first_row, nt_stride);
+    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? -1 : first_row, nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
-        if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
+        if (h->aug_identity) build_queue_inverse(P, nt, nt_stride, h->order, items);
+        else if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
         else build_queue_general(P, nt, nt_total, first_row, items);
         agp_handle::Queue qu;
         qu.n_items = (int)(items.size() / 2);
@@ -772,7 +819,7 @@ int agp_lml_run_append(agp_handle* h) {
     if (!h) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no resident batch");
     if (h->staged) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: not available with AGP_PATH=staged");
-    if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the resident batch carries prediction points");
+    if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the resident batch carries appended rows");
     if (h->n_factored < 0 || !h->factor_clean)
         return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no clean factor resident (run + fetch with info == 0 for every particle first)");
     if (h->view.n < h->n_factored) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the data prefix shrank; use agp_lml_run");
@@ -814,6 +861,54 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
     return rc;
 }
 
+int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                       const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
+                       double* grad_params_out, double* grad_noise_out, int32_t* info_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_lml_grad_batch: not available with AGP_PATH=staged");
+    if (P > 0 && (!lml_out || !grad_noise_out || !info_out || !prog_len || !n_params)) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: bad argument");
+    size_t total_params = 0;
+    for (int p = 0; p < P; ++p) {
+        if (n_params[p] > agp::AGP_GRAD_MAX_PARAMS || prog_len[p] > 64)
+            return fail(h, AGP_ERR_PROGRAM, "agp_lml_grad_batch: particle " + std::to_string(p) + ": at most 64 nodes and 64 parameters per kernel");
+        total_params += (size_t)(n_params[p] > 0 ? n_params[p] : 0);
+    }
+    if (total_params > 0 && !grad_params_out) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: null gradient output");
+    int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, nullptr, 0, nullptr, n > 0);
+    if (rc != AGP_OK) return rc;
+    if (P == 0) return AGP_OK;
+    if (n == 0) {  // empty mvnormal: score 0, no dependence on anything
+        for (int p = 0; p < P; ++p) lml_out[p] = 0.0, grad_noise_out[p] = 0.0, info_out[p] = 0;
+        for (size_t j = 0; j < total_params; ++j) grad_params_out[j] = 0.0;
+        return AGP_OK;
+    }
+    const int blocks = agp::grad_blocks_per_particle(h->view);
+    const size_t partial_doubles = (size_t)P * blocks * (agp::AGP_GRAD_MAX_PARAMS + 1);
+    if ((rc = grow_device(h, &h->d_grad, &h->cap_grad, (partial_doubles + total_params + P + 2) * 8)) != AGP_OK) return rc;
+    if ((rc = run_fused(h)) != AGP_OK) return rc;
+    h->n_factored = -1;  // the resident factor belongs to an augmented matrix
+    double* d_gparams = h->d_grad + partial_doubles;
+    double* d_gnoise = d_gparams + total_params;
+    agp::launch_grad(h->view, P, h->d_param_prefix, h->d_grad, d_gparams, d_gnoise, h->stream);
+    h->launches += 2;
+    if ((rc = check_launch(h, "grad")) != AGP_OK) return rc;
+    if (total_params > 0) AGP_CUDA(h, cudaMemcpyAsync(grad_params_out, d_gparams, total_params * 8, cudaMemcpyDeviceToHost, h->stream));
+    AGP_CUDA(h, cudaMemcpyAsync(grad_noise_out, d_gnoise, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+    rc = agp_lml_fetch(h, lml_out, info_out);  // synchronises
+    h->factor_clean = false;
+    if (rc != AGP_OK) return rc;
+    const double nan = std::nan("");
+    size_t o = 0;
+    for (int p = 0; p < P; ++p) {  // gradients of a failed factorisation are undefined
+        if (info_out[p] != 0) {
+            grad_noise_out[p] = nan;
+            for (int j = 0; j < n_params[p]; ++j) grad_params_out[o + j] = nan;
+        }
+        o += n_params[p];
+    }
+    return AGP_OK;
+}
+
 int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     if (!h) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_trace: no resident batch");
@@ -849,7 +944,8 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
     if (P < 0 || nt < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
-    build_queue(P, nt, nt, order, items);
+    if (order >= 100) build_queue_inverse(P, nt, 2 * nt, order - 100, items);  // identity-augmented schedule, counters laid out for 2 nt
+    else build_queue(P, nt, nt, order, items);
     return export_queue(items, items_out, cap);
 }
 

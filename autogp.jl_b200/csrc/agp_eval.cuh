@@ -162,6 +162,121 @@ __device__ __forceinline__ void eval_entries8(const AgpInstr* __restrict__ prog,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Reverse-mode derivative of one covariance entry with respect to every kernel parameter
+// (vectorised form of src/GP.jl:137-503): forward sweep over the compiled program keeping every
+// node value, backward sweep pushing the adjoint to the leaves, where `acc(j, d)` receives
+// d = adjoint * dk/dparams[j] with j indexing the particle's params[] slice in wire order
+// (Julia fieldnames order).  This is what ReverseDiff computes through eval_cov for Gen.hmc /
+// Gen.map_optimize (src/inference_utils.jl:63-67, src/Greedy.jl:95, 370).
+// ------------------------------------------------------------------------------------------
+constexpr int AGP_GRAD_MAX_NODES = 64;
+
+template <class Acc>
+__device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ prog, int m, double t1, double t2, double seed, Acc&& acc) {
+    double val[AGP_GRAD_MAX_NODES], adj[AGP_GRAD_MAX_NODES];
+    unsigned char opa[AGP_GRAD_MAX_NODES], opb[AGP_GRAD_MAX_NODES];  // operand node indices (s1, s0)
+    unsigned char stack[AGP_MAX_STACK + 1];
+    int sp = 0;
+    const double dx = t1 - t2, adx = fabs(dx);
+    for (int q = 0; q < m; ++q) {
+        const int op = prog[q].op;
+        const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        adj[q] = 0.0;
+        if (op <= AGP_I_WN) {
+            double v;
+            switch (op) {
+                case AGP_I_CONST: v = a; break;
+                case AGP_I_LINEAR: v = b + c * ((t1 - a) * (t2 - a)); break;
+                case AGP_I_SE: v = b * exp(((-0.5 * dx) * dx) / a); break;
+                case AGP_I_GE: v = c * exp(-pow(adx / a, b)); break;
+                case AGP_I_PER: { double sn = sin(a * adx); v = c * exp(b * (sn * sn)); break; }
+                default: v = (t1 == t2) ? a : 0.0; break;
+            }
+            val[q] = v;
+            stack[sp++] = (unsigned char)q;
+        } else {
+            const int ib = stack[--sp], ia = stack[--sp];  // s0, s1
+            opa[q] = (unsigned char)ia;
+            opb[q] = (unsigned char)ib;
+            double v;
+            if (op == AGP_I_PLUS) v = val[ia] + val[ib];
+            else if (op == AGP_I_TIMES) v = val[ia] * val[ib];
+            else {
+                const double kl = (op == AGP_I_CP) ? val[ia] : val[ib], kr = (op == AGP_I_CP) ? val[ib] : val[ia];
+                const double g1 = sigma_cp(t1, a, b), g2 = sigma_cp(t2, a, b);
+                v = (g1 * g2) * kl + ((1.0 - g1) * (1.0 - g2)) * kr;
+            }
+            val[q] = v;
+            stack[sp++] = (unsigned char)q;
+        }
+    }
+    adj[m - 1] = seed;
+    for (int q = m - 1; q >= 0; --q) {
+        const double g = adj[q];
+        const int op = prog[q].op, off = prog[q].pad;
+        const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        switch (op) {
+            case AGP_I_CONST: acc(off, g); break;
+            case AGP_I_WN: acc(off, (t1 == t2) ? g : 0.0); break;
+            case AGP_I_LINEAR: {  // bias + amp (t1 - c0)(t2 - c0): params (intercept c0, bias, amplitude)
+                const double u1 = t1 - a, u2 = t2 - a;
+                acc(off, g * (-c * (u1 + u2)));
+                acc(off + 1, g);
+                acc(off + 2, g * (u1 * u2));
+                break;
+            }
+            case AGP_I_SE: {  // amp exp(-dx^2 / (2 l^2)): params (lengthscale l, amplitude); a = l^2
+                const double e = exp(((-0.5 * dx) * dx) / a);
+                const double l = sqrt(a);
+                acc(off, g * (val[q] * (dx * dx) / (a * l)));
+                acc(off + 1, g * e);
+                break;
+            }
+            case AGP_I_GE: {  // amp exp(-(|dx| / l)^gamma): params (l, gamma, amp)
+                const double u = adx / a;
+                const double w = pow(u, b);
+                acc(off, g * (val[q] * b * w / a));
+                acc(off + 1, (u > 0.0) ? g * (-val[q] * w * log(u)) : 0.0);
+                acc(off + 2, g * exp(-w));
+                break;
+            }
+            case AGP_I_PER: {  // amp exp(b s^2), s = sin(a |dx|), a = pi / p, b = -2 / l^2: params (l, p, amp)
+                const double arg = a * adx;
+                const double sn = sin(arg), cs = cos(arg);
+                const double l = sqrt(-2.0 / b), per = 3.14159265358979323846 / a;
+                acc(off, g * (val[q] * (sn * sn) * (-2.0 * b / l)));          // db/dl = 4 / l^3 = -2 b / l
+                acc(off + 1, g * (val[q] * b * 2.0 * sn * cs * adx * (-a / per)));  // da/dp = -pi / p^2 = -a / p
+                acc(off + 2, g * exp(b * (sn * sn)));
+                break;
+            }
+            case AGP_I_PLUS:
+                adj[opa[q]] += g;
+                adj[opb[q]] += g;
+                break;
+            case AGP_I_TIMES:
+                adj[opa[q]] += g * val[opb[q]];
+                adj[opb[q]] += g * val[opa[q]];
+                break;
+            default: {  // ChangePoint: params (location, scale)
+                const int il = (op == AGP_I_CP) ? opa[q] : opb[q], ir = (op == AGP_I_CP) ? opb[q] : opa[q];
+                const double kl = val[il], kr = val[ir];
+                const double u1 = (a - t1) / b, u2 = (a - t2) / b;
+                const double th1 = tanh(u1), th2 = tanh(u2);
+                const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
+                const double dg1 = 0.5 * (1.0 - th1 * th1) / b, dg2 = 0.5 * (1.0 - th2 * th2) / b;  // d sigma / d location
+                adj[il] += g * (g1 * g2);
+                adj[ir] += g * ((1.0 - g1) * (1.0 - g2));
+                const double dk1 = g2 * kl - (1.0 - g2) * kr, dk2 = g1 * kl - (1.0 - g1) * kr;   // dk / d sigma(t1), d sigma(t2)
+                acc(off, g * (dk1 * dg1 + dk2 * dg2));
+                acc(off + 1, g * (-(dk1 * dg1 * u1 + dk2 * dg2 * u2)));
+                break;
+            }
+        }
+    }
+    return val[m - 1];
+}
+
 // E entries at once; deep trees (need > 4) fall back to pairs to bound register use.
 template <int E>
 __device__ __forceinline__ void eval_entries(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E], const double (&t2)[E],

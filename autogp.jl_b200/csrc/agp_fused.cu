@@ -127,7 +127,7 @@ __device__ __forceinline__ Smem smem_view() {
 // always start from minus the tile), which takes the long early part of the contraction of the
 // next diagonal tile and of the panel below it off the per-particle critical path.
 __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag, bool partial,
-                                       int j0, int j1, int extra_flag, int extra_need) {
+                                       bool yinit, int j0, int j1, int need_k, int need_i, int extra_flag, int extra_need) {
     const Smem s = smem_view();
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -136,12 +136,13 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
     double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
     double* stages = s.region;
 
-    // rows i and k of L must be final for all block columns < j1; a continuation item also needs
-    // the partial tile of its predecessor (extra_flag)
-    if (j1 > 0) {
+    // the operand tile rows k and i must be final over the contraction range (counter values chosen by
+    // the queue builder); a continuation item also needs the partial tile of its predecessor
+    if (need_k > 0 || need_i > 0 || extra_flag >= 0) {
         if (tid == 0) {
-            bool ok = wait_ge(q.rowdone + p * q.nt_stride + k, 2 * j1, q.err, q.wait_timeout_ns);
-            if (ok && !diag) ok = wait_ge(q.rowdone + p * q.nt_stride + i, 2 * j1, q.err, q.wait_timeout_ns);
+            bool ok = true;
+            if (need_k > 0) ok = wait_ge(q.rowdone + p * q.nt_stride + k, need_k, q.err, q.wait_timeout_ns);
+            if (ok && need_i > 0) ok = wait_ge(q.rowdone + p * q.nt_stride + i, need_i, q.err, q.wait_timeout_ns);
             if (ok && extra_flag >= 0) ok = wait_ge(q.head + extra_flag, extra_need, q.err, q.wait_timeout_ns);
             s.ctl[1] = ok ? 1 : 0;
         }
@@ -284,7 +285,7 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
     double y_old = 0.0;
     if (lane < 8) {
         const int gr = row0 + warp * 8 + lane;
-        y_old = (k == 0) ? ((gr < n) ? v.xs[gr] : 0.0) : __ldcg(yp + gr);
+        y_old = yinit ? ((gr < n) ? v.xs[gr] : 0.0) : __ldcg(yp + gr);
     }
 
 #pragma unroll 1
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
         bool ok;
         stamp(q, idx, 0);
         if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z, dep.w);
-        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, (it.x & ITEM_PARTIAL) != 0, dep.x, dep.y, dep.z, dep.w);
+        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, (it.x & ITEM_PARTIAL) != 0, (it.x & ITEM_YINIT) != 0,
+                            dep.x & 0xffff, dep.x >> 16, dep.y & 0xffff, dep.y >> 16, dep.z, dep.w);
         if (!ok) break;
         stamp(q, idx, 5);
         if (q.trace != nullptr && threadIdx.x == 0) {
@@ -694,6 +696,8 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
                 if (gr < n) {  // gc <= gr < n
                     out = val[j];
                     if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
+                } else if (v.aug_identity && gr >= lt) {
+                    out = (gr - lt == gc) ? 1.0 : 0.0;  // [I 0]: the appended rows solve to L^{-T}, -K^{-1}, -alpha
                 } else if (gr >= lt && gr < lt + v.n_pred && (gc < n || gc >= lt)) {
                     out = val[j];  // K(t, t*) and K(t*, t*), no noise (src/GP.jl:743-747)
                 } else {
@@ -736,6 +740,89 @@ void launch_predict_extract(const BatchView& v, int P, const double* noise_pred,
     int bx = (int)((e + 255) / 256);
     if (bx > 1024) bx = 1024;
     agp_predict_extract_kernel<<<dim3(bx, P), 256, 0, s>>>(v, noise_pred, mean_out, cov_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gradient of the log marginal likelihood (Gen mvnormal logpdf_grad + ReverseDiff
+// through eval_cov in the reference):   dLML/dtheta = 1/2 sum_ik A_ik dK_ik/dtheta,
+// A = alpha alpha^T - K^{-1}.  After the identity-augmented factorisation the trailing lower tiles
+// hold -K^{-1} and the appended forward-solve entries hold -alpha, so
+//   A_ik = y[lt+i] y[lt+k] + L[lt+i][lt+k].
+// One CTA = 64 rows x 128 columns of a lower tile; every thread walks its entries through the
+// reverse-mode interpreter and keeps per-parameter sums; the CTA reduces them in a fixed order and
+// a second kernel adds the per-CTA partials in a fixed order (bitwise reproducible, no atomics).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __restrict__ param_off, double* __restrict__ partial) {
+    __shared__ AgpInstr prog_s[PROG_SMEM];
+    __shared__ double red[FT / 32][AGP_GRAD_MAX_PARAMS + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = blockIdx.y;
+    const int t = blockIdx.x >> 1, h = blockIdx.x & 1;
+    int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    const int k = t - i * (i + 1) / 2;
+    const int row0 = i * TB + h * UM, col0 = k * TB;
+    const int ld = v.ld, n = v.n, lt = v.nt * TB;
+    const double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    const double* __restrict__ nal = v.y + (long long)p * ld + lt;  // -alpha
+    const int poff = v.prog_off[p];
+    const int pm = v.prog_off[p + 1] - poff;
+    {
+        const double* src = reinterpret_cast<const double*>(v.prog + poff);
+        double* dst = reinterpret_cast<double*>(prog_s);
+        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
+    }
+    __syncthreads();
+    const int np = param_off[p + 1] - param_off[p];  // host guarantees np <= AGP_GRAD_MAX_PARAMS
+    double g[AGP_GRAD_MAX_PARAMS + 1];
+    for (int j = 0; j <= np; ++j) g[j] = 0.0;
+    const int c = tid & (UN - 1), rbase = tid >> 7;
+    const int gc = col0 + c;
+    if (gc < n) {
+        const double tcol = v.ts[gc];
+        const double nac = nal[gc];
+#pragma unroll 1
+        for (int e = 0; e < 32; ++e) {
+            const int gr = row0 + rbase + 2 * e;
+            if (gr >= n || gc > gr) continue;
+            const double A = nal[gr] * nac + Lp[(long long)(lt + gr) * ld + lt + gc];
+            const double wgt = (gr == gc) ? A : 2.0 * A;  // off-diagonal entries count twice (symmetry)
+            eval_entry_grad(prog_s, pm, tcol, v.ts[gr], wgt, [&](int j, double d) { g[j] += d; });
+            if (gr == gc) g[np] += A;  // dK/dnoise = I
+        }
+    }
+    for (int j = 0; j <= np; ++j) {
+        const double sres = warp_sum(g[j]);
+        if (lane == 0) red[warp][j] = sres;
+    }
+    __syncthreads();
+    if (tid <= np) {
+        double sres = 0.0;
+#pragma unroll
+        for (int w = 0; w < FT / 32; ++w) sres += red[w][tid];
+        partial[((long long)p * gridDim.x + blockIdx.x) * (AGP_GRAD_MAX_PARAMS + 1) + tid] = sres;
+    }
+}
+
+__global__ void agp_grad_reduce_kernel(const double* __restrict__ partial, int blocks, const int* __restrict__ param_off, double* __restrict__ grad_out,
+                                       double* __restrict__ gnoise_out) {
+    const int p = blockIdx.x, j = threadIdx.x;
+    const int np = param_off[p + 1] - param_off[p];
+    if (j > np) return;
+    double sres = 0.0;
+    for (int b = 0; b < blocks; ++b) sres += partial[((long long)p * blocks + b) * (AGP_GRAD_MAX_PARAMS + 1) + j];
+    if (j < np) grad_out[param_off[p] + j] = 0.5 * sres;
+    else gnoise_out[p] = 0.5 * sres;
+}
+
+int grad_blocks_per_particle(const BatchView& v) { return v.nt * (v.nt + 1); }
+
+void launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, cudaStream_t s) {
+    if (P <= 0 || v.nt <= 0) return;
+    const int blocks = grad_blocks_per_particle(v);
+    agp_grad_kernel<<<dim3(blocks, P), FT, 0, s>>>(v, param_off, partial);
+    agp_grad_reduce_kernel<<<P, AGP_GRAD_MAX_PARAMS + 1, 0, s>>>(partial, blocks, param_off, grad_out, gnoise_out);
 }
 
 cudaError_t configure_fused() {

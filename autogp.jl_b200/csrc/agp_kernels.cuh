@@ -36,16 +36,21 @@ struct BatchView {
     int nt_total;            // tile rows in the matrix: nt + ceil(n_pred / TB)
     int n_pred;              // appended time points (0 for a plain LML batch)
     double* cum;             // [P][ld/TB][2] running (sum log L_ii, sum z_i^2) after each block column
+    int aug_identity;        // appended rows carry [I 0] instead of kernel values: their Schur complement is -K^{-1}
+                             // and their forward-solve entries are -alpha (agp_lml_grad_batch)
 };
 
 // ---- persistent dataflow scheduler (agp_fused.cu) ------------------------------------------
 // Work items: two int4 each,
 //   {type | h << 8 | ITEM_PARTIAL?, particle, block column k, tile row i}   ITEM_PARTIAL: store-only item,
 //                          the tile in L receives K - sum_{j0<=j<j1} (no solve, no factorisation follows from it)
-//   {j0, j1, extra_flag, extra_need}: contraction range [j0, j1) in block columns; for a continuation
-//   item, the index (relative to SchedView::head) and value of the counter its predecessor bumps;
-//   POTF2 carries in extra_need how many DIAG items finish its tile.
-enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_PARTIAL = 1 << 9 };
+//                          ITEM_YINIT: this panel is the first of its tile row (starts the forward-solve entry from xs)
+//   {j0 | j1 << 16, need_k | need_i << 16, extra_flag, extra_need}: contraction range [j0, j1) in block
+//   columns; the values rowdone[p][k] / rowdone[p][i] must have reached (finished panel items of the
+//   two operand tile rows); for a continuation item, the index (relative to SchedView::head) and
+//   value of the counter its predecessor bumps; POTF2 carries in extra_need how many DIAG items
+//   finish its tile.
+enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_PARTIAL = 1 << 9, ITEM_YINIT = 1 << 10 };
 
 struct SchedView {
     const int4* items;  // in-order queue (2 x int4 per item): every item's producers sit earlier in the list
@@ -64,6 +69,11 @@ struct SchedView {
 // Gram fill: lower tiles of tile rows [row_tile0, nt_total) of every particle  <-  K(ts,ts) + noise*I
 // (runs before launch_chol)
 void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s);
+// dLML/dparams, dLML/dnoise out of the identity-augmented factorisation (agp_lml_grad_batch):
+// partial[P][blocks][AGP_GRAD_MAX_PARAMS + 1] per-CTA sums, then grad_out / gnoise_out
+constexpr int AGP_GRAD_MAX_PARAMS = 64;
+void launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, cudaStream_t s);
+int grad_blocks_per_particle(const BatchView& v);
 // Predictive mean / covariance out of an augmented factorisation (agp_predict_batch)
 void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
 // One launch = the whole batch: Cholesky + solve + logdet for every particle.

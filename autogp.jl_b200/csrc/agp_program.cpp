@@ -40,6 +40,7 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
         const TNode& nd = t[f.id];
         const double* p = params + nd.off;
         AgpInstr in{};
+        in.pad = nd.off;  // where this node's parameters sit in the caller's array (gradient output order)
         if (nd.left < 0) {
             switch (nd.op) {
                 case AGP_OP_CONSTANT: in.op = AGP_I_CONST; in.a = p[0]; break;

@@ -27,7 +27,7 @@ enum AgpDevOp : int32_t {
 
 struct __attribute__((aligned(16))) AgpInstr {
     int32_t op;
-    int32_t pad;
+    int32_t pad;  // index of the node's first parameter in the particle's params[] slice (wire order)
     double a, b, c;
 };
 

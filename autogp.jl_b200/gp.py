@@ -279,6 +279,27 @@ class Engine:
         is resident — the caller then falls back to :meth:`run`."""
         self._check(self._lib.agp_lml_run_append(self._h))
 
+    def lml_grad_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs):
+        """LML and its gradient: returns (lml[P], grads, grad_noise[P], info[P]) where ``grads[p]`` is the
+        gradient with respect to particle p's parameters in ``encode_program(node)[2]`` order."""
+        prog_len, ops, offs, n_params, params, noise = self.pack_batch(nodes, noises)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        P = len(prog_len)
+        lml = np.empty(P, dtype=np.float64)
+        gparams = np.empty(max(int(n_params.sum()), 1), dtype=np.float64)
+        gnoise = np.empty(P, dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_lml_grad_batch(self._h, P, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                                 _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                                 _f64p(lml), _f64p(gparams), _f64p(gnoise), _i32p(info)))
+        self._P = P
+        cuts = np.concatenate([[0], np.cumsum(n_params)])
+        grads = [gparams[cuts[p]:cuts[p + 1]].copy() for p in range(P)]
+        return lml, grads, gnoise, info
+
     # ---- site 3 -------------------------------------------------------------------------
     def predict_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs, ts_pred,
                       noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -137,6 +137,28 @@ int agp_lml_set_prefix(agp_handle* h, int32_t n_prefix);
  * for every particle; otherwise AGP_ERR_STATE and the caller falls back to agp_lml_run. */
 int agp_lml_run_append(agp_handle* h);
 
+/* ---- gradient of site 2 ------------------------------------------------------------------------ */
+
+/* lml_out[p] as agp_lml_batch, plus its gradient with respect to every kernel parameter and the noise:
+ *   grad_params_out  concatenated like `params` (particle p's slice has n_params[p] entries, in the
+ *                    same wire order: Julia fieldnames order per node, nodes in unroll order)
+ *   grad_noise_out[P]
+ * This is what Gen.hmc (src/inference_utils.jl:63-67) and Gen.map_optimize (src/Greedy.jl:95, 370)
+ * obtain from mvnormal's logpdf_grad (cov_deriv = (alpha alpha' - K^{-1}) / 2, with a second Cholesky
+ * and an explicit inverse) followed by ReverseDiff back through eval_cov; here
+ *   dLML/dtheta = 1/2 sum_ik (alpha alpha' - K^{-1})_ik dK_ik/dtheta
+ * comes from ONE identity-augmented factorisation (the rows [I 0] appended below K solve to L^{-T}
+ * and leave -K^{-1} and -alpha behind: a blocked trtri + lauum on the same work queue) and a
+ * reverse-mode walk of the kernel program per covariance entry; no n x n gradient leaves the GPU.
+ * Gradients are with respect to the parameters as passed (amplitudes, lengthscales, ...); the
+ * caller applies the chain rule of Model.transform_param.  info_out[p] != 0: lml and gradients NaN.
+ * Limits: 64 nodes and 64 parameters per kernel.  Replaces the resident batch of the handle. */
+int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                       const int32_t* param_off, const int32_t* n_params, const double* params,
+                       const double* noise, const double* ts, const double* xs, int32_t n,
+                       double* lml_out, double* grad_params_out, double* grad_noise_out,
+                       int32_t* info_out);
+
 /* ---- site 3: predictive distribution ---------------------------------------------------------- */
 
 /* For each particle p: the conditional multivariate normal  X(ts_pred) | X(ts) = xs  of
@@ -171,7 +193,8 @@ int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
  * hold 3 floats. */
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 
-/* The in-order work queue the persistent kernel executes for P particles x nt block columns
+/* (order >= 100: the identity-augmented schedule of agp_lml_grad_batch built on order - 100.)
+ * The in-order work queue the persistent kernel executes for P particles x nt block columns
  * (host-only, no GPU needed): items_out receives up to `cap` items as 8 int32 each
  * {type | half << 8 | store_only << 9, particle, block column k, tile row i, j0, j1, extra_flag,
  * extra_need}, type 0 = DIAG, 1 = POTF2, 2 = PANEL; [j0, j1) = contraction range in block columns; extra_flag

@@ -383,6 +383,69 @@ def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, noise_pred=None) -
     return mu, cc
 
 
+# ----------------------------------------------------------------------------------------
+# Gradient of the LML (what Gen.hmc / map_optimize obtain from mvnormal.logpdf_grad + ReverseDiff
+# through eval_cov: src/inference_utils.jl:63-67, src/Greedy.jl:95, 370).  Two independent routes,
+# neither of which differentiates a kernel analytically:
+#   lml_grad_fd        central differences of log_marginal_likelihood itself
+#   lml_grad_dense_fd  1/2 tr((alpha alpha' - K^-1) dK/dtheta) with dK/dtheta by central differences
+# ----------------------------------------------------------------------------------------
+
+
+def with_params(node: Node, params: np.ndarray) -> Node:
+    """Rebuild `node` with the parameter vector of encode_program(node)[2] replaced by `params`
+    (wire order: nodes in unroll order, Julia fieldnames order per node)."""
+    it = iter(np.asarray(params, dtype=np.float64).tolist())
+
+    def build(nd):
+        if isinstance(nd, LEAVES):
+            vals = {f: next(it) for f in nd.__dataclass_fields__}
+            return type(nd)(**vals)
+        left, right = build(nd.left), build(nd.right)
+        if isinstance(nd, ChangePoint):
+            return ChangePoint(left, right, next(it), next(it))
+        return type(nd)(left, right)
+
+    return build(node)
+
+
+def _stencil5(f, x0: float, hstep: float):
+    """Fourth-order central difference (-f(2h) + 8 f(h) - 8 f(-h) + f(-2h)) / 12h."""
+    return (-f(x0 + 2 * hstep) + 8.0 * f(x0 + hstep) - 8.0 * f(x0 - hstep) + f(x0 - 2 * hstep)) / (12.0 * hstep)
+
+
+def lml_grad_fd(node: Node, noise: float, ts, xs, rel_step: float = 1e-5) -> Tuple[np.ndarray, float]:
+    params = encode_program(node)[2]
+    g = np.zeros_like(params)
+    for j in range(len(params)):
+        def f(v, j=j):
+            q = params.copy()
+            q[j] = v
+            return log_marginal_likelihood(with_params(node, q), noise, ts, xs)
+        g[j] = _stencil5(f, params[j], rel_step * max(abs(params[j]), 1e-3))
+    gn = _stencil5(lambda v: log_marginal_likelihood(node, v, ts, xs), noise, rel_step * max(abs(noise), 1e-3))
+    return g, gn
+
+
+def lml_grad_dense_fd(node: Node, noise: float, ts, xs, rel_step: float = 1e-5) -> Tuple[np.ndarray, float]:
+    ts = np.asarray(ts, dtype=np.float64)
+    xs = np.asarray(xs, dtype=np.float64)
+    K = compute_cov_matrix_vectorized(node, noise, ts)
+    Kinv = np.linalg.inv(K)
+    alpha = Kinv @ xs
+    A = np.outer(alpha, alpha) - Kinv
+    params = encode_program(node)[2]
+    g = np.zeros_like(params)
+    for j in range(len(params)):
+        def f(v, j=j):
+            q = params.copy()
+            q[j] = v
+            return eval_cov(with_params(node, q), ts)
+        dK = _stencil5(f, params[j], rel_step * max(abs(params[j]), 1e-3))
+        g[j] = 0.5 * float(np.sum(A * dK))
+    return g, 0.5 * float(np.trace(A))
+
+
 def mvn_logpdf(x: np.ndarray, mu: np.ndarray, cov: np.ndarray) -> float:
     return mvnormal_logpdf(np.asarray(x) - np.asarray(mu), cov)
 

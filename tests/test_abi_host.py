@@ -129,23 +129,31 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row):
-    """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu): every wait
-    must already be satisfied by EARLIER items, and the items must tile every contraction exactly."""
-    DIAG, POTF2, PANEL, PARTIAL = 0, 1, 2, 1 << 9
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None):
+    """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
+    counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
+    every tile an item reads must be final, and the items must tile every contraction exactly.
+    first_col(i): first block column with a non-zero tile in tile row i (0 except for the rows of
+    the inverse schedule)."""
+    DIAG, POTF2, PANEL, PARTIAL, YINIT = 0, 1, 2, 1 << 9, 1 << 10
+    first_col = first_col or (lambda i: 0)
     nts = nt_total  # the builders lay the counters out for nt_stride = nt_total
     counters = np.zeros(32 + 3 * P * nts + P, dtype=np.int64)
     rowdone = lambda p, i: 32 + p * nts + i
     diagu = lambda p, k: 32 + P * nts + p * nts + k
     ppre = lambda p, i: 32 + 2 * P * nts + p * nts + i
     fdone = lambda p: 32 + 3 * P * nts + p
+    final = {}      # (p, row, col) -> finished halves of the solved panel L[row][col]
     for p in range(P):  # continuation: rows above first_row are final, first_row diagonal tiles factored
         for i in range(first_row):
             counters[rowdone(p, i)] = 2 * i
+            for j in range(i):
+                final[(p, i, j)] = 2
         counters[fdone(p)] = first_row
     covered, n_diag, stored = {}, {}, set()
-    for x, p, k, i, j0, j1, flag, need in buf.tolist():
-        t, h, partial = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL)
+    for x, p, k, i, f4, f5, flag, need in buf.tolist():
+        t, h, partial, yinit = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL), bool(x & YINIT)
+        j0, j1, need_k, need_i = f4 & 0xFFFF, f4 >> 16, f5 & 0xFFFF, f5 >> 16
         assert 0 <= p < P and 0 <= k < nt_total
         if t == POTF2:
             assert k < nt and counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
@@ -154,15 +162,17 @@ def _replay_queue(buf, P, nt, nt_total, first_row):
             continue
         assert (t == DIAG and i == k) or (t == PANEL and k < i < nt_total)
         assert i >= first_row and 0 <= j0 <= j1 <= min(k, nt)
-        assert covered.get((p, i, k, h), 0) == j0, "contraction ranges must be contiguous"
+        start = max(first_col(i), first_col(k)) if j1 > 0 else 0
+        assert covered.get((p, i, k, h), min(start, j1)) == j0, "contraction ranges must be contiguous"
         covered[(p, i, k, h)] = j1
-        if j1 > 0:
-            assert counters[rowdone(p, k)] >= 2 * j1
-            if t == PANEL:
-                assert counters[rowdone(p, i)] >= 2 * j1
-            if flag >= 0:
-                assert flag == (diagu(p, k) if t == DIAG else ppre(p, i)) and counters[flag] >= need
-        assert (flag >= 0) == (j0 > 0)
+        # the kernel's waits
+        assert counters[rowdone(p, k)] >= need_k and (t == DIAG or counters[rowdone(p, i)] >= need_i)
+        if flag >= 0:
+            assert flag == (diagu(p, k) if t == DIAG else ppre(p, i)) and counters[flag] >= need
+        assert (flag >= 0) == (j0 > start)
+        # what it reads is final
+        for j in range(j0, j1):
+            assert final.get((p, k, j), 0) == 2 and final.get((p, i, j), 0) == 2, (t, p, k, i, j)
         if t == DIAG:
             counters[diagu(p, k)] += 1
             n_diag[(p, k)] = n_diag.get((p, k), 0) + 1
@@ -174,18 +184,20 @@ def _replay_queue(buf, P, nt, nt_total, first_row):
                 stored.add((p, i, k, h))
         else:
             assert k < nt and j1 == k
+            assert yinit == (k == first_col(i)), "the first panel of a tile row starts the forward-solve entry"
             assert counters[fdone(p)] >= k + 1      # L_kk ready for the triangular solve
             counters[rowdone(p, i)] += 1
+            final[(p, i, k)] = final.get((p, i, k), 0) + 1
     for p in range(P):
         assert counters[fdone(p)] == nt
         for i in range(first_row, nt_total):
-            assert counters[rowdone(p, i)] == 2 * min(i, nt)
-            for k in range(i + 1):
+            assert counters[rowdone(p, i)] == 2 * (min(i, nt) - first_col(i))
+            for k in range(first_col(i), i + 1):
                 for h in (0, 1):
                     if k < nt:
-                        assert covered[(p, i, k, h)] == k         # finished: contraction over all of [0, k)
-                    else:
-                        assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # Schur complement tile
+                        assert covered[(p, i, k, h)] == k         # finished: contraction over all of [first, k)
+                    elif first_col(k) <= first_col(i):
+                        assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # trailing (Schur complement) tile
 
 
 @pytest.mark.parametrize("order", [0, 1, 2])
@@ -216,3 +228,16 @@ def test_continuation_queues_replay(P, nt, nt_total, first_row):
     buf = np.zeros((n_items, 8), dtype=np.int32)
     lib.agp_queue_build_general(P, nt, nt_total, first_row, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
     _replay_queue(buf, P, nt, nt_total, first_row)
+
+
+@pytest.mark.parametrize("P,nt,order", [(1, 1, 2), (2, 3, 0), (2, 5, 2), (1, 9, 2)])
+def test_inverse_schedule_replay(P, nt, order):
+    """Identity-augmented factorisation of agp_lml_grad_batch: tile row nt + a solves to block row a of
+    L^{-T} (non-zero from block column a on), the trailing tiles receive -K^{-1}."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build(P, nt, 100 + order, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    lib.agp_queue_build(P, nt, 100 + order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
+    _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0)

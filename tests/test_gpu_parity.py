@@ -453,3 +453,87 @@ def test_predictive_not_positive_definite_raises(engine):
     ts, xs = o.synthetic_series(150)
     with pytest.raises(agp.PosDefException):
         agp.predictive_mvn(agp.Constant(1.0), -2.0, ts, xs, np.linspace(0, 1, 5), engine=engine)
+
+
+# ---- §8 f-1: gradient of the LML ---------------------------------------------------------------------
+
+GRAD_RTOL = 2e-6   # finite-difference oracle: truncation + round-off of central differences, not the GPU path
+
+
+def _grad_close(got, ref, rtol=GRAD_RTOL):
+    got, ref = np.asarray(got), np.asarray(ref)
+    return np.all(np.abs(got - ref) <= rtol * np.maximum(1.0, np.abs(ref)) + rtol * np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("n", [1, 37, 128, 200, 300])
+def test_lml_gradient_matches_finite_difference_oracle(engine, n):
+    """agp_lml_grad_batch against two CPU routes that never differentiate a kernel analytically
+    (central differences of the oracle LML; 1/2 tr((aa' - K^-1) dK) with dK by central differences),
+    on a ragged batch covering every leaf type and operator."""
+    ts, xs = o.synthetic_series(max(n, 2))
+    ts, xs = ts[:n], xs[:n]
+    trees = ["se*per+lin", "se+wn", "ge+per*lin", "cp(lin,se)"]
+    parts = [o.synthetic_particle(20 + p, t) for p, t in enumerate(trees)]
+    parts.append((o.Plus(o.Times(o.Constant(0.7), o.GammaExponential(0.3, 1.4, 0.8)),
+                         o.ChangePoint(o.Periodic(0.5, 0.3, 1.2), o.Linear(0.2, 0.4, 0.9), 0.45, 0.08)), 0.05))
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    lml, grads, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0)
+    assert H.rel_err(lml, oracle_lmls(parts, ts, xs)) <= LML_RTOL_TIGHT
+    for p, (nd, nz) in enumerate(parts):
+        g_fd, gn_fd = o.lml_grad_fd(nd, nz, ts, xs)
+        g_dn, gn_dn = o.lml_grad_dense_fd(nd, nz, ts, xs)
+        assert len(grads[p]) == len(g_fd)
+        assert _grad_close(grads[p], g_dn), (p, grads[p], g_dn)
+        assert _grad_close(grads[p], g_fd, 2e-5), (p, grads[p], g_fd)
+        assert abs(gnoise[p] - gn_dn) <= 1e-8 * max(1.0, abs(gn_dn)), (p, gnoise[p], gn_dn)
+        assert abs(gnoise[p] - gn_fd) <= 2e-5 * max(1.0, abs(gn_fd))
+
+
+def test_lml_gradient_full_size_directional_derivative(engine):
+    """n = 2048 (BASELINE.json configs[1] tree): the gradient must predict the change of the GPU LML
+    itself along a random direction in parameter space; bitwise reproducible."""
+    import autogp.jl_b200 as agp
+
+    n, P = 2048, 4
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(P)]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    lml, grads, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0)
+    again = engine.lml_grad_batch(nodes, noises, ts, xs)
+    assert all(np.array_equal(a, b) for a, b in zip(grads, again[1])) and np.array_equal(gnoise, again[2])
+    rng = np.random.default_rng(9)
+    for p, (nd, nz) in enumerate(parts):
+        params = o.encode_program(nd)[2]
+        d = rng.normal(size=params.size) * np.abs(params)
+        dn = rng.normal() * nz
+        hstep = 1e-6
+        up = H.to_agp(o.with_params(nd, params + hstep * d))
+        dnn = H.to_agp(o.with_params(nd, params - hstep * d))
+        f_up, _ = engine.lml_batch([up], [nz + hstep * dn], ts, xs)
+        f_dn, _ = engine.lml_batch([dnn], [nz - hstep * dn], ts, xs)
+        fd = (f_up[0] - f_dn[0]) / (2 * hstep)
+        an = float(np.dot(grads[p], d) + gnoise[p] * dn)
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (p, fd, an)
+    assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
+
+
+def test_lml_gradient_edge_cases(engine):
+    import autogp.jl_b200 as agp
+    from autogp.jl_b200 import _lib
+
+    ts, xs = o.synthetic_series(150)
+    # empty data: score 0, zero gradient
+    lml, grads, gnoise, info = engine.lml_grad_batch([agp.SquaredExponential(0.3, 1.0)], [0.1], ts[:0], xs[:0])
+    assert lml[0] == 0.0 and np.all(grads[0] == 0.0) and gnoise[0] == 0.0 and info[0] == 0
+    # not positive definite: NaN gradient, LAPACK info
+    lml, grads, gnoise, info = engine.lml_grad_batch([agp.Constant(1.0), agp.SquaredExponential(0.3, 1.0)], [-2.0, 0.1], ts, xs)
+    assert info[0] != 0 and np.isnan(lml[0]) and np.all(np.isnan(grads[0])) and np.isnan(gnoise[0])
+    assert info[1] == 0 and np.all(np.isfinite(grads[1]))
+    # too many parameters for the gradient path is an error, not a crash
+    big = agp.Constant(1.0)
+    for _ in range(70):
+        big = agp.Plus(big, agp.Constant(0.5))
+    with pytest.raises(_lib.AgpError):
+        engine.lml_grad_batch([big], [0.1], ts, xs)

@@ -7,8 +7,8 @@ from .gp import (  # noqa: F401
     depth, encode_program, eval_cov, predictive_mvn, size, unroll,
 )
 from .model import (  # noqa: F401
-    JITTER, PosDefException, log_marginal_likelihoods, log_marginal_likelihoods_info, mvnormal_logpdf,
-    transform_param, untransform_param,
+    JITTER, PosDefException, log_marginal_likelihood_grads, log_marginal_likelihoods, log_marginal_likelihoods_info,
+    mvnormal_logpdf, transform_param, transform_param_grad, untransform_param,
 )
 from . import smc  # noqa: F401
 

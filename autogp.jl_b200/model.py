@@ -72,6 +72,31 @@ def untransform_param(field: str, param: float, prior=PRIOR) -> float:
     return untransform_log_normal(param, p["mu"], p["sigma"])
 
 
+def transform_param_grad(field: str, z: float, prior=PRIOR) -> float:
+    """d transform_param(field, z) / dz — the chain-rule factor that takes the gradient with respect to
+    a kernel parameter (agp_lml_grad_batch) to the gradient with respect to the latent z that
+    ``Gen.hmc`` / ``Gen.map_optimize`` move (src/inference_utils.jl:63-67, src/Greedy.jl:95)."""
+    if field == "gamma":
+        p = prior["gamma"]
+        s = 1.0 / (1.0 + math.exp(-(p["mu"] + p["sigma"] * z)))
+        return p["scale"] * s * (1.0 - s) * p["sigma"]
+    p = prior["period"] if field == "period" else prior["wildcard"]
+    return transform_log_normal(z, p["mu"], p["sigma"]) * p["sigma"]
+
+
+def log_marginal_likelihood_grads(nodes: Sequence[gp.Node], noises: Sequence[float], ts, xs, *,
+                                  engine: Optional[gp.Engine] = None, check: bool = True):
+    """Scores and gradients of every particle in one fused GPU call: (lml[P], grads, grad_noise[P]) with
+    ``grads[p]`` in the order of ``gp.encode_program(nodes[p])[2]`` — the ``logpdf_grad`` of the custom Gen
+    distribution sketched in INTEGRATION.md (``has_argument_grads`` true for params and noise)."""
+    lml, grads, gnoise, info = (engine or gp.default_engine()).lml_grad_batch(nodes, noises, ts, xs)
+    if check:
+        bad = np.nonzero(info)[0]
+        if bad.size:
+            raise PosDefException(int(info[bad[0]]), int(bad[0]))
+    return lml, grads, gnoise
+
+
 def log_marginal_likelihoods(nodes: Sequence[gp.Node], noises: Sequence[float], ts, xs, *,
                              engine: Optional[gp.Engine] = None, check: bool = True) -> np.ndarray:
     """Scores ``xs ~ mvnormal(0, K_p + noise_p I)`` for every particle p in one fused GPU call.

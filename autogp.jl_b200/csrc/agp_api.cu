@@ -52,21 +52,7 @@ struct agp_handle {
     unsigned char* h_gin = nullptr;  size_t cap_hgin = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
-    // particle groups: independent chains of (update, potf2, trsm) launches on side streams so
-    // that one group's latency-bound diagonal factorisation overlaps another group's GEMMs
-    static constexpr int kMaxGroups = 8;
-    int groups = 0;  // 0 = choose from P
-    cudaStream_t gstream[kMaxGroups] = {};
-    cudaEvent_t gfork = nullptr, gjoin[kMaxGroups] = {};
-    // cached CUDA graph of one full run
-    cudaGraphExec_t graph_exec = nullptr;
-    BatchView graph_view{};
-    int graph_P = -1, graph_groups = -1;
-    int64_t graph_kernels = 0;
-    bool use_graph = true;
-
-    // persistent dataflow path (default): work queues per (P, nt) shape + dependency counters
-    bool staged = false;  // AGP_PATH=staged selects the one-launch-per-stage path (A/B measurements)
+    // persistent dataflow kernel: work queues per batch shape + dependency counters
     int order = 2;        // queue order variant (AGP_ORDER)
     int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
     unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
@@ -156,25 +142,13 @@ int agp_create(int device, agp_handle** out) {
     agp_handle* h = new agp_handle();
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_kernels() != cudaSuccess || agp::configure_fused() != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_fused() != cudaSuccess ||
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&h->h_sync), 2 * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         delete h;
         return AGP_ERR_CUDA;
     }
-    bool ok = cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming) == cudaSuccess;
-    for (int g = 0; ok && g < agp_handle::kMaxGroups; ++g)
-        ok = cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->gjoin[g], cudaEventDisableTiming) == cudaSuccess;
-    if (!ok) {
-        cudaGetLastError();
-        agp_destroy(h);
-        return AGP_ERR_CUDA;
-    }
-    if (const char* e = getenv("AGP_GROUPS")) h->groups = atoi(e);
-    if (const char* e = getenv("AGP_GRAPH")) h->use_graph = atoi(e) != 0;
-    if (const char* e = getenv("AGP_PATH")) h->staged = strcmp(e, "staged") == 0;
     if (const char* e = getenv("AGP_ORDER")) h->order = atoi(e);
     if (const char* e = getenv("AGP_WAIT_TIMEOUT_MS")) h->wait_timeout_ns = 1000000ull * (unsigned long long)atoll(e);
     if (const char* e = getenv("AGP_CTAS_PER_SM")) h->ctas_per_sm = atoi(e) >= 1 ? atoi(e) : 1;
@@ -202,12 +176,6 @@ void agp_destroy(agp_handle* h) {
     cudaFreeHost(h->h_res);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-    if (h->gfork) cudaEventDestroy(h->gfork);
-    for (int g = 0; g < agp_handle::kMaxGroups; ++g) {
-        if (h->gjoin[g]) cudaEventDestroy(h->gjoin[g]);
-        if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
-    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -332,14 +300,12 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     int rc;
     if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
     if ((rc = grow_device(h, &h->d_in, &h->cap_in, in_bytes)) != AGP_OK) return rc;
-    // work arena: y[P][ld] z[P][ld] logdet[P] zz[P] cum[P][ld/128][2] dinv[P][ld/128][4096] (one set of
-    // diagonal-block inverses per block column: the persistent kernel factors column k+1 while
-    // column k is still being solved)
+    // work arena: y[P][ld] z[P][ld] cum[P][ld/128][2] dinv[P][ld/128][4096] (one set of diagonal-block
+    // inverses per block column: the persistent kernel factors column k+1 while column k is still
+    // being solved)
     size_t off_y = 0;
     size_t off_z = off_y + (size_t)P * ld * 8;
-    size_t off_ld = off_z + (size_t)P * ld * 8;
-    size_t off_zz = off_ld + (size_t)P * 8;
-    size_t off_cum = off_zz + (size_t)P * 8;
+    size_t off_cum = off_z + (size_t)P * ld * 8;
     size_t off_dinv = align_up(off_cum + (size_t)P * (ld / TB) * 2 * 8, 256);
     size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * 4096 * 8;
     if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
@@ -387,8 +353,6 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     v.prog = reinterpret_cast<const AgpInstr*>(h->d_in + off_instr);
     v.y = reinterpret_cast<double*>(h->d_work + off_y);
     v.z = reinterpret_cast<double*>(h->d_work + off_z);
-    v.logdet_half = reinterpret_cast<double*>(h->d_work + off_ld);
-    v.zz = reinterpret_cast<double*>(h->d_work + off_zz);
     v.aug_identity = aug_identity ? 1 : 0;
     h->aug_identity = aug_identity;
     h->d_param_prefix = reinterpret_cast<const int*>(h->d_in + off_pprefix);
@@ -646,46 +610,8 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     return check_launch(h, "chol");
 }
 
-static int pick_groups(const agp_handle* h) {
-    int g = h->groups;
-    if (g <= 0) g = h->P >= 32 ? 4 : (h->P >= 8 ? 2 : 1);
-    if (g > agp_handle::kMaxGroups) g = agp_handle::kMaxGroups;
-    if (g > h->P) g = h->P;
-    return g < 1 ? 1 : g;
-}
-
-// Enqueue one full factorisation sweep for particles [p0, p0+Pg) on stream s.
-static void enqueue_chain(const BatchView& view, int p0, int Pg, cudaStream_t s, int64_t* kernels) {
-    BatchView v = view;
-    v.p0 = p0;
-    for (int k = 0; k < v.nt; ++k) {
-        agp::launch_update(v, Pg, k, s);
-        agp::launch_potf2(v, Pg, k, s);
-        agp::launch_trsm(v, Pg, k, s);
-        *kernels += (k < v.nt - 1) ? 3 : 2;
-    }
-}
-
-// Fork the particle groups onto the side streams and join them back into the main stream.
-static int enqueue_groups(agp_handle* h, int G, int64_t* kernels) {
-    const int P = h->P;
-    if (G == 1) {
-        enqueue_chain(h->view, 0, P, h->stream, kernels);
-        return AGP_OK;
-    }
-    AGP_CUDA(h, cudaEventRecord(h->gfork, h->stream));
-    for (int g = 0; g < G; ++g) {
-        int lo = (int)((long long)P * g / G), hi = (int)((long long)P * (g + 1) / G);
-        AGP_CUDA(h, cudaStreamWaitEvent(h->gstream[g], h->gfork, 0));
-        enqueue_chain(h->view, lo, hi - lo, h->gstream[g], kernels);
-        AGP_CUDA(h, cudaEventRecord(h->gjoin[g], h->gstream[g]));
-        AGP_CUDA(h, cudaStreamWaitEvent(h->stream, h->gjoin[g], 0));
-    }
-    return AGP_OK;
-}
-
-static int run_impl(agp_handle* h, float* stage_ms) {
-    BatchView& v = h->view;
+static int run_impl(agp_handle* h, float* kernel_ms) {
+    const BatchView& v = h->view;
     const int P = h->P;
     if (P == 0) return AGP_OK;
     if (v.n == 0) {
@@ -694,66 +620,7 @@ static int run_impl(agp_handle* h, float* stage_ms) {
         AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, res_bytes, h->stream));
         return AGP_OK;
     }
-    v.p0 = 0;
-    if (!h->staged) return run_fused(h, nullptr, stage_ms);
-    if (stage_ms) {
-        // serialised, one stream, events around every launch
-        for (int k = 0; k < v.nt; ++k) {
-            for (int st = 0; st < 3; ++st) {
-                if (st == 2 && k == v.nt - 1) break;
-                AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-                if (st == 0) agp::launch_update(v, P, k, h->stream);
-                else if (st == 1) agp::launch_potf2(v, P, k, h->stream);
-                else agp::launch_trsm(v, P, k, h->stream);
-                float ms;
-                AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-                AGP_CUDA(h, cudaEventSynchronize(h->ev1));
-                AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-                stage_ms[st] += ms;
-                h->launches += 1;
-            }
-        }
-        return check_launch(h, "lml");
-    }
-    const int G = pick_groups(h);
-    if (!h->use_graph) {
-        int64_t kernels = 0;
-        int rc = enqueue_groups(h, G, &kernels);
-        if (rc != AGP_OK) return rc;
-        h->launches += kernels;
-        return check_launch(h, "lml");
-    }
-    const bool cached = h->graph_exec && h->graph_P == P && h->graph_groups == G && memcmp(&h->graph_view, &v, sizeof(BatchView)) == 0;
-    if (!cached) {
-        if (h->graph_exec) {
-            AGP_CUDA(h, cudaStreamSynchronize(h->stream));
-            cudaGraphExecDestroy(h->graph_exec);
-            h->graph_exec = nullptr;
-        }
-        cudaGraph_t graph = nullptr;
-        int64_t kernels = 0;
-        AGP_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_groups(h, G, &kernels);
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-        if (rc != AGP_OK) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        if (e != cudaSuccess) return fail(h, AGP_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) {
-            h->graph_exec = nullptr;
-            return fail(h, AGP_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
-        }
-        h->graph_view = v;
-        h->graph_P = P;
-        h->graph_groups = G;
-        h->graph_kernels = kernels;
-    }
-    AGP_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-    h->launches += h->graph_kernels;
-    return AGP_OK;
+    return run_fused(h, nullptr, kernel_ms);
 }
 
 int agp_lml_run(agp_handle* h) {
@@ -818,7 +685,6 @@ int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev) 
 int agp_lml_run_append(agp_handle* h) {
     if (!h) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no resident batch");
-    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: not available with AGP_PATH=staged");
     if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_run_append: the resident batch carries appended rows");
     if (h->n_factored < 0 || !h->factor_clean)
         return fail(h, AGP_ERR_STATE, "agp_lml_run_append: no clean factor resident (run + fetch with info == 0 for every particle first)");
@@ -835,7 +701,6 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
                       const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred,
                       int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out) {
     if (!h) return AGP_ERR_ARG;
-    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_predict_batch: not available with AGP_PATH=staged");
     if (m < 0 || (P > 0 && m > 0 && (!mean_out || !cov_out)) || (P > 0 && !info_out)) return fail(h, AGP_ERR_ARG, "agp_predict_batch: bad argument");
     int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, ts_pred, m, noise_pred);
     if (rc != AGP_OK) return rc;
@@ -865,7 +730,6 @@ int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const 
                        const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
                        double* grad_params_out, double* grad_noise_out, int32_t* info_out) {
     if (!h) return AGP_ERR_ARG;
-    if (h->staged) return fail(h, AGP_ERR_STATE, "agp_lml_grad_batch: not available with AGP_PATH=staged");
     if (P > 0 && (!lml_out || !grad_noise_out || !info_out || !prog_len || !n_params)) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: bad argument");
     size_t total_params = 0;
     for (int p = 0; p < P; ++p) {

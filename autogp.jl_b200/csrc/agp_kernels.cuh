@@ -24,13 +24,10 @@ struct BatchView {
     const int* prog_off;     // [P+1]
     const int* prog_need;    // [P] register-stack depth
     const double* noise;     // [P]
-    double* logdet_half;     // [P] sum log L_ii
-    double* zz;              // [P] sum z_i^2
     double* lml;             // [P]
     int* info;               // [P]
     double* dinv;            // [P][ld/128][4][32][32] inverses of the diagonal 32x32 blocks of every L_kk
-    int p0;                  // first particle of this launch (particle groups run on separate streams)
-    // persistent path: rows beyond the factored block (prediction points appended at a tile
+    // rows beyond the factored block (prediction points appended at a tile
     // boundary, see agp_predict_batch) and per-block-column running sums (so a factorisation can be
     // continued from any block column, see agp_lml_run_append)
     int nt_total;            // tile rows in the matrix: nt + ceil(n_pred / TB)
@@ -80,17 +77,8 @@ void launch_predict_extract(const BatchView& v, int P, const double* noise_pred,
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s);
 cudaError_t configure_fused();
 
-// ---- staged path (one launch per stage and block column; kept for A/B measurements) ----------
-// Left-looking block column k:  tiles (i,k), i>=k  <-  K(ts_i, ts_k) - sum_{j<k} L_ij L_kj^T
-void launch_update(const BatchView& v, int P, int k, cudaStream_t s);
-// Diagonal tile: Cholesky, z_k, logdet, info, 32x32 diagonal-block inverses; last column writes lml
-void launch_potf2(const BatchView& v, int P, int k, cudaStream_t s);
-// Panel below the diagonal: L_ik = C_ik L_kk^{-T};  y_i -= L_ik z_k
-void launch_trsm(const BatchView& v, int P, int k, cudaStream_t s);
 // Stand-alone Gram matrix (drop-in for compute_cov_matrix[_vectorized]): column-major, both triangles
 void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n, double noise, int form,
                  double* K, cudaStream_t s);
-// one-time: opt in to >48 KB dynamic shared memory
-cudaError_t configure_kernels();
 
 }  // namespace agp

@@ -283,7 +283,6 @@ def main():
     # followed by ONE launch of agp_chol_kernel (persistent dataflow kernel: FP64 DMMA contraction,
     # diagonal Cholesky, panel solves, forward solve, log det), which dominates.  Algorithmic work of
     # that launch = P * n^3 / 3 flops.
-    staged = os.environ.get("AGP_PATH", "") == "staged"
     gram_ms, chol_ms = [], []
     for _ in range(7):
         a, b, _c = eng.stage_times()
@@ -303,8 +302,7 @@ def main():
     n_entries = P * (n * (n + 1) / 2.0)
     roofline = {
         "bound": "tensor",
-        "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)" if not staged
-                  else "staged path: update launches of one step",
+        "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)",
         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
         "traffic": traffic,
         "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "

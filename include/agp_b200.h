@@ -188,8 +188,7 @@ int64_t agp_launch_count(const agp_handle* h);
  * returns total milliseconds in *ms_out. */
 int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
 /* Per-kernel device time of ONE run (ms), CUDA events on the handle's stream around each launch:
- * {agp_gramfill_kernel, agp_chol_kernel, 0} — for the roofline line in bench.py.  (With
- * AGP_PATH=staged: the serialised sums of the update / potf2 / trsm launches.)  stage_ms must
+ * {agp_gramfill_kernel, agp_chol_kernel, 0} — for the roofline line in bench.py.  stage_ms must
  * hold 3 floats. */
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 

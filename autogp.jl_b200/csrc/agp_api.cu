@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <tuple>
@@ -351,6 +352,8 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     v.prog_off = reinterpret_cast<const int*>(h->d_in + off_poff);
     v.prog_need = reinterpret_cast<const int*>(h->d_in + off_need);
     v.prog = reinterpret_cast<const AgpInstr*>(h->d_in + off_instr);
+    v.max_prog_len = 0;
+    for (int p = 0; p < P; ++p) v.max_prog_len = std::max(v.max_prog_len, (int)(poff[p + 1] - poff[p]));
     v.y = reinterpret_cast<double*>(h->d_work + off_y);
     v.z = reinterpret_cast<double*>(h->d_work + off_z);
     v.aug_identity = aug_identity ? 1 : 0;

@@ -5,24 +5,36 @@
 // 481-483, 493-503; scalar forms :135-491).  This translation unit is compiled with
 // -fmad=false so no multiply-add is contracted: every +,* rounds once, as in Julia where each
 // broadcast statement materialises.  Remaining differences to the CPU path come only from the
-// exp/sin/pow/tanh implementations (CUDA libdevice vs openlibm).
+// exp/sin/pow/tanh implementations (agp_math.cuh / CUDA libdevice vs openlibm); divisions by a node
+// constant are correctly rounded (agp_math.cuh: div_const_v), i.e. identical to Julia's `/`.
 //
 // The operand stack lives in D registers (shift on push/pop) — D = 4 covers every tree with
 // fewer than 16 leaves, D = 8 the rest (host guarantees need <= AGP_MAX_STACK).
 #pragma once
+#include "agp_math.cuh"
 #include "agp_program.h"
 
 namespace agp {
 
+// sigma(t) = 0.5 (1 + tanh((location - t) / scale)), src/GP.jl:481-483, for E points at once
+template <int E>
+__device__ __forceinline__ void sigma_cp_v(const double (&t)[E], double location, double scale, double rscale, bool fast, double (&g)[E]) {
+    double u[E], q[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) u[e] = location - t[e];
+    div_const_v<E>(u, scale, rscale, fast, q);
+#pragma unroll
+    for (int e = 0; e < E; ++e) g[e] = 0.5 * (1.0 + slow_tanh(q[e]));
+}
 
 __device__ __forceinline__ double sigma_cp(double x, double location, double scale) {
-    // src/GP.jl:481-483
+    // src/GP.jl:481-483 (scalar twin, used by the gradient interpreter)
     return 0.5 * (1.0 + tanh((location - x) / scale));
 }
 
-// E independent entries are evaluated per interpreter pass (instruction-level parallelism hides
-// the latency of the FP64 transcendental chains and amortises the dispatch); the stack holds
-// E values per level.
+// E independent entries are evaluated per interpreter pass in lock-step (agp_math.cuh): the
+// instruction-level parallelism hides the latency of the FP64 chains and amortises the dispatch;
+// the stack holds E values per level.
 template <int D, int E>
 struct RegStack {
     double s[D][E];
@@ -55,14 +67,18 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int e = 0; e < E; ++e) st.s[i][e] = 0.0;
-    double dx[E], adx[E];
+    double dx[E];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        dx[e] = t1[e] - t2[e];
-        adx[e] = fabs(dx[e]);
-    }
+    for (int e = 0; e < E; ++e) dx[e] = t1[e] - t2[e];
+#pragma unroll 1
     for (int q = 0; q < m; ++q) {
-        const int op = prog[q].op;
+        // keep the per-leaf expressions of dx inside their switch case: hoisted out of the loop they
+        // would all stay live across every other node (registers), for programs that may not use them
+#pragma unroll
+        for (int e = 0; e < E; ++e) asm volatile("" : "+d"(dx[e]));
+        const int opw = prog[q].op;
+        const int op = opw & 0xff;
+        const bool fast = (opw & AGP_I_FASTDIV) != 0;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
         double v[E];
         switch (op) {
@@ -79,24 +95,43 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 }
                 st.push(v);
                 break;
-            case AGP_I_SE:  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245
+            case AGP_I_SE: {  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245; c = 1 / l^2
+                double w[E], u[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = b * exp(((-0.5 * dx[e]) * dx[e]) / a);
+                for (int e = 0; e < E; ++e) w[e] = (-0.5 * dx[e]) * dx[e];
+                div_const_v<E>(w, a, c, fast, u);
+                exp_v<E>(u, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b * v[e];
                 st.push(v);
                 break;
-            case AGP_I_GE:
+            }
+            case AGP_I_GE: {  // amp * exp(-(|dx| / l)^gamma), src/GP.jl:285-289; d = 1 / l
+                double w[E], u[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = c * exp(-pow(adx[e] / a, b));
+                for (int e = 0; e < E; ++e) w[e] = fabs(dx[e]);
+                div_const_v<E>(w, a, prog[q].d, fast, u);
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = -slow_pow(u[e], b);
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * v[e];
                 st.push(v);
                 break;
-            case AGP_I_PER:  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
+            }
+            case AGP_I_PER: {  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
+                double w[E], u[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    double sn = sin(a * adx[e]);
-                    v[e] = c * exp(b * (sn * sn));
-                }
+                for (int e = 0; e < E; ++e) w[e] = a * fabs(dx[e]);
+                sin2_v<E>(w, u);
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = b * u[e];
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * v[e];
                 st.push(v);
                 break;
+            }
             case AGP_I_WN:
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
@@ -112,19 +147,20 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                 for (int e = 0; e < E; ++e) v[e] = st.s[1][e] * st.s[0][e];
                 st.reduce(v);
                 break;
-            default: {  // AGP_I_CP / AGP_I_CP_SWAP
+            default: {  // AGP_I_CP / AGP_I_CP_SWAP; c = 1 / scale
+                double g1[E], g2[E];
+                sigma_cp_v<E>(t1, a, b, c, fast, g1);
+                sigma_cp_v<E>(t2, a, b, c, fast, g2);
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     double kl = (op == AGP_I_CP) ? st.s[1][e] : st.s[0][e];
                     double kr = (op == AGP_I_CP) ? st.s[0][e] : st.s[1][e];
-                    double g1 = sigma_cp(t1[e], a, b);
-                    double g2 = sigma_cp(t2[e], a, b);
                     if (form == 0) {  // vectorised: sig_1 .* k_1 + sig_2 .* k_2   (GP.jl:494-501)
-                        double sig1 = g1 * g2;
-                        double sig2 = (1.0 - g1) * (1.0 - g2);
+                        double sig1 = g1[e] * g2[e];
+                        double sig2 = (1.0 - g1[e]) * (1.0 - g2[e]);
                         v[e] = sig1 * kl + sig2 * kr;
                     } else {  // scalar: s1*k_l*s2 + (1-s1)*k_r*(1-s2)            (GP.jl:485-491)
-                        v[e] = (g1 * kl) * g2 + ((1.0 - g1) * kr) * (1.0 - g2);
+                        v[e] = (g1[e] * kl) * g2[e] + ((1.0 - g1[e]) * kr) * (1.0 - g2[e]);
                     }
                 }
                 st.reduce(v);
@@ -136,28 +172,33 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     for (int e = 0; e < E; ++e) out[e] = st.s[0][e];
 }
 
-// Eight entries at once for shallow programs (register stack of 2 covers e.g. Plus(Times(SE,
-// Periodic),Linear) after Sethi-Ullman ordering): twice the independent FP64 chains per thread
-// for the latency-bound epilogue of the persistent kernel.  Deeper programs run as 2 x 4 or 4 x 2.
-__device__ __forceinline__ void eval_entries8(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[8], const double (&t2)[8],
-                                              int form, double (&out)[8]) {
+// Deep trees (stack depth > 4): two entries at a time, out of line (one copy of the big-stack interpreter).
+static __device__ __noinline__ void eval_pair_deep(const AgpInstr* __restrict__ prog, int m, double t1a, double t1b, double t2a, double t2b, int form,
+                                            double* o0, double* o1) {
+    const double a1[2] = {t1a, t1b}, a2[2] = {t2a, t2b};
+    double o2[2];
+    eval_program<AGP_MAX_STACK, 2>(prog, m, a1, a2, form, o2);
+    *o0 = o2[0];
+    *o1 = o2[1];
+}
+
+// E entries at once (E even).  Shallow programs (register stack of 2 covers e.g.
+// Plus(Times(SE,Periodic),Linear) after Sethi-Ullman ordering) and programs up to stack depth 4 run
+// E-wide; deeper trees fall back to pairs to bound register use.
+template <int E>
+__device__ __forceinline__ void eval_entries(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E], const double (&t2)[E],
+                                             int form, double (&out)[E]) {
     if (need <= 2) {
-        eval_program<2, 8>(prog, m, t1, t2, form, out);
+        eval_program<2, E>(prog, m, t1, t2, form, out);
     } else if (need <= 4) {
-#pragma unroll
-        for (int h = 0; h < 8; h += 4) {
-            double a1[4] = {t1[h], t1[h + 1], t1[h + 2], t1[h + 3]}, a2[4] = {t2[h], t2[h + 1], t2[h + 2], t2[h + 3]}, o4[4];
-            eval_program<4, 4>(prog, m, a1, a2, form, o4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) out[h + e] = o4[e];
-        }
+        eval_program<4, E>(prog, m, t1, t2, form, out);
     } else {
-#pragma unroll 1
-        for (int h = 0; h < 8; h += 2) {
-            double a1[2] = {t1[h], t1[h + 1]}, a2[2] = {t2[h], t2[h + 1]}, o2[2];
-            eval_program<AGP_MAX_STACK, 2>(prog, m, a1, a2, form, o2);
-            out[h] = o2[0];
-            out[h + 1] = o2[1];
+#pragma unroll
+        for (int h = 0; h < E; h += 2) {
+            double o0, o1;
+            eval_pair_deep(prog, m, t1[h], t1[h + 1], t2[h], t2[h + 1], form, &o0, &o1);
+            out[h] = o0;
+            out[h + 1] = o1;
         }
     }
 }
@@ -180,7 +221,7 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
     int sp = 0;
     const double dx = t1 - t2, adx = fabs(dx);
     for (int q = 0; q < m; ++q) {
-        const int op = prog[q].op;
+        const int op = prog[q].op & 0xff;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
         adj[q] = 0.0;
         if (op <= AGP_I_WN) {
@@ -214,7 +255,7 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
     adj[m - 1] = seed;
     for (int q = m - 1; q >= 0; --q) {
         const double g = adj[q];
-        const int op = prog[q].op, off = prog[q].pad;
+        const int op = prog[q].op & 0xff, off = prog[q].pad;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
         switch (op) {
             case AGP_I_CONST: acc(off, g); break;
@@ -275,23 +316,6 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
         }
     }
     return val[m - 1];
-}
-
-// E entries at once; deep trees (need > 4) fall back to pairs to bound register use.
-template <int E>
-__device__ __forceinline__ void eval_entries(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E], const double (&t2)[E],
-                                             int form, double (&out)[E]) {
-    if (need <= 4) {
-        eval_program<4, E>(prog, m, t1, t2, form, out);
-    } else {
-#pragma unroll
-        for (int h = 0; h < E; h += 2) {
-            double a1[2] = {t1[h], t1[h + 1]}, a2[2] = {t2[h], t2[h + 1]}, o2[2];
-            eval_program<AGP_MAX_STACK, 2>(prog, m, a1, a2, form, o2);
-            out[h] = o2[0];
-            out[h + 1] = o2[1];
-        }
-    }
 }
 
 }  // namespace agp

@@ -618,10 +618,20 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
 
 // ------------------------------------------------------------------------------------------
 // Gram fill: L tile (i,k), i >= k  <-  K(ts_i, ts_k) [+ noise I]; identity in the padding rows.
-// grid (2 * nt(nt+1)/2, P): one CTA = 64 rows x 128 columns; thread -> column, 32 rows, eight
+// grid (2 * nt(nt+1)/2, P): one CTA = 64 rows x 128 columns; thread -> column, 32 rows, E
 // entries per interpreter pass; rows are written as coalesced 1 KB segments.
 // ------------------------------------------------------------------------------------------
-template <int E, int MINB>
+#ifndef AGP_GF_E
+#define AGP_GF_E 4
+#endif
+#ifndef AGP_GF_MINB
+#define AGP_GF_MINB 2
+#endif
+constexpr int GF_E = AGP_GF_E, GF_MINB = AGP_GF_MINB;
+
+// LONGPROG = false: every program of the batch fits the shared-memory cache (the interpreter then reads
+// instructions with LDS instead of generic loads); the host picks the variant per batch.
+template <int E, int MINB, bool LONGPROG>
 __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int tile_id0) {
     __shared__ __align__(128) double ts_r[UM];
     __shared__ __align__(128) double ts_c[UN];
@@ -653,12 +663,10 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
     }
     const int poff = v.prog_off[p];
     const int pm = v.prog_off[p + 1] - poff;
-    const AgpInstr* prog = v.prog + poff;
-    if (pm <= PROG_SMEM) {
-        const double* src = reinterpret_cast<const double*>(prog);
+    if (!LONGPROG) {
+        const double* src = reinterpret_cast<const double*>(v.prog + poff);
         double* dst = reinterpret_cast<double*>(prog_s);
-        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];
-        prog = prog_s;
+        for (int w = tid; w < pm * AGP_INSTR_DOUBLES; w += FT) dst[w] = src[w];
     }
     mbar_wait(&bar, 0);
     __syncthreads();
@@ -680,8 +688,8 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
                 t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
                 t2[j] = ts_r[rbase + 2 * (E * eb + j)];
             }
-            if constexpr (E == 8) eval_entries8(prog, pm, need, t1, t2, 0, val);
-            else eval_entries<E>(prog, pm, need, t1, t2, 0, val);
+            if (LONGPROG) eval_entries<E>(v.prog + poff, pm, need, t1, t2, 0, val);
+            else eval_entries<E>(prog_s, pm, need, t1, t2, 0, val);
         }
 #pragma unroll
         for (int j = 0; j < E; ++j) {
@@ -771,7 +779,7 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
     {
         const double* src = reinterpret_cast<const double*>(v.prog + poff);
         double* dst = reinterpret_cast<double*>(prog_s);
-        for (int w = tid; w < pm * 4; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
+        for (int w = tid; w < pm * AGP_INSTR_DOUBLES; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
     }
     __syncthreads();
     const int np = param_off[p + 1] - param_off[p];  // host guarantees np <= AGP_GRAD_MAX_PARAMS
@@ -834,9 +842,9 @@ void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s) {
     const int tile_id0 = row_tile0 * (row_tile0 + 1) / 2;  // lower tiles are numbered row by row
     const int tiles = v.nt_total * (v.nt_total + 1) / 2 - tile_id0;
     dim3 grid(2 * tiles, P);  // 2 row halves per tile
-    // eight entries per interpreter pass, two CTAs per SM: measured equal (within 3 %) to 4 entries x
-    // 2-3 CTAs and 2 entries x 4 CTAs — the kernel is bound by FP64 issue, not by latency
-    agp_gramfill_kernel<8, 2><<<grid, FT, 0, s>>>(v, tile_id0);
+    // four entries per interpreter pass in lock-step (agp_math.cuh), two CTAs per SM
+    if (v.max_prog_len <= PROG_SMEM) agp_gramfill_kernel<GF_E, GF_MINB, false><<<grid, FT, 0, s>>>(v, tile_id0);
+    else agp_gramfill_kernel<GF_E, GF_MINB, true><<<grid, FT, 0, s>>>(v, tile_id0);
 }
 
 void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {

@@ -19,6 +19,7 @@ constexpr int PROG_SMEM = 64;      // instructions cached in shared memory
 constexpr int GT = 64;
 constexpr int GR_THREADS = 256;
 
+template <bool LONGPROG>
 __global__ void __launch_bounds__(GR_THREADS) agp_gram_kernel(const AgpInstr* __restrict__ prog_g, int m, int need, const double* __restrict__ ts,
                                                              int n, double noise, int form, double* __restrict__ K) {
     __shared__ double tile[GT][GT + 1];
@@ -37,12 +38,10 @@ __global__ void __launch_bounds__(GR_THREADS) agp_gram_kernel(const AgpInstr* __
         tsi[tid] = (i0 + tid < n) ? ts[i0 + tid] : 0.0;
         tsj[tid] = (j0 + tid < n) ? ts[j0 + tid] : 0.0;
     }
-    const AgpInstr* prog = prog_g;
-    if (m <= PROG_SMEM) {
+    if (!LONGPROG) {  // the program fits the shared-memory cache: the interpreter reads it with LDS
         const double* src = reinterpret_cast<const double*>(prog_g);
         double* dst = reinterpret_cast<double*>(prog_s);
-        for (int q = tid; q < m * 4; q += GR_THREADS) dst[q] = src[q];
-        prog = prog_s;
+        for (int q = tid; q < m * AGP_INSTR_DOUBLES; q += GR_THREADS) dst[q] = src[q];
     }
     __syncthreads();
     const int il = tid & (GT - 1);
@@ -58,7 +57,8 @@ __global__ void __launch_bounds__(GR_THREADS) agp_gram_kernel(const AgpInstr* __
             t1[j] = up ? tsi[il] : tsj[jl];
             t2[j] = up ? tsj[jl] : tsi[il];
         }
-        eval_entries<4>(prog, m, need, t1, t2, form, val);
+        if (LONGPROG) eval_entries<4>(prog_g, m, need, t1, t2, form, val);
+        else eval_entries<4>(prog_s, m, need, t1, t2, form, val);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int jl = (tid >> 6) + (e4 * 4 + j) * 4;
@@ -92,7 +92,8 @@ void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n,
     if (n <= 0) return;
     int nt = (n + GT - 1) / GT;
     int blocks = nt * (nt + 1) / 2;
-    agp_gram_kernel<<<blocks, GR_THREADS, 0, s>>>(prog, m, need, ts, n, noise, form, K);
+    if (m <= PROG_SMEM) agp_gram_kernel<false><<<blocks, GR_THREADS, 0, s>>>(prog, m, need, ts, n, noise, form, K);
+    else agp_gram_kernel<true><<<blocks, GR_THREADS, 0, s>>>(prog, m, need, ts, n, noise, form, K);
 }
 
 }  // namespace agp

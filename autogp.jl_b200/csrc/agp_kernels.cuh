@@ -23,6 +23,7 @@ struct BatchView {
     const AgpInstr* prog;    // concatenated device programs
     const int* prog_off;     // [P+1]
     const int* prog_need;    // [P] register-stack depth
+    int max_prog_len;        // longest program of the batch (instructions)
     const double* noise;     // [P]
     double* lml;             // [P]
     int* info;               // [P]

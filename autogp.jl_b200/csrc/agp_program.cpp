@@ -30,6 +30,13 @@ int n_node_params(int32_t op) {
     }
 }
 
+// x / a may run as x * (1/a) + two exact-remainder corrections (agp_math.cuh: div_const_v) when neither
+// a nor 1/a is near the ends of the exponent range; otherwise the device divides generically.
+bool fast_divisor(double a) {
+    const double m = std::fabs(a);
+    return std::isfinite(a) && m > 0x1p-500 && m < 0x1p500;
+}
+
 void emit(const std::vector<TNode>& t, int id, const double* params, std::vector<AgpInstr>& out) {
     // explicit stack instead of recursion: trees can be deep (max_depth = -1, src/GP.jl:1127)
     struct Frame { int id; int state; bool swapped; };
@@ -45,8 +52,16 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
             switch (nd.op) {
                 case AGP_OP_CONSTANT: in.op = AGP_I_CONST; in.a = p[0]; break;
                 case AGP_OP_LINEAR: in.op = AGP_I_LINEAR; in.a = p[0]; in.b = p[1]; in.c = p[2]; break;
-                case AGP_OP_SQUARED_EXPONENTIAL: in.op = AGP_I_SE; in.a = p[0] * p[0]; in.b = p[1]; break;
-                case AGP_OP_GAMMA_EXPONENTIAL: in.op = AGP_I_GE; in.a = p[0]; in.b = p[1]; in.c = p[2]; break;
+                case AGP_OP_SQUARED_EXPONENTIAL:
+                    in.op = AGP_I_SE; in.a = p[0] * p[0]; in.b = p[1];
+                    in.c = 1.0 / in.a;
+                    if (fast_divisor(in.a)) in.op |= AGP_I_FASTDIV;
+                    break;
+                case AGP_OP_GAMMA_EXPONENTIAL:
+                    in.op = AGP_I_GE; in.a = p[0]; in.b = p[1]; in.c = p[2];
+                    in.d = 1.0 / in.a;
+                    if (fast_divisor(in.a)) in.op |= AGP_I_FASTDIV;
+                    break;
                 case AGP_OP_PERIODIC:
                     in.op = AGP_I_PER;
                     in.a = M_PI / p[1];
@@ -71,7 +86,11 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
         } else {
             if (nd.op == AGP_OP_PLUS) in.op = AGP_I_PLUS;
             else if (nd.op == AGP_OP_TIMES) in.op = AGP_I_TIMES;
-            else { in.op = f.swapped ? AGP_I_CP_SWAP : AGP_I_CP; in.a = p[0]; in.b = p[1]; }
+            else {
+                in.op = f.swapped ? AGP_I_CP_SWAP : AGP_I_CP; in.a = p[0]; in.b = p[1];
+                in.c = 1.0 / in.b;
+                if (fast_divisor(in.b)) in.op |= AGP_I_FASTDIV;
+            }
             out.push_back(in);
             st.pop_back();
         }

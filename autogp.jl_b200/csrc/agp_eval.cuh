@@ -70,84 +70,26 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
     double dx[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) dx[e] = t1[e] - t2[e];
+    int opw = prog[0].op;
 #pragma unroll 1
-    for (int q = 0; q < m; ++q) {
+    for (int q = 0; q < m;) {
         // keep the per-leaf expressions of dx inside their switch case: hoisted out of the loop they
         // would all stay live across every other node (registers), for programs that may not use them
 #pragma unroll
         for (int e = 0; e < E; ++e) asm volatile("" : "+d"(dx[e]));
-        const int opw = prog[q].op;
         const int op = opw & 0xff;
         const bool fast = (opw & AGP_I_FASTDIV) != 0;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        const int opw_next = (q + 1 < m) ? prog[q + 1].op : -1;
         double v[E];
-        switch (op) {
-            case AGP_I_CONST:
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = a;
-                st.push(v);
-                break;
-            case AGP_I_LINEAR:
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    double cc = (t1[e] - a) * (t2[e] - a);
-                    v[e] = b + c * cc;
-                }
-                st.push(v);
-                break;
-            case AGP_I_SE: {  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245; c = 1 / l^2
-                double w[E], u[E];
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = (-0.5 * dx[e]) * dx[e];
-                div_const_v<E>(w, a, c, fast, u);
-                exp_v<E>(u, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = b * v[e];
-                st.push(v);
-                break;
-            }
-            case AGP_I_GE: {  // amp * exp(-(|dx| / l)^gamma), src/GP.jl:285-289; d = 1 / l
-                double w[E], u[E];
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = fabs(dx[e]);
-                div_const_v<E>(w, a, prog[q].d, fast, u);
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = -slow_pow(u[e], b);
-                exp_v<E>(w, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = c * v[e];
-                st.push(v);
-                break;
-            }
-            case AGP_I_PER: {  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
-                double w[E], u[E];
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = a * fabs(dx[e]);
-                sin2_v<E>(w, u);
-#pragma unroll
-                for (int e = 0; e < E; ++e) w[e] = b * u[e];
-                exp_v<E>(w, v);
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = c * v[e];
-                st.push(v);
-                break;
-            }
-            case AGP_I_WN:
-#pragma unroll
-                for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
-                st.push(v);
-                break;
-            case AGP_I_PLUS:
+        if (op >= AGP_I_PLUS) {  // binary node on the two top entries
+            if (op == AGP_I_PLUS) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = st.s[1][e] + st.s[0][e];
-                st.reduce(v);
-                break;
-            case AGP_I_TIMES:
+            } else if (op == AGP_I_TIMES) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) v[e] = st.s[1][e] * st.s[0][e];
-                st.reduce(v);
-                break;
-            default: {  // AGP_I_CP / AGP_I_CP_SWAP; c = 1 / scale
+            } else {  // AGP_I_CP / AGP_I_CP_SWAP; c = 1 / scale
                 double g1[E], g2[E];
                 sigma_cp_v<E>(t1, a, b, c, fast, g1);
                 sigma_cp_v<E>(t2, a, b, c, fast, g2);
@@ -163,9 +105,81 @@ __device__ __forceinline__ void eval_program(const AgpInstr* __restrict__ prog, 
                         v[e] = (g1[e] * kl) * g2[e] + ((1.0 - g1[e]) * kr) * (1.0 - g2[e]);
                     }
                 }
-                st.reduce(v);
+            }
+            st.reduce(v);
+            opw = opw_next;
+            ++q;
+            continue;
+        }
+        switch (op) {
+            case AGP_I_CONST:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = a;
+                break;
+            case AGP_I_LINEAR:
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    double cc = (t1[e] - a) * (t2[e] - a);
+                    v[e] = b + c * cc;
+                }
+                break;
+            case AGP_I_SE: {  // amp * exp((-0.5 * dx * dx) / l^2), src/GP.jl:241-245; c = 1 / l^2
+                double w[E], u[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = (-0.5 * dx[e]) * dx[e];
+                div_const_v<E>(w, a, c, fast, u);
+                exp_v<E>(u, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b * v[e];
                 break;
             }
+            case AGP_I_GE: {  // amp * exp(-(|dx| / l)^gamma), src/GP.jl:285-289; d = 1 / l
+                double w[E], u[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = fabs(dx[e]);
+                div_const_v<E>(w, a, prog[q].d, fast, u);
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = -slow_pow(u[e], b);
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * v[e];
+                break;
+            }
+            case AGP_I_PER: {  // amp * exp((-2/l^2) * sin((pi/p) * |dx|)^2), src/GP.jl:331-336
+                double w[E], u[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = a * fabs(dx[e]);
+                sin2_v<E>(w, u);
+#pragma unroll
+                for (int e = 0; e < E; ++e) w[e] = b * u[e];
+                exp_v<E>(w, v);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * v[e];
+                break;
+            }
+            default:  // AGP_I_WN
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
+                break;
+        }
+        // A leaf that is the right operand of the Plus / Times that follows it combines with the stack
+        // top directly (same operands, same order, same rounding as push + reduce): one interpreter
+        // step and no stack traffic for the usual chains  k1 * k2 + k3 ...
+        const int nop = opw_next & 0xff;
+        if (opw_next >= 0 && nop == AGP_I_PLUS) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) st.s[0][e] = st.s[0][e] + v[e];
+            opw = (q + 2 < m) ? prog[q + 2].op : -1;
+            q += 2;
+        } else if (opw_next >= 0 && nop == AGP_I_TIMES) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) st.s[0][e] = st.s[0][e] * v[e];
+            opw = (q + 2 < m) ? prog[q + 2].op : -1;
+            q += 2;
+        } else {
+            st.push(v);
+            opw = opw_next;
+            ++q;
         }
     }
 #pragma unroll

@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
     const int c = tid & (UN - 1), rbase = tid >> 7;
     const int gc = col0 + c;
     const double tcol = ts_c[c];
+    const bool plain = !diag && row0 + UM <= n && col0 + UN <= n;
 #pragma unroll 1
     for (int eb = 0; eb < 32 / E; ++eb) {
         double t1[E], t2[E], val[E];
@@ -690,6 +691,13 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
             }
             if (LONGPROG) eval_entries<E>(v.prog + poff, pm, need, t1, t2, 0, val);
             else eval_entries<E>(prog_s, pm, need, t1, t2, 0, val);
+        }
+        if (plain) {
+            // interior tile (all rows and columns are observations, no diagonal): nothing to decide per entry
+            double* dst = Lp + (long long)(row0 + rbase + 2 * E * eb) * ld + gc;
+#pragma unroll
+            for (int j = 0; j < E; ++j) dst[(long long)(2 * j) * ld] = val[j];
+            continue;
         }
 #pragma unroll
         for (int j = 0; j < E; ++j) {

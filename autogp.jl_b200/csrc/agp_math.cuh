@@ -64,6 +64,12 @@ AGP_MATH_CONST double kSinC[6] = {1.58969099521155010221e-10, -2.505076025340686
 
 #define AGP_SHIFT 6755399441055744.0  // 1.5 * 2^52: adding it rounds to the nearest integer
 
+// argument-reduction constants, kept in the constant bank next to the coefficients (as immediates the
+// compiler re-materialises each 64-bit value with two moves per use)
+//   [0] log2(e)  [1] -ln2 hi  [2] -ln2 lo  [3] 2/pi  [4] -pi/2 hi  [5] -pi/2 mid  [6] +pi/2 lo
+AGP_MATH_CONST double kRed[7] = {1.4426950408889634e+00, -6.9314718055994529e-01, -2.3190468138462996e-17, 6.3661977236758138e-01,
+                                 -1.5707963267948966e+00, -6.1232339957367660e-17, 1.4973849048591698e-33};
+
 template <int E>
 AGP_MATH_FN void exp_v(const double (&x)[E], double (&y)[E]) {
     double r[E], p[E];
@@ -71,11 +77,11 @@ AGP_MATH_FN void exp_v(const double (&x)[E], double (&y)[E]) {
     unsigned bad = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const double t = fma(x[e], 1.4426950408889634e+00, AGP_SHIFT);
+        const double t = fma(x[e], kRed[0], AGP_SHIFT);
         ni[e] = f64_lo(t);
         const double n = t - AGP_SHIFT;
-        r[e] = fma(n, -6.9314718055994529e-01, x[e]);
-        r[e] = fma(n, -2.3190468138462996e-17, r[e]);
+        r[e] = fma(n, kRed[1], x[e]);
+        r[e] = fma(n, kRed[2], r[e]);
         p[e] = kExpC[0];
         bad |= (unsigned)((unsigned)(f64_hi(x[e]) & 0x7fffffff) >= 0x4085e000u);  // |x| >= 700, inf, nan
     }
@@ -102,14 +108,14 @@ AGP_MATH_FN void sin2_v(const double (&x)[E], double (&y)[E]) {
     unsigned bad = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const double t = fma(x[e], 6.3661977236758138e-01, AGP_SHIFT);
+        const double t = fma(x[e], kRed[3], AGP_SHIFT);
         odd[e] = f64_lo(t) & 1;
         const double n = t - AGP_SHIFT;
         // three-constant Cody-Waite reduction (the first step is exact for |x| <= 1e5); r carries the
         // reduced argument to half an ulp, like libdevice's sin on this range
-        r[e] = fma(n, -1.5707963267948966e+00, x[e]);
-        r[e] = fma(n, -6.1232339957367660e-17, r[e]);
-        r[e] = fma(n, 1.4973849048591698e-33, r[e]);
+        r[e] = fma(n, kRed[4], x[e]);
+        r[e] = fma(n, kRed[5], r[e]);
+        r[e] = fma(n, kRed[6], r[e]);
         z[e] = r[e] * r[e];
         p[e] = kSinC[0];
         bad |= (unsigned)((unsigned)(f64_hi(x[e]) & 0x7fffffff) >= 0x40f86a00u);  // |x| > 1e5, inf, nan
@@ -147,7 +153,7 @@ AGP_MATH_FN bool div_needs_slow(double x) {
 
 template <int E>
 AGP_MATH_FN void div_const_v(const double (&x)[E], double a, double ra, bool fast, double (&y)[E]) {
-    unsigned bad = fast ? 0u : 1u;
+    unsigned worst = fast ? 0u : 0xffffffffu;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         double q = x[e] * ra;
@@ -155,9 +161,11 @@ AGP_MATH_FN void div_const_v(const double (&x)[E], double a, double ra, bool fas
         q = fma(rem, ra, q);
         rem = fma(-a, q, x[e]);
         y[e] = fma(rem, ra, q);
-        bad |= (unsigned)div_needs_slow(x[e]);
+        // exponent window as one unsigned distance; zeros trip it too and are sorted out below (rare)
+        const unsigned d = ((unsigned)f64_hi(x[e]) & 0x7ff00000u) - 0x1ff00000u;
+        worst = worst > d ? worst : d;
     }
-    if (bad) {
+    if (worst >= 0x40000000u) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
             if (!fast || div_needs_slow(x[e])) y[e] = slow_div(x[e], a);

@@ -54,7 +54,7 @@ struct agp_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // persistent dataflow kernel: work queues per batch shape + dependency counters
-    int order = 2;        // queue order variant (AGP_ORDER)
+    int order = 3;        // queue order variant (AGP_ORDER)
     int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
     unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
     int num_sms = 0;
@@ -416,7 +416,98 @@ struct QueueLayout {
     int flag_ppre(int p, int i) const { return 32 + 2 * P * nt_stride + p * nt_stride + i; }
 };
 
+// order 3: order 2 for the early block columns (bulk panels tile row by tile row, so the rows the next
+//          look-ahead items read finish first), and the last AGP_LATE block columns RIGHT-LOOKING: when the
+//          switch column is reached every tile of the trailing triangle is brought up to date over [0,k) by
+//          one store-only item, and from then on every block column only adds single products
+//          (final panel = last product + solve; trailing tiles one product each).  Late block columns have
+//          too few tiles for all CTAs: their per-particle critical path then no longer waits for
+//          contractions that could have been done earlier.
+struct TileState {
+    int P, nt, nt_stride;
+    std::vector<int> cov, n_ppre, n_diag;  // coverage per tile, partial / diag item counts
+    std::vector<int4>* items;
+    TileState(int P_, int nt_, int nts, std::vector<int4>* it) : P(P_), nt(nt_), nt_stride(nts), cov((size_t)P_ * nt_ * nt_, 0), n_ppre((size_t)P_ * nt_, 0), n_diag((size_t)P_ * nt_, 0), items(it) {}
+    int flag_diagu(int p, int k) const { return 32 + P * nt_stride + p * nt_stride + k; }
+    int flag_ppre(int p, int i) const { return 32 + 2 * P * nt_stride + p * nt_stride + i; }
+    void potf2(int p, int k) {
+        items->push_back(make_int4(agp::ITEM_POTF2, p, k, k));
+        items->push_back(make_int4(0, 0, -1, n_diag[(size_t)p * nt + k]));
+    }
+    // advance tile (i,k) to coverage j1 (final when j1 == k): both row halves
+    void tile(int p, int i, int k, int j1) {
+        int& c = cov[((size_t)p * nt + i) * nt + k];
+        const int j0 = c;
+        const bool fin = j1 == k;
+        for (int h = 0; h < 2; ++h) {
+            if (i == k) {
+                const int cnt = n_diag[(size_t)p * nt + k];
+                items->push_back(make_int4(agp::ITEM_DIAG | (h << 8) | (fin ? 0 : agp::ITEM_PARTIAL), p, k, i));
+                items->push_back(make_int4(j0 | (j1 << 16), 2 * j1, j0 > 0 ? flag_diagu(p, k) : -1, j0 > 0 ? cnt : 0));
+            } else {
+                const int cnt = n_ppre[(size_t)p * nt + i];
+                items->push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (fin ? 0 : agp::ITEM_PARTIAL) | (k == 0 ? agp::ITEM_YINIT : 0), p, k, i));
+                items->push_back(make_int4(j0 | (j1 << 16), (2 * j1) | ((2 * j1) << 16), j0 > 0 ? flag_ppre(p, i) : -1, j0 > 0 ? cnt : 0));
+            }
+        }
+        if (i == k) n_diag[(size_t)p * nt + k] += 2;
+        else if (!fin) n_ppre[(size_t)p * nt + i] += 2;
+        c = j1;
+    }
+};
+
+static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vector<int4>& items) {
+    items.clear();
+    TileState b(P, nt, nt_stride, &items);
+    const int split_from = 3;
+    auto split = [&](int k) { return k >= split_from && k < nt; };
+    const int ks = std::max(nt - late, 1);  // first block column of the right-looking phase
+    for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);
+    for (int p = 0; p < P; ++p) b.potf2(p, 0);
+    struct T { int p, i, k, j1; };
+    for (int k = 0; k < nt - 1; ++k) {
+        for (int p = 0; p < P; ++p) b.tile(p, k + 1, k, k);  // panels of tile row k+1 first
+        if (k < ks) {
+            std::vector<T> la;  // look-ahead store-only items over [0,k)
+            if (split(k + 1) && k >= 1)
+                for (int p = 0; p < P; ++p) {
+                    la.push_back({p, k + 1, k + 1, k});
+                    if (k + 2 < nt) la.push_back({p, k + 2, k + 1, k});
+                }
+            if (k + 1 == ks && k >= 1)  // the switch: the rest of the trailing triangle
+                for (int p = 0; p < P; ++p)
+                    for (int c = k + 1; c < nt; ++c)
+                        for (int i = c; i < nt; ++i)
+                            if (!(split(k + 1) && c == k + 1 && (i == k + 1 || i == k + 2))) la.push_back({p, i, c, k});
+            std::vector<T> bulk;
+            for (int i = k + 2; i < nt; ++i)
+                for (int p = 0; p < P; ++p) bulk.push_back({p, i, k, k});
+            const size_t nb = bulk.size(), c1 = nb / 3, c2 = 2 * nb / 3;
+            for (size_t a = 0; a < c1; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
+            for (const T& a : la) b.tile(a.p, a.i, a.k, a.j1);
+            for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
+            for (size_t a = c1; a < c2; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
+            for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+            for (size_t a = c2; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
+        } else {
+            for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
+            for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+            for (int i = k + 2; i < nt; ++i)
+                for (int p = 0; p < P; ++p) b.tile(p, i, k, k);
+            for (int c = k + 2; c < nt; ++c)
+                for (int i = c; i < nt; ++i)
+                    for (int p = 0; p < P; ++p) b.tile(p, i, c, k + 1);
+        }
+    }
+}
+
 static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int4>& items) {
+    if (order >= 3 && nt > 1) {
+        int late = 4;
+        if (const char* e = getenv("AGP_LATE")) late = atoi(e);
+        build_queue_order3(P, nt, nt_stride, late, items);
+        return;
+    }
     const QueueLayout lay{P, nt, nt_stride};
     const int split_from = 3;  // block columns below this are too short to be worth splitting
     auto split = [&](int k) { return order >= 2 && k >= split_from && k < nt; };  // tile (k,k) and (k+1,k) are split

@@ -51,6 +51,7 @@ constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + 64;
 
 static_assert(NSTAGE * STAGE_D <= REGION_D, "pipeline stages must fit in the region");
 static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region");
+static_assert(UM * XS + 4 * 32 * 32 <= REGION_D, "X rows + the solve's ring of four 32x32 operand blocks");
 static_assert(2 * (FUSED_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
@@ -288,62 +289,83 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
         y_old = yinit ? ((gr < n) ? v.xs[gr] : 0.0) : __ldcg(yp + gr);
     }
 
-#pragma unroll 1
-    for (int jb = 0; jb < 4; ++jb) {
-        // panel jb of L_kk: rows [32 jb, 32 jb + 32), columns [0, 32 jb) from L, diagonal block from dinv
-        const int nch = (jb + 1) * 16;
-        for (int w = tid; w < 32 * nch; w += FT) {
-            int r = w / nch, ch = w - r * nch;
-            if (ch < jb * 16) cp_async16(Ls + r * XS + ch * 2, Lp + (long long)(o + jb * 32 + r) * ld + o + ch * 2);
-            else cp_async16(Ls + r * XS + ch * 2, dinv + jb * 1024 + r * 32 + (ch - jb * 16) * 2);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        // two accumulator sets (even / odd k of each LDS.128 pair): 8 independent DMMA chains
-        double acc0[4][2], acc1[4][2];
+    // Blocked substitution over the four 32-column blocks of L_kk:  X_jb = (C_jb - sum_{m<jb} X_m L[jb,m]^T) inv(L[jb,jb])^T.
+    // The ten 32x32 operand blocks (six of L_kk, four inverted diagonal blocks) stream through a ring of four
+    // shared-memory slots, three blocks ahead of the math, so their L2 latency is paid once, not per block.
+    // Each warp owns 8 rows of X, so the block-to-block dependency is warp-local.
+    constexpr int SB = 32 * 32;  // doubles per slot, 16-byte chunks XOR-swizzled (conflict-free LDS.128)
+    auto blk_swz = [](int row, int chunk) { return row * 32 + ((chunk ^ ((row & 1) << 2)) << 1); };
+    auto load_block = [&](int b) {
+        // b -> (jb, m): 0:(0,0) 1:(1,0) 2:(1,1) 3:(2,0) 4:(2,1) 5:(2,2) 6:(3,0) 7:(3,1) 8:(3,2) 9:(3,3); m == jb: inverse block
+        const int jb = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
+        const int mb = b - jb * (jb + 1) / 2;
+        double* dst = Ls + (b & 3) * SB;
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
-        // S = sum_{m<jb} X_m L[jb,m]^T
-#pragma unroll 2
-        for (int kk = 0; kk < jb * 32; kk += 8) {
-            const double2 a = *reinterpret_cast<const double2*>(xrow + kk + 2 * c4);
+        for (int e = 0; e < 2; ++e) {
+            const int w = tid + e * FT;
+            const int r = w >> 4, ch = w & 15;
+            const double* src = (mb < jb) ? Lp + (long long)(o + jb * 32 + r) * ld + o + mb * 32 + ch * 2 : dinv + jb * 1024 + r * 32 + ch * 2;
+            cp_async16(dst + blk_swz(r, ch), src);
+        }
+    };
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        load_block(b);
+        cp_async_commit();
+    }
+    // two accumulator sets (even / odd k of each LDS.128 pair): 8 independent DMMA chains
+    double acc0[4][2], acc1[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
+    int jb = 0, mb = 0;
+#pragma unroll 1
+    for (int b = 0; b < 10; ++b) {
+        cp_async_wait<2>();
+        __syncthreads();  // block b has landed for everyone, and everyone is done with the slot of block b-1
+        if (b + 3 < 10) load_block(b + 3);
+        cp_async_commit();
+        const double* Bs = Ls + (b & 3) * SB;
+        if (mb == jb) {
+            // T = C_jb - S  (own rows only), then X_jb = T inv(L_jb,jb)^T
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                const double2 b = *reinterpret_cast<const double2*>(Ls + (nb * 8 + g) * XS + kk + 2 * c4);
-                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
-                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
+                double2* ptr = reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4);
+                double2 t = *ptr;
+                t.x -= acc0[nb][0] + acc1[nb][0];
+                t.y -= acc0[nb][1] + acc1[nb][1];
+                *ptr = t;
+                acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
             }
+            __syncwarp();
         }
-        // T = C_jb - S  (own rows only: warp-local dependency)
-#pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
-            double2* ptr = reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4);
-            double2 t = *ptr;
-            t.x -= acc0[nb][0] + acc1[nb][0];
-            t.y -= acc0[nb][1] + acc1[nb][1];
-            *ptr = t;
-            acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
-        }
-        __syncwarp();
-        // X_jb = T inv(L_jb,jb)^T
+        const double* xa = xrow + mb * 32;
 #pragma unroll
         for (int kk = 0; kk < 32; kk += 8) {
-            const double2 a = *reinterpret_cast<const double2*>(xrow + jb * 32 + kk + 2 * c4);
+            const double2 a = *reinterpret_cast<const double2*>(xa + kk + 2 * c4);
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                const double2 b = *reinterpret_cast<const double2*>(Ls + (nb * 8 + g) * XS + jb * 32 + kk + 2 * c4);
-                dmma884(acc0[nb][0], acc0[nb][1], a.x, b.x);
-                dmma884(acc1[nb][0], acc1[nb][1], a.y, b.y);
+                const double2 bb = *reinterpret_cast<const double2*>(Bs + blk_swz(nb * 8 + g, (kk >> 1) + c4));
+                dmma884(acc0[nb][0], acc0[nb][1], a.x, bb.x);
+                dmma884(acc1[nb][0], acc1[nb][1], a.y, bb.y);
             }
         }
-        __syncwarp();
+        if (mb == jb) {
+            __syncwarp();
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-            *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) =
-                make_double2(acc0[nb][0] + acc1[nb][0], acc0[nb][1] + acc1[nb][1]);
-        __syncthreads();  // panel buffer is reused by the next block
+            for (int nb = 0; nb < 4; ++nb) {
+                *reinterpret_cast<double2*>(xrow + jb * 32 + nb * 8 + 2 * c4) =
+                    make_double2(acc0[nb][0] + acc1[nb][0], acc0[nb][1] + acc1[nb][1]);
+                acc0[nb][0] = acc0[nb][1] = acc1[nb][0] = acc1[nb][1] = 0.0;
+            }
+            __syncwarp();
+            ++jb;
+            mb = 0;
+        } else {
+            ++mb;
+        }
     }
+    cp_async_wait<0>();
+    __syncthreads();
 
     // store L_ik rows (coalesced) and fold the forward solve: y_i -= L_ik z_k
     double dot_mine = 0.0;

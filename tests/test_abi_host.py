@@ -200,7 +200,7 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None):
                         assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # trailing (Schur complement) tile
 
 
-@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
 @pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16), (2, 23)])
 def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     """Deadlock-freedom of the persistent kernel (agp_fused.cu): CTAs pop items in queue order and a

@@ -26,7 +26,7 @@ def to_agp(nd):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-    order = int(os.environ.get("AGP_ORDER", "2"))
+    order = int(os.environ.get("AGP_ORDER", "3"))
     eng = agp.Engine(0)
     ts, xs = o.synthetic_series(n)
     parts = [o.synthetic_particle(p) for p in range(P)]
@@ -61,6 +61,8 @@ def main():
             w1 = s[:, 1] - s[:, 0]
             mm = s[:, 2] - s[:, 1]
             if t == 2:
+                fin = (items[m, 0] & (1 << 9)) == 0   # final panels only carry the solve stamps
+                s, w1, mm = s[fin], w1[fin], mm[fin]
                 gr = s[:, 3] - s[:, 2]
                 w2 = s[:, 4] - s[:, 3]
                 tr = s[:, 5] - s[:, 4]
@@ -75,7 +77,7 @@ def main():
     # per-block-column view of the panels
     print("per block column k: panel items mean us (wait1, mma, gram, waitF, trsm) and the wall-clock window of the column")
     for k in range(nt):
-        m = (typ == 2) & (items[:, 2] == k) & (items[:, 5] == k)   # final panel items
+        m = (typ == 2) & (items[:, 2] == k) & ((items[:, 0] & (1 << 9)) == 0)   # final panel items
         if not m.any():
             continue
         s = st[m].astype(np.float64) * 1e-3

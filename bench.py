@@ -275,11 +275,11 @@ def main():
     e2e_value = world * P * e2e_steps / dt
     ld = -(-n // 128) * 128
     n_instr = int(packed[0].sum())
-    h2d = 2 * ld * 8 + P * 8 + (P + 1) * 4 + P * 4 + n_instr * 32
+    h2d = 2 * ld * 8 + 2 * P * 8 + 2 * (P + 1) * 4 + P * 4 + n_instr * 48  # the packed input arena (agp_api.cu: upload_impl)
     d2h = P * 8 + P * 4
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
-    # One step = agp_gramfill_kernel (kernel-tree interpreter -> K tiles in HBM, FP64-issue bound)
+    # One step = agp_gramfill_kernel (kernel-tree interpreter -> K tiles in HBM, issue / FP64-pipe bound)
     # followed by ONE launch of agp_chol_kernel (persistent dataflow kernel: FP64 DMMA contraction,
     # diagonal Cholesky, panel solves, forward solve, log det), which dominates.  Algorithmic work of
     # that launch = P * n^3 / 3 flops.
@@ -311,7 +311,7 @@ def main():
         "algorithmic_flops_per_launch": flops,
         "gramfill_kernel": {"avg_launch_ms": gram_ms, "entries_per_s": n_entries / (gram_ms * 1e-3),
                             "hbm_write_GBps": 8.0 * n_entries / (gram_ms * 1e-3) * 1e-9,
-                            "bound": "FP64 issue (2 exp + 1 sin + 1 div per entry), not HBM"},
+                            "bound": "instruction issue / FP64 pipe (2 exp + 1 sin + 1 division per entry in FP64; ncu: FP64 pipe ~48 % busy, issue slots ~64 %), not HBM"},
         "whole_step": {"flops": world * flops, "achieved": flops / (ms_per_step * 1e-3) * 1e-12,
                        "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
     }

@@ -31,5 +31,5 @@ for p in range(min(a.check, a.P)):
     ref = o.log_marginal_likelihood(*parts[p], ts, xs)
     msg += f" relerr[{p}]={abs(lml[p]-ref)/abs(ref):.1e}"
 fl = a.P * a.n ** 3 / 3
-print(f"order={os.environ.get("AGP_ORDER","3")} n={a.n} P={a.P}: {ms:.3f} ms/run {a.P/ms*1e3:.0f} LML/s "
+print(f"order={os.environ.get('AGP_ORDER','3')} n={a.n} P={a.P}: {ms:.3f} ms/run {a.P/ms*1e3:.0f} LML/s "
       f"{fl/ms*1e-9:.2f} TF/s info_ok={bool(np.all(info==0))}{msg}", flush=True)

@@ -27,6 +27,6 @@ st = np.array([eng.stage_times() for _ in range(a.reps)])
 ms = eng.time_runs(a.reps) / a.reps
 lml, info = eng.fetch()
 ref = o.log_marginal_likelihood(*parts[0], ts, xs)
-print(f"lib={os.environ.get('AGP_LIB','default')} order={os.environ.get("AGP_ORDER","3")} n={a.n} P={a.P} tree={a.tree}: "
+print(f"lib={os.environ.get('AGP_LIB','default')} order={os.environ.get('AGP_ORDER','3')} n={a.n} P={a.P} tree={a.tree}: "
       f"{ms:.3f} ms/run  gramfill {np.median(st[:,0]):.3f} ms  chol {np.median(st[:,1]):.3f} ms  info_ok={bool(np.all(info==0))} "
       f"relerr[0]={abs(lml[0]-ref)/abs(ref):.1e}", flush=True)

@@ -39,6 +39,8 @@ struct agp_handle {
     double* d_grad = nullptr; size_t cap_grad = 0;  // per-CTA partial sums + gradients
     const int* d_param_prefix = nullptr;            // [P+1] prefix sums of n_params (inside the input arena)
     BatchView view{};
+    agp::TmaMaps tma{};          // TMA descriptors over d_L for the current (pointer, ld, P)
+    double* tma_L = nullptr; int tma_ld = 0; long long tma_rows = 0;
 
     // device workspaces (grow-only)
     double* d_L = nullptr;       size_t cap_L = 0;       // bytes
@@ -692,7 +694,13 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         AGP_CUDA(h, cudaEventElapsedTime(&kernel_ms[0], h->ev0, h->ev1));
         AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     }
-    agp::launch_chol(v, q, h->ctas_per_sm * h->num_sms, h->stream);
+    if (h->tma_L != v.L || h->tma_ld != h->ld || h->tma_rows != (long long)P * h->ld) {
+        if (!agp::make_tma_maps(v.L, h->ld, (long long)P * h->ld, &h->tma)) return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the factor matrix");
+        h->tma_L = v.L;
+        h->tma_ld = h->ld;
+        h->tma_rows = (long long)P * h->ld;
+    }
+    agp::launch_chol(v, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
     if (kernel_ms) {
         AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         AGP_CUDA(h, cudaEventSynchronize(h->ev1));

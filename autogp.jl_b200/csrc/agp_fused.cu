@@ -47,7 +47,7 @@ constexpr int REGION_D = UM * XS + 32 * XS;  // X rows + one 32-row panel of L_k
 constexpr int PROG_SMEM = 64;
 // tail of the shared-memory image (doubles): zs[TB] ys[TB] Ri[TB] red[16]
 constexpr int TAIL_D = 3 * TB + 16;
-constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + 64;
+constexpr int FUSED_SMEM = (REGION_D + TAIL_D) * 8 + 64 + 64;  // + ctl[16] ints + full[4], empty[4] mbarriers
 
 static_assert(NSTAGE * STAGE_D <= REGION_D, "pipeline stages must fit in the region");
 static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region");
@@ -55,6 +55,8 @@ static_assert(UM * XS + 4 * 32 * 32 <= REGION_D, "X rows + the solve's ring of f
 static_assert(2 * (FUSED_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
+// double offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] tile written by TMA with SWIZZLE_128B
+__device__ __forceinline__ int swz128(int row, int chunk) { return row * KC + ((chunk ^ (row & 7)) << 1); }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -81,6 +83,34 @@ __device__ bool wait_ge(const int* flag, int need, int* err, unsigned long long 
     }
 }
 
+// mbarrier wait that cannot hang the device: gives up (and raises the scheduler error flag) after the same limit
+// as the dependency waits
+__device__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int* err, unsigned long long limit_ns) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if ((spins & 1023u) == 1023u) {
+            if (ld_relaxed_gpu(err) != 0) return false;
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > limit_ns) {
+                atomicExch(err, 1);
+                return false;
+            }
+        }
+    }
+}
+
 // diagnostics: thread 0 stamps phase boundaries of item `idx` when tracing is on
 __device__ __forceinline__ void stamp(const SchedView& q, int idx, int slot) {
     if (q.trace != nullptr && threadIdx.x == 0) q.trace[(long long)idx * 8 + slot] = (long long)globaltimer_ns();
@@ -88,6 +118,7 @@ __device__ __forceinline__ void stamp(const SchedView& q, int idx, int slot) {
 
 // all threads: release this item's global writes, then bump the counter
 __device__ __forceinline__ void signal_done(int* counter) {
+    fence_proxy_async();  // this item's shared-memory traffic is ordered before the next item's TMA copies into the same buffers
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -104,11 +135,13 @@ struct Smem {
     double* ys;
     double* Ri;
     double* red;
-    int* ctl;  // [0] item index, [1] wait result, [2] potf2 info
+    int* ctl;  // [0] item index, [1] wait result, [2] potf2 info, [4] pipeline chunks issued so far by this CTA (mbarrier phases)
+    uint64_t* full;   // [NSTAGE] stage filled (TMA transaction bytes)
+    uint64_t* empty;  // [NSTAGE] stage read by all 8 warps
 };
 
 __device__ __forceinline__ Smem smem_view() {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];  // TMA destinations with SWIZZLE_128B need 1 KB alignment
     Smem s;
     s.region = reinterpret_cast<double*>(smem_raw);
     s.zs = s.region + REGION_D;
@@ -116,6 +149,8 @@ __device__ __forceinline__ Smem smem_view() {
     s.Ri = s.ys + TB;
     s.red = s.Ri + TB;
     s.ctl = reinterpret_cast<int*>(s.red + 16);
+    s.full = reinterpret_cast<uint64_t*>(s.ctl + 16);
+    s.empty = s.full + NSTAGE;
     return s;
 }
 
@@ -127,7 +162,7 @@ __device__ __forceinline__ Smem smem_view() {
 // receives K - sum_{j<j1}; either a later item with j0 = j1 picks it up from there (the accumulators
 // always start from minus the tile), which takes the long early part of the contraction of the
 // next diagonal tile and of the panel below it off the per-particle critical path.
-__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, int idx, int p, int k, int i, int h, bool diag, bool partial,
+__device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx, int p, int k, int i, int h, bool diag, bool partial,
                                        bool yinit, int j0, int j1, int need_k, int need_i, int extra_flag, int extra_need) {
     const Smem s = smem_view();
     const int tid = threadIdx.x;
@@ -166,6 +201,27 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
         signal_done(q.diagu + p * q.nt_stride + k);
         return true;
     }
+    const int nchunk = ((j1 - j0) * TB) / KC;
+    // Operand pipeline: one thread issues 2-D TMA tensor copies (B: 128 rows of tile row k, A: the item's 64 rows;
+    // 16 columns = 128 bytes per row, hardware 128-byte swizzle) into a ring of NSTAGE stages; full[] carries the
+    // transaction bytes, empty[] the eight warps' "fragments are in registers".  No CTA-wide barrier and no copy
+    // instructions in the MMA warps' LSU queue.  The barriers live for the whole kernel: G0 counts the chunks
+    // this CTA has issued so far, which gives every stage use its phase parity.
+    const int G0 = s.ctl[4];
+    const int ccol = j0 * TB, brow = p * ld + col0, arow = p * ld + row0;
+    auto produce = [&](int c) {  // thread 0 only
+        const int G = G0 + c, st = G % NSTAGE;
+        if (G >= NSTAGE && !mbar_wait_bounded(s.empty + st, ((G / NSTAGE) - 1) & 1, q.err, q.wait_timeout_ns)) return;
+        double* Bs = stages + st * STAGE_D;
+        mbar_expect_tx(s.full + st, (diag ? UN : UN + UM) * KC * 8);
+        tma_load_2d(Bs, &maps.b, ccol + c * KC, brow, s.full + st);
+        if (!diag) tma_load_2d(Bs + UN * KC, &maps.a, ccol + c * KC, arow, s.full + st);
+    };
+    if (tid == 0) {
+        fence_proxy_async();
+        for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) produce(c);
+    }
+    // (after the first copies are in flight, so the two L2 round trips overlap)
     double acc[4][4][2];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb)
@@ -177,48 +233,28 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
             acc[mb][nb][1] = -kv.y;
         }
 
-    const int nchunk = ((j1 - j0) * TB) / KC;
-    const double* __restrict__ Ag = Lp + (long long)row0 * ld + j0 * TB;
-    const double* __restrict__ Bg = Lp + (long long)col0 * ld + j0 * TB;
-
-    auto load_stage = [&](int st, int chunk) {
-        double* Bs = stages + st * STAGE_D;  // [UN][KC]
-        double* As = Bs + UN * KC;           // [UM][KC]
-        const int kk0 = chunk * KC;
-#pragma unroll
-        for (int e = 0; e < (UN * KC / 2) / FT; ++e) {  // 4
-            int w = tid + e * FT;
-            int row = w >> 3, ch = w & 7;
-            cp_async16(Bs + swz(row, ch), Bg + (long long)row * ld + kk0 + ch * 2);
-        }
-        if (!diag) {
-#pragma unroll
-            for (int e = 0; e < (UM * KC / 2) / FT; ++e) {  // 2
-                int w = tid + e * FT;
-                int row = w >> 3, ch = w & 7;
-                cp_async16(As + swz(row, ch), Ag + (long long)row * ld + kk0 + ch * 2);
-            }
-        }
-    };
-
-#pragma unroll
-    for (int st = 0; st < NSTAGE - 1; ++st) {
-        if (st < nchunk) load_stage(st, st);
-        cp_async_commit();
-    }
     for (int ch = 0; ch < nchunk; ++ch) {
-        cp_async_wait<NSTAGE - 2>();
-        __syncthreads();
-        const double* Bs = stages + (ch % NSTAGE) * STAGE_D;
+        const int G = G0 + ch, st = G % NSTAGE;
+        if (tid == 0 && ch + NSTAGE - 1 < nchunk) produce(ch + NSTAGE - 1);
+        if (!mbar_wait_bounded(s.full + st, (G / NSTAGE) & 1, q.err, q.wait_timeout_ns)) return false;
+        const double* Bs = stages + st * STAGE_D;
         const double* As = diag ? Bs + h * UM * KC : Bs + UN * KC;  // diagonal tile: A rows are a slice of B
+        // lane c4 takes the 16-byte chunks 2 c4 + ks of a row (a permutation of k shared by A and B): with the
+        // 128-byte swizzle the eight lanes of an LDS.128 phase then hit eight different chunk columns
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {
+        for (int ks = 0; ks < 2; ++ks) {
+            double2 a[4], b[4];
             if (active) {
-                double2 a[4], b[4];
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz(wm * 32 + mb * 8 + g, ks * 4 + c4));
+                for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz128(wm * 32 + mb * 8 + g, 2 * c4 + ks));
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz(wn * 32 + nb * 8 + g, ks * 4 + c4));
+                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz128(wn * 32 + nb * 8 + g, 2 * c4 + ks));
+            }
+            if (ks == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s.empty + st);  // this warp holds its last fragments of the stage
+            }
+            if (active) {
 #pragma unroll
                 for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
@@ -228,16 +264,9 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, i
 #pragma unroll
                     for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
             }
-            if (ks == 0) {
-                // refill behind the first half of the chunk's math so the copy instructions issue
-                // while the tensor pipe is busy
-                int nxt = ch + NSTAGE - 1;
-                if (nxt < nchunk) load_stage(nxt % NSTAGE, nxt);
-                cp_async_commit();
-            }
         }
     }
-    cp_async_wait<0>();
+    if (tid == 0) s.ctl[4] = G0 + nchunk;
     __syncthreads();
     stamp(q, idx, 2);
 
@@ -612,8 +641,17 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
 
 }  // namespace
 
-__global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView q) {
+__global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView q, const __grid_constant__ TmaMaps maps) {
     const Smem s = smem_view();
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < NSTAGE; ++st) {
+            mbar_init(s.full + st, 1);
+            mbar_init(s.empty + st, FT / 32);
+        }
+        mbar_fence_init();
+        s.ctl[4] = 0;
+    }
+    __syncthreads();
 
     for (;;) {
         if (threadIdx.x == 0) s.ctl[0] = atomicAdd(q.head, 1);
@@ -625,7 +663,7 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
         bool ok;
         stamp(q, idx, 0);
         if (type == ITEM_POTF2) ok = do_potf2(v, q, idx, it.y, it.z, dep.w);
-        else ok = do_update(v, q, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, (it.x & ITEM_PARTIAL) != 0, (it.x & ITEM_YINIT) != 0,
+        else ok = do_update(v, q, maps, idx, it.y, it.z, it.w, h, type == ITEM_DIAG, (it.x & ITEM_PARTIAL) != 0, (it.x & ITEM_YINIT) != 0,
                             dep.x & 0xffff, dep.x >> 16, dep.y & 0xffff, dep.y >> 16, dep.z, dep.w);
         if (!ok) break;
         stamp(q, idx, 5);
@@ -877,10 +915,30 @@ void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s) {
     else agp_gramfill_kernel<GF_E, GF_MINB, true><<<grid, FT, 0, s>>>(v, tile_id0);
 }
 
-void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s) {
+void launch_chol(const BatchView& v, const SchedView& q, const TmaMaps& maps, int ctas, cudaStream_t s) {
     if (q.n_items <= 0) return;
     if (ctas > q.n_items) ctas = q.n_items;
-    agp_chol_kernel<<<ctas, FT, FUSED_SMEM, s>>>(v, q);
+    agp_chol_kernel<<<ctas, FT, FUSED_SMEM, s>>>(v, q, maps);
+}
+
+bool make_tma_maps(double* L, int ld, long long rows, TmaMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box_a[2] = {(cuuint32_t)KC, (cuuint32_t)UM}, box_b[2] = {(cuuint32_t)KC, (cuuint32_t)UN}, estr[2] = {1, 1};
+    const CUresult r1 = encode(&out->a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, L, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r2 = encode(&out->b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, L, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
 }
 
 }  // namespace agp

@@ -1,5 +1,6 @@
 // Kernel launch interface shared by agp_kernels.cu and agp_api.cu.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -74,8 +75,15 @@ void launch_grad(const BatchView& v, int P, const int* param_off, double* partia
 int grad_blocks_per_particle(const BatchView& v);
 // Predictive mean / covariance out of an augmented factorisation (agp_predict_batch)
 void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
+// 2-D TMA descriptors over L viewed as one [P * ld][ld] FP64 matrix: boxes of 16 columns (128 bytes, hardware
+// 128-byte swizzle) x 64 rows (A operand: the item's rows) and x 128 rows (B operand: tile row k)
+struct TmaMaps {
+    CUtensorMap a, b;
+};
+// returns false when the driver refuses the descriptor (reported by the caller)
+bool make_tma_maps(double* L, int ld, long long rows, TmaMaps* out);
 // One launch = the whole batch: Cholesky + solve + logdet for every particle.
-void launch_chol(const BatchView& v, const SchedView& q, int ctas, cudaStream_t s);
+void launch_chol(const BatchView& v, const SchedView& q, const TmaMaps& maps, int ctas, cudaStream_t s);
 cudaError_t configure_fused();
 
 // Stand-alone Gram matrix (drop-in for compute_cov_matrix[_vectorized]): column-major, both triangles

@@ -464,6 +464,8 @@ static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vect
     const int split_from = 3;
     auto split = [&](int k) { return k >= split_from && k < nt; };
     const int ks = std::max(nt - late, 1);  // first block column of the right-looking phase
+    double pos_la = 0.0, pos_diag = 1.0 / 3, pos_potf2 = 0.5;
+    if (const char* e = getenv("AGP_POS")) sscanf(e, "%lf,%lf,%lf", &pos_la, &pos_diag, &pos_potf2);  // developer A/B
     for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);
     for (int p = 0; p < P; ++p) b.potf2(p, 0);
     struct T { int p, i, k, j1; };
@@ -484,9 +486,13 @@ static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vect
             std::vector<T> bulk;
             for (int i = k + 2; i < nt; ++i)
                 for (int p = 0; p < P; ++p) bulk.push_back({p, i, k, k});
-            const size_t nb = bulk.size(), c1 = nb / 3, c2 = 2 * nb / 3;
-            for (size_t a = 0; a < c1; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
+            // the look-ahead items, DIAG(k+1) and POTF2(k+1) are interleaved into the bulk of column k at these
+            // fractions (tuned with tools/queue_sim.py, confirmed on the device: profiles/r01_order_tuning.txt)
+            const size_t nb = bulk.size();
+            const size_t c0 = (size_t)(pos_la * nb), c1 = std::max(c0, (size_t)(pos_diag * nb)), c2 = std::max(c1, (size_t)(pos_potf2 * nb));
+            for (size_t a = 0; a < c0; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
             for (const T& a : la) b.tile(a.p, a.i, a.k, a.j1);
+            for (size_t a = c0; a < c1; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
             for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
             for (size_t a = c1; a < c2; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
             for (int p = 0; p < P; ++p) b.potf2(p, k + 1);

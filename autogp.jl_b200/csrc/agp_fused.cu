@@ -644,6 +644,9 @@ __device__ __noinline__ bool do_potf2(const BatchView& v, const SchedView& q, in
 __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView q, const __grid_constant__ TmaMaps maps) {
     const Smem s = smem_view();
     if (threadIdx.x == 0) {
+        // the two TMA descriptors are fetched now, not on the first copy of the first item
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b) : "memory");
         for (int st = 0; st < NSTAGE; ++st) {
             mbar_init(s.full + st, 1);
             mbar_init(s.empty + st, FT / 32);

@@ -294,6 +294,20 @@ def test_smc_step_single_gpu(engine):
     assert np.allclose(state.log_weights, prev, rtol=1e-10)  # sum of increments telescopes to the last score
 
 
+def test_full_size_repeated_runs_never_corrupt_a_particle(engine):
+    """The persistent kernel's operand pipeline (TMA copies, mbarriers, cross-CTA counters) under full load:
+    every run of the headline workload must report info == 0 everywhere and reproduce the first run bit for bit
+    (a rare pipeline race shows up as ONE particle with a wrong tile and a non-positive pivot)."""
+    n, P = 2048, 64
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(P)]
+    first, info = gpu_lmls(engine, parts, ts, xs)
+    assert np.all(info == 0) and np.all(np.isfinite(first))
+    for _ in range(7):
+        again, info = gpu_lmls(engine, parts, ts, xs)
+        assert np.all(info == 0) and np.array_equal(again, first)
+
+
 # ---- BASELINE.json full sizes: size-independent properties ------------------------------------
 
 def test_full_size_n2048_p64_properties(engine):

@@ -93,6 +93,35 @@ def test_gram_changepoint_saturates_exactly(engine):
     assert np.array_equal(K[:20, :20], R[:20, :20])  # sigma == 1 exactly: pure Linear block, bit-exact
 
 
+def test_gram_extreme_arguments_take_the_fallback_paths(engine):
+    """The interpreter's own exp / sin^2 / constant division (agp_math.cuh) hand arguments outside their fast
+    ranges to libdevice: exp arguments below -700 (tiny lengthscales: results underflow through the denormals to
+    0), sin arguments above 1e5 (tiny periods), divisors near the ends of the exponent range, zero numerators
+    (the diagonal) — all inside one warp next to ordinary entries."""
+    ts = np.linspace(0.0, 1.0, 96)
+    cases = [
+        o.SquaredExponential(0.0262, 1.7),                  # -0.5 dx^2 / l^2 spans 0 .. -728: fast path, fallback, denormals
+        o.Periodic(0.9, 1.7e-5, 0.8),                       # (pi / p) |dx| up to 1.8e5: Payne-Hanek fallback of sin
+        o.Periodic(0.05, 0.31, 1.2),                        # -2/l^2 = -800: exp arguments down to -800
+        o.SquaredExponential(1e-160, 1.0),                  # l^2 = 1e-320 (denormal divisor): generic division
+        o.SquaredExponential(3e155, 1.0),                   # l^2 overflows to inf: every off-diagonal argument is -0
+        o.GammaExponential(1e-3, 1.9, 1.1),                 # (|dx| / l)^gamma up to 5e5: exp fallback after pow
+        o.Plus(o.Times(o.SquaredExponential(0.03, 1.0), o.Periodic(0.07, 2e-5, 1.0)), o.Linear(0.2, 0.1, 0.4)),
+    ]
+    for k in cases:
+        with np.errstate(all="ignore"):
+            R = o.compute_cov_matrix_vectorized(k, 0.0, ts)
+        K = engine.gram(H.to_agp(k), 0.0, ts)
+        assert np.all(np.isfinite(K)) == np.all(np.isfinite(R)), k
+        big = np.abs(R) > 1e-290          # denormal results: libm implementations differ in the last denormal bits
+        # exponent arguments here reach several hundred, so an ulp of argument error is hundreds of ulps of the result:
+        # the tolerance scales with the magnitude of log K instead of the fixed 64 eps of the fixture sweep
+        cond = np.maximum(1.0, np.abs(np.log(np.maximum(np.abs(R), 1e-300))))
+        assert np.all(np.abs(K - R)[big] <= (16 * EPS * cond * np.abs(R))[big]), k
+        assert np.all(np.abs(K[~big]) <= 1e-289), k
+        assert np.array_equal(K, K.T)
+
+
 def test_gram_does_not_mutate_inputs_and_empty(engine):
     ts = np.linspace(0, 1, 10)
     ts0 = ts.copy()

@@ -20,7 +20,7 @@ EXPORTS = (
     "agp_lml_device_results", "agp_lml_set_prefix",
     "agp_stream", "agp_synchronize", "agp_launch_count", "agp_lml_time", "agp_lml_stage_times",
     "agp_queue_build", "agp_queue_build_general", "agp_lml_trace",
-    "agp_lml_run_append", "agp_predict_batch", "agp_lml_grad_batch",
+    "agp_lml_run_append", "agp_predict_batch", "agp_lml_grad_batch", "agp_lml_copy_factor",
 )
 
 AGP_OK, AGP_ERR_ARG, AGP_ERR_PROGRAM, AGP_ERR_CUDA, AGP_ERR_NOMEM, AGP_ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.agp_lml_run.restype = C.c_int
     lib.agp_lml_fetch.argtypes = [vp, f64p, i32p]
     lib.agp_lml_fetch.restype = C.c_int
+    lib.agp_lml_copy_factor.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.agp_lml_copy_factor.restype = C.c_int
     lib.agp_lml_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.agp_lml_device_results.restype = C.c_int
     lib.agp_lml_set_prefix.argtypes = [vp, C.c_int32]

@@ -782,6 +782,19 @@ int agp_lml_fetch(agp_handle* h, double* lml_out, int32_t* info_out) {
     return AGP_OK;
 }
 
+int agp_lml_copy_factor(agp_handle* h, int32_t particle, double* factor_out, int32_t* ld_out) {
+    if (!h || !ld_out) return AGP_ERR_ARG;
+    if (!h->uploaded || h->n_factored < 0) return fail(h, AGP_ERR_STATE, "agp_lml_copy_factor: no factor resident (run the batch first)");
+    if (particle < 0 || particle >= h->P) return fail(h, AGP_ERR_ARG, "agp_lml_copy_factor: particle out of range");
+    *ld_out = h->ld;
+    if (!factor_out) return AGP_OK;
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    AGP_CUDA(h, cudaMemcpyAsync(factor_out, h->view.L + (long long)particle * h->view.mat_stride, (size_t)h->ld * h->ld * 8, cudaMemcpyDeviceToHost,
+                                h->stream));
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AGP_OK;
+}
+
 int agp_lml_device_results(agp_handle* h, double** lml_dev, int32_t** info_dev) {
     if (!h || !lml_dev || !info_dev) return AGP_ERR_ARG;
     if (!h->uploaded) return fail(h, AGP_ERR_STATE, "agp_lml_device_results: no resident batch");

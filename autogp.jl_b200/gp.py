@@ -331,6 +331,15 @@ class Engine:
         self._check(self._lib.agp_lml_fetch(self._h, _f64p(lml), _i32p(info)))
         return lml, info
 
+    def factor(self, particle: int) -> np.ndarray:
+        """Lower Cholesky factor of one particle of the resident batch ([ld, ld], rows >= n are padding); its
+        transpose is the upper factor of cholesky(Symmetric(K)) that the reference's MvNormal holds."""
+        ld = C.c_int32(0)
+        self._check(self._lib.agp_lml_copy_factor(self._h, particle, None, C.byref(ld)))
+        out = np.empty((ld.value, ld.value), dtype=np.float64)
+        self._check(self._lib.agp_lml_copy_factor(self._h, particle, _f64p(out), C.byref(ld)))
+        return np.tril(out)
+
     def device_results(self) -> Tuple[int, int]:
         a, b = C.c_void_p(), C.c_void_p()
         self._check(self._lib.agp_lml_device_results(self._h, C.byref(a), C.byref(b)))

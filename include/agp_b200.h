@@ -213,6 +213,12 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
  * query it).  tools/trace_report.py turns this into per-phase / per-SM utilisation. */
 int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items);
 
+/* Diagnostics: copy the factor of one particle of the resident batch to the host: ld x ld doubles, row-major, lower
+ * triangle = L (== the column-major upper factor U = L' that cholesky(Symmetric(K)) returns in Julia, which is what
+ * PDMats keeps inside the MvNormal of src/Model.jl:136); rows/columns >= n are padding.  *ld_out receives ld
+ * (factor_out may be NULL to query it).  Valid after agp_lml_run / agp_lml_batch. */
+int agp_lml_copy_factor(agp_handle* h, int32_t particle, double* factor_out, int32_t* ld_out);
+
 #ifdef __cplusplus
 }
 #endif

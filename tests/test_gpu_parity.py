@@ -323,6 +323,22 @@ def test_smc_step_single_gpu(engine):
     assert np.allclose(state.log_weights, prev, rtol=1e-10)  # sum of increments telescopes to the last score
 
 
+def test_factor_reproduces_the_gram_matrix(engine):
+    """agp_lml_copy_factor: L L' = K + noise I to rounding, and L' is the upper factor LAPACK dpotrf('U') returns."""
+    import scipy.linalg as sla
+
+    n = 300
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p, "se*per+lin") for p in range(3)]
+    gpu_lmls(engine, parts, ts, xs)
+    for p, (nd, nz) in enumerate(parts):
+        L = engine.factor(p)[:n, :n]
+        K = o.compute_cov_matrix_vectorized(nd, nz, ts)
+        assert np.max(np.abs(L @ L.T - K)) <= 1e-12 * np.max(np.abs(K))
+        U = sla.cholesky(K, lower=False)
+        assert np.max(np.abs(L.T - U)) <= 1e-9 * np.max(np.abs(U))
+
+
 def test_full_size_repeated_runs_never_corrupt_a_particle(engine):
     """The persistent kernel's operand pipeline (TMA copies, mbarriers, cross-CTA counters) under full load:
     every run of the headline workload must report info == 0 everywhere and reproduce the first run bit for bit

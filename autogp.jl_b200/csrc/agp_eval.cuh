@@ -230,6 +230,9 @@ constexpr int AGP_GRAD_MAX_NODES = 64;
 template <class Acc>
 __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ prog, int m, double t1, double t2, double seed, Acc&& acc) {
     double val[AGP_GRAD_MAX_NODES], adj[AGP_GRAD_MAX_NODES];
+    // per-leaf intermediates of the forward sweep that the backward sweep needs again (the exponential before the
+    // amplitude; sin / cos of the Periodic argument; the power of the GammaExponential): computed once
+    double ex[AGP_GRAD_MAX_NODES], u1s[AGP_GRAD_MAX_NODES], u2s[AGP_GRAD_MAX_NODES];
     unsigned char opa[AGP_GRAD_MAX_NODES], opb[AGP_GRAD_MAX_NODES];  // operand node indices (s1, s0)
     unsigned char stack[AGP_MAX_STACK + 1];
     int sp = 0;
@@ -243,9 +246,36 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
             switch (op) {
                 case AGP_I_CONST: v = a; break;
                 case AGP_I_LINEAR: v = b + c * ((t1 - a) * (t2 - a)); break;
-                case AGP_I_SE: v = b * exp(((-0.5 * dx) * dx) / a); break;
-                case AGP_I_GE: v = c * exp(-pow(adx / a, b)); break;
-                case AGP_I_PER: { double sn = sin(a * adx); v = c * exp(b * (sn * sn)); break; }
+                case AGP_I_SE: {
+                    const double xin[1] = {((-0.5 * dx) * dx) / a};
+                    double e1[1];
+                    exp_v<1>(xin, e1);
+                    ex[q] = e1[0];
+                    v = b * e1[0];
+                    break;
+                }
+                case AGP_I_GE: {
+                    const double w = pow(adx / a, b);
+                    const double xin[1] = {-w};
+                    double e1[1];
+                    exp_v<1>(xin, e1);
+                    ex[q] = e1[0];
+                    u1s[q] = w;
+                    v = c * e1[0];
+                    break;
+                }
+                case AGP_I_PER: {
+                    double sn, cs;
+                    sincos(a * adx, &sn, &cs);
+                    const double xin[1] = {b * (sn * sn)};
+                    double e1[1];
+                    exp_v<1>(xin, e1);
+                    ex[q] = e1[0];
+                    u1s[q] = sn;
+                    u2s[q] = cs;
+                    v = c * e1[0];
+                    break;
+                }
                 default: v = (t1 == t2) ? a : 0.0; break;
             }
             val[q] = v;
@@ -259,7 +289,10 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
             else if (op == AGP_I_TIMES) v = val[ia] * val[ib];
             else {
                 const double kl = (op == AGP_I_CP) ? val[ia] : val[ib], kr = (op == AGP_I_CP) ? val[ib] : val[ia];
-                const double g1 = sigma_cp(t1, a, b), g2 = sigma_cp(t2, a, b);
+                const double th1 = tanh((a - t1) / b), th2 = tanh((a - t2) / b);
+                u1s[q] = th1;
+                u2s[q] = th2;
+                const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
                 v = (g1 * g2) * kl + ((1.0 - g1) * (1.0 - g2)) * kr;
             }
             val[q] = v;
@@ -281,28 +314,24 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
                 acc(off + 2, g * (u1 * u2));
                 break;
             }
-            case AGP_I_SE: {  // amp exp(-dx^2 / (2 l^2)): params (lengthscale l, amplitude); a = l^2
-                const double e = exp(((-0.5 * dx) * dx) / a);
-                const double l = sqrt(a);
-                acc(off, g * (val[q] * (dx * dx) / (a * l)));
-                acc(off + 1, g * e);
+            case AGP_I_SE: {  // amp exp(-dx^2 / (2 l^2)): params (lengthscale l, amplitude); a = l^2, d = l
+                acc(off, g * (val[q] * (dx * dx) / (a * prog[q].d)));
+                acc(off + 1, g * ex[q]);
                 break;
             }
             case AGP_I_GE: {  // amp exp(-(|dx| / l)^gamma): params (l, gamma, amp)
                 const double u = adx / a;
-                const double w = pow(u, b);
+                const double w = u1s[q];
                 acc(off, g * (val[q] * b * w / a));
                 acc(off + 1, (u > 0.0) ? g * (-val[q] * w * log(u)) : 0.0);
-                acc(off + 2, g * exp(-w));
+                acc(off + 2, g * ex[q]);
                 break;
             }
-            case AGP_I_PER: {  // amp exp(b s^2), s = sin(a |dx|), a = pi / p, b = -2 / l^2: params (l, p, amp)
-                const double arg = a * adx;
-                const double sn = sin(arg), cs = cos(arg);
-                const double l = sqrt(-2.0 / b), per = 3.14159265358979323846 / a;
-                acc(off, g * (val[q] * (sn * sn) * (-2.0 * b / l)));          // db/dl = 4 / l^3 = -2 b / l
-                acc(off + 1, g * (val[q] * b * 2.0 * sn * cs * adx * (-a / per)));  // da/dp = -pi / p^2 = -a / p
-                acc(off + 2, g * exp(b * (sn * sn)));
+            case AGP_I_PER: {  // amp exp(b s^2), s = sin(a |dx|), a = pi / p, b = -2 / l^2: params (l, p, amp); d = l, reserved = p
+                const double sn = u1s[q], cs = u2s[q];
+                acc(off, g * (val[q] * (sn * sn) * (-2.0 * b / prog[q].d)));          // db/dl = 4 / l^3 = -2 b / l
+                acc(off + 1, g * (val[q] * b * 2.0 * sn * cs * adx * (-a / prog[q].reserved)));  // da/dp = -pi / p^2 = -a / p
+                acc(off + 2, g * ex[q]);
                 break;
             }
             case AGP_I_PLUS:
@@ -317,7 +346,7 @@ __device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ p
                 const int il = (op == AGP_I_CP) ? opa[q] : opb[q], ir = (op == AGP_I_CP) ? opb[q] : opa[q];
                 const double kl = val[il], kr = val[ir];
                 const double u1 = (a - t1) / b, u2 = (a - t2) / b;
-                const double th1 = tanh(u1), th2 = tanh(u2);
+                const double th1 = u1s[q], th2 = u2s[q];
                 const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
                 const double dg1 = 0.5 * (1.0 - th1 * th1) / b, dg2 = 0.5 * (1.0 - th2 * th2) / b;  // d sigma / d location
                 adj[il] += g * (g1 * g2);

@@ -741,11 +741,14 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
     const int gc = col0 + c;
     const double tcol = ts_c[c];
     const bool plain = !diag && row0 + UM <= n && col0 + UN <= n;
+    const bool no_kernel_rows = v.aug_identity && row0 >= v.nt * TB;
 #pragma unroll 1
     for (int eb = 0; eb < 32 / E; ++eb) {
         double t1[E], t2[E], val[E];
         const int rlast = rbase + 2 * (E * eb + E - 1);
-        const bool skip = diag && c > rlast + h * UM;  // strictly-upper part of a diagonal tile: zeros
+        // nothing to evaluate: the strictly-upper part of a diagonal tile (zeros), and every appended row of an
+        // identity-augmented batch ([I 0]: agp_lml_grad_batch — three quarters of that matrix)
+        const bool skip = (diag && c > rlast + h * UM) || no_kernel_rows;
         if (!skip) {
 #pragma unroll
             for (int j = 0; j < E; ++j) {

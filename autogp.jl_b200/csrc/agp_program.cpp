@@ -55,6 +55,7 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
                 case AGP_OP_SQUARED_EXPONENTIAL:
                     in.op = AGP_I_SE; in.a = p[0] * p[0]; in.b = p[1];
                     in.c = 1.0 / in.a;
+                    in.d = p[0];  // the lengthscale itself (gradient interpreter)
                     if (fast_divisor(in.a)) in.op |= AGP_I_FASTDIV;
                     break;
                 case AGP_OP_GAMMA_EXPONENTIAL:
@@ -67,6 +68,8 @@ void emit(const std::vector<TNode>& t, int id, const double* params, std::vector
                     in.a = M_PI / p[1];
                     in.b = -2.0 / (p[0] * p[0]);
                     in.c = p[2];
+                    in.d = p[0];         // lengthscale and period themselves (gradient interpreter)
+                    in.reserved = p[1];
                     break;
                 default: in.op = AGP_I_WN; in.a = p[0]; break;
             }

@@ -15,9 +15,9 @@
 enum AgpDevOp : int32_t {
     AGP_I_CONST = 0,   // a = value
     AGP_I_LINEAR = 1,  // a = intercept, b = bias, c = amplitude
-    AGP_I_SE = 2,      // a = lengthscale^2, b = amplitude, c = 1 / lengthscale^2
+    AGP_I_SE = 2,      // a = lengthscale^2, b = amplitude, c = 1 / lengthscale^2, d = lengthscale
     AGP_I_GE = 3,      // a = lengthscale, b = gamma, c = amplitude, d = 1 / lengthscale
-    AGP_I_PER = 4,     // a = pi/period, b = -2/lengthscale^2, c = amplitude
+    AGP_I_PER = 4,     // a = pi/period, b = -2/lengthscale^2, c = amplitude, d = lengthscale, reserved = period
     AGP_I_WN = 5,      // a = value
     AGP_I_PLUS = 6,
     AGP_I_TIMES = 7,
@@ -32,7 +32,7 @@ struct __attribute__((aligned(16))) AgpInstr {
     int32_t op;   // AgpDevOp | flags
     int32_t pad;  // index of the node's first parameter in the particle's params[] slice (wire order)
     double a, b, c, d;
-    double reserved;  // keeps sizeof == 48 (three 16-byte shared-memory loads)
+    double reserved;  // sizeof == 48 (three 16-byte shared-memory loads); Periodic keeps its period here
 };
 #define AGP_INSTR_DOUBLES 6  // sizeof(AgpInstr) / 8
 

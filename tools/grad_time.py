@@ -1,0 +1,16 @@
+import os, sys, time
+import numpy as np
+ROOT='/root/repo'
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'oracle'))
+import autogp_oracle as o
+import autogp.jl_b200 as agp
+from tools.dev_check import to_agp
+eng=agp.Engine(0)
+n,P=2048,64
+ts,xs=o.synthetic_series(n)
+parts=[o.synthetic_particle(p) for p in range(P)]
+nodes,noises=[to_agp(nd) for nd,_ in parts],[nz for _,nz in parts]
+for _ in range(3): eng.lml_grad_batch(nodes,noises,ts,xs)
+t0=time.perf_counter()
+for _ in range(5): eng.lml_grad_batch(nodes,noises,ts,xs)
+print('grad ms/call',(time.perf_counter()-t0)/5*1e3)

@@ -1,6 +1,8 @@
+"""Wall time of agp_lml_grad_batch (LML + gradient, host buffers) at n = 2048, 64 particles; run under
+`ncu --metrics gpu__time_duration.sum` for the per-kernel split (Gram fill / factorisation + inverse / gradient interpreter)."""
 import os, sys, time
 import numpy as np
-ROOT='/root/repo'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'oracle'))
 import autogp_oracle as o
 import autogp.jl_b200 as agp

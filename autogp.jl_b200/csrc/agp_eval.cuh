@@ -227,138 +227,253 @@ __device__ __forceinline__ void eval_entries(const AgpInstr* __restrict__ prog, 
 // ------------------------------------------------------------------------------------------
 constexpr int AGP_GRAD_MAX_NODES = 64;
 
-template <class Acc>
-__device__ __forceinline__ double eval_entry_grad(const AgpInstr* __restrict__ prog, int m, double t1, double t2, double seed, Acc&& acc) {
-    double val[AGP_GRAD_MAX_NODES], adj[AGP_GRAD_MAX_NODES];
-    // per-leaf intermediates of the forward sweep that the backward sweep needs again (the exponential before the
-    // amplitude; sin / cos of the Periodic argument; the power of the GammaExponential): computed once
-    double ex[AGP_GRAD_MAX_NODES], u1s[AGP_GRAD_MAX_NODES], u2s[AGP_GRAD_MAX_NODES];
-    unsigned char opa[AGP_GRAD_MAX_NODES], opb[AGP_GRAD_MAX_NODES];  // operand node indices (s1, s0)
+// Operand node indices of every binary node (s1 = left-hand stack operand, s0 = right-hand): a property of the
+// program, so it is derived once per CTA (one thread) instead of per entry.
+__device__ __forceinline__ void grad_operands(const AgpInstr* __restrict__ prog, int m, unsigned char* opa, unsigned char* opb) {
     unsigned char stack[AGP_MAX_STACK + 1];
     int sp = 0;
-    const double dx = t1 - t2, adx = fabs(dx);
+    for (int q = 0; q < m; ++q) {
+        if ((prog[q].op & 0xff) > AGP_I_WN) {
+            const int ib = stack[--sp], ia = stack[--sp];
+            opa[q] = (unsigned char)ia;
+            opb[q] = (unsigned char)ib;
+        } else {
+            opa[q] = opb[q] = 0;
+        }
+        stack[sp++] = (unsigned char)q;
+    }
+}
+
+// E entries at once (independent chains hide the local-memory and FP64 latencies); acc(j, d) receives the SUM over
+// the E entries of  seed_e * dk_e / dparams[j].
+template <int E, class Acc>
+__device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ prog, int m, const unsigned char* __restrict__ opa,
+                                                  const unsigned char* __restrict__ opb, const double (&t1)[E], const double (&t2)[E],
+                                                  const double (&seed)[E], Acc&& acc) {
+    double val[AGP_GRAD_MAX_NODES][E], adj[AGP_GRAD_MAX_NODES][E];
+    // per-leaf intermediates of the forward sweep that the backward sweep needs again (the exponential before the
+    // amplitude; sin / cos of the Periodic argument; the power of the GammaExponential; tanh of the ChangePoint)
+    double ex[AGP_GRAD_MAX_NODES][E], u1s[AGP_GRAD_MAX_NODES][E], u2s[AGP_GRAD_MAX_NODES][E];
+    double dx[E], adx[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        dx[e] = t1[e] - t2[e];
+        adx[e] = fabs(dx[e]);
+    }
     for (int q = 0; q < m; ++q) {
         const int op = prog[q].op & 0xff;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
-        adj[q] = 0.0;
-        if (op <= AGP_I_WN) {
-            double v;
-            switch (op) {
-                case AGP_I_CONST: v = a; break;
-                case AGP_I_LINEAR: v = b + c * ((t1 - a) * (t2 - a)); break;
-                case AGP_I_SE: {
-                    const double xin[1] = {((-0.5 * dx) * dx) / a};
-                    double e1[1];
-                    exp_v<1>(xin, e1);
-                    ex[q] = e1[0];
-                    v = b * e1[0];
-                    break;
+        double v[E];
+        switch (op) {
+            case AGP_I_CONST:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = a;
+                break;
+            case AGP_I_LINEAR:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b + c * ((t1[e] - a) * (t2[e] - a));
+                break;
+            case AGP_I_SE: {
+                double xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) xin[e] = ((-0.5 * dx[e]) * dx[e]) / a;
+                exp_v<E>(xin, e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ex[q][e] = e1[e];
+                    v[e] = b * e1[e];
                 }
-                case AGP_I_GE: {
-                    const double w = pow(adx / a, b);
-                    const double xin[1] = {-w};
-                    double e1[1];
-                    exp_v<1>(xin, e1);
-                    ex[q] = e1[0];
-                    u1s[q] = w;
-                    v = c * e1[0];
-                    break;
+                break;
+            }
+            case AGP_I_GE: {
+                double xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double w = pow(adx[e] / a, b);
+                    u1s[q][e] = w;
+                    xin[e] = -w;
                 }
-                case AGP_I_PER: {
+                exp_v<E>(xin, e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ex[q][e] = e1[e];
+                    v[e] = c * e1[e];
+                }
+                break;
+            }
+            case AGP_I_PER: {
+                double xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
                     double sn, cs;
-                    sincos(a * adx, &sn, &cs);
-                    const double xin[1] = {b * (sn * sn)};
-                    double e1[1];
-                    exp_v<1>(xin, e1);
-                    ex[q] = e1[0];
-                    u1s[q] = sn;
-                    u2s[q] = cs;
-                    v = c * e1[0];
-                    break;
+                    sincos(a * adx[e], &sn, &cs);
+                    u1s[q][e] = sn;
+                    u2s[q][e] = cs;
+                    xin[e] = b * (sn * sn);
                 }
-                default: v = (t1 == t2) ? a : 0.0; break;
+                exp_v<E>(xin, e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    ex[q][e] = e1[e];
+                    v[e] = c * e1[e];
+                }
+                break;
             }
-            val[q] = v;
-            stack[sp++] = (unsigned char)q;
-        } else {
-            const int ib = stack[--sp], ia = stack[--sp];  // s0, s1
-            opa[q] = (unsigned char)ia;
-            opb[q] = (unsigned char)ib;
-            double v;
-            if (op == AGP_I_PLUS) v = val[ia] + val[ib];
-            else if (op == AGP_I_TIMES) v = val[ia] * val[ib];
-            else {
-                const double kl = (op == AGP_I_CP) ? val[ia] : val[ib], kr = (op == AGP_I_CP) ? val[ib] : val[ia];
-                const double th1 = tanh((a - t1) / b), th2 = tanh((a - t2) / b);
-                u1s[q] = th1;
-                u2s[q] = th2;
-                const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
-                v = (g1 * g2) * kl + ((1.0 - g1) * (1.0 - g2)) * kr;
+            case AGP_I_WN:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
+                break;
+            case AGP_I_PLUS: {
+                const int ia = opa[q], ib = opb[q];
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = val[ia][e] + val[ib][e];
+                break;
             }
-            val[q] = v;
-            stack[sp++] = (unsigned char)q;
+            case AGP_I_TIMES: {
+                const int ia = opa[q], ib = opb[q];
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = val[ia][e] * val[ib][e];
+                break;
+            }
+            default: {  // ChangePoint
+                const int il = (op == AGP_I_CP) ? opa[q] : opb[q], ir = (op == AGP_I_CP) ? opb[q] : opa[q];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double th1 = tanh((a - t1[e]) / b), th2 = tanh((a - t2[e]) / b);
+                    u1s[q][e] = th1;
+                    u2s[q][e] = th2;
+                    const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
+                    v[e] = (g1 * g2) * val[il][e] + ((1.0 - g1) * (1.0 - g2)) * val[ir][e];
+                }
+                break;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            val[q][e] = v[e];
+            adj[q][e] = 0.0;
         }
     }
-    adj[m - 1] = seed;
+#pragma unroll
+    for (int e = 0; e < E; ++e) adj[m - 1][e] = seed[e];
     for (int q = m - 1; q >= 0; --q) {
-        const double g = adj[q];
         const int op = prog[q].op & 0xff, off = prog[q].pad;
         const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        double g[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) g[e] = adj[q][e];
         switch (op) {
-            case AGP_I_CONST: acc(off, g); break;
-            case AGP_I_WN: acc(off, (t1 == t2) ? g : 0.0); break;
+            case AGP_I_CONST: {
+                double s0 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) s0 += g[e];
+                acc(off, s0);
+                break;
+            }
+            case AGP_I_WN: {
+                double s0 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) s0 += (t1[e] == t2[e]) ? g[e] : 0.0;
+                acc(off, s0);
+                break;
+            }
             case AGP_I_LINEAR: {  // bias + amp (t1 - c0)(t2 - c0): params (intercept c0, bias, amplitude)
-                const double u1 = t1 - a, u2 = t2 - a;
-                acc(off, g * (-c * (u1 + u2)));
-                acc(off + 1, g);
-                acc(off + 2, g * (u1 * u2));
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double u1 = t1[e] - a, u2 = t2[e] - a;
+                    s0 += g[e] * (-c * (u1 + u2));
+                    s1 += g[e];
+                    s2 += g[e] * (u1 * u2);
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
                 break;
             }
             case AGP_I_SE: {  // amp exp(-dx^2 / (2 l^2)): params (lengthscale l, amplitude); a = l^2, d = l
-                acc(off, g * (val[q] * (dx * dx) / (a * prog[q].d)));
-                acc(off + 1, g * ex[q]);
+                const double al = a * prog[q].d;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    s0 += g[e] * (val[q][e] * (dx[e] * dx[e]) / al);
+                    s1 += g[e] * ex[q][e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
                 break;
             }
             case AGP_I_GE: {  // amp exp(-(|dx| / l)^gamma): params (l, gamma, amp)
-                const double u = adx / a;
-                const double w = u1s[q];
-                acc(off, g * (val[q] * b * w / a));
-                acc(off + 1, (u > 0.0) ? g * (-val[q] * w * log(u)) : 0.0);
-                acc(off + 2, g * ex[q]);
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double u = adx[e] / a, w = u1s[q][e];
+                    s0 += g[e] * (val[q][e] * b * w / a);
+                    s1 += (u > 0.0) ? g[e] * (-val[q][e] * w * log(u)) : 0.0;
+                    s2 += g[e] * ex[q][e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
                 break;
             }
             case AGP_I_PER: {  // amp exp(b s^2), s = sin(a |dx|), a = pi / p, b = -2 / l^2: params (l, p, amp); d = l, reserved = p
-                const double sn = u1s[q], cs = u2s[q];
-                acc(off, g * (val[q] * (sn * sn) * (-2.0 * b / prog[q].d)));          // db/dl = 4 / l^3 = -2 b / l
-                acc(off + 1, g * (val[q] * b * 2.0 * sn * cs * adx * (-a / prog[q].reserved)));  // da/dp = -pi / p^2 = -a / p
-                acc(off + 2, g * ex[q]);
+                const double dbdl = -2.0 * b / prog[q].d;       // db/dl = 4 / l^3 = -2 b / l
+                const double dadp = -a / prog[q].reserved;      // da/dp = -pi / p^2 = -a / p
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double sn = u1s[q][e], cs = u2s[q][e];
+                    s0 += g[e] * (val[q][e] * (sn * sn) * dbdl);
+                    s1 += g[e] * (val[q][e] * b * 2.0 * sn * cs * adx[e] * dadp);
+                    s2 += g[e] * ex[q][e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
                 break;
             }
-            case AGP_I_PLUS:
-                adj[opa[q]] += g;
-                adj[opb[q]] += g;
+            case AGP_I_PLUS: {
+                const int ia = opa[q], ib = opb[q];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    adj[ia][e] += g[e];
+                    adj[ib][e] += g[e];
+                }
                 break;
-            case AGP_I_TIMES:
-                adj[opa[q]] += g * val[opb[q]];
-                adj[opb[q]] += g * val[opa[q]];
+            }
+            case AGP_I_TIMES: {
+                const int ia = opa[q], ib = opb[q];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double va = val[ia][e], vb = val[ib][e];
+                    adj[ia][e] += g[e] * vb;
+                    adj[ib][e] += g[e] * va;
+                }
                 break;
+            }
             default: {  // ChangePoint: params (location, scale)
                 const int il = (op == AGP_I_CP) ? opa[q] : opb[q], ir = (op == AGP_I_CP) ? opb[q] : opa[q];
-                const double kl = val[il], kr = val[ir];
-                const double u1 = (a - t1) / b, u2 = (a - t2) / b;
-                const double th1 = u1s[q], th2 = u2s[q];
-                const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
-                const double dg1 = 0.5 * (1.0 - th1 * th1) / b, dg2 = 0.5 * (1.0 - th2 * th2) / b;  // d sigma / d location
-                adj[il] += g * (g1 * g2);
-                adj[ir] += g * ((1.0 - g1) * (1.0 - g2));
-                const double dk1 = g2 * kl - (1.0 - g2) * kr, dk2 = g1 * kl - (1.0 - g1) * kr;   // dk / d sigma(t1), d sigma(t2)
-                acc(off, g * (dk1 * dg1 + dk2 * dg2));
-                acc(off + 1, g * (-(dk1 * dg1 * u1 + dk2 * dg2 * u2)));
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double kl = val[il][e], kr = val[ir][e];
+                    const double u1 = (a - t1[e]) / b, u2 = (a - t2[e]) / b;
+                    const double th1 = u1s[q][e], th2 = u2s[q][e];
+                    const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
+                    const double dg1 = 0.5 * (1.0 - th1 * th1) / b, dg2 = 0.5 * (1.0 - th2 * th2) / b;  // d sigma / d location
+                    adj[il][e] += g[e] * (g1 * g2);
+                    adj[ir][e] += g[e] * ((1.0 - g1) * (1.0 - g2));
+                    const double dk1 = g2 * kl - (1.0 - g2) * kr, dk2 = g1 * kl - (1.0 - g1) * kr;   // dk / d sigma(t1), d sigma(t2)
+                    s0 += g[e] * (dk1 * dg1 + dk2 * dg2);
+                    s1 += g[e] * (-(dk1 * dg1 * u1 + dk2 * dg2 * u2));
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
                 break;
             }
         }
     }
-    return val[m - 1];
 }
 
 }  // namespace agp

@@ -687,6 +687,9 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(BatchView v, SchedView 
 #ifndef AGP_GF_E
 #define AGP_GF_E 4
 #endif
+#ifndef AGP_GRAD_E
+#define AGP_GRAD_E 2
+#endif
 #ifndef AGP_GF_MINB
 #define AGP_GF_MINB 2
 #endif
@@ -836,6 +839,7 @@ void launch_predict_extract(const BatchView& v, int P, const double* noise_pred,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __restrict__ param_off, double* __restrict__ partial) {
     __shared__ AgpInstr prog_s[PROG_SMEM];
+    __shared__ unsigned char opa_s[PROG_SMEM], opb_s[PROG_SMEM];
     __shared__ double red[FT / 32][AGP_GRAD_MAX_PARAMS + 1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = blockIdx.y;
@@ -856,6 +860,8 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
         for (int w = tid; w < pm * AGP_INSTR_DOUBLES; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
     }
     __syncthreads();
+    if (tid == 0) grad_operands(prog_s, pm, opa_s, opb_s);
+    __syncthreads();
     const int np = param_off[p + 1] - param_off[p];  // host guarantees np <= AGP_GRAD_MAX_PARAMS
     double g[AGP_GRAD_MAX_PARAMS + 1];
     for (int j = 0; j <= np; ++j) g[j] = 0.0;
@@ -864,14 +870,27 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
     if (gc < n) {
         const double tcol = v.ts[gc];
         const double nac = nal[gc];
+        constexpr int GE_ = AGP_GRAD_E;  // entries per interpreter pass
 #pragma unroll 1
-        for (int e = 0; e < 32; ++e) {
-            const int gr = row0 + rbase + 2 * e;
-            if (gr >= n || gc > gr) continue;
-            const double A = nal[gr] * nac + Lp[(long long)(lt + gr) * ld + lt + gc];
-            const double wgt = (gr == gc) ? A : 2.0 * A;  // off-diagonal entries count twice (symmetry)
-            eval_entry_grad(prog_s, pm, tcol, v.ts[gr], wgt, [&](int j, double d) { g[j] += d; });
-            if (gr == gc) g[np] += A;  // dK/dnoise = I
+        for (int e0 = 0; e0 < 32; e0 += GE_) {
+            double t1[GE_], t2[GE_], wgt[GE_];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < GE_; ++u) {
+                const int gr = row0 + rbase + 2 * (e0 + u);
+                const bool ok = gr < n && gc <= gr;
+                t1[u] = tcol;
+                t2[u] = ok ? v.ts[gr] : tcol;  // an entry outside the lower triangle runs as a (k(t,t), weight 0) dummy
+                double A = 0.0;
+                if (ok) {
+                    A = nal[gr] * nac + Lp[(long long)(lt + gr) * ld + lt + gc];
+                    if (gr == gc) g[np] += A;  // dK/dnoise = I
+                }
+                wgt[u] = ok ? ((gr == gc) ? A : 2.0 * A) : 0.0;  // off-diagonal entries count twice (symmetry)
+                any = any || ok;
+            }
+            if (!any) continue;
+            eval_entries_grad<GE_>(prog_s, pm, opa_s, opb_s, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
         }
     }
     for (int j = 0; j <= np; ++j) {

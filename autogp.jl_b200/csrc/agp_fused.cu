@@ -5,8 +5,9 @@
 // queue; every item's producers sit EARLIER in the queue, so a consumer that spins on a
 // dependency counter always waits for a CTA that is already running: no deadlock, no
 // co-residency requirement, no tail waves between the stages of a block column, and the two
-// CTAs of an SM drift apart so one CTA's Gram/solve epilogue (issue-bound FP64 ALU work) fills
-// the gaps of the other's DMMA main loop.
+// CTAs of an SM drift apart so one CTA's solve / factorisation phases fill the gaps of the other's
+// DMMA main loop.  The contraction operands arrive by 2-D TMA tensor copies through a ring of
+// four stages guarded by full/empty mbarriers (no CTA barrier in the main loop).
 //
 // agp_gramfill_kernel runs first: it evaluates every particle's kernel-tree program over the lower
 // 128x128 tiles and leaves K(ts,ts) + noise*I in L (ts slices staged by 1-D TMA bulk copies, all

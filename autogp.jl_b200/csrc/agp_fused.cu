@@ -242,10 +242,10 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
         const double* As = diag ? Bs + h * UM * KC : Bs + UN * KC;  // diagonal tile: A rows are a slice of B
         // lane c4 takes the 16-byte chunks 2 c4 + ks of a row (a permutation of k shared by A and B): with the
         // 128-byte swizzle the eight lanes of an LDS.128 phase then hit eight different chunk columns
-        // KEEP the loads and the DMMAs of a k-step in separate conditional blocks.  Without them ptxas software-pipelines
-        // this loop and issues the next LDS.128 into fragment registers that DMMAs issued just before still have to
-        // read; with two CTAs sharing the FP64 pipe such a DMMA can still be queued, and a few lanes then multiply
-        // the wrong fragment: one wrong row / 8x8 block of a tile in ~1 of 10^4 items (profiles/r01_diag_item_bisect.txt).
+        // KEEP the loads and the DMMAs of a k-step in separate conditional blocks.  The same loop without them (same
+        // arithmetic, differently scheduled SASS) produced one wrong row / 8x8 block of a tile in ~1 of 10^4 items,
+        // only with two CTAs per SM (profiles/r01_diag_item_bisect.txt; suspected: a fragment register overwritten by
+        // an LDS.128 while a queued DMMA still has to read it).  Re-run tools/stress_check.py after any change here.
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             double2 a[4], b[4];

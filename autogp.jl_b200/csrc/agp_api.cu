@@ -36,6 +36,7 @@ struct agp_handle {
     bool factor_clean = false;  // the last fetch saw info == 0 for every particle
     double* d_pred = nullptr; size_t cap_pred = 0;  // predictive means + covariances
     bool aug_identity = false;  // the resident batch is identity-augmented (agp_lml_grad_batch)
+    bool trtri_only = false;    // ... and only L^{-T} is wanted, not -K^{-1} (agp_lml_grad_noise_batch)
     double* d_grad = nullptr; size_t cap_grad = 0;  // per-CTA partial sums + gradients
     const int* d_param_prefix = nullptr;            // [P+1] prefix sums of n_params (inside the input arena)
     BatchView view{};
@@ -622,7 +623,7 @@ static void build_queue_general(int P, int nt, int nt_total, int first_row, std:
 // and the trailing tile (nt + a, nt + b), b <= a, receives the Schur complement
 // 0 - sum_{j >= a} L^{-T}[a][j] L^{-T}[b][j]^T = -K^{-1}[a][b] as a store-only item over [a, nt) (a blocked
 // lauum at n^3/3 flops).  The forward-solve entries of the appended rows end as 0 - L^{-T} z = -alpha.
-static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::vector<int4>& items) {
+static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::vector<int4>& items, bool with_lauum = true) {
     build_queue(P, nt, nt_stride, order, items);
     for (int k = 0; k < nt; ++k)
         for (int p = 0; p < P; ++p)
@@ -631,6 +632,7 @@ static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::ve
                     items.push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (k == a ? agp::ITEM_YINIT : 0), p, k, nt + a));
                     items.push_back(pack_dep(a, k, 2 * k, 2 * (k - a), -1, 0));
                 }
+    if (!with_lauum) return;  // dLML/dnoise needs |L^{-1}|_F only
     for (int p = 0; p < P; ++p)
         for (int a = 0; a < nt; ++a)
             for (int b = 0; b <= a; ++b)
@@ -645,11 +647,11 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
     const int nt_total = v.nt_total;
-    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? -1 : first_row, nt_stride);
+    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? (h->trtri_only ? -2 : -1) : first_row, nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
-        if (h->aug_identity) build_queue_inverse(P, nt, nt_stride, h->order, items);
+        if (h->aug_identity) build_queue_inverse(P, nt, nt_stride, h->order, items, !h->trtri_only);
         else if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
         else build_queue_general(P, nt, nt_total, first_row, items);
         agp_handle::Queue qu;
@@ -847,13 +849,13 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
     return rc;
 }
 
-int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
-                       const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
-                       double* grad_params_out, double* grad_noise_out, int32_t* info_out) {
+static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                     const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
+                     double* grad_params_out, double* grad_noise_out, int32_t* info_out, bool noise_only) {
     if (!h) return AGP_ERR_ARG;
     if (P > 0 && (!lml_out || !grad_noise_out || !info_out || !prog_len || !n_params)) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: bad argument");
     size_t total_params = 0;
-    for (int p = 0; p < P; ++p) {
+    for (int p = 0; p < P && !noise_only; ++p) {
         if (n_params[p] > agp::AGP_GRAD_MAX_PARAMS || prog_len[p] > 64)
             return fail(h, AGP_ERR_PROGRAM, "agp_lml_grad_batch: particle " + std::to_string(p) + ": at most 64 nodes and 64 parameters per kernel");
         total_params += (size_t)(n_params[p] > 0 ? n_params[p] : 0);
@@ -861,20 +863,22 @@ int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     if (total_params > 0 && !grad_params_out) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: null gradient output");
     int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, nullptr, 0, nullptr, n > 0);
     if (rc != AGP_OK) return rc;
+    h->trtri_only = noise_only;
     if (P == 0) return AGP_OK;
     if (n == 0) {  // empty mvnormal: score 0, no dependence on anything
         for (int p = 0; p < P; ++p) lml_out[p] = 0.0, grad_noise_out[p] = 0.0, info_out[p] = 0;
         for (size_t j = 0; j < total_params; ++j) grad_params_out[j] = 0.0;
         return AGP_OK;
     }
-    const int blocks = agp::grad_blocks_per_particle(h->view);
-    const size_t partial_doubles = (size_t)P * blocks * (agp::AGP_GRAD_MAX_PARAMS + 1);
+    const int blocks = noise_only ? agp::noise_grad_blocks_per_particle(h->view) : agp::grad_blocks_per_particle(h->view);
+    const size_t partial_doubles = (size_t)P * blocks * (noise_only ? 1 : agp::AGP_GRAD_MAX_PARAMS + 1);
     if ((rc = grow_device(h, &h->d_grad, &h->cap_grad, (partial_doubles + total_params + P + 2) * 8)) != AGP_OK) return rc;
     if ((rc = run_fused(h)) != AGP_OK) return rc;
     h->n_factored = -1;  // the resident factor belongs to an augmented matrix
     double* d_gparams = h->d_grad + partial_doubles;
     double* d_gnoise = d_gparams + total_params;
-    agp::launch_grad(h->view, P, h->d_param_prefix, h->d_grad, d_gparams, d_gnoise, h->stream);
+    if (noise_only) agp::launch_noise_grad(h->view, P, h->d_grad, d_gnoise, h->stream);
+    else agp::launch_grad(h->view, P, h->d_param_prefix, h->d_grad, d_gparams, d_gnoise, h->stream);
     h->launches += 2;
     if ((rc = check_launch(h, "grad")) != AGP_OK) return rc;
     if (total_params > 0) AGP_CUDA(h, cudaMemcpyAsync(grad_params_out, d_gparams, total_params * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -887,11 +891,23 @@ int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     for (int p = 0; p < P; ++p) {  // gradients of a failed factorisation are undefined
         if (info_out[p] != 0) {
             grad_noise_out[p] = nan;
-            for (int j = 0; j < n_params[p]; ++j) grad_params_out[o + j] = nan;
+            for (int j = 0; j < n_params[p] && !noise_only; ++j) grad_params_out[o + j] = nan;
         }
         o += n_params[p];
     }
     return AGP_OK;
+}
+
+int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                       const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
+                       double* grad_params_out, double* grad_noise_out, int32_t* info_out) {
+    return grad_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, lml_out, grad_params_out, grad_noise_out, info_out, false);
+}
+
+int agp_lml_grad_noise_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                             const double* params, const double* noise, const double* ts, const double* xs, int32_t n, double* lml_out,
+                             double* grad_noise_out, int32_t* info_out) {
+    return grad_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, lml_out, nullptr, grad_noise_out, info_out, true);
 }
 
 int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
@@ -929,7 +945,8 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
     if (P < 0 || nt < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
-    if (order >= 100) build_queue_inverse(P, nt, 2 * nt, order - 100, items);  // identity-augmented schedule, counters laid out for 2 nt
+    if (order >= 200) build_queue_inverse(P, nt, 2 * nt, order - 200, items, false);  // factorisation + trtri only (noise gradient)
+    else if (order >= 100) build_queue_inverse(P, nt, 2 * nt, order - 100, items);  // identity-augmented schedule, counters laid out for 2 nt
     else build_queue(P, nt, nt, order, items);
     return export_queue(items, items_out, cap);
 }

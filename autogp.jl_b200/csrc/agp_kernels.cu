@@ -96,4 +96,64 @@ void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n,
     else agp_gram_kernel<true><<<blocks, GR_THREADS, 0, s>>>(prog, m, need, ts, n, noise, form, K);
 }
 
+// ------------------------------------------------------------------------------------------
+// dLML/dnoise alone (agp_lml_grad_noise_batch):  dK/dnoise = I, so
+//   dLML/dnoise = 1/2 tr(alpha alpha^T - K^{-1}) = 1/2 (|alpha|^2 - |L^{-1}|_F^2).
+// After the factorisation + blocked trtri of the identity-augmented matrix (no lauum pass, no kernel-tree
+// walk), row lt + r of L holds row r of L^{-T} (zero left of tile column r / 128) and y[lt + r] = -alpha_r.
+// One CTA sums NG_ROWS rows, one warp per row at a time, lanes along the row (coalesced); fixed summation
+// order: lane-strided partial sums -> warp shuffle tree -> per-warp -> per-CTA -> second kernel over CTAs.
+// ------------------------------------------------------------------------------------------
+constexpr int NG_THREADS = 256, NG_ROWS = 32;
+
+__global__ void __launch_bounds__(NG_THREADS) agp_noise_grad_kernel(BatchView v, double* __restrict__ partial) {
+    __shared__ double red[NG_THREADS / 32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = blockIdx.y;
+    const int ld = v.ld, n = v.n, lt = v.nt * TB;
+    const double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
+    const double* __restrict__ nal = v.y + (long long)p * ld + lt;
+    double acc = 0.0;
+    for (int rr = warp; rr < NG_ROWS; rr += NG_THREADS / 32) {
+        const int r = blockIdx.x * NG_ROWS + rr;
+        if (r >= n) break;
+        const double* row = Lp + (long long)(lt + r) * ld;
+        double sq = 0.0;
+        for (int c = (r / TB) * TB + lane; c < n; c += 32) {
+            const double x = row[c];
+            sq += x * x;
+        }
+        acc -= sq;
+        if (lane == 0) {
+            const double a = nal[r];
+            acc += a * a;
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double sres = 0.0;
+#pragma unroll
+        for (int w = 0; w < NG_THREADS / 32; ++w) sres += red[w];
+        partial[(long long)p * gridDim.x + blockIdx.x] = sres;
+    }
+}
+
+__global__ void agp_noise_grad_reduce_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ gnoise_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double sres = 0.0;
+    for (int b = 0; b < blocks; ++b) sres += partial[(long long)p * blocks + b];
+    gnoise_out[p] = 0.5 * sres;
+}
+
+int noise_grad_blocks_per_particle(const BatchView& v) { return (v.n + NG_ROWS - 1) / NG_ROWS; }
+
+void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnoise_out, cudaStream_t s) {
+    if (P <= 0 || v.n <= 0) return;
+    const int blocks = noise_grad_blocks_per_particle(v);
+    agp_noise_grad_kernel<<<dim3(blocks, P), NG_THREADS, 0, s>>>(v, partial);
+    agp_noise_grad_reduce_kernel<<<P, 1, 0, s>>>(partial, blocks, gnoise_out);
+}
+
 }  // namespace agp

@@ -73,6 +73,9 @@ void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s);
 constexpr int AGP_GRAD_MAX_PARAMS = 64;
 void launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, cudaStream_t s);
 int grad_blocks_per_particle(const BatchView& v);
+// dLML/dnoise alone out of factorisation + trtri (agp_lml_grad_noise_batch): partial[P][blocks] per-CTA sums
+void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnoise_out, cudaStream_t s);
+int noise_grad_blocks_per_particle(const BatchView& v);
 // Predictive mean / covariance out of an augmented factorisation (agp_predict_batch)
 void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
 // 2-D TMA descriptors over L viewed as one [P * ld][ld] FP64 matrix: boxes of 16 columns (128 bytes, hardware

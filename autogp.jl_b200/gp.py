@@ -300,6 +300,24 @@ class Engine:
         grads = [gparams[cuts[p]:cuts[p + 1]].copy() for p in range(P)]
         return lml, grads, gnoise, info
 
+    def lml_grad_noise_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs):
+        """LML and dLML/dnoise only (the noise move of the reference's HMC): returns (lml[P], grad_noise[P], info[P]).
+        Factorisation + triangular inverse, no K^{-1}, no kernel-tree walk: ~0.6 of ``lml_grad_batch``."""
+        prog_len, ops, offs, n_params, params, noise = self.pack_batch(nodes, noises)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        P = len(prog_len)
+        lml = np.empty(P, dtype=np.float64)
+        gnoise = np.empty(P, dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_lml_grad_noise_batch(self._h, P, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                                       _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                                       _f64p(lml), _f64p(gnoise), _i32p(info)))
+        self._P = P
+        return lml, gnoise, info
+
     # ---- site 3 -------------------------------------------------------------------------
     def predict_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs, ts_pred,
                       noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -110,6 +110,7 @@ class Chains:
     grad_zn: Optional[np.ndarray] = None
     n_calls: int = 0                          # batched GPU calls issued so far
     n_evals: int = 0                          # particle evaluations inside them
+    n_noise_only_calls: int = 0               # of n_calls: the cheaper noise-gradient-only calls
     stats: dict = field(default_factory=lambda: {"mh": 0, "mh_trials": 0, "hmc": 0, "hmc_trials": 0, "not_pd": 0})
 
     @property
@@ -120,13 +121,19 @@ class Chains:
         return np.array([noise_of(z) for z in self.z_noise])
 
 
-def _evaluate(ch: Chains, nodes, z_list, z_noise, ts, xs, engine):
-    """LML and latent-space gradients of the given candidate states: one batched call."""
+def _evaluate(ch: Chains, nodes, z_list, z_noise, ts, xs, engine, noise_only: bool = False):
+    """LML and latent-space gradients of the given candidate states: one batched call.  ``noise_only``: the cheaper
+    ``agp_lml_grad_noise_batch`` (no K^-1, no kernel-tree walk); the parameter gradients come back as None."""
     noises = [noise_of(z) for z in z_noise]
-    lml, gparams, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
     ch.n_calls += 1
     ch.n_evals += len(nodes)
-    gz = [latent_gradient(nd, z, g) for nd, z, g in zip(nodes, z_list, gparams)]
+    if noise_only:
+        lml, gnoise, info = engine.lml_grad_noise_batch(nodes, noises, ts, xs)
+        ch.n_noise_only_calls += 1
+        gz = [None] * len(nodes)
+    else:
+        lml, gparams, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
+        gz = [latent_gradient(nd, z, g) for nd, z, g in zip(nodes, z_list, gparams)]
     gzn = np.array([g * model.transform_param_grad("noise", z) for g, z in zip(gnoise, z_noise)])
     ok = np.asarray(info) == 0
     ok &= np.isfinite(lml)
@@ -159,7 +166,8 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
     the leaf/changepoint latents (``select="params"``) or the noise latent (``select="noise"``): momenta ~ N(0, I),
     L leapfrog steps ``p += eps/2·∇; z += eps·p; ∇ = ∇score(z); p += eps/2·∇``, accept with probability
     ``exp(score' − score + logN(p') − logN(p))`` where ``score = LML + Σ logN(z)`` over the selection (everything else
-    in the trace is unchanged and cancels).  Returns the accepted mask over ``active``.  L batched calls."""
+    in the trace is unchanged and cancels).  Returns the accepted mask over ``active``.  L batched calls (for the noise
+    move L − 1 of them are the cheaper ``agp_lml_grad_noise_batch``)."""
     assert select in ("params", "noise")
     if ch.lml is None:
         refresh(ch, ts, xs, engine)
@@ -185,7 +193,8 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
     gz = [ch.grad_z[p] for p in active]
     gzn = ch.grad_zn[active].copy()
     cand_nodes = list(nodes)
-    for _ in range(L):
+    cheap_noise = select == "noise" and hasattr(engine, "lml_grad_noise_batch")
+    for step in range(L):
         for a in range(A):
             if alive[a]:
                 mom[a] = mom[a] + (eps / 2) * grad[a]
@@ -208,7 +217,9 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
                 if alive[a] and not (abs(sel[a][0]) < 700.0):      # exp(-1.5 + z) would overflow / NaN
                     alive[a] = False
             zns = np.array([sel[a][0] if alive[a] else zn0[a] for a in range(A)])
-        lml, gz, gzn, ok = _evaluate(ch, cand_nodes, zs, zns, ts, xs, engine)
+        # a noise trajectory needs dLML/dnoise only; its LAST evaluation is a full one so that the cached parameter
+        # gradients of an accepted state are current for the parameter move that follows
+        lml, gz, gzn, ok = _evaluate(ch, cand_nodes, zs, zns, ts, xs, engine, noise_only=cheap_noise and step < L - 1)
         newly_dead = alive & ~ok
         ch.stats["not_pd"] += int(newly_dead.sum())
         alive &= ok

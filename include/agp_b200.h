@@ -159,6 +159,18 @@ int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const 
                        double* lml_out, double* grad_params_out, double* grad_noise_out,
                        int32_t* info_out);
 
+/* The same call when only dLML/dnoise is wanted — the noise move of rejuvenate_particle_parameters
+ * (`Gen.hmc(trace, Gen.select(:noise); L, eps)`, src/inference_smc_anneal_data.jl:65-67), half of all HMC
+ * gradient evaluations of a run.  dK/dnoise = I, so
+ *   dLML/dnoise = 1/2 tr(alpha alpha' - K^{-1}) = 1/2 (|alpha|^2 - |L^{-1}|_F^2):
+ * factorisation + blocked trtri (2 n^3/3 flops), no lauum pass and no kernel-program walk — about 0.6 of the
+ * time of agp_lml_grad_batch.  Same arguments and conventions otherwise (no program-size limit).
+ * The value agrees with agp_lml_grad_batch's grad_noise_out to rounding (different summation order). */
+int agp_lml_grad_noise_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                             const int32_t* param_off, const int32_t* n_params, const double* params,
+                             const double* noise, const double* ts, const double* xs, int32_t n,
+                             double* lml_out, double* grad_noise_out, int32_t* info_out);
+
 /* ---- site 3: predictive distribution ---------------------------------------------------------- */
 
 /* For each particle p: the conditional multivariate normal  X(ts_pred) | X(ts) = xs  of
@@ -192,7 +204,8 @@ int agp_lml_time(agp_handle* h, int32_t reps, float* ms_out);
  * hold 3 floats. */
 int agp_lml_stage_times(agp_handle* h, float* stage_ms);
 
-/* (order >= 100: the identity-augmented schedule of agp_lml_grad_batch built on order - 100.)
+/* (order >= 100: the identity-augmented schedule of agp_lml_grad_batch built on order - 100;
+ *  order >= 200: that of agp_lml_grad_noise_batch — factorisation + trtri only — built on order - 200.)
  * The in-order work queue the persistent kernel executes for P particles x nt block columns
  * (host-only, no GPU needed): items_out receives up to `cap` items as 8 int32 each
  * {type | half << 8 | store_only << 9, particle, block column k, tile row i, j0, j1, extra_flag,

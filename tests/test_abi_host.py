@@ -129,7 +129,7 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None):
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True):
     """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
     counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
     every tile an item reads must be final, and the items must tile every contraction exactly.
@@ -196,6 +196,8 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None):
                 for h in (0, 1):
                     if k < nt:
                         assert covered[(p, i, k, h)] == k         # finished: contraction over all of [first, k)
+                    elif not expect_trailing:
+                        assert (p, i, k, h) not in covered
                     elif first_col(k) <= first_col(i):
                         assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # trailing (Schur complement) tile
 
@@ -241,3 +243,22 @@ def test_inverse_schedule_replay(P, nt, order):
     buf = np.zeros((n_items, 8), dtype=np.int32)
     lib.agp_queue_build(P, nt, 100 + order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
     _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0)
+
+
+@pytest.mark.parametrize("P,nt,order", [(1, 1, 3), (2, 4, 3), (1, 9, 2)])
+def test_trtri_only_schedule_replay(P, nt, order):
+    """agp_lml_grad_noise_batch: the identity-augmented schedule without its lauum pass — the same items as the full
+    inverse schedule up to the first trailing store-only item, and nothing after."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build(P, nt, 200 + order, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    lib.agp_queue_build(P, nt, 200 + order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
+    _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0, expect_trailing=False)
+    n_full = lib.agp_queue_build(P, nt, 100 + order, None, 0)
+    full = np.zeros((n_full, 8), dtype=np.int32)
+    lib.agp_queue_build(P, nt, 100 + order, full.ctypes.data_as(C.POINTER(C.c_int32)), n_full)
+    assert n_full - n_items == P * nt * (nt + 1)          # two half items per trailing lower tile
+    assert np.array_equal(full[:n_items], buf)
+    assert not np.any(buf[:, 2] >= nt)                    # no item factors or updates a trailing block column

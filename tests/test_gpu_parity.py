@@ -578,6 +578,62 @@ def test_lml_gradient_full_size_directional_derivative(engine):
     assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
 
 
+@pytest.mark.parametrize("n", [1, 77, 128, 300, 1000])
+def test_noise_only_gradient_matches_the_full_gradient_call_and_the_oracle(engine, n):
+    """agp_lml_grad_noise_batch (factorisation + trtri, 1/2 (|alpha|^2 - |L^-1|_F^2)) against agp_lml_grad_batch's noise
+    gradient (1/2 tr(alpha alpha' - K^-1) out of the full inverse) and the dense oracle route; ragged batch, every node type."""
+    ts, xs = o.synthetic_series(max(n, 2))
+    ts, xs = ts[:n], xs[:n]
+    trees = ["se*per+lin", "se+wn", "ge+per*lin", "cp(lin,se)"]
+    parts = [o.synthetic_particle(40 + p, t) for p, t in enumerate(trees)]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    lml_f, _, gn_f, info_f = engine.lml_grad_batch(nodes, noises, ts, xs)
+    lml, gn, info = engine.lml_grad_noise_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0) and np.all(info_f == 0)
+    assert np.array_equal(lml, lml_f)                      # same factorisation items, same arithmetic
+    assert H.rel_err(lml, oracle_lmls(parts, ts, xs)) <= LML_RTOL_TIGHT
+    for p, (nd, nz) in enumerate(parts):
+        # both are differences of two large sums (|alpha|^2 and tr K^-1): compare at the scale of the larger one
+        K = o.compute_cov_matrix_vectorized(nd, nz, ts)
+        Kinv = np.linalg.inv(K)
+        alpha = Kinv @ xs
+        scale = max(float(alpha @ alpha), float(np.trace(Kinv)), 1.0)
+        ref = 0.5 * (float(alpha @ alpha) - float(np.trace(Kinv)))
+        assert abs(gn[p] - gn_f[p]) <= 1e-12 * scale, (p, gn[p], gn_f[p])
+        assert abs(gn[p] - ref) <= 1e-9 * scale, (p, gn[p], ref)
+    again = engine.lml_grad_noise_batch(nodes, noises, ts, xs)
+    assert np.array_equal(gn, again[1])                    # fixed summation order
+
+
+def test_noise_only_gradient_full_size_and_edge_cases(engine):
+    import autogp.jl_b200 as agp
+
+    n, P = 2048, 6
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p) for p in range(P)]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    lml, gn, info = engine.lml_grad_noise_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0)
+    hstep = 1e-6
+    for p in range(P):   # the derivative of the GPU LML itself along the noise
+        up, _ = engine.lml_batch([nodes[p]], [noises[p] * (1 + hstep)], ts, xs)
+        dn, _ = engine.lml_batch([nodes[p]], [noises[p] * (1 - hstep)], ts, xs)
+        fd = (up[0] - dn[0]) / (2 * hstep * noises[p])
+        assert abs(fd - gn[p]) <= 1e-5 * max(1.0, abs(fd)), (p, fd, gn[p])
+    # a plain LML batch after the augmented one is unaffected by the leftover state
+    assert np.array_equal(engine.lml_batch(nodes, noises, ts, xs)[0], lml)
+    # empty data, failed factorisation, and no program-size limit on this path
+    lml, gn, info = engine.lml_grad_noise_batch([agp.SquaredExponential(0.3, 1.0)], [0.1], ts[:0], xs[:0])
+    assert lml[0] == 0.0 and gn[0] == 0.0 and info[0] == 0
+    lml, gn, info = engine.lml_grad_noise_batch([agp.Constant(1.0), agp.SquaredExponential(0.3, 1.0)], [-2.0, 0.1], ts[:150], xs[:150])
+    assert info[0] != 0 and np.isnan(lml[0]) and np.isnan(gn[0]) and info[1] == 0 and np.isfinite(gn[1])
+    big = agp.Constant(1.0)
+    for _ in range(70):
+        big = agp.Plus(big, agp.Constant(0.5))
+    lml, gn, info = engine.lml_grad_noise_batch([big], [0.1], ts[:150], xs[:150])
+    assert info[0] == 0 and np.isfinite(gn[0])
+
+
 def test_lml_gradient_edge_cases(engine):
     import autogp.jl_b200 as agp
     from autogp.jl_b200 import _lib

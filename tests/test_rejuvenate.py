@@ -51,6 +51,15 @@ class OracleEngine:
         return np.array(lml), grads, np.array(gn), np.array(info, dtype=np.int32)
 
 
+class OracleEngineWithNoiseCall(OracleEngine):
+    """... plus the noise-gradient-only call of the real engine."""
+
+    def lml_grad_noise_batch(self, nodes, noises, ts, xs):
+        lml, _, gn, info = OracleEngine.lml_grad_batch(self, nodes, noises, ts, xs)
+        self.batches[-1] = ("noise", len(nodes))
+        return lml, gn, info
+
+
 def start_state(P, seed=5):
     rng = np.random.default_rng(seed)
     trees = [
@@ -143,6 +152,20 @@ def test_small_steps_conserve_the_hamiltonian():
         assert math.isclose(ch.lml[p], o.log_marginal_likelihood(from_agp(ch.nodes[p]), rj.noise_of(ch.z_noise[p]), ts, xs), rel_tol=1e-12)
     acc = rj.hmc_lockstep(ch, np.arange(P), ts, xs, select="noise", L=2, eps=1e-4, rngs=rj.particle_rngs(4, P), engine=eng)
     assert acc.all() and len(eng.batches) == 7                 # no second refresh: the cache is current
+
+
+def test_noise_moves_use_the_cheap_call_except_for_their_last_step():
+    P, cfg, seed = 4, {"L_param": 2, "L_noise": 4, "eps_param": 0.03, "eps_noise": 0.03}, 6
+    plain, acc_plain, _ = run_joint(P, 2, cfg, seed)
+    eng = OracleEngineWithNoiseCall()
+    cheap, acc_cheap, _ = run_joint(P, 2, cfg, seed, engine=eng)
+    assert cheap.nodes == plain.nodes and np.array_equal(cheap.z_noise, plain.z_noise) and acc_cheap == acc_plain
+    kinds = [k for k, _ in eng.batches]
+    assert kinds == ["grad"] + (["grad"] * 2 + ["noise"] * 3 + ["grad"]) * 2
+    assert cheap.n_noise_only_calls == 6 and cheap.n_calls == len(kinds)
+    for p in range(P):   # the cache after a noise move holds the parameter gradients of the accepted state
+        g, _ = o.lml_grad_dense_fd(from_agp(cheap.nodes[p]), rj.noise_of(cheap.z_noise[p]), *series(20))
+        np.testing.assert_array_equal(cheap.grad_z[p], rj.latent_gradient(cheap.nodes[p], rj.latents(cheap.nodes[p]), g))
 
 
 def test_consecutive_rejections_shrink_the_batch():

@@ -16,3 +16,11 @@ for _ in range(3): eng.lml_grad_batch(nodes,noises,ts,xs)
 t0=time.perf_counter()
 for _ in range(5): eng.lml_grad_batch(nodes,noises,ts,xs)
 print('grad ms/call',(time.perf_counter()-t0)/5*1e3)
+for _ in range(3): eng.lml_grad_noise_batch(nodes,noises,ts,xs)
+t0=time.perf_counter()
+for _ in range(5): eng.lml_grad_noise_batch(nodes,noises,ts,xs)
+print('noise-only grad ms/call',(time.perf_counter()-t0)/5*1e3)
+for _ in range(3): eng.lml_batch(nodes,noises,ts,xs)
+t0=time.perf_counter()
+for _ in range(5): eng.lml_batch(nodes,noises,ts,xs)
+print('lml ms/call',(time.perf_counter()-t0)/5*1e3)

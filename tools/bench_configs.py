@@ -92,6 +92,30 @@ def main():
         emit({"what": "f-1 lml + gradient, end to end (host buffers)", "n": n, "particles": P, "ms_per_call": dt * 1e3,
               "grads_per_s": P / dt, "algorithmic_tflops (n^3: chol + trtri + lauum)": P * n ** 3 / dt * 1e-12, "info_ok": bool(np.all(info == 0))})
 
+        eng.lml_grad_noise_batch(nodes, noises, ts, xs)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lml, gnoise, info = eng.lml_grad_noise_batch(nodes, noises, ts, xs)
+        dt = (time.perf_counter() - t0) / reps
+        emit({"what": "f-1 lml + noise gradient only, end to end (host buffers)", "n": n, "particles": P, "ms_per_call": dt * 1e3,
+              "grads_per_s": P / dt, "algorithmic_tflops (2 n^3 / 3: chol + trtri)": P * 2 * n ** 3 / 3 / dt * 1e-12,
+              "info_ok": bool(np.all(info == 0))})
+
+    # ---- a9 / f-4: one round of rejuvenate_particle_parameters for all particles in lock step (L = 10 + 10 leapfrog steps)
+    from autogp.jl_b200 import rejuvenate as rj
+    n, P = 2048, 64
+    ts, xs = o.synthetic_series(n)
+    nodes, noises = batch(P)
+    ch = rj.Chains(list(nodes), np.array([agp.untransform_param("noise", nz - agp.JITTER) for nz in noises]))
+    rj.refresh(ch, ts, xs, eng)
+    c0 = ch.n_calls
+    t0 = time.perf_counter()
+    acc, trials = rj.rejuvenate_parameters_lockstep(ch, np.arange(P), 1, ts, xs, rngs=rj.particle_rngs(0, P), engine=eng)
+    dt = time.perf_counter() - t0
+    emit({"what": "a9 lock-step parameter rejuvenation, one HMC round (params L=10, noise L=10), wall", "n": n, "particles": P,
+          "ms": dt * 1e3, "batched_calls": ch.n_calls - c0, "noise_only_calls": ch.n_noise_only_calls,
+          "accepted": int(sum(acc.values())), "leapfrog_evaluations_per_s": P * (ch.n_calls - c0) / dt})
+
     # ---- predictive MVN
     n, m, P = 2048, 256, 64
     ts, xs = o.synthetic_series(n)

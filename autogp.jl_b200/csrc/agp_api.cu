@@ -35,6 +35,8 @@ struct agp_handle {
     int n_factored = -1;     // observations covered by the factor resident in d_L (-1: none), for agp_lml_run_append
     bool factor_clean = false;  // the last fetch saw info == 0 for every particle
     double* d_pred = nullptr; size_t cap_pred = 0;  // predictive means + covariances
+    unsigned char* d_comp = nullptr; size_t cap_comp = 0;  // summand programs of agp_predict_sum_batch
+    agp::ComponentView comp{};   // comp.M > 0: rewrite the appended rows after the Gram fill (agp_predict_sum_batch)
     bool aug_identity = false;  // the resident batch is identity-augmented (agp_lml_grad_batch)
     bool trtri_only = false;    // ... and only L^{-T} is wanted, not -K^{-1} (agp_lml_grad_noise_batch)
     double* d_grad = nullptr; size_t cap_grad = 0;  // per-CTA partial sums + gradients
@@ -172,6 +174,7 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_gin);
     cudaFree(h->d_sync);
     cudaFree(h->d_pred);
+    cudaFree(h->d_comp);
     cudaFree(h->d_grad);
     for (auto& kv : h->queues) cudaFree(kv.second.d_items);
     cudaFreeHost(h->h_sync);
@@ -264,6 +267,7 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     h->uploaded = false;
     h->n_factored = -1;
     h->factor_clean = false;
+    h->comp.M = 0;
     if (P < 0 || n < 0 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)) || (m > 0 && !ts_pred && !aug_identity))
         return fail(h, AGP_ERR_ARG, "agp_lml_upload: bad argument");
     if (P > 65535) return fail(h, AGP_ERR_ARG, "agp_lml_upload: at most 65535 particles per batch");
@@ -696,6 +700,10 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     q.wait_timeout_ns = h->wait_timeout_ns;
     if (kernel_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     agp::launch_gramfill(v, P, first_row, h->stream);
+    if (h->comp.M > 0) {
+        agp::launch_component_fill(v, P, h->comp, h->stream);
+        h->launches += 1;
+    }
     if (kernel_ms) {
         AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         AGP_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -847,6 +855,108 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
     rc = agp_lml_fetch(h, lml.data(), info_out);  // synchronises; info: LAPACK code of the training block
     h->factor_clean = false;
     return rc;
+}
+
+// Joint posterior of the summands of a sum kernel and of the observable at ts_pred (infer_gp_sum, src/GP.jl:904-993).
+int agp_predict_sum_batch(agp_handle* h, int32_t P, int32_t M, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off,
+                          const int32_t* n_params, const double* params, const double* noise, const double* ts, const double* xs, int32_t n,
+                          const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (P < 0 || M < 1 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise || !info_out)) ||
+        (P > 0 && m > 0 && (!mean_out || !cov_out || !ts_pred)))
+        return fail(h, AGP_ERR_ARG, "agp_predict_sum_batch: bad argument");
+    if (P == 0) return AGP_OK;
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    // the observation kernel: k_1 + k_2 + ... + k_M as ONE program per particle (postfix: k_1 k_2 + k_3 + ...), its
+    // parameter slice the concatenation of the summands' slices; and every summand compiled on its own
+    std::vector<int32_t> c_len(P), c_ops, c_off, c_np(P);
+    std::vector<AgpInstr> comp_instr;
+    std::vector<int32_t> comp_off((size_t)P * M + 1, 0), comp_need((size_t)P * M, 1);
+    {
+        size_t o = 0, po = 0;
+        std::string err;
+        for (int p = 0; p < P; ++p) {
+            int len = 0, shift = 0;
+            for (int c = 0; c < M; ++c) {
+                const int q = p * M + c;
+                if (prog_len[q] <= 0 || n_params[q] < 0) return fail(h, AGP_ERR_PROGRAM, "agp_predict_sum_batch: particle " + std::to_string(p) + ": empty summand");
+                for (int j = 0; j < prog_len[q]; ++j) {
+                    c_ops.push_back(ops[o + j]);
+                    c_off.push_back(param_off[o + j] + shift);
+                }
+                comp_off[q] = (int32_t)comp_instr.size();
+                int need = 1;
+                int rc = agp_compile_program(ops + o, param_off + o, prog_len[q], params ? params + po : nullptr, n_params[q], comp_instr, &need, err);
+                if (rc != AGP_OK) return fail(h, rc, "agp_predict_sum_batch: particle " + std::to_string(p) + " summand " + std::to_string(c) + ": " + err);
+                comp_need[q] = need;
+                len += prog_len[q];
+                if (c > 0) {
+                    c_ops.push_back(AGP_OP_PLUS);
+                    c_off.push_back(0);
+                    ++len;
+                }
+                o += prog_len[q];
+                po += n_params[q];
+                shift += n_params[q];
+            }
+            c_len[p] = len;
+            c_np[p] = shift;
+        }
+        comp_off[(size_t)P * M] = (int32_t)comp_instr.size();
+    }
+    const int mt = (M + 1) * m;  // appended rows: F_1(T*) ... F_M(T*), X(T*)
+    std::vector<double> tp_ext((size_t)(mt > 0 ? mt : 1));
+    for (int g = 0; g <= M; ++g)
+        for (int a = 0; a < m; ++a) tp_ext[(size_t)g * m + a] = ts_pred[a];
+    // the extraction kernel adds its noise_pred[p] to EVERY diagonal entry; only the X(T*) block carries it (:963), so
+    // the resident copy is a zero vector and the host adds the X* diagonal after the copy back
+    const std::vector<double> zeros((size_t)P, 0.0);
+    int rc = upload_impl(h, P, c_len.data(), c_ops.data(), c_off.data(), c_np.data(), params, noise, ts, xs, n, tp_ext.data(), mt, zeros.data());
+    if (rc != AGP_OK) return rc;
+    // summand programs -> device
+    const size_t off_b = align_up(comp_instr.size() * sizeof(AgpInstr), 16);
+    const size_t need_b = align_up(off_b + comp_off.size() * 4, 16);
+    const size_t comp_bytes = need_b + comp_need.size() * 4;
+    if ((rc = grow_device(h, &h->d_comp, &h->cap_comp, comp_bytes)) != AGP_OK) return rc;
+    {
+        std::vector<unsigned char> img(comp_bytes, 0);  // pageable: staged before cudaMemcpyAsync returns
+        memcpy(img.data(), comp_instr.data(), comp_instr.size() * sizeof(AgpInstr));
+        memcpy(img.data() + off_b, comp_off.data(), comp_off.size() * 4);
+        memcpy(img.data() + need_b, comp_need.data(), comp_need.size() * 4);
+        AGP_CUDA(h, cudaMemcpyAsync(h->d_comp, img.data(), comp_bytes, cudaMemcpyHostToDevice, h->stream));
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    h->comp.prog = reinterpret_cast<const AgpInstr*>(h->d_comp);
+    h->comp.off = reinterpret_cast<const int*>(h->d_comp + off_b);
+    h->comp.need = reinterpret_cast<const int*>(h->d_comp + need_b);
+    h->comp.M = (m > 0) ? M : 0;
+    h->comp.m_each = m;
+    const size_t mean_bytes = (size_t)P * mt * 8, cov_bytes = (size_t)P * mt * mt * 8;
+    if ((rc = grow_device(h, &h->d_pred, &h->cap_pred, mean_bytes + cov_bytes + 16)) != AGP_OK) return rc;
+    AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, align_up((size_t)P * 8, 16) + (size_t)P * 4, h->stream));
+    rc = run_fused(h);
+    h->comp.M = 0;
+    if (rc != AGP_OK) return rc;
+    h->n_factored = -1;  // the resident factor belongs to an augmented matrix
+    if (mt > 0) {
+        double* d_mean = h->d_pred;
+        double* d_cov = h->d_pred + (size_t)P * mt;
+        agp::launch_predict_extract(h->view, P, h->view.noise + P, d_mean, d_cov, h->stream);  // noise_pred slot: zeros
+        h->launches += 1;
+        if ((rc = check_launch(h, "predict_extract")) != AGP_OK) return rc;
+        AGP_CUDA(h, cudaMemcpyAsync(mean_out, d_mean, mean_bytes, cudaMemcpyDeviceToHost, h->stream));
+        AGP_CUDA(h, cudaMemcpyAsync(cov_out, d_cov, cov_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    std::vector<double> lml(P);
+    rc = agp_lml_fetch(h, lml.data(), info_out);  // synchronises; info: LAPACK code of the training block
+    h->factor_clean = false;
+    if (rc != AGP_OK) return rc;
+    for (int p = 0; p < P; ++p) {
+        const double np_ = noise_pred ? noise_pred[p] : noise[p];  // default: noise_pred = noise (:915)
+        double* cov = cov_out + (size_t)p * mt * mt;
+        for (int a = 0; a < m; ++a) cov[(size_t)(M * m + a) * mt + M * m + a] += np_;
+    }
+    return AGP_OK;
 }
 
 static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,

@@ -156,4 +156,62 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
     agp_noise_grad_reduce_kernel<<<P, 1, 0, s>>>(partial, blocks, gnoise_out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Joint posterior of the summands of a sum kernel (agp_predict_sum_batch; infer_gp_sum, src/GP.jl:904-993).
+// The batch was uploaded with the kernel  k_1 + ... + k_M  and (M + 1) copies of the m prediction points appended:
+// appended row  g m + a  stands for F_g(t*_a) for g < M and for X(t*_a) for g = M.  agp_gramfill_kernel has filled
+// every appended row with the SUM kernel; this kernel rewrites what differs (one CTA per appended row):
+//   row F_g :  columns of the observations   <- k_g(t_c, t*_a)          Cov[F_g(T*), X(T)]   = Ktp[g]'   (:955-956)
+//              trailing columns of F_g       <- k_g(t*_a', t*_a)         Cov[F_g(T*)]         = Kpp[g]    (:948)
+//              trailing columns of F_g', g' < g  <- 0                    independent summands
+//   row X*  :  trailing columns of F_g'      <- k_g'(t*_a', t*_a)        Cov[X(T*), F_g'(T*)] = Kpp[g']'  (:951-952)
+// (the observation columns and the X*/X* block of row X* already hold the sum kernel, :960-963).  Entries are
+// evaluated as the upper-triangle element of the joint matrix over z = [ts; ts_pred] (smaller index first), as
+// compute_cov_matrix_vectorized does (:929).
+// ------------------------------------------------------------------------------------------
+constexpr int CF_THREADS = 256;
+
+__device__ __forceinline__ void component_segment(const AgpInstr* __restrict__ prog, int pm, int need, const double* __restrict__ tsrc, int count,
+                                                  int a, double ta, bool minmax, double* __restrict__ dst) {
+    for (int j = 2 * threadIdx.x; j < count; j += 2 * CF_THREADS) {
+        const int j1 = (j + 1 < count) ? j + 1 : j;
+        const double u0 = tsrc[j], u1 = tsrc[j1];
+        const bool f0 = minmax && j > a, f1 = minmax && j1 > a;   // the column's point comes after the row's in z
+        const double t1[2] = {f0 ? ta : u0, f1 ? ta : u1};
+        const double t2[2] = {f0 ? u0 : ta, f1 ? u1 : ta};
+        double val[2];
+        eval_entries<2>(prog, pm, need, t1, t2, 0, val);
+        dst[j] = val[0];
+        if (j1 != j) dst[j1] = val[1];
+    }
+}
+
+__global__ void __launch_bounds__(CF_THREADS) agp_component_fill_kernel(BatchView v, ComponentView cv) {
+    const int p = blockIdx.y, rp = blockIdx.x;
+    const int M = cv.M, me = cv.m_each;
+    const int g = rp / me, a = rp - g * me;
+    const int lt = v.nt * TB, n = v.n;
+    double* __restrict__ row = v.L + (long long)p * v.mat_stride + (long long)(lt + rp) * v.ld;
+    const double* __restrict__ tp = v.ts + lt;  // the prediction points (first copy)
+    const double ta = tp[a];
+    if (g < M) {
+        const int c = p * M + g;
+        const AgpInstr* prog = cv.prog + cv.off[c];
+        const int pm = cv.off[c + 1] - cv.off[c], need = cv.need[c];
+        component_segment(prog, pm, need, v.ts, n, a, ta, false, row);                         // Cov[F_g(t*_a), X(T)]
+        for (int j = threadIdx.x; j < g * me; j += CF_THREADS) row[lt + j] = 0.0;                // earlier summands: independent
+        component_segment(prog, pm, need, tp, a + 1, a, ta, false, row + lt + g * me);         // Cov[F_g(t*_a), F_g(t*_a')], a' <= a
+    } else {
+        for (int gq = 0; gq < M; ++gq) {
+            const int c = p * M + gq;
+            component_segment(cv.prog + cv.off[c], cv.off[c + 1] - cv.off[c], cv.need[c], tp, me, a, ta, true, row + lt + gq * me);
+        }
+    }
+}
+
+void launch_component_fill(const BatchView& v, int P, const ComponentView& cv, cudaStream_t s) {
+    if (P <= 0 || cv.M <= 0 || cv.m_each <= 0) return;
+    agp_component_fill_kernel<<<dim3((cv.M + 1) * cv.m_each, P), CF_THREADS, 0, s>>>(v, cv);
+}
+
 }  // namespace agp

@@ -76,6 +76,17 @@ int grad_blocks_per_particle(const BatchView& v);
 // dLML/dnoise alone out of factorisation + trtri (agp_lml_grad_noise_batch): partial[P][blocks] per-CTA sums
 void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnoise_out, cudaStream_t s);
 int noise_grad_blocks_per_particle(const BatchView& v);
+// Summand programs of agp_predict_sum_batch: component c of particle p = instructions [off[p M + c], off[p M + c + 1])
+struct ComponentView {
+    const AgpInstr* prog;
+    const int* off;   // [P * M + 1]
+    const int* need;  // [P * M] operand-stack depth
+    int M;            // summands per particle
+    int m_each;       // prediction points
+};
+// rewrites the appended rows of a batch uploaded with the sum kernel and (M + 1) copies of the prediction points
+// (runs between launch_gramfill and launch_chol)
+void launch_component_fill(const BatchView& v, int P, const ComponentView& cv, cudaStream_t s);
 // Predictive mean / covariance out of an augmented factorisation (agp_predict_batch)
 void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
 // 2-D TMA descriptors over L viewed as one [P * ld][ld] FP64 matrix: boxes of 16 columns (128 bytes, hardware

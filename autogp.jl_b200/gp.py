@@ -343,6 +343,41 @@ class Engine:
         self._P = P
         return mean, cov, info
 
+    def predict_sum_batch(self, summands: Sequence[Sequence[Node]], noises: Sequence[float], ts, xs, ts_pred,
+                          noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """``infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993) for every particle:
+        ``summands[p]`` are the M additive components of particle p's kernel (same M for all).  Returns
+        (mean[P, d], cov[P, d, d], info[P]), d = (M + 1) m, over [F_1(T*); ...; F_M(T*); X(T*)] — without the JITTER
+        the reference adds when it wraps the result in an MvNormal (:981)."""
+        P = len(summands)
+        M = len(summands[0]) if P else 1
+        if M < 1 or any(len(sm) != M for sm in summands):
+            raise ValueError("every particle needs the same number (>= 1) of summands")
+        flat = [nd for sm in summands for nd in sm]
+        prog_len, ops, offs, n_params, params, _ = self.pack_batch(flat, [0.0] * len(flat))
+        noise = np.ascontiguousarray(noises, dtype=np.float64)
+        if noise.shape[0] != P:
+            raise ValueError("one noise value per particle")
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        tp = np.ascontiguousarray(ts_pred, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        m = tp.shape[0]
+        d = (M + 1) * m
+        npred = None if noise_pred is None else np.ascontiguousarray(noise_pred, dtype=np.float64)
+        if npred is not None and npred.shape[0] != P:
+            raise ValueError("one noise_pred value per particle")
+        mean = np.empty((P, d), dtype=np.float64)
+        cov = np.empty((P, d, d), dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_predict_sum_batch(self._h, P, M, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                                    _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                                    _f64p(tp), m, None if npred is None else _f64p(npred),
+                                                    _f64p(mean), _f64p(cov), _i32p(info)))
+        self._P = P
+        return mean, cov, info
+
     def fetch(self) -> Tuple[np.ndarray, np.ndarray]:
         lml = np.empty(self._P, dtype=np.float64)
         info = np.empty(self._P, dtype=np.int32)
@@ -432,6 +467,23 @@ def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, *, noise_pred: Opt
         from .model import PosDefException
         raise PosDefException(int(info[0]), 0)
     return mean[0], cov[0]
+
+
+def infer_gp_sum(nodes: Sequence[Node], noise: float, ts, xs, ts_pred, *, noise_pred: Optional[float] = None,
+                 engine: Optional[Engine] = None):
+    """``GP.infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993): posterior over the latent
+    summands F_i(ts_pred) and the observable X(ts_pred) of  X = sum_i F_i + eps.  Returns
+    ``(mean, cov, indexes)`` where ``cov`` includes the reference's ``JITTER * I`` (:981) and ``indexes`` =
+    ``{"F": [range per summand], "X": range}`` (0-based; :984-987)."""
+    from .model import JITTER, PosDefException
+
+    eng = engine or default_engine()
+    mean, cov, info = eng.predict_sum_batch([list(nodes)], [noise], ts, xs, ts_pred, None if noise_pred is None else [noise_pred])
+    if info[0] != 0:
+        raise PosDefException(int(info[0]), 0)
+    m, M = len(np.atleast_1d(ts_pred)), len(nodes)
+    cov = cov[0] + JITTER * np.eye(cov.shape[1])
+    return mean[0], cov, {"F": [range(i * m, (i + 1) * m) for i in range(M)], "X": range(M * m, (M + 1) * m)}
 
 
 def compute_cov_matrix(node: Node, noise: float, ts, *, engine: Optional[Engine] = None) -> np.ndarray:

@@ -189,6 +189,22 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
                       const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out,
                       double* cov_out, int32_t* info_out);
 
+/* Joint posterior of the M summands of a sum kernel and of the observable at the prediction points —
+ * `infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)` (src/GP.jl:904-993), the decomposition of a
+ * forecast into its additive components.  The observations follow k_1 + ... + k_M + noise I; summand c of
+ * particle p is program p*M + c of the wire arrays (prog_len[P*M], n_params[P*M]; param_off relative to
+ * the summand's own parameter slice; the slices of one particle are contiguous in params).  Outputs per
+ * particle, d = (M+1) m:  mean_out[d] and cov_out[d][d] of  [F_1(T*); ...; F_M(T*); X(T*)]  given X(T) = xs:
+ *   mu = S_ab K^{-1} xs,   Sigma = S_aa - S_ab K^{-1} S_ba            (:977-979)
+ * with noise_pred (NULL: noise) on the X(T*) diagonal only (:963).  The caller adds the JITTER of :981 when it
+ * builds the MvNormal.  One factorisation: the (M+1) m rows ride along as appended tile rows, like
+ * agp_predict_batch.  M must be the same for all particles of a call.  Replaces the resident batch. */
+int agp_predict_sum_batch(agp_handle* h, int32_t P, int32_t M, const int32_t* prog_len, const int32_t* ops,
+                          const int32_t* param_off, const int32_t* n_params, const double* params,
+                          const double* noise, const double* ts, const double* xs, int32_t n,
+                          const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out,
+                          double* cov_out, int32_t* info_out);
+
 /* ---- plumbing -------------------------------------------------------------------------- */
 
 /* cudaStream_t of the handle (as void*), for event timing / stream ordering by the caller. */

@@ -634,6 +634,69 @@ def test_noise_only_gradient_full_size_and_edge_cases(engine):
     assert info[0] == 0 and np.isfinite(gn[0])
 
 
+@pytest.mark.parametrize("n,m", [(60, 5), (300, 130), (1000, 33)])
+def test_infer_gp_sum_matches_the_oracle(engine, n, m):
+    """agp_predict_sum_batch against the restated infer_gp_sum (src/GP.jl:904-993): three particles with different
+    summands in one call, prediction points inside and beyond the data, noise_pred default and explicit."""
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(n)
+    tp = np.concatenate([np.linspace(1.0, 1.3, m - m // 2), ts[: m // 2]])
+    sets = [
+        [o.Linear(0.2, 0.4, 0.9), o.Periodic(0.5, 0.3, 1.2), o.GammaExponential(0.3, 1.4, 0.8)],
+        [o.Times(o.SquaredExponential(0.4, 0.7), o.Periodic(0.9, 0.25, 1.1)), o.Constant(0.3), o.Linear(0.5, 0.1, 0.6)],
+        [o.ChangePoint(o.Linear(0.3, 0.2, 0.8), o.SquaredExponential(0.2, 0.5), 0.6, 0.05), o.WhiteNoise(0.05), o.SquaredExponential(0.1, 0.2)],
+    ]
+    noises = [0.07, 0.02, 0.11]
+    for npred in (None, [0.0, 0.3, 0.01]):
+        mean, cov, info = engine.predict_sum_batch([[H.to_agp(nd) for nd in st] for st in sets], noises, ts, xs, tp, npred)
+        assert np.all(info == 0)
+        for p, st in enumerate(sets):
+            mu_o, cov_o, idx = o.infer_gp_sum(st, noises[p], ts, xs, tp, noise_pred=None if npred is None else npred[p])
+            cov_o = cov_o - o.JITTER * np.eye(cov_o.shape[0])        # the C-ABI leaves the MvNormal's jitter to the caller
+            scale = max(np.max(np.abs(cov_o)), 1e-12)
+            assert np.max(np.abs(mean[p] - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o))), (p, np.max(np.abs(mean[p] - mu_o)))
+            assert np.max(np.abs(cov[p] - cov_o)) <= 1e-8 * scale, (p, np.max(np.abs(cov[p] - cov_o)), scale)
+            assert np.array_equal(cov[p], cov[p].T)
+    # the single-particle mirror of the reference function (adds the jitter, raises on a non-PD training block)
+    mu1, cov1, idx1 = agp.infer_gp_sum([H.to_agp(nd) for nd in sets[0]], noises[0], ts, xs, tp)
+    mu_o, cov_o, idx_o = o.infer_gp_sum(sets[0], noises[0], ts, xs, tp)
+    assert [list(r) for r in idx1["F"]] == [list(r) for r in idx_o["F"]] and list(idx1["X"]) == list(idx_o["X"])
+    assert np.max(np.abs(cov1 - cov_o)) <= 1e-8 * np.max(np.abs(cov_o)) and np.max(np.abs(mu1 - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o)))
+
+
+def test_infer_gp_sum_edge_cases(engine):
+    import autogp.jl_b200 as agp
+    from autogp.jl_b200 import _lib
+    from autogp.jl_b200.model import PosDefException
+
+    ts, xs = o.synthetic_series(150)
+    tp = np.array([1.05])
+    # one summand, one prediction point: F* and X* differ by the noise only
+    mean, cov, info = engine.predict_sum_batch([[agp.SquaredExponential(0.3, 1.0)]], [0.1], ts, xs, tp)
+    assert info[0] == 0 and mean.shape == (1, 2) and abs(mean[0, 0] - mean[0, 1]) <= 1e-12
+    assert abs(cov[0, 1, 1] - cov[0, 0, 0] - 0.1) <= 1e-12 and abs(cov[0, 0, 1] - cov[0, 0, 0]) <= 1e-12
+    # X* block == agp_predict_batch of the Plus kernel
+    nodes = [agp.Linear(0.2, 0.4, 0.9), agp.Periodic(0.5, 0.3, 1.2)]
+    tp = np.linspace(1.0, 1.2, 140)
+    mean, cov, info = engine.predict_sum_batch([nodes], [0.05], ts, xs, tp)
+    m2, c2, _ = engine.predict_batch([agp.Plus(nodes[0], nodes[1])], [0.05], ts, xs, tp)
+    X = slice(2 * 140, 3 * 140)
+    assert np.max(np.abs(mean[0, X] - m2[0])) <= 1e-10 and np.max(np.abs(cov[0, X, X] - c2[0])) <= 1e-10 * np.max(np.abs(c2[0]))
+    # no observations: the posterior is the prior
+    mean, cov, info = engine.predict_sum_batch([nodes], [0.05], ts[:0], xs[:0], tp[:4])
+    K0 = o.compute_cov_matrix_vectorized(o.Linear(0.2, 0.4, 0.9), 0.0, tp[:4])
+    assert np.all(mean == 0.0) and np.max(np.abs(cov[0, :4, :4] - K0)) <= 1e-14 and np.all(cov[0, :4, 4:8] == 0.0)
+    # ragged summand counts and a non-PD training block
+    with pytest.raises(ValueError):
+        engine.predict_sum_batch([nodes, nodes[:1]], [0.05, 0.05], ts, xs, tp)
+    with pytest.raises(PosDefException):
+        agp.infer_gp_sum([agp.Constant(1.0)], -2.0, ts, xs, tp[:3], engine=engine)
+    # a later plain LML batch is unaffected
+    lml, info = engine.lml_batch([agp.Plus(nodes[0], nodes[1])], [0.05], ts, xs)
+    assert info[0] == 0 and H.rel_err(lml, [o.log_marginal_likelihood(o.Plus(o.Linear(0.2, 0.4, 0.9), o.Periodic(0.5, 0.3, 1.2)), 0.05, ts, xs)]) <= LML_RTOL_TIGHT
+
+
 def test_lml_gradient_edge_cases(engine):
     import autogp.jl_b200 as agp
     from autogp.jl_b200 import _lib

@@ -155,3 +155,30 @@ def test_transform_param_grad_is_the_derivative():
             hstep = 1e-6
             fd = (agp.transform_param(f, z + hstep) - agp.transform_param(f, z - hstep)) / (2 * hstep)
             assert agp.transform_param_grad(f, z) == pytest.approx(fd, rel=1e-8)
+
+
+def test_infer_gp_sum_restatement_is_consistent_with_the_predictive_mvn():
+    """src/GP.jl:904-993 restated: the X(T*) block is the predictive MVN of the Plus kernel (+ JITTER), the summand
+    means add up to the noiseless prediction, a single summand reproduces X* up to the noise, and summing the latent
+    blocks (with their cross-covariances) gives the covariance of the noiseless X*."""
+    ts, xs = o.synthetic_series(40)
+    tp = np.linspace(0.9, 1.3, 7)
+    nodes = [o.Linear(0.2, 0.4, 0.9), o.Periodic(0.5, 0.3, 1.2), o.GammaExponential(0.3, 1.4, 0.8)]
+    noise, npred = 0.07, 0.02
+    mu, cov, idx = o.infer_gp_sum(nodes, noise, ts, xs, tp, noise_pred=npred)
+    m = len(tp)
+    assert mu.shape == (4 * m,) and cov.shape == (4 * m, 4 * m) and list(idx["X"]) == list(range(3 * m, 4 * m))
+    mu_x, cov_x = o.predictive_mvn(o.Plus(o.Plus(nodes[0], nodes[1]), nodes[2]), noise, ts, xs, tp, noise_pred=npred)
+    X = list(idx["X"])
+    np.testing.assert_allclose(mu[X], mu_x, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(cov[np.ix_(X, X)], cov_x + o.JITTER * np.eye(m), rtol=1e-9, atol=1e-12)
+    F = [list(r) for r in idx["F"]]
+    np.testing.assert_allclose(sum(mu[f] for f in F), mu_x, rtol=1e-9, atol=1e-12)
+    tot = sum(cov[np.ix_(fa, fb)] for fa in F for fb in F)
+    np.testing.assert_allclose(tot, cov_x - npred * np.eye(m) + 3 * o.JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
+    # Cov[F_i*, X*] = sum_j Cov[F_i*, F_j*]  (X* = sum F* + independent noise)
+    for fa in F:
+        np.testing.assert_allclose(cov[np.ix_(fa, X)], sum(cov[np.ix_(fa, fb)] for fb in F) - o.JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
+    mu1, cov1, idx1 = o.infer_gp_sum(nodes[:1], noise, ts, xs, tp)
+    np.testing.assert_allclose(mu1[list(idx1["F"][0])], mu1[list(idx1["X"])], rtol=1e-12)
+    np.testing.assert_allclose(cov1[:m, :m] + noise * np.eye(m), cov1[m:, m:], rtol=1e-10, atol=1e-12)

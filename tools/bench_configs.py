@@ -128,8 +128,21 @@ def main():
     dt = (time.perf_counter() - t0) / 3
     emit({"what": "f-3 predictive MVN, end to end (host buffers)", "n": n, "m": m, "particles": P, "ms_per_call": dt * 1e3,
           "predictions_per_s": P / dt, "d2h_bytes": int(mean.nbytes + cov.nbytes), "info_ok": bool(np.all(info == 0))})
+    # ---- infer_gp_sum: joint posterior of the two summands of the bench tree + the observable at 128 points
+    n, m, P = 2048, 128, 64
+    ts, xs = o.synthetic_series(n)
+    tp = np.linspace(1.0, 1.2, m)
+    nodes, noises = batch(P)
+    sums = [[nd.left, nd.right] for nd in nodes]      # Plus(Times(SE, PER), LIN) = (SE x PER) + LIN
+    eng.predict_sum_batch(sums, noises, ts, xs, tp)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        mean, cov, info = eng.predict_sum_batch(sums, noises, ts, xs, tp)
+    dt = (time.perf_counter() - t0) / reps
+    emit({"what": "f-3 infer_gp_sum (2 summands + observable), end to end (host buffers)", "n": n, "m": m, "particles": P,
+          "ms_per_call": dt * 1e3, "posteriors_per_s": P / dt, "d2h_bytes": int(mean.nbytes + cov.nbytes), "info_ok": bool(np.all(info == 0))})
     eng.close()
-
 
 if __name__ == "__main__":
     main()

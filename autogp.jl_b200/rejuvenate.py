@@ -282,6 +282,99 @@ def rejuvenate_parameters_lockstep(ch: Chains, particles, n_hmc: int, ts, xs, *,
 
 
 # ------------------------------------------------------------------------------------------------
+# Gen.map_optimize, all traces in lock step (greedy search: src/Greedy.jl:93-101, 366-374)
+# ------------------------------------------------------------------------------------------------
+def _log_prior(z: np.ndarray, zn: float, infer_noise: bool) -> float:
+    return _logpdf_std_normal(z) + (_logpdf_std_normal(np.array([zn])) if infer_noise else 0.0)
+
+
+def map_optimize_lockstep(ch: Chains, particles, ts, xs, *, engine, max_opt: int = 500, max_step_size: float = 0.1,
+                          tau: float = 0.5, min_step_size: float = 1e-16, infer_noise: bool = True) -> dict:
+    """The parameter optimisation of the greedy search for many candidate traces at once:
+
+        for i = 1:MAX_OPT;  trace = Gen.map_optimize(trace, select(noise, leaf latents...));  stop when the score stops changing
+
+    (src/Greedy.jl:93-101, 366-374), where ``Gen.map_optimize`` is one gradient step with backtracking line search
+    (step = max_step_size, halved by ``tau`` until the score does not get worse, given up below ``min_step_size``).
+    score = LML + log N(z; 0, I) over the selected latents.  Every backtracking trial of all still-searching traces is one
+    ``agp_lml_batch`` call, every accepted step one ``agp_lml_grad_batch`` call for the traces that moved.
+    Returns {particle: (iterations, final score)}."""
+    if ch.lml is None:
+        refresh(ch, ts, xs, engine)
+    active = [int(p) for p in particles]
+    iters = {p: 0 for p in active}
+    z = {p: latents(ch.nodes[p]) for p in active}
+    score = {p: ch.lml[p] + _log_prior(z[p], ch.z_noise[p], infer_noise) for p in active}
+    for _ in range(max_opt):
+        if not active:
+            break
+        # ---- one Gen.map_optimize per active trace: backtracking line search along the gradient of the score
+        grad = {p: ch.grad_z[p] - z[p] for p in active}
+        gradn = {p: (ch.grad_zn[p] - ch.z_noise[p]) if infer_noise else 0.0 for p in active}
+        step = {p: max_step_size for p in active}
+        searching = list(active)
+        new_state = {}
+        while searching:
+            cands, zs, zns, who = [], [], [], []
+            for p in searching:
+                zc, znc = z[p] + grad[p] * step[p], ch.z_noise[p] + gradn[p] * step[p]
+                try:
+                    if not abs(znc) < 700.0:
+                        raise OverflowError
+                    cands.append(with_latents(ch.nodes[p], zc))
+                except (AssertionError, OverflowError, ValueError):
+                    cands.append(None)
+                zs.append(zc)
+                zns.append(znc)
+                who.append(p)
+            ok_idx = [i for i, c in enumerate(cands) if c is not None]
+            lml = np.full(len(cands), -np.inf)
+            if ok_idx:
+                l2, info = engine.lml_batch([cands[i] for i in ok_idx], [noise_of(zns[i]) for i in ok_idx], ts, xs)
+                ch.n_calls += 1
+                ch.n_evals += len(ok_idx)
+                for j, i in enumerate(ok_idx):
+                    if info[j] == 0 and np.isfinite(l2[j]):
+                        lml[i] = l2[j]
+            still = []
+            for i, p in enumerate(who):
+                new_score = lml[i] + _log_prior(zs[i], zns[i], infer_noise)
+                if new_score - score[p] >= 0.0:                 # it got better (or stayed): take it
+                    new_state[p] = (cands[i], zs[i], zns[i], new_score)
+                elif step[p] < min_step_size:                   # it got worse and the step is exhausted: keep the trace
+                    pass
+                else:
+                    step[p] *= tau
+                    still.append(p)
+            searching = still
+        # ---- commit, and stop the traces whose score did not change (Greedy.jl:97-100)
+        nxt = []
+        for p in active:
+            iters[p] += 1
+            if p in new_state:
+                nd, zc, znc, sc = new_state[p]
+                changed = sc != score[p]
+                ch.nodes[p], z[p], score[p] = nd, zc, sc
+                ch.z_noise[p] = znc
+                if changed:
+                    nxt.append(p)
+        active = nxt
+        if active:   # gradients at the new points: one batched call
+            nodes = [ch.nodes[p] for p in active]
+            l2, gz, gzn, ok = _evaluate(ch, nodes, [z[p] for p in active], ch.z_noise[active], ts, xs, engine)
+            for a, p in enumerate(active):
+                ch.lml[p], ch.grad_z[p], ch.grad_zn[p] = l2[a], gz[a], gzn[a]
+    # traces that finished on an accepted step of equal score keep a cache from before that step: refresh lazily
+    stale = [p for p in iters if abs((ch.lml[p] + _log_prior(z[p], ch.z_noise[p], infer_noise)) - score[p]) > 0.0]
+    if stale:
+        nodes = [ch.nodes[p] for p in stale]
+        l2, gz, gzn, ok = _evaluate(ch, nodes, [z[p] for p in stale], ch.z_noise[stale], ts, xs, engine)
+        for a, p in enumerate(stale):
+            ch.lml[p], ch.grad_z[p], ch.grad_zn[p] = l2[a], gz[a], gzn[a]
+    return {p: (iters[p], score[p]) for p in iters}
+
+
+# ------------------------------------------------------------------------------------------------
 # structure moves: one batched score per MH iteration
 # ------------------------------------------------------------------------------------------------
 # A proposer returns, for one particle, the proposed tree and the log of every factor of the MH ratio EXCEPT the

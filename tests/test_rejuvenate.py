@@ -244,6 +244,63 @@ def test_structure_loop_with_parameter_moves_runs_only_the_accepted_particles():
         assert math.isclose(ch.lml[p], o.log_marginal_likelihood(from_agp(ch.nodes[p]), rj.noise_of(ch.z_noise[p]), ts, xs), rel_tol=1e-12)
 
 
+def _map_optimize_one(node, zn, ts, xs, max_opt, max_step_size=0.1, tau=0.5, min_step_size=1e-16):
+    """Gen.map_optimize + the loop of Greedy.jl:93-101 for ONE trace, written out directly on the oracle."""
+    def score_of(nd, z, zn_):
+        return (o.log_marginal_likelihood(from_agp(nd), rj.noise_of(zn_), ts, xs)
+                - 0.5 * np.dot(z, z) - z.size * 0.5 * math.log(2 * math.pi) - 0.5 * zn_ * zn_ - 0.5 * math.log(2 * math.pi))
+
+    def grad_of(nd, z, zn_):
+        g, gn = o.lml_grad_dense_fd(from_agp(nd), rj.noise_of(zn_), ts, xs)
+        return rj.latent_gradient(nd, z, g) - z, gn * agp.transform_param_grad("noise", zn_) - zn_
+
+    iters, z = 0, rj.latents(node)
+    score = score_of(node, z, zn)
+    g, gn = grad_of(node, z, zn)
+    for _ in range(max_opt):
+        iters += 1
+        step, new = max_step_size, None
+        while True:
+            cz, czn = z + g * step, zn + gn * step
+            cand = rj.with_latents(node, cz)
+            new_score = score_of(cand, cz, czn)
+            if new_score - score >= 0:
+                new = (cand, cz, czn, new_score)
+                break
+            if step < min_step_size:
+                break
+            step *= tau
+        if new is None:
+            break
+        unchanged = new[3] == score
+        node, z, zn, score = new
+        if unchanged:
+            break
+        g, gn = grad_of(node, z, zn)
+    return node, zn, score, iters
+
+
+def test_lockstep_map_optimize_equals_trace_by_trace_optimisation():
+    P = 5
+    nodes, zn = start_state(P, seed=8)
+    ts, xs = series(24)
+    ch = rj.Chains(list(nodes), zn.copy())
+    eng = OracleEngine()
+    out = rj.map_optimize_lockstep(ch, np.arange(P), ts, xs, engine=eng, max_opt=6)
+    for p in range(P):
+        nd, z1, sc, iters = _map_optimize_one(nodes[p], zn[p], ts, xs, 6)
+        assert out[p][0] == iters
+        assert ch.nodes[p] == nd and ch.z_noise[p] == z1
+        assert abs(out[p][1] - sc) <= 1e-12 * abs(sc)
+        start = o.log_marginal_likelihood(from_agp(nodes[p]), rj.noise_of(zn[p]), ts, xs) + rj._log_prior(rj.latents(nodes[p]), zn[p], True)
+        assert out[p][1] >= start                                    # the score never gets worse
+        # the cache describes the final state
+        assert math.isclose(ch.lml[p], o.log_marginal_likelihood(from_agp(ch.nodes[p]), rj.noise_of(ch.z_noise[p]), ts, xs), rel_tol=1e-12)
+    # every backtracking trial of all searching traces was ONE batched call
+    assert all(k in ("lml", "grad") for k, _ in eng.batches) and max(b for _, b in eng.batches) <= P
+    assert sum(1 for k, _ in eng.batches if k == "lml") >= max(v[0] for v in out.values())
+
+
 @pytest.mark.gpu
 def test_gpu_chains_follow_the_oracle_chains():
     """The same lock-step loops through the C-ABI and through the oracle stand-in: identical decisions, latents equal
@@ -265,3 +322,25 @@ def test_gpu_chains_follow_the_oracle_chains():
         np.testing.assert_allclose(rj.latents(g.nodes[p]), rj.latents(c.nodes[p]), atol=1e-6, rtol=0)
         assert abs(g.z_noise[p] - c.z_noise[p]) <= 1e-6
         assert abs(g.lml[p] - c.lml[p]) <= 1e-8 * abs(c.lml[p]) + 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_map_optimize_climbs_like_the_oracle_run():
+    """Greedy search's parameter optimisation through the C-ABI: scores never decrease, the reported score is the oracle's
+    score of the final state, and the climb matches the run on the oracle stand-in (the trajectories may differ at the
+    level of the oracle's finite-difference gradient error, the scores they reach may not by more than 1e-6)."""
+    P, n = 5, 96
+    nodes, zn = start_state(P, seed=8)
+    ts, xs = series(n)
+    runs = []
+    for eng in (agp.Engine(0), OracleEngine()):
+        ch = rj.Chains(list(nodes), zn.copy())
+        runs.append((ch, rj.map_optimize_lockstep(ch, np.arange(P), ts, xs, engine=eng, max_opt=12)))
+    (g, og), (c, oc) = runs
+    for p in range(P):
+        start = o.log_marginal_likelihood(from_agp(nodes[p]), rj.noise_of(zn[p]), ts, xs) + rj._log_prior(rj.latents(nodes[p]), zn[p], True)
+        final = o.log_marginal_likelihood(from_agp(g.nodes[p]), rj.noise_of(g.z_noise[p]), ts, xs) + rj._log_prior(rj.latents(g.nodes[p]), g.z_noise[p], True)
+        assert og[p][1] >= start - 1e-9 * abs(start)
+        assert abs(og[p][1] - final) <= 1e-9 * abs(final)
+        assert abs(og[p][1] - oc[p][1]) <= 1e-6 * abs(oc[p][1]) + 1e-6
+    assert any(og[p][1] > rj._log_prior(rj.latents(nodes[p]), zn[p], True) + o.log_marginal_likelihood(from_agp(nodes[p]), rj.noise_of(zn[p]), ts, xs) + 1e-3 for p in range(P))

@@ -31,8 +31,13 @@ class OracleEngine:
 
     def lml_batch(self, nodes, noises, ts, xs):
         self.batches.append(("lml", len(nodes)))
-        lml = np.array([o.log_marginal_likelihood(from_agp(nd), nz, ts, xs) for nd, nz in zip(nodes, noises)])
-        return lml, np.zeros(len(nodes), dtype=np.int32)
+        lml, info = np.full(len(nodes), np.nan), np.zeros(len(nodes), dtype=np.int32)
+        for i, (nd, nz) in enumerate(zip(nodes, noises)):
+            try:
+                lml[i] = o.log_marginal_likelihood(from_agp(nd), nz, ts, xs)
+            except o.PosDefException as e:        # what the C-ABI reports through info
+                info[i] = max(int(getattr(e, "info", 1)), 1)
+        return lml, info
 
     def lml_grad_batch(self, nodes, noises, ts, xs):
         self.batches.append(("grad", len(nodes)))
@@ -45,7 +50,7 @@ class OracleEngine:
             try:
                 g, g_noise = o.lml_grad_dense_fd(ond, nz, ts, xs)
                 val = o.log_marginal_likelihood(ond, nz, ts, xs)
-            except (np.linalg.LinAlgError, ValueError, FloatingPointError):
+            except (np.linalg.LinAlgError, ValueError, FloatingPointError, o.PosDefException):
                 g, g_noise, val = np.full(len(o.encode_program(ond)[2]), np.nan), np.nan, np.nan
             lml.append(val); grads.append(g); gn.append(g_noise); info.append(0 if np.isfinite(val) else 1)
         return np.array(lml), grads, np.array(gn), np.array(info, dtype=np.int32)
@@ -326,21 +331,33 @@ def test_gpu_chains_follow_the_oracle_chains():
 
 @pytest.mark.gpu
 def test_gpu_map_optimize_climbs_like_the_oracle_run():
-    """Greedy search's parameter optimisation through the C-ABI: scores never decrease, the reported score is the oracle's
-    score of the final state, and the climb matches the run on the oracle stand-in (the trajectories may differ at the
-    level of the oracle's finite-difference gradient error, the scores they reach may not by more than 1e-6)."""
+    """Greedy search's parameter optimisation through the C-ABI.  One Gen.map_optimize step (gradient + backtracking)
+    lands where the same step on the oracle stand-in lands (1e-5: the oracle's finite-difference gradient error times
+    the step); over many steps the score never decreases and the reported score is the oracle's score of the final
+    state.  (Whole trajectories are not compared: a halving decision at a near-tie may legitimately differ.)"""
     P, n = 5, 96
     nodes, zn = start_state(P, seed=8)
     ts, xs = series(n)
-    runs = []
-    for eng in (agp.Engine(0), OracleEngine()):
+
+    def score_of(nd, z_noise):
+        return o.log_marginal_likelihood(from_agp(nd), rj.noise_of(z_noise), ts, xs) + rj._log_prior(rj.latents(nd), z_noise, True)
+
+    gpu = agp.Engine(0)
+    one = []
+    for eng in (gpu, OracleEngine()):
         ch = rj.Chains(list(nodes), zn.copy())
-        runs.append((ch, rj.map_optimize_lockstep(ch, np.arange(P), ts, xs, engine=eng, max_opt=12)))
-    (g, og), (c, oc) = runs
+        one.append((ch, rj.map_optimize_lockstep(ch, np.arange(P), ts, xs, engine=eng, max_opt=1)))
+    (g, og), (c, oc) = one
     for p in range(P):
-        start = o.log_marginal_likelihood(from_agp(nodes[p]), rj.noise_of(zn[p]), ts, xs) + rj._log_prior(rj.latents(nodes[p]), zn[p], True)
-        final = o.log_marginal_likelihood(from_agp(g.nodes[p]), rj.noise_of(g.z_noise[p]), ts, xs) + rj._log_prior(rj.latents(g.nodes[p]), g.z_noise[p], True)
-        assert og[p][1] >= start - 1e-9 * abs(start)
-        assert abs(og[p][1] - final) <= 1e-9 * abs(final)
-        assert abs(og[p][1] - oc[p][1]) <= 1e-6 * abs(oc[p][1]) + 1e-6
-    assert any(og[p][1] > rj._log_prior(rj.latents(nodes[p]), zn[p], True) + o.log_marginal_likelihood(from_agp(nodes[p]), rj.noise_of(zn[p]), ts, xs) + 1e-3 for p in range(P))
+        np.testing.assert_allclose(rj.latents(g.nodes[p]), rj.latents(c.nodes[p]), rtol=0, atol=1e-5)
+        assert abs(g.z_noise[p] - c.z_noise[p]) <= 1e-5 and abs(og[p][1] - oc[p][1]) <= 1e-6 * abs(oc[p][1]) + 1e-6
+    ch = rj.Chains(list(nodes), zn.copy())
+    out = rj.map_optimize_lockstep(ch, np.arange(P), ts, xs, engine=gpu, max_opt=12)
+    climbed = 0
+    for p in range(P):
+        start, final = score_of(nodes[p], zn[p]), score_of(ch.nodes[p], ch.z_noise[p])
+        assert out[p][1] >= start - 1e-9 * abs(start) and out[p][1] >= og[p][1] - 1e-9 * abs(og[p][1])
+        assert abs(out[p][1] - final) <= 1e-9 * abs(final)
+        assert abs(ch.lml[p] + rj._log_prior(rj.latents(ch.nodes[p]), ch.z_noise[p], True) - out[p][1]) <= 1e-9 * abs(final)   # cache is current
+        climbed += out[p][1] > start + 1e-3
+    assert climbed >= 3

@@ -147,3 +147,48 @@ def smc_step(state: ParticleState, ts, xs, *, engine: Optional[gp.Engine] = None
     state.log_weights = state.log_weights + (new_scores - state.scores)
     state.scores = new_scores
     return new_scores
+
+
+def rejuvenate(state: ParticleState, ts, xs, *, n_mcmc: int, n_hmc: int, propose, seed: int,
+               engine: Optional[gp.Engine] = None, group=None, hmc_config: Optional[dict] = None,
+               infer_noise: bool = True) -> dict:
+    """Step 4 of ``run_smc_anneal_data`` (src/inference_smc_anneal_data.jl:236-250): ``rejuvenate_particle_structure``
+    on every particle.  Each rank rejuvenates ITS shard in lock step on its own GPU (``rejuvenate.py``: one batched call
+    per MH proposal / leapfrog step of the whole shard); particle p draws from the random stream (seed, p) whatever
+    rank it lives on, so the result does not depend on the number of GPUs.  The rejuvenated kernels are a few hundred
+    bytes per particle: one all-gather of them replicates the state for the next resampling step.  MCMC moves leave
+    the log-weights alone and replace the trace scores."""
+    import torch.distributed as dist
+
+    from . import model, rejuvenate as rj
+
+    P = len(state.nodes)
+    dist_on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if dist_on else 1
+    rank = dist.get_rank(group) if dist_on else 0
+    lo, hi = shard_range(P, rank, world)
+    eng = engine or gp.default_engine()
+    z_noise = np.array([model.untransform_param("noise", nz - model.JITTER) for nz in state.noises[lo:hi]])
+    ch = rj.Chains(list(state.nodes[lo:hi]), z_noise.copy())
+    rngs = rj.particle_rngs(seed, P)[lo:hi]
+    stats = rj.rejuvenate_structure_lockstep(ch, n_mcmc, n_hmc, propose, ts, xs, seed=seed, engine=eng, rngs=rngs,
+                                             hmc_config=hmc_config, infer_noise=infer_noise) if hi > lo else dict(ch.stats)
+    z0 = z_noise
+    # a noise the chain did not move keeps its bits (exp(log(x)) is not always x)
+    new_noises = [state.noises[lo + a] if z == z0[a] else rj.noise_of(z) for a, z in enumerate(ch.z_noise)]
+    mine = (lo, ch.nodes, new_noises, None if ch.lml is None else ch.lml.tolist(), stats)
+    if world > 1:
+        shards = [None] * world
+        dist.all_gather_object(shards, mine, group=group)
+    else:
+        shards = [mine]
+    total = {}
+    for lo_r, nodes, noises, lml, st in shards:
+        for a, nd in enumerate(nodes):
+            state.nodes[lo_r + a] = nd
+            state.noises[lo_r + a] = noises[a]
+            if lml is not None:
+                state.scores[lo_r + a] = lml[a]
+        for k, v in st.items():
+            total[k] = total.get(k, 0) + v
+    return total

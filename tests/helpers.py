@@ -23,6 +23,61 @@ def to_agp(nd):
     return cls(to_agp(nd.left), to_agp(nd.right))
 
 
+def from_agp(nd):
+    """autogp.jl_b200 node -> oracle node."""
+    import autogp.jl_b200 as agp
+
+    cls = getattr(o, type(nd).__name__)
+    if isinstance(nd, agp.LeafNode):
+        return cls(**nd.__dict__)
+    if isinstance(nd, agp.ChangePoint):
+        return cls(from_agp(nd.left), from_agp(nd.right), nd.location, nd.scale)
+    return cls(from_agp(nd.left), from_agp(nd.right))
+
+
+class OracleEngine:
+    """Checker-side stand-in with the two Engine methods the loops call."""
+
+    def __init__(self, fail=None):
+        self.batches = []
+        self.fail = fail            # callable(node, noise) -> bool: report "not positive definite"
+
+    def lml_batch(self, nodes, noises, ts, xs):
+        self.batches.append(("lml", len(nodes)))
+        lml, info = np.full(len(nodes), np.nan), np.zeros(len(nodes), dtype=np.int32)
+        for i, (nd, nz) in enumerate(zip(nodes, noises)):
+            try:
+                lml[i] = o.log_marginal_likelihood(from_agp(nd), nz, ts, xs)
+            except o.PosDefException as e:        # what the C-ABI reports through info
+                info[i] = max(int(getattr(e, "info", 1)), 1)
+        return lml, info
+
+    def lml_grad_batch(self, nodes, noises, ts, xs):
+        self.batches.append(("grad", len(nodes)))
+        lml, grads, gn, info = [], [], [], []
+        for nd, nz in zip(nodes, noises):
+            ond = from_agp(nd)
+            if self.fail is not None and self.fail(nd, nz):
+                lml.append(np.nan); grads.append(np.full(len(o.encode_program(ond)[2]), np.nan)); gn.append(np.nan); info.append(3)
+                continue
+            try:
+                g, g_noise = o.lml_grad_dense_fd(ond, nz, ts, xs)
+                val = o.log_marginal_likelihood(ond, nz, ts, xs)
+            except (np.linalg.LinAlgError, ValueError, FloatingPointError, o.PosDefException):
+                g, g_noise, val = np.full(len(o.encode_program(ond)[2]), np.nan), np.nan, np.nan
+            lml.append(val); grads.append(g); gn.append(g_noise); info.append(0 if np.isfinite(val) else 1)
+        return np.array(lml), grads, np.array(gn), np.array(info, dtype=np.int32)
+
+
+class OracleEngineWithNoiseCall(OracleEngine):
+    """... plus the noise-gradient-only call of the real engine."""
+
+    def lml_grad_noise_batch(self, nodes, noises, ts, xs):
+        lml, _, gn, info = OracleEngine.lml_grad_batch(self, nodes, noises, ts, xs)
+        self.batches[-1] = ("noise", len(nodes))
+        return lml, gn, info
+
+
 def reparameterize(nd, slope, intercept):
     """GP.reparameterize(node, LinearTransform(slope, intercept)) — src/GP.jl:142,168,205-209,
     247-250,291-294,338-341,382-386,425-429,505-511 (used only to replay test_GP.jl identities)."""

@@ -95,3 +95,56 @@ def test_two_rank_smc_matches_single_process(P):
             assert np.allclose(w, want[1], rtol=0, atol=0)
             assert e == want[2] and r == want[3] and m == want[4]
             assert nodes == [repr(n) for n in want[5]]
+
+
+# ---- a full SMC round with rejuvenation: reweight -> resample -> lock-step rejuvenation of the shard -> all-gather ----
+def _run_rounds_with_rejuvenation(P, group=None):
+    from autogp.jl_b200 import rejuvenate as rj, smc
+
+    parts = [o.synthetic_particle(p, "ge+per*lin") for p in range(P)]
+    state = smc.ParticleState(nodes=[H.to_agp(nd) for nd, _ in parts], noises=[nz for _, nz in parts])
+    eng = H.OracleEngine()
+    ts, xs = o.synthetic_series(36)
+    cfg = {"L_param": 2, "L_noise": 2, "eps_param": 0.03, "eps_noise": 0.03, "n_exit": 1}
+    out = []
+    for step, seed in ((18, 5), (36, 6)):
+        smc.smc_step(state, ts[:step], xs[:step], engine=eng, group=group)
+        smc.maybe_resample(state, ess_threshold=P / 2, seed=seed)
+        stats = smc.rejuvenate(state, ts[:step], xs[:step], n_mcmc=2, n_hmc=1, propose=rj.leaf_swap_proposal, seed=100 + seed,
+                               engine=eng, group=group, hmc_config=cfg)
+        out.append(([repr(nd) for nd in state.nodes], list(state.noises), state.scores.tolist(), state.log_weights.tolist(), stats))
+    return out, sum(b for _, b in eng.batches)
+
+
+def _worker_rejuv(rank, world, port, P, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank,) + _run_rounds_with_rejuvenation(P))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_smc_round_with_rejuvenation_matches_single_process():
+    P = 5
+    ref, ref_evals = _run_rounds_with_rejuvenation(P)
+    assert any(r[4]["mh"] > 0 for r in ref) and any(r[4]["hmc_trials"] > 0 for r in ref)
+    # the scores the state carries after rejuvenation are the LMLs of the rejuvenated particles
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_rejuv, args=(r, 2, port, P, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rounds, evals in results:
+        assert evals < ref_evals                       # each rank evaluated only its shard
+        for got, want in zip(rounds, ref):
+            assert got[0] == want[0] and got[1] == want[1]          # same kernels, same noises, bitwise
+            assert got[2] == want[2] and got[3] == want[3]
+            assert got[4] == want[4]                                # same accept / reject counts, summed over ranks
+    assert sum(r[2] for r in results) == ref_evals

@@ -49,6 +49,22 @@ def main():
               "tflops": fl / ms * 1e-9, "frac_of_fp64_peak": fl / ms * 1e-9 / PEAK, "gramfill_ms": g, "chol_kernel_ms": c,
               "chol_kernel_tflops": fl / c * 1e-9, "info_ok": bool(np.all(info == 0))})
 
+    # ---- configs[0] (n = 128, 4 particles, Plus(SE, WN): the reference's own CPU-runnable case) and the small-n regime:
+    # latency of one end-to-end call with host buffers (launch + copies + one tile per particle), and the same with a
+    # batch large enough to fill the GPU
+    for n, P, tree in ((128, 4, "se+wn"), (128, 64, "se*per+lin"), (128, 1024, "se*per+lin"), (512, 256, "se*per+lin")):
+        ts, xs = o.synthetic_series(n)
+        nodes, noises = batch(P, tree)
+        packed = eng.pack_batch(nodes, noises)
+        eng.lml_batch_packed(packed, ts, xs)
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lml, info = eng.lml_batch_packed(packed, ts, xs)
+        dt = (time.perf_counter() - t0) / reps
+        emit({"what": "lml end-to-end call (host buffers, programs packed once)", "n": n, "particles": P, "tree": tree,
+              "us_per_call": dt * 1e6, "lml_per_s": P / dt, "info_ok": bool(np.all(info == 0))})
+
     # ---- prefix-growing schedules: full re-score vs block-append
     def schedule_run(name, n_full, P, prefixes):
         ts, xs = o.synthetic_series(n_full)

@@ -349,11 +349,10 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
             }
         }
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            val[q][e] = v[e];
-            adj[q][e] = 0.0;
-        }
+        for (int e = 0; e < E; ++e) val[q][e] = v[e];
     }
+    // (the program is a tree: every node has exactly one parent, which ASSIGNS the child's adjoint in the backward sweep
+    // before the child is visited — no zero-initialisation, no read-modify-write of the adjoint array)
 #pragma unroll
     for (int e = 0; e < E; ++e) adj[m - 1][e] = seed[e];
     for (int q = m - 1; q >= 0; --q) {
@@ -437,8 +436,8 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
                 const int ia = opa[q], ib = opb[q];
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    adj[ia][e] += g[e];
-                    adj[ib][e] += g[e];
+                    adj[ia][e] = g[e];
+                    adj[ib][e] = g[e];
                 }
                 break;
             }
@@ -447,8 +446,8 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const double va = val[ia][e], vb = val[ib][e];
-                    adj[ia][e] += g[e] * vb;
-                    adj[ib][e] += g[e] * va;
+                    adj[ia][e] = g[e] * vb;
+                    adj[ib][e] = g[e] * va;
                 }
                 break;
             }
@@ -462,8 +461,8 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
                     const double th1 = u1s[q][e], th2 = u2s[q][e];
                     const double g1 = 0.5 * (1.0 + th1), g2 = 0.5 * (1.0 + th2);
                     const double dg1 = 0.5 * (1.0 - th1 * th1) / b, dg2 = 0.5 * (1.0 - th2 * th2) / b;  // d sigma / d location
-                    adj[il][e] += g[e] * (g1 * g2);
-                    adj[ir][e] += g[e] * ((1.0 - g1) * (1.0 - g2));
+                    adj[il][e] = g[e] * (g1 * g2);
+                    adj[ir][e] = g[e] * ((1.0 - g1) * (1.0 - g2));
                     const double dk1 = g2 * kl - (1.0 - g2) * kr, dk2 = g1 * kl - (1.0 - g1) * kr;   // dk / d sigma(t1), d sigma(t2)
                     s0 += g[e] * (dk1 * dg1 + dk2 * dg2);
                     s1 += g[e] * (-(dk1 * dg1 * u1 + dk2 * dg2 * u2));

@@ -469,14 +469,46 @@ def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, *, noise_pred: Opt
     return mean[0], cov[0]
 
 
+def split_kernel_sop(node: Node, leaf_type: type) -> Tuple[Node, Node]:
+    """``GP.split_kernel_sop(node, T)`` (src/GP.jl:603-655): read the kernel as a sum of products and return
+    ``(k_T, k_nT)`` — the addends with a factor of base-kernel type ``leaf_type`` and the addends without one, with
+    ``Constant(0)`` standing for an empty side.  ``predict_mvn_sum`` (src/api.jl) feeds the pair to ``infer_gp_sum``."""
+    def merge_plus(a, b):                                   # merge_split_operand(::Plus, ...), :642-648
+        if a is None:
+            return b
+        return a if b is None else Plus(a, b)
+
+    def helper(nd):
+        if isinstance(nd, LeafNode):                        # :614-615
+            return (nd, None) if type(nd) is leaf_type else (None, nd)
+        la, lb = helper(nd.left)
+        ra, rb = helper(nd.right)
+        if isinstance(nd, Times):                           # :617-631: distribute the product over the two sides
+            mult = lambda a, b: None if a is None or b is None else Times(a, b)
+            l_sop = merge_plus(merge_plus(mult(la, ra), mult(la, rb)), mult(lb, ra))
+            return l_sop, mult(lb, rb)
+        if isinstance(nd, ChangePoint):                     # :650-656: an empty side becomes Constant(0)
+            def merge_cp(a, b):
+                if a is None and b is None:
+                    return None
+                return ChangePoint(Constant(0.0) if a is None else a, Constant(0.0) if b is None else b, nd.location, nd.scale)
+            return merge_cp(la, ra), merge_cp(lb, rb)
+        return merge_plus(la, ra), merge_plus(lb, rb)       # Plus, :633-639
+
+    a, b = helper(node)
+    return (Constant(0.0) if a is None else a), (Constant(0.0) if b is None else b)   # :604-608
+
+
 def infer_gp_sum(nodes: Sequence[Node], noise: float, ts, xs, ts_pred, *, noise_pred: Optional[float] = None,
                  engine: Optional[Engine] = None):
     """``GP.infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993): posterior over the latent
     summands F_i(ts_pred) and the observable X(ts_pred) of  X = sum_i F_i + eps.  Returns
-    ``(mean, cov, indexes)`` where ``cov`` includes the reference's ``JITTER * I`` (:981) and ``indexes`` =
+    ``(mean, cov, indexes)`` where ``cov`` includes the reference's ``JITTER * I`` (:981; the GP module's own
+    ``JITTER = 1e-8``, src/GP.jl:760 — not Model.jl's 1e-5) and ``indexes`` =
     ``{"F": [range per summand], "X": range}`` (0-based; :984-987)."""
-    from .model import JITTER, PosDefException
+    from .model import PosDefException
 
+    JITTER = 1e-8  # src/GP.jl:760
     eng = engine or default_engine()
     mean, cov, info = eng.predict_sum_batch([list(nodes)], [noise], ts, xs, ts_pred, None if noise_pred is None else [noise_pred])
     if info[0] != 0:

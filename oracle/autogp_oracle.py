@@ -234,6 +234,7 @@ def compute_cov_matrix(node: Node, noise: float, ts) -> np.ndarray:
 # ----------------------------------------------------------------------------------------
 
 JITTER = 1e-5  # Model.jl:22
+GP_JITTER = 1e-8  # the GP module's own constant (src/GP.jl:760), used by infer_gp_sum
 PRIOR = {  # GP.jl:1133-1137
     "gamma": dict(scale=2.0, mu=0.0, sigma=1.0),
     "period": dict(mu=-1.5, sigma=1.0),
@@ -385,7 +386,7 @@ def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, noise_pred=None) -
 
 def infer_gp_sum(nodes: List[Node], noise: float, ts, xs, ts_pred, noise_pred=None):
     """src/GP.jl:904-993, block by block: joint prior over Z = [F_1(T*); ...; F_m(T*); X(T*); X(T)], conditioned on
-    X(T) = xs.  Returns (mean, cov incl. JITTER, index ranges F / X)."""
+    X(T) = xs.  Returns (mean, cov incl. GP.JITTER, index ranges F / X)."""
     ts = np.asarray(ts, dtype=np.float64)
     xs = np.asarray(xs, dtype=np.float64)
     ts_pred = np.asarray(ts_pred, dtype=np.float64)
@@ -426,7 +427,7 @@ def infer_gp_sum(nodes: List[Node], noise: float, ts, xs, ts_pred, noise_pred=No
     solve = lambda B: scipy.linalg.cho_solve((U, False), B)
     mu = S_ab @ solve(xs)                                               # :978
     cov = S_aa - S_ab @ solve(S_ab.T)                                   # :979
-    cov = 0.5 * (cov + cov.T) + JITTER * np.eye(len(keep))              # :980-981
+    cov = 0.5 * (cov + cov.T) + GP_JITTER * np.eye(len(keep))           # :980-981 (GP.JITTER, :760)
     return mu, cov, {"F": [range(i * p, (i + 1) * p) for i in range(m)], "X": range(d_lat, d_lat + p)}
 
 

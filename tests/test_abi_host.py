@@ -262,3 +262,31 @@ def test_trtri_only_schedule_replay(P, nt, order):
     assert n_full - n_items == P * nt * (nt + 1)          # two half items per trailing lower tile
     assert np.array_equal(full[:n_items], buf)
     assert not np.any(buf[:, 2] >= nt)                    # no item factors or updates a trailing block column
+
+
+def test_split_kernel_sop_follows_the_reference_examples():
+    """GP.split_kernel_sop (src/GP.jl:603-655): the docstring examples (:589-600) and the ChangePoint rule."""
+    import autogp.jl_b200 as agp
+
+    l, p, c = agp.Linear(1.0), agp.Periodic(1.0, 1.0), agp.Constant(1.0)
+    zero = agp.Constant(0.0)
+    split = agp.split_kernel_sop
+    assert split(l, agp.Linear) == (l, zero)
+    assert split(l, agp.Periodic) == (zero, l)
+    assert split(l * p + l * c, agp.Periodic) == (l * p, l * c)
+    assert split(p * p, agp.Periodic) == (p * p, zero)
+    a, b = split((l + p) * (l + p), agp.Periodic)
+    assert a == (p * p + p * l) + l * p and b == l * l          # "p*l+p*p+l*p, l*l" up to the order of the addends
+    cp = agp.ChangePoint(l * p, c, 0.4, 0.01)
+    assert split(cp, agp.Periodic) == (agp.ChangePoint(l * p, zero, 0.4, 0.01), agp.ChangePoint(zero, c, 0.4, 0.01))
+    assert split(agp.ChangePoint(l, c, 0.4, 0.01), agp.Periodic) == (zero, agp.ChangePoint(l, c, 0.4, 0.01))
+    # the two sides add up to the kernel (sum-of-products expansion), checked on the oracle's Gram matrices
+    import autogp_oracle as o
+    from helpers import from_agp
+
+    ts = np.linspace(0, 1, 17)
+    tree = agp.Plus(agp.Times(agp.Plus(agp.Linear(0.3, 0.2, 0.7), agp.Periodic(0.6, 0.25, 1.1)), agp.SquaredExponential(0.4, 0.9)),
+                    agp.ChangePoint(agp.Periodic(0.5, 0.3, 0.8), agp.GammaExponential(0.3, 1.2, 0.5), 0.5, 0.05))
+    ka, kb = split(tree, agp.Periodic)
+    total = o.eval_cov(from_agp(ka), ts) + o.eval_cov(from_agp(kb), ts)
+    np.testing.assert_allclose(total, o.eval_cov(from_agp(tree), ts), rtol=1e-13, atol=1e-15)

@@ -653,7 +653,7 @@ def test_infer_gp_sum_matches_the_oracle(engine, n, m):
         assert np.all(info == 0)
         for p, st in enumerate(sets):
             mu_o, cov_o, idx = o.infer_gp_sum(st, noises[p], ts, xs, tp, noise_pred=None if npred is None else npred[p])
-            cov_o = cov_o - o.JITTER * np.eye(cov_o.shape[0])        # the C-ABI leaves the MvNormal's jitter to the caller
+            cov_o = cov_o - o.GP_JITTER * np.eye(cov_o.shape[0])        # the C-ABI leaves the MvNormal's jitter to the caller
             scale = max(np.max(np.abs(cov_o)), 1e-12)
             assert np.max(np.abs(mean[p] - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o))), (p, np.max(np.abs(mean[p] - mu_o)))
             assert np.max(np.abs(cov[p] - cov_o)) <= 1e-8 * scale, (p, np.max(np.abs(cov[p] - cov_o)), scale)
@@ -663,6 +663,27 @@ def test_infer_gp_sum_matches_the_oracle(engine, n, m):
     mu_o, cov_o, idx_o = o.infer_gp_sum(sets[0], noises[0], ts, xs, tp)
     assert [list(r) for r in idx1["F"]] == [list(r) for r in idx_o["F"]] and list(idx1["X"]) == list(idx_o["X"])
     assert np.max(np.abs(cov1 - cov_o)) <= 1e-8 * np.max(np.abs(cov_o)) and np.max(np.abs(mu1 - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o)))
+
+
+def test_predict_mvn_sum_flow_split_then_infer(engine):
+    """predict_mvn_sum (src/api.jl): split every particle's kernel on a base-kernel type, then infer_gp_sum over the two
+    sides — against the oracle on the same pairs, incl. a particle whose split has an empty (Constant(0)) side."""
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(200)
+    tp = np.linspace(1.0, 1.25, 40)
+    parts = [o.synthetic_particle(3, "se*per+lin"), o.synthetic_particle(4, "ge+per*lin"), o.synthetic_particle(5, "se+wn")]
+    pairs = [agp.split_kernel_sop(H.to_agp(nd), agp.Periodic) for nd, _ in parts]
+    assert pairs[2][0] == agp.Constant(0.0)                      # no Periodic factor anywhere in particle 2
+    noises = [nz for _, nz in parts]
+    mean, cov, info = engine.predict_sum_batch([list(pr) for pr in pairs], noises, ts, xs, tp)
+    assert np.all(info == 0)
+    for p, pr in enumerate(pairs):
+        mu_o, cov_o, idx = o.infer_gp_sum([H.from_agp(nd) for nd in pr], noises[p], ts, xs, tp)
+        cov_o = cov_o - o.GP_JITTER * np.eye(cov_o.shape[0])
+        assert np.max(np.abs(mean[p] - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o)))
+        assert np.max(np.abs(cov[p] - cov_o)) <= 1e-8 * np.max(np.abs(cov_o))
+    assert np.all(mean[2, :40] == 0.0) and np.all(cov[2, :40, :] == 0.0)     # the empty side has a zero posterior
 
 
 def test_infer_gp_sum_edge_cases(engine):

@@ -171,14 +171,14 @@ def test_infer_gp_sum_restatement_is_consistent_with_the_predictive_mvn():
     mu_x, cov_x = o.predictive_mvn(o.Plus(o.Plus(nodes[0], nodes[1]), nodes[2]), noise, ts, xs, tp, noise_pred=npred)
     X = list(idx["X"])
     np.testing.assert_allclose(mu[X], mu_x, rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(cov[np.ix_(X, X)], cov_x + o.JITTER * np.eye(m), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(cov[np.ix_(X, X)], cov_x + o.GP_JITTER * np.eye(m), rtol=1e-9, atol=1e-12)
     F = [list(r) for r in idx["F"]]
     np.testing.assert_allclose(sum(mu[f] for f in F), mu_x, rtol=1e-9, atol=1e-12)
     tot = sum(cov[np.ix_(fa, fb)] for fa in F for fb in F)
-    np.testing.assert_allclose(tot, cov_x - npred * np.eye(m) + 3 * o.JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(tot, cov_x - npred * np.eye(m) + 3 * o.GP_JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
     # Cov[F_i*, X*] = sum_j Cov[F_i*, F_j*]  (X* = sum F* + independent noise)
     for fa in F:
-        np.testing.assert_allclose(cov[np.ix_(fa, X)], sum(cov[np.ix_(fa, fb)] for fb in F) - o.JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(cov[np.ix_(fa, X)], sum(cov[np.ix_(fa, fb)] for fb in F) - o.GP_JITTER * np.eye(m), rtol=1e-8, atol=1e-10)
     mu1, cov1, idx1 = o.infer_gp_sum(nodes[:1], noise, ts, xs, tp)
     np.testing.assert_allclose(mu1[list(idx1["F"][0])], mu1[list(idx1["X"])], rtol=1e-12)
     np.testing.assert_allclose(cov1[:m, :m] + noise * np.eye(m), cov1[m:, m:], rtol=1e-10, atol=1e-12)

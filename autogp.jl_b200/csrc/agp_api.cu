@@ -908,7 +908,7 @@ int agp_predict_sum_batch(agp_handle* h, int32_t P, int32_t M, const int32_t* pr
     std::vector<double> tp_ext((size_t)(mt > 0 ? mt : 1));
     for (int g = 0; g <= M; ++g)
         for (int a = 0; a < m; ++a) tp_ext[(size_t)g * m + a] = ts_pred[a];
-    // the extraction kernel adds its noise_pred[p] to EVERY diagonal entry; only the X(T*) block carries it (:963), so
+    // the extraction kernel adds its noise_pred[p] to EVERY diagonal entry; only the X(T*) block carries it (:967), so
     // the resident copy is a zero vector and the host adds the X* diagonal after the copy back
     const std::vector<double> zeros((size_t)P, 0.0);
     int rc = upload_impl(h, P, c_len.data(), c_ops.data(), c_off.data(), c_np.data(), params, noise, ts, xs, n, tp_ext.data(), mt, zeros.data());

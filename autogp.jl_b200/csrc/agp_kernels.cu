@@ -161,13 +161,13 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
 // The batch was uploaded with the kernel  k_1 + ... + k_M  and (M + 1) copies of the m prediction points appended:
 // appended row  g m + a  stands for F_g(t*_a) for g < M and for X(t*_a) for g = M.  agp_gramfill_kernel has filled
 // every appended row with the SUM kernel; this kernel rewrites what differs (one CTA per appended row):
-//   row F_g :  columns of the observations   <- k_g(t_c, t*_a)          Cov[F_g(T*), X(T)]   = Ktp[g]'   (:955-956)
-//              trailing columns of F_g       <- k_g(t*_a', t*_a)         Cov[F_g(T*)]         = Kpp[g]    (:948)
+//   row F_g :  columns of the observations   <- k_g(t_c, t*_a)          Cov[F_g(T*), X(T)]   = Ktp[g]'   (:959-960)
+//              trailing columns of F_g       <- k_g(t*_a', t*_a)         Cov[F_g(T*)]         = Kpp[g]    (:952)
 //              trailing columns of F_g', g' < g  <- 0                    independent summands
-//   row X*  :  trailing columns of F_g'      <- k_g'(t*_a', t*_a)        Cov[X(T*), F_g'(T*)] = Kpp[g']'  (:951-952)
-// (the observation columns and the X*/X* block of row X* already hold the sum kernel, :960-963).  Entries are
+//   row X*  :  trailing columns of F_g'      <- k_g'(t*_a', t*_a)        Cov[X(T*), F_g'(T*)] = Kpp[g']'  (:955-956)
+// (the observation columns and the X*/X* block of row X* already hold the sum kernel, :964-967).  Entries are
 // evaluated as the upper-triangle element of the joint matrix over z = [ts; ts_pred] (smaller index first), as
-// compute_cov_matrix_vectorized does (:929).
+// compute_cov_matrix_vectorized does (:923).
 // ------------------------------------------------------------------------------------------
 constexpr int CF_THREADS = 256;
 

@@ -348,7 +348,7 @@ class Engine:
         """``infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993) for every particle:
         ``summands[p]`` are the M additive components of particle p's kernel (same M for all).  Returns
         (mean[P, d], cov[P, d, d], info[P]), d = (M + 1) m, over [F_1(T*); ...; F_M(T*); X(T*)] — without the JITTER
-        the reference adds when it wraps the result in an MvNormal (:981)."""
+        the reference adds when it wraps the result in an MvNormal (:986)."""
         P = len(summands)
         M = len(summands[0]) if P else 1
         if M < 1 or any(len(sm) != M for sm in summands):
@@ -503,9 +503,9 @@ def infer_gp_sum(nodes: Sequence[Node], noise: float, ts, xs, ts_pred, *, noise_
                  engine: Optional[Engine] = None):
     """``GP.infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993): posterior over the latent
     summands F_i(ts_pred) and the observable X(ts_pred) of  X = sum_i F_i + eps.  Returns
-    ``(mean, cov, indexes)`` where ``cov`` includes the reference's ``JITTER * I`` (:981; the GP module's own
+    ``(mean, cov, indexes)`` where ``cov`` includes the reference's ``JITTER * I`` (:986; the GP module's own
     ``JITTER = 1e-8``, src/GP.jl:760 — not Model.jl's 1e-5) and ``indexes`` =
-    ``{"F": [range per summand], "X": range}`` (0-based; :984-987)."""
+    ``{"F": [range per summand], "X": range}`` (0-based; :989-992)."""
     from .model import PosDefException
 
     JITTER = 1e-8  # src/GP.jl:760

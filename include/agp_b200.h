@@ -195,8 +195,8 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
  * particle p is program p*M + c of the wire arrays (prog_len[P*M], n_params[P*M]; param_off relative to
  * the summand's own parameter slice; the slices of one particle are contiguous in params).  Outputs per
  * particle, d = (M+1) m:  mean_out[d] and cov_out[d][d] of  [F_1(T*); ...; F_M(T*); X(T*)]  given X(T) = xs:
- *   mu = S_ab K^{-1} xs,   Sigma = S_aa - S_ab K^{-1} S_ba            (:977-979)
- * with noise_pred (NULL: noise) on the X(T*) diagonal only (:963).  The caller adds the JITTER of :981 (GP.JITTER = 1e-8, :760) when it
+ *   mu = S_ab K^{-1} xs,   Sigma = S_aa - S_ab K^{-1} S_ba            (:982-984)
+ * with noise_pred (NULL: noise) on the X(T*) diagonal only (:967).  The caller adds the JITTER of :986 (GP.JITTER = 1e-8, :760) when it
  * builds the MvNormal.  One factorisation: the (M+1) m rows ride along as appended tile rows, like
  * agp_predict_batch.  M must be the same for all particles of a call.  Replaces the resident batch. */
 int agp_predict_sum_batch(agp_handle* h, int32_t P, int32_t M, const int32_t* prog_len, const int32_t* ops,

@@ -394,40 +394,40 @@ def infer_gp_sum(nodes: List[Node], noise: float, ts, xs, ts_pred, noise_pred=No
     noise_pred = noise if noise_pred is None else noise_pred            # :915
     z = np.concatenate([ts, ts_pred])                                   # :921
     Ktt, Ktp, Kpp = [], [], []
-    for nd in nodes:                                                    # :922-931
+    for nd in nodes:                                                    # :922-930
         Ki = compute_cov_matrix_vectorized(nd, 0.0, z)
         a, b, c = Ki[:n, :n], Ki[:n, n:], Ki[n:, n:]
         Ktt.append(0.5 * (a + a.T))
         Ktp.append(b)
         Kpp.append(0.5 * (c + c.T))
-    S_tt, S_tp, S_pp = Ktt[0].copy(), Ktp[0].copy(), Kpp[0].copy()      # reduce(+, ...), :934-936
+    S_tt, S_tp, S_pp = Ktt[0].copy(), Ktp[0].copy(), Kpp[0].copy()      # reduce(+, ...), :933-935
     for i in range(1, m):
         S_tt, S_tp, S_pp = S_tt + Ktt[i], S_tp + Ktp[i], S_pp + Kpp[i]
     d_lat, d_all = m * p, m * p + p + n
     Sigma = np.zeros((d_all, d_all))
     xP = np.arange(d_lat, d_lat + p)
     xT = np.arange(d_lat + p, d_all)
-    for i in range(m):                                                  # :945-957
+    for i in range(m):                                                  # :947-961
         lP = np.arange(i * p, (i + 1) * p)
         Sigma[np.ix_(lP, lP)] = Kpp[i]
         Sigma[np.ix_(lP, xP)] = Kpp[i]
         Sigma[np.ix_(xP, lP)] = Kpp[i].T
         Sigma[np.ix_(lP, xT)] = Ktp[i].T
         Sigma[np.ix_(xT, lP)] = Ktp[i]
-    Sigma[np.ix_(xT, xT)] = S_tt + noise * np.eye(n)                    # :960-963
+    Sigma[np.ix_(xT, xT)] = S_tt + noise * np.eye(n)                    # :964-967
     Sigma[np.ix_(xT, xP)] = S_tp
     Sigma[np.ix_(xP, xT)] = S_tp.T
     Sigma[np.ix_(xP, xP)] = S_pp + noise_pred * np.eye(p)
-    Sigma = 0.5 * (Sigma + Sigma.T)                                     # :966
-    keep = np.concatenate([np.arange(d_lat), xP])                       # :969-970
+    Sigma = 0.5 * (Sigma + Sigma.T)                                     # :970
+    keep = np.concatenate([np.arange(d_lat), xP])                       # :973-974
     S_aa, S_ab, S_bb = Sigma[np.ix_(keep, keep)], Sigma[np.ix_(keep, xT)], Sigma[np.ix_(xT, xT)]
     import scipy.linalg
 
-    U = cholesky_upper(S_bb)                                            # :977
+    U = cholesky_upper(S_bb)                                            # :982
     solve = lambda B: scipy.linalg.cho_solve((U, False), B)
-    mu = S_ab @ solve(xs)                                               # :978
-    cov = S_aa - S_ab @ solve(S_ab.T)                                   # :979
-    cov = 0.5 * (cov + cov.T) + GP_JITTER * np.eye(len(keep))           # :980-981 (GP.JITTER, :760)
+    mu = S_ab @ solve(xs)                                               # :983
+    cov = S_aa - S_ab @ solve(S_ab.T)                                   # :984
+    cov = 0.5 * (cov + cov.T) + GP_JITTER * np.eye(len(keep))           # :985-986 (GP.JITTER, :760)
     return mu, cov, {"F": [range(i * p, (i + 1) * p) for i in range(m)], "X": range(d_lat, d_lat + p)}
 
 

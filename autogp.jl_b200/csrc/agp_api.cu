@@ -701,7 +701,16 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     q.trace = d_trace;
     q.wait_timeout_ns = h->wait_timeout_ns;
     if (kernel_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    agp::launch_gramfill(v, P, first_row, h->stream);
+    if (h->aug_identity) {
+        // the kernel tree is evaluated over the observation block only; the appended [I 0] rows are plain stores
+        BatchView obs = v;
+        obs.nt_total = v.nt;
+        agp::launch_gramfill(obs, P, first_row, h->stream);
+        agp::launch_augfill(v, P, h->stream);
+        h->launches += 1;
+    } else {
+        agp::launch_gramfill(v, P, first_row, h->stream);
+    }
     if (h->comp.M > 0) {
         agp::launch_component_fill(v, P, h->comp, h->stream);
         h->launches += 1;

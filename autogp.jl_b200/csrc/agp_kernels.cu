@@ -157,6 +157,33 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
 }
 
 // ------------------------------------------------------------------------------------------
+// Appended rows of an identity-augmented batch (agp_lml_grad_batch): row lt + r = e_r' over the observation columns,
+// zeros over the trailing block, up to the end of the row's diagonal tile (only lower tiles are ever read).  Pure
+// stores: 16 bytes per thread and instruction, one CTA per row — the Gram-fill kernel spends as long on these 392
+// tiles per particle as on the 136 it has to evaluate.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agp_augfill_kernel(BatchView v) {
+    const int p = blockIdx.y, r = blockIdx.x;
+    const int lt = v.nt * TB;
+    const int ncol = lt + (r / TB + 1) * TB;  // multiple of 128
+    double2* __restrict__ row = reinterpret_cast<double2*>(v.L + (long long)p * v.mat_stride + (long long)(lt + r) * v.ld);
+    for (int c2 = threadIdx.x; c2 < ncol / 2; c2 += 256) {
+        double2 out = make_double2(0.0, 0.0);
+        if (c2 == (r >> 1)) {
+            if (r & 1) out.y = 1.0;
+            else out.x = 1.0;
+        }
+        row[c2] = out;
+    }
+}
+
+void launch_augfill(const BatchView& v, int P, cudaStream_t s) {
+    const int rows = (v.nt_total - v.nt) * TB;
+    if (P <= 0 || rows <= 0) return;
+    agp_augfill_kernel<<<dim3(rows, P), 256, 0, s>>>(v);
+}
+
+// ------------------------------------------------------------------------------------------
 // Joint posterior of the summands of a sum kernel (agp_predict_sum_batch; infer_gp_sum, src/GP.jl:904-993).
 // The batch was uploaded with the kernel  k_1 + ... + k_M  and (M + 1) copies of the m prediction points appended:
 // appended row  g m + a  stands for F_g(t*_a) for g < M and for X(t*_a) for g = M.  agp_gramfill_kernel has filled

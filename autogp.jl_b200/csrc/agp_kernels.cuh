@@ -76,6 +76,8 @@ int grad_blocks_per_particle(const BatchView& v);
 // dLML/dnoise alone out of factorisation + trtri (agp_lml_grad_noise_batch): partial[P][blocks] per-CTA sums
 void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnoise_out, cudaStream_t s);
 int noise_grad_blocks_per_particle(const BatchView& v);
+// [I 0] rows and the zero trailing block of an identity-augmented batch (tile rows nt .. nt_total)
+void launch_augfill(const BatchView& v, int P, cudaStream_t s);
 // Summand programs of agp_predict_sum_batch: component c of particle p = instructions [off[p M + c], off[p M + c + 1])
 struct ComponentView {
     const AgpInstr* prog;

@@ -606,6 +606,23 @@ static void build_queue_general(int P, int nt, int nt_total, int first_row, std:
         items.push_back(pack_dep(j0, j1, type == agp::ITEM_POTF2 ? 0 : 2 * j1, type == agp::ITEM_PANEL ? 2 * j1 : 0, -1, need));
     };
     items.clear();
+    if (first_row == 0 && nt_total > nt && nt > 0) {
+        // prediction rows behind a full factorisation: the observation block keeps the tuned schedule, the appended tile
+        // rows are solved block column by block column behind it (each panel needs tile row k final and its own
+        // earlier tiles), then the Schur complement items
+        int order = 3;
+        if (const char* e = getenv("AGP_ORDER")) order = atoi(e);
+        build_queue(P, nt, nt_total, order, items);
+        for (int k = 0; k < nt; ++k)
+            for (int p = 0; p < P; ++p)
+                for (int i = nt; i < nt_total; ++i)
+                    for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, 0, p, k, i, 0, k, 0);
+        for (int p = 0; p < P; ++p)
+            for (int i = nt; i < nt_total; ++i)
+                for (int k = nt; k <= i; ++k)
+                    for (int h = 0; h < 2; ++h) push(i == k ? agp::ITEM_DIAG : agp::ITEM_PANEL, h, 1, p, k, i, 0, nt, 0);
+        return;
+    }
     for (int k = 0; k < nt; ++k) {
         if (k >= first_row) {
             for (int p = 0; p < P; ++p)

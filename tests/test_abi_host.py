@@ -218,7 +218,7 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
 
 
 @pytest.mark.parametrize("P,nt,nt_total,first_row", [(2, 4, 4, 2), (3, 6, 6, 5), (1, 3, 3, 0), (2, 4, 6, 0), (1, 1, 2, 0),
-                                                     (2, 0, 2, 0), (3, 5, 6, 0)])
+                                                     (2, 0, 2, 0), (3, 5, 6, 0), (2, 16, 19, 0), (1, 9, 12, 0)])
 def test_continuation_queues_replay(P, nt, nt_total, first_row):
     """Block-append (tile rows >= first_row only) and predictive (extra tile rows below the factored
     block) schedules obey the same rules."""

@@ -20,7 +20,7 @@ EXPORTS = (
     "agp_lml_device_results", "agp_lml_set_prefix",
     "agp_stream", "agp_synchronize", "agp_launch_count", "agp_lml_time", "agp_lml_stage_times",
     "agp_queue_build", "agp_queue_build_general", "agp_lml_trace",
-    "agp_lml_run_append", "agp_predict_batch", "agp_predict_sum_batch", "agp_lml_grad_batch", "agp_lml_grad_noise_batch", "agp_lml_copy_factor",
+    "agp_lml_run_append", "agp_predict_batch", "agp_predict_marginals_batch", "agp_predict_sum_batch", "agp_queue_build_marginals", "agp_lml_grad_batch", "agp_lml_grad_noise_batch", "agp_lml_copy_factor",
 )
 
 AGP_OK, AGP_ERR_ARG, AGP_ERR_PROGRAM, AGP_ERR_CUDA, AGP_ERR_NOMEM, AGP_ERR_STATE = 0, -1, -2, -3, -4, -5
@@ -92,6 +92,10 @@ def load() -> C.CDLL:
     lib.agp_lml_run_append.restype = C.c_int
     lib.agp_predict_batch.argtypes = up_args + [f64p, C.c_int32, f64p, f64p, f64p, i32p]
     lib.agp_predict_batch.restype = C.c_int
+    lib.agp_predict_marginals_batch.argtypes = up_args + [f64p, C.c_int32, f64p, f64p, f64p, i32p]
+    lib.agp_predict_marginals_batch.restype = C.c_int
+    lib.agp_queue_build_marginals.argtypes = [C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64]
+    lib.agp_queue_build_marginals.restype = C.c_int64
     lib.agp_predict_sum_batch.argtypes = [vp, C.c_int32, C.c_int32] + up_args[2:] + [f64p, C.c_int32, f64p, f64p, f64p, i32p]
     lib.agp_predict_sum_batch.restype = C.c_int
     lib.agp_lml_grad_batch.argtypes = up_args + [f64p, f64p, f64p, i32p]

@@ -39,6 +39,7 @@ struct agp_handle {
     agp::ComponentView comp{};   // comp.M > 0: rewrite the appended rows after the Gram fill (agp_predict_sum_batch)
     bool aug_identity = false;  // the resident batch is identity-augmented (agp_lml_grad_batch)
     bool trtri_only = false;    // ... and only L^{-T} is wanted, not -K^{-1} (agp_lml_grad_noise_batch)
+    bool pred_diag_only = false;  // predictive marginals: only the diagonal tiles of the Schur complement (agp_predict_marginals_batch)
     double* d_grad = nullptr; size_t cap_grad = 0;  // per-CTA partial sums + gradients
     const int* d_param_prefix = nullptr;            // [P+1] prefix sums of n_params (inside the input arena)
     BatchView view{};
@@ -268,6 +269,7 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     h->n_factored = -1;
     h->factor_clean = false;
     h->comp.M = 0;
+    h->pred_diag_only = false;
     if (P < 0 || n < 0 || m < 0 || (P > 0 && (!prog_len || !ops || !param_off || !n_params || !noise)) || (n > 0 && (!ts || !xs)) || (m > 0 && !ts_pred && !aug_identity))
         return fail(h, AGP_ERR_ARG, "agp_lml_upload: bad argument");
     if (P > 65535) return fail(h, AGP_ERR_ARG, "agp_lml_upload: at most 65535 particles per batch");
@@ -598,7 +600,7 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
 //   nt_total > nt        tile rows >= nt hold prediction points: they are solved against every L_kk
 //                        (PANEL) and their mutual tiles receive the Schur complement
 //                        K_22 - L_21 L_21^T as store-only items over [0, nt) (agp_predict_batch)
-static void build_queue_general(int P, int nt, int nt_total, int first_row, std::vector<int4>& items) {
+static void build_queue_general(int P, int nt, int nt_total, int first_row, std::vector<int4>& items, bool trailing_diag_only = false) {
     auto push = [&](int type, int h, int partial, int p, int k, int i, int j0, int j1, int need) {
         int flags = partial ? agp::ITEM_PARTIAL : 0;
         if (type == agp::ITEM_PANEL && k == 0) flags |= agp::ITEM_YINIT;
@@ -619,7 +621,7 @@ static void build_queue_general(int P, int nt, int nt_total, int first_row, std:
                     for (int h = 0; h < 2; ++h) push(agp::ITEM_PANEL, h, 0, p, k, i, 0, k, 0);
         for (int p = 0; p < P; ++p)
             for (int i = nt; i < nt_total; ++i)
-                for (int k = nt; k <= i; ++k)
+                for (int k = trailing_diag_only ? i : nt; k <= i; ++k)  // marginals: only the diagonal tiles of the Schur complement
                     for (int h = 0; h < 2; ++h) push(i == k ? agp::ITEM_DIAG : agp::ITEM_PANEL, h, 1, p, k, i, 0, nt, 0);
         return;
     }
@@ -670,13 +672,13 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
     const int nt_total = v.nt_total;
-    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? (h->trtri_only ? -2 : -1) : first_row, nt_stride);
+    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? (h->trtri_only ? -2 : -1) : (h->pred_diag_only && first_row == 0 && nt > 0 ? -3 : first_row), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
         if (h->aug_identity) build_queue_inverse(P, nt, nt_stride, h->order, items, !h->trtri_only);
         else if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
-        else build_queue_general(P, nt, nt_total, first_row, items);
+        else build_queue_general(P, nt, nt_total, first_row, items, h->pred_diag_only);
         agp_handle::Queue qu;
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
@@ -856,15 +858,16 @@ int agp_lml_run_append(agp_handle* h) {
     return run_fused(h, nullptr, nullptr, first_row);
 }
 
-int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
-                      const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred,
-                      int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out) {
+static int predict_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                        const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred,
+                        int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out, bool marginals) {
     if (!h) return AGP_ERR_ARG;
     if (m < 0 || (P > 0 && m > 0 && (!mean_out || !cov_out)) || (P > 0 && !info_out)) return fail(h, AGP_ERR_ARG, "agp_predict_batch: bad argument");
     int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, ts_pred, m, noise_pred);
     if (rc != AGP_OK) return rc;
     if (P == 0) return AGP_OK;
-    const size_t mean_bytes = (size_t)P * m * 8, cov_bytes = (size_t)P * m * m * 8;
+    h->pred_diag_only = marginals;
+    const size_t mean_bytes = (size_t)P * m * 8, cov_bytes = (size_t)P * m * (marginals ? 1 : m) * 8;
     if ((rc = grow_device(h, &h->d_pred, &h->cap_pred, mean_bytes + cov_bytes + 16)) != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, align_up((size_t)P * 8, 16) + (size_t)P * 4, h->stream));  // info = 0 when nothing is factored
     if ((rc = run_fused(h)) != AGP_OK) return rc;
@@ -873,7 +876,8 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
         const double* d_npred = h->view.noise + P;  // noise_pred[P] follows noise[P] in the input arena
         double* d_mean = h->d_pred;
         double* d_cov = h->d_pred + (size_t)P * m;
-        agp::launch_predict_extract(h->view, P, d_npred, d_mean, d_cov, h->stream);
+        if (marginals) agp::launch_predict_extract_marginals(h->view, P, d_npred, d_mean, d_cov, h->stream);
+        else agp::launch_predict_extract(h->view, P, d_npred, d_mean, d_cov, h->stream);
         h->launches += 1;
         if ((rc = check_launch(h, "predict_extract")) != AGP_OK) return rc;
         AGP_CUDA(h, cudaMemcpyAsync(mean_out, d_mean, mean_bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -883,6 +887,18 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
     rc = agp_lml_fetch(h, lml.data(), info_out);  // synchronises; info: LAPACK code of the training block
     h->factor_clean = false;
     return rc;
+}
+
+int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off, const int32_t* n_params,
+                      const double* params, const double* noise, const double* ts, const double* xs, int32_t n, const double* ts_pred,
+                      int32_t m, const double* noise_pred, double* mean_out, double* cov_out, int32_t* info_out) {
+    return predict_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, ts_pred, m, noise_pred, mean_out, cov_out, info_out, false);
+}
+
+int agp_predict_marginals_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops, const int32_t* param_off,
+                                const int32_t* n_params, const double* params, const double* noise, const double* ts, const double* xs, int32_t n,
+                                const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out, double* var_out, int32_t* info_out) {
+    return predict_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, ts_pred, m, noise_pred, mean_out, var_out, info_out, true);
 }
 
 // Joint posterior of the summands of a sum kernel and of the observable at ts_pred (infer_gp_sum, src/GP.jl:904-993).
@@ -1077,6 +1093,13 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
     if (P < 0 || nt < 0 || nt_total < nt || first_row < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
     build_queue_general(P, nt, nt_total, first_row, items);
+    return export_queue(items, items_out, cap);
+}
+
+int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32_t* items_out, int64_t cap) {
+    if (P < 0 || nt < 0 || nt_total < nt) return AGP_ERR_ARG;
+    std::vector<int4> items;
+    build_queue_general(P, nt, nt_total, 0, items, true);
     return export_queue(items, items_out, cap);
 }
 

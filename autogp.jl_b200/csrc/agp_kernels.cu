@@ -157,6 +157,28 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
 }
 
 // ------------------------------------------------------------------------------------------
+// Predictive marginals (agp_predict_marginals_batch): mean and the DIAGONAL of the conditional covariance — what
+// `predict`'s quantiles read (Distributions.quantile of the marginals, src/GP.jl).  m values per particle leave the GPU
+// instead of m^2.
+// ------------------------------------------------------------------------------------------
+__global__ void agp_predict_marginals_kernel(BatchView v, const double* __restrict__ noise_pred, double* __restrict__ mean_out,
+                                             double* __restrict__ var_out) {
+    const int p = blockIdx.y;
+    const int m = v.n_pred, o = v.nt * TB, ld = v.ld;
+    const double* Lp = v.L + (long long)p * v.mat_stride;
+    const double np_ = noise_pred[p];
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) {
+        mean_out[(long long)p * m + a] = -v.y[(long long)p * ld + o + a];
+        var_out[(long long)p * m + a] = Lp[(long long)(o + a) * ld + o + a] + np_;
+    }
+}
+
+void launch_predict_extract_marginals(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* var_out, cudaStream_t s) {
+    if (P <= 0 || v.n_pred <= 0) return;
+    agp_predict_marginals_kernel<<<dim3((v.n_pred + 255) / 256, P), 256, 0, s>>>(v, noise_pred, mean_out, var_out);
+}
+
+// ------------------------------------------------------------------------------------------
 // Appended rows of an identity-augmented batch (agp_lml_grad_batch): row lt + r = e_r' over the observation columns,
 // zeros over the trailing block, up to the end of the row's diagonal tile (only lower tiles are ever read).  Pure
 // stores: 16 bytes per thread and instruction, one CTA per row — the Gram-fill kernel spends as long on these 392

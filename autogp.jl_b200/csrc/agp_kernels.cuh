@@ -78,6 +78,7 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
 int noise_grad_blocks_per_particle(const BatchView& v);
 // [I 0] rows and the zero trailing block of an identity-augmented batch (tile rows nt .. nt_total)
 void launch_augfill(const BatchView& v, int P, cudaStream_t s);
+void launch_predict_extract_marginals(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* var_out, cudaStream_t s);
 // Summand programs of agp_predict_sum_batch: component c of particle p = instructions [off[p M + c], off[p M + c + 1])
 struct ComponentView {
     const AgpInstr* prog;

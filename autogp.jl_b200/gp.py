@@ -343,6 +343,30 @@ class Engine:
         self._P = P
         return mean, cov, info
 
+    def predict_marginals_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs, ts_pred,
+                                noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Mean and marginal variance of X(ts_pred) | X(ts) = xs for every particle — what ``predict``'s quantiles read
+        (src/api.jl:633-699): returns (mean[P, m], var[P, m], info[P]); no m x m covariance is formed or copied."""
+        prog_len, ops, offs, n_params, params, noise = self.pack_batch(nodes, noises)
+        ts = np.ascontiguousarray(ts, dtype=np.float64)
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        tp = np.ascontiguousarray(ts_pred, dtype=np.float64)
+        if ts.shape != xs.shape:
+            raise ValueError("ts and xs must have equal length")
+        P, m = len(prog_len), tp.shape[0]
+        npred = None if noise_pred is None else np.ascontiguousarray(noise_pred, dtype=np.float64)
+        if npred is not None and npred.shape[0] != P:
+            raise ValueError("one noise_pred value per particle")
+        mean = np.empty((P, m), dtype=np.float64)
+        var = np.empty((P, m), dtype=np.float64)
+        info = np.empty(P, dtype=np.int32)
+        self._check(self._lib.agp_predict_marginals_batch(self._h, P, _i32p(prog_len), _i32p(ops), _i32p(offs), _i32p(n_params),
+                                                          _f64p(params), _f64p(noise), _f64p(ts), _f64p(xs), ts.shape[0],
+                                                          _f64p(tp), m, None if npred is None else _f64p(npred),
+                                                          _f64p(mean), _f64p(var), _i32p(info)))
+        self._P = P
+        return mean, var, info
+
     def predict_sum_batch(self, summands: Sequence[Sequence[Node]], noises: Sequence[float], ts, xs, ts_pred,
                           noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """``infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)`` (src/GP.jl:904-993) for every particle:

@@ -189,6 +189,17 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
                       const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out,
                       double* cov_out, int32_t* info_out);
 
+/* The same conditional distribution reduced to its marginals: mean_out[P][m] and var_out[P][m] = diag(cov) — what
+ * `predict` reads (`Distributions.quantile(dist, p)` of the marginals, src/api.jl:633-699).  Only the diagonal
+ * tiles of the Schur complement are formed and m values per particle leave the GPU instead of m^2 (the m x m
+ * covariances dominate agp_predict_batch's end-to-end time from m ~ 256 on).  Bitwise equal to the diagonal of
+ * agp_predict_batch's cov_out. */
+int agp_predict_marginals_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
+                                const int32_t* param_off, const int32_t* n_params, const double* params,
+                                const double* noise, const double* ts, const double* xs, int32_t n,
+                                const double* ts_pred, int32_t m, const double* noise_pred, double* mean_out,
+                                double* var_out, int32_t* info_out);
+
 /* Joint posterior of the M summands of a sum kernel and of the observable at the prediction points —
  * `infer_gp_sum(nodes, noise, ts, xs, ts_pred; noise_pred)` (src/GP.jl:904-993), the decomposition of a
  * forecast into its additive components.  The observations follow k_1 + ... + k_M + noise I; summand c of
@@ -235,6 +246,8 @@ int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out
  * nt_total - nt tile rows of prediction points below the factored block (agp_predict_batch). */
 int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t first_row,
                                 int32_t* items_out, int64_t cap);
+/* ... and of agp_predict_marginals_batch (first_row = 0, only the diagonal tiles of the trailing block). */
+int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32_t* items_out, int64_t cap);
 
 /* Diagnostics: one traced run of the resident batch.  trace_out receives 8 int64 per work item
  * (queue order): globaltimer ns at {pop, producers ready, contraction done, Gram done, L_kk

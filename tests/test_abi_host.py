@@ -290,3 +290,24 @@ def test_split_kernel_sop_follows_the_reference_examples():
     ka, kb = split(tree, agp.Periodic)
     total = o.eval_cov(from_agp(ka), ts) + o.eval_cov(from_agp(kb), ts)
     np.testing.assert_allclose(total, o.eval_cov(from_agp(tree), ts), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("P,nt,nt_total", [(2, 4, 6), (1, 16, 19), (3, 1, 2)])
+def test_marginals_queue_replay(P, nt, nt_total):
+    """agp_predict_marginals_batch: the predictive schedule with only the diagonal tiles of the trailing block."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build_marginals(P, nt, nt_total, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    lib.agp_queue_build_marginals(P, nt, nt_total, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items)
+    n_full = lib.agp_queue_build_general(P, nt, nt_total, 0, None, 0)
+    extra = nt_total - nt
+    assert n_full - n_items == P * extra * (extra - 1)            # two half items per off-diagonal trailing tile
+    # same replay rules; off-diagonal trailing tiles must be absent
+    trailing = [(int(r[2]), int(r[3])) for r in buf if r[2] >= nt]
+    assert trailing and all(k == i for k, i in trailing)
+    full = np.zeros((n_full, 8), dtype=np.int32)
+    lib.agp_queue_build_general(P, nt, nt_total, 0, full.ctypes.data_as(C.POINTER(C.c_int32)), n_full)
+    keep = np.array([not (r[2] >= nt and r[2] != r[3]) for r in full])
+    assert np.array_equal(full[keep], buf)                        # the full predictive queue minus those tiles

@@ -665,6 +665,25 @@ def test_infer_gp_sum_matches_the_oracle(engine, n, m):
     assert np.max(np.abs(cov1 - cov_o)) <= 1e-8 * np.max(np.abs(cov_o)) and np.max(np.abs(mu1 - mu_o)) <= 1e-8 * max(1.0, np.max(np.abs(mu_o)))
 
 
+@pytest.mark.parametrize("n,m", [(300, 1), (300, 130), (1000, 300), (0, 5)])
+def test_predictive_marginals_are_the_diagonal_of_the_predictive_covariance(engine, n, m):
+    """agp_predict_marginals_batch against agp_predict_batch (bitwise: the same diagonal-tile items) and the oracle."""
+    ts, xs = o.synthetic_series(max(n, 2))
+    ts, xs = ts[:n], xs[:n]
+    tp = np.linspace(0.9, 1.3, m)
+    parts = [o.synthetic_particle(60 + p, t) for p, t in enumerate(["se*per+lin", "ge+per*lin", "cp(lin,se)"])]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    for npred in (None, [0.0, 0.2, 0.05]):
+        mean, var, info = engine.predict_marginals_batch(nodes, noises, ts, xs, tp, npred)
+        mean_f, cov_f, info_f = engine.predict_batch(nodes, noises, ts, xs, tp, npred)
+        assert np.all(info == 0) and np.array_equal(mean, mean_f)
+        assert np.array_equal(var, np.diagonal(cov_f, axis1=1, axis2=2))
+        if n > 0:
+            for p, (nd, nz) in enumerate(parts):
+                mu_o, cov_o = o.predictive_mvn(nd, nz, ts, xs, tp, noise_pred=None if npred is None else npred[p])
+                assert np.max(np.abs(var[p] - np.diag(cov_o))) <= 1e-8 * max(np.max(np.abs(cov_o)), 1e-12)
+
+
 def test_predict_mvn_sum_flow_split_then_infer(engine):
     """predict_mvn_sum (src/api.jl): split every particle's kernel on a base-kernel type, then infer_gp_sum over the two
     sides — against the oracle on the same pairs, incl. a particle whose split has an empty (Constant(0)) side."""

@@ -158,7 +158,7 @@ void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnois
 
 // ------------------------------------------------------------------------------------------
 // Predictive marginals (agp_predict_marginals_batch): mean and the DIAGONAL of the conditional covariance — what
-// `predict`'s quantiles read (Distributions.quantile of the marginals, src/GP.jl).  m values per particle leave the GPU
+// `predict`'s quantiles read (Distributions.quantile, src/GP.jl:1006-1012: mean and sqrt(diag(cov))).  m values per particle leave the GPU
 // instead of m^2.
 // ------------------------------------------------------------------------------------------
 __global__ void agp_predict_marginals_kernel(BatchView v, const double* __restrict__ noise_pred, double* __restrict__ mean_out,

@@ -346,7 +346,8 @@ class Engine:
     def predict_marginals_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs, ts_pred,
                                 noise_pred: Optional[Sequence[float]] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """Mean and marginal variance of X(ts_pred) | X(ts) = xs for every particle — what ``predict``'s quantiles read
-        (src/api.jl:633-699): returns (mean[P, m], var[P, m], info[P]); no m x m covariance is formed or copied."""
+        (src/api.jl:633-699 -> ``Distributions.quantile``, src/GP.jl:1006-1012: mean and sqrt(diag(cov)) only): returns
+        (mean[P, m], var[P, m], info[P]); no m x m covariance is formed or copied."""
         prog_len, ops, offs, n_params, params, noise = self.pack_batch(nodes, noises)
         ts = np.ascontiguousarray(ts, dtype=np.float64)
         xs = np.ascontiguousarray(xs, dtype=np.float64)

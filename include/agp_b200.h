@@ -190,7 +190,8 @@ int agp_predict_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const i
                       double* cov_out, int32_t* info_out);
 
 /* The same conditional distribution reduced to its marginals: mean_out[P][m] and var_out[P][m] = diag(cov) — what
- * `predict` reads (`Distributions.quantile(dist, p)` of the marginals, src/api.jl:633-699).  Only the diagonal
+ * `predict` reads (src/api.jl:633-699: `Distributions.quantile(dist, p)`, src/GP.jl:1006-1012, uses mean and
+ * sqrt(diag(cov)) only).  Only the diagonal
  * tiles of the Schur complement are formed and m values per particle leave the GPU instead of m^2 (the m x m
  * covariances dominate agp_predict_batch's end-to-end time from m ~ 256 on).  Bitwise equal to the diagonal of
  * agp_predict_batch's cov_out. */

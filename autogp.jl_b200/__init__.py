@@ -8,7 +8,7 @@ from .gp import (  # noqa: F401
 )
 from .model import (  # noqa: F401
     JITTER, PosDefException, log_marginal_likelihood_grads, log_marginal_likelihoods, log_marginal_likelihoods_info,
-    mvnormal_logpdf, transform_param, transform_param_grad, untransform_param,
+    mvnormal_logpdf, predictive_logpdfs, transform_param, transform_param_grad, untransform_param,
 )
 from . import rejuvenate, smc  # noqa: F401
 

@@ -120,3 +120,35 @@ def log_marginal_likelihoods_info(nodes, noises, ts, xs, *, engine: Optional[gp.
 def mvnormal_logpdf(node: gp.Node, noise: float, ts, xs, *, engine: Optional[gp.Engine] = None) -> float:
     """One particle: ``logpdf(mvnormal, xs, zeros(n), compute_cov_matrix_vectorized(node, noise, ts))``."""
     return float(log_marginal_likelihoods([node], [noise], ts, xs, engine=engine)[0])
+
+
+def predictive_logpdfs(nodes: Sequence[gp.Node], noises: Sequence[float], ts, xs, ts_new, xs_new, *,
+                       engine: Optional[gp.Engine] = None) -> np.ndarray:
+    """``logpdf(MvNormal(node, noise, ts, xs, ts_new), xs_new)`` for every particle — the held-out score of
+    ``predict_proba`` with the default ``noise_pred = noise``.  Computed through the identity the reference's own
+    test asserts (test/experiment_hmc.jl:111-132), ``log p(x_new | x) = LML(ts ∪ ts_new) − LML(ts)``, with the second
+    factorisation CONTINUED from the first (``agp_lml_run_append``): no m x m predictive covariance is ever formed."""
+    eng = engine or gp.default_engine()
+    ts, xs = np.asarray(ts, dtype=np.float64), np.asarray(xs, dtype=np.float64)
+    ts_new, xs_new = np.asarray(ts_new, dtype=np.float64), np.asarray(xs_new, dtype=np.float64)
+    if ts.shape != xs.shape or ts_new.shape != xs_new.shape:
+        raise ValueError("time points and values must have equal length")
+    n = ts.shape[0]
+    eng.upload(nodes, noises, np.concatenate([ts, ts_new]), np.concatenate([xs, xs_new]))
+    if n > 0:
+        eng.set_prefix(n)
+        eng.run()
+        before, info = eng.fetch()
+        if np.any(info != 0):
+            bad = int(np.nonzero(info)[0][0])
+            raise PosDefException(int(info[bad]), bad)
+        eng.set_prefix(n + ts_new.shape[0])
+        eng.run_append()
+    else:   # nothing observed yet: the empty mvnormal scores 0 and there is no factor to continue
+        before = np.zeros(len(nodes))
+        eng.run()
+    after, info = eng.fetch()
+    if np.any(info != 0):
+        bad = int(np.nonzero(info)[0][0])
+        raise PosDefException(int(info[bad]), bad)
+    return after - before

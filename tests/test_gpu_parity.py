@@ -684,6 +684,25 @@ def test_predictive_marginals_are_the_diagonal_of_the_predictive_covariance(engi
                 assert np.max(np.abs(var[p] - np.diag(cov_o))) <= 1e-8 * max(np.max(np.abs(cov_o)), 1e-12)
 
 
+@pytest.mark.parametrize("n,m", [(200, 37), (128, 128), (1000, 5), (0, 40)])
+def test_predictive_logpdf_through_the_append_identity(engine, n, m):
+    """model.predictive_logpdfs (LML(ts u ts_new) - LML(ts), second factorisation continued from the first) against the
+    oracle's logpdf of the dense predictive MVN — the identity of test/experiment_hmc.jl:111-132."""
+    import autogp.jl_b200 as agp
+
+    ts_all, xs_all = o.synthetic_series(n + m)
+    ts, xs, tn, xn = ts_all[:n], xs_all[:n], ts_all[n:], xs_all[n:]
+    parts = [o.synthetic_particle(70 + p, t) for p, t in enumerate(["se*per+lin", "ge+per*lin", "se+wn"])]
+    got = agp.predictive_logpdfs([H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs, tn, xn, engine=engine)
+    for p, (nd, nz) in enumerate(parts):
+        if n > 0:
+            mu, cov = o.predictive_mvn(nd, nz, ts, xs, tn)
+        else:
+            mu, cov = np.zeros(m), o.compute_cov_matrix_vectorized(nd, nz, tn)
+        want = o.mvn_logpdf(xn, mu, cov)
+        assert abs(got[p] - want) <= 1e-8 * max(abs(want), 1.0) + 1e-9 * abs(o.log_marginal_likelihood(nd, nz, ts_all, xs_all)), (p, got[p], want)
+
+
 def test_predict_mvn_sum_flow_split_then_infer(engine):
     """predict_mvn_sum (src/api.jl): split every particle's kernel on a base-kernel type, then infer_gp_sum over the two
     sides — against the oracle on the same pairs, incl. a particle whose split has an empty (Constant(0)) side."""

@@ -494,6 +494,21 @@ def predictive_mvn(node: Node, noise: float, ts, xs, ts_pred, *, noise_pred: Opt
     return mean[0], cov[0]
 
 
+def marginal_quantiles(mean, var, quantiles: Sequence[float]) -> np.ndarray:
+    """``Distributions.quantile(dist::MvNormal, p)`` (src/GP.jl:1006-1012): quantiles of the MARGINALS,
+    ``quantile(Normal(mu_i, sqrt(cov_ii)), q)`` — [m, len(quantiles)] from the mean and marginal variance that
+    ``Engine.predict_marginals_batch`` returns for one particle."""
+    from statistics import NormalDist
+
+    mean = np.asarray(mean, dtype=np.float64)
+    std = np.sqrt(np.asarray(var, dtype=np.float64))
+    z = np.array([-np.inf if q == 0.0 else np.inf if q == 1.0 else NormalDist().inv_cdf(float(q)) for q in quantiles])
+    with np.errstate(invalid="ignore"):
+        out = mean[:, None] + std[:, None] * z[None, :]
+    out[std == 0.0, :] = mean[std == 0.0, None]   # a degenerate marginal is a point mass (0 * inf otherwise)
+    return out
+
+
 def split_kernel_sop(node: Node, leaf_type: type) -> Tuple[Node, Node]:
     """``GP.split_kernel_sop(node, T)`` (src/GP.jl:603-655): read the kernel as a sum of products and return
     ``(k_T, k_nT)`` — the addends with a factor of base-kernel type ``leaf_type`` and the addends without one, with

@@ -311,3 +311,20 @@ def test_marginals_queue_replay(P, nt, nt_total):
     lib.agp_queue_build_general(P, nt, nt_total, 0, full.ctypes.data_as(C.POINTER(C.c_int32)), n_full)
     keep = np.array([not (r[2] >= nt and r[2] != r[3]) for r in full])
     assert np.array_equal(full[keep], buf)                        # the full predictive queue minus those tiles
+
+
+def test_marginal_quantiles_match_the_normal_quantile_function():
+    """Distributions.quantile(::MvNormal, p) of the reference (src/GP.jl:1006-1012) reads mean and sqrt(diag(cov)) only."""
+    import scipy.stats
+
+    import autogp.jl_b200 as agp
+
+    mean = np.array([0.0, 1.5, -2.0, 3.0])
+    var = np.array([1.0, 0.25, 4.0, 0.0])
+    qs = [0.025, 0.5, 0.975]
+    got = agp.marginal_quantiles(mean, var, qs)
+    want = np.stack([scipy.stats.norm.ppf(q, loc=mean, scale=np.sqrt(var)) for q in qs], axis=1)
+    want[3, :] = 3.0                                      # a degenerate marginal is a point mass
+    assert got.shape == (4, 3)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    assert np.all(agp.marginal_quantiles(mean[:3], var[:3], [0.0, 1.0]) == np.array([[-np.inf, np.inf]] * 3))

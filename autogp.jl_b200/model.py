@@ -124,8 +124,9 @@ def mvnormal_logpdf(node: gp.Node, noise: float, ts, xs, *, engine: Optional[gp.
 
 def predictive_logpdfs(nodes: Sequence[gp.Node], noises: Sequence[float], ts, xs, ts_new, xs_new, *,
                        engine: Optional[gp.Engine] = None) -> np.ndarray:
-    """``logpdf(MvNormal(node, noise, ts, xs, ts_new), xs_new)`` for every particle — the held-out score of
-    ``predict_proba`` with the default ``noise_pred = noise``.  Computed through the identity the reference's own
+    """``logpdf(MvNormal(node, noise, ts, xs, ts_new), xs_new)`` for every particle — the per-particle ``logp`` of
+    ``predict_proba`` (src/api.jl:686-699; default ``noise_pred = noise``; in the model's transformed units, the
+    reference's linear ``y_transform`` adds the constant ``-m log|slope|``).  Computed through the identity the reference's own
     test asserts (test/experiment_hmc.jl:111-132), ``log p(x_new | x) = LML(ts ∪ ts_new) − LML(ts)``, with the second
     factorisation CONTINUED from the first (``agp_lml_run_append``): no m x m predictive covariance is ever formed."""
     eng = engine or gp.default_engine()

@@ -84,5 +84,31 @@ def main():
     print("wrote", len(kernels), "kernels")
 
 
+def sum_fixture_inputs():
+    """infer_gp_sum / noise-gradient / marginals fixture: the Plus benchmark of experiment_hmc.jl:181 read as two summands."""
+    ts_h = np.linspace(0.0, 10.0, 1000)[::25]
+    xs_h = fixture_xs(ts_h / 10.0)
+    return [o.Linear(0.5), o.Periodic(2.0, 1.0)], 0.05 + o.JITTER, ts_h, xs_h, np.array([0.3, 4.9, 10.0, 10.5, 12.0])
+
+
+def main_sum():
+    """Separate file (the fixtures above are frozen): values of the oracle restatements added for SURVEY §8 f."""
+    nodes, noise, ts, xs, tp = sum_fixture_inputs()
+    mu, cov, _ = o.infer_gp_sum(nodes, noise, ts, xs, tp, noise_pred=0.0)
+    whole = o.Plus(nodes[0], nodes[1])
+    mu_p, cov_p = o.predictive_mvn(whole, noise, ts, xs, tp)
+    g, gn = o.lml_grad_dense_fd(whole, noise, ts, xs)
+    out = {"infer_gp_sum_mean": mu.tolist(), "infer_gp_sum_cov": cov.tolist(), "predictive_mean": mu_p.tolist(),
+           "predictive_var": np.diag(cov_p).tolist(), "lml_grad_noise": gn, "lml": o.log_marginal_likelihood(whole, noise, ts, xs)}
+    with open(os.path.join(HERE, "sum_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote sum_golden.json")
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if len(sys.argv) > 1 and sys.argv[1] == "sum":
+        main_sum()
+    else:
+        main()

@@ -182,3 +182,28 @@ def test_infer_gp_sum_restatement_is_consistent_with_the_predictive_mvn():
     mu1, cov1, idx1 = o.infer_gp_sum(nodes[:1], noise, ts, xs, tp)
     np.testing.assert_allclose(mu1[list(idx1["F"][0])], mu1[list(idx1["X"])], rtol=1e-12)
     np.testing.assert_allclose(cov1[:m, :m] + noise * np.eye(m), cov1[m:, m:], rtol=1e-10, atol=1e-12)
+
+
+def test_sum_fixture_pins_the_restatements_added_for_the_next_rows():
+    """tests/golden/sum_golden.json (make_golden.py sum): infer_gp_sum, predictive marginals and the noise gradient of the
+    oracle on the Plus benchmark of experiment_hmc.jl:181 — a regression pin of the checker itself."""
+    import json
+    import os
+
+    import make_golden
+
+    with open(os.path.join(os.path.dirname(make_golden.__file__), "sum_golden.json")) as f:
+        gold = json.load(f)
+    nodes, noise, ts, xs, tp = make_golden.sum_fixture_inputs()
+    mu, cov, _ = o.infer_gp_sum(nodes, noise, ts, xs, tp, noise_pred=0.0)
+    np.testing.assert_allclose(mu, gold["infer_gp_sum_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(cov, gold["infer_gp_sum_cov"], rtol=1e-9, atol=1e-11)
+    whole = o.Plus(nodes[0], nodes[1])
+    mu_p, cov_p = o.predictive_mvn(whole, noise, ts, xs, tp)
+    np.testing.assert_allclose(mu_p, gold["predictive_mean"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(np.diag(cov_p), gold["predictive_var"], rtol=1e-9, atol=1e-11)
+    assert abs(o.lml_grad_dense_fd(whole, noise, ts, xs)[1] - gold["lml_grad_noise"]) <= 1e-9 * abs(gold["lml_grad_noise"])
+    assert abs(o.log_marginal_likelihood(whole, noise, ts, xs) - gold["lml"]) <= 1e-11 * abs(gold["lml"])
+    # the X* block of the decomposition (noise_pred = 0) is the noiseless prediction of the whole kernel
+    X = slice(2 * len(tp), 3 * len(tp))
+    np.testing.assert_allclose(np.asarray(gold["infer_gp_sum_mean"])[X], gold["predictive_mean"], rtol=1e-8, atol=1e-10)

@@ -31,6 +31,14 @@
 #include "agp_kernels.cuh"
 #include "agp_ptx.cuh"
 
+// Switches that reproduce the round-1 stage race (profiles/r02_race_experiments.txt, tools/race_variants.sh); all 0 = product.
+#ifndef AGP_X_SIMPLE
+#define AGP_X_SIMPLE 0            // main loop without the `if (active)` blocks: ptxas then places the last LDS of a stage right before the release
+#endif
+#ifndef AGP_X_NO_RELEASE_FENCE
+#define AGP_X_NO_RELEASE_FENCE 0  // drop the cross-proxy fence between a warp's reads of a stage and the stage's release (THE BUG: 1 bad run in 4)
+#endif
+
 namespace agp {
 
 namespace {
@@ -55,7 +63,6 @@ static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region
 static_assert(UM * XS + 4 * 32 * 32 <= REGION_D, "X rows + the solve's ring of four 32x32 operand blocks");
 static_assert(2 * (FUSED_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 
-__device__ __forceinline__ int swz(int row, int chunk) { return row * KC + ((chunk ^ ((row & 1) << 2)) << 1); }
 // double offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] tile written by TMA with SWIZZLE_128B
 __device__ __forceinline__ int swz128(int row, int chunk) { return row * KC + ((chunk ^ (row & 7)) << 1); }
 
@@ -120,6 +127,7 @@ __device__ __forceinline__ void stamp(const SchedView& q, int idx, int slot) {
 // all threads: release this item's global writes, then bump the counter
 __device__ __forceinline__ void signal_done(int* counter) {
     fence_proxy_async();  // this item's shared-memory traffic is ordered before the next item's TMA copies into the same buffers
+    fence_proxy_async_global();  // this thread's generic-proxy stores to L are ordered before the TMA (async-proxy) reads of the CTAs the counter releases
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -219,7 +227,7 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
         if (!diag) tma_load_2d(Bs + UN * KC, &maps.a, ccol + c * KC, arow, s.full + st);
     };
     if (tid == 0) {
-        fence_proxy_async();
+        fence_proxy_async_all();  // after the acquire of the dependency counters, before this item's first async-proxy reads of L
         for (int c = 0; c < NSTAGE - 1 && c < nchunk; ++c) produce(c);
     }
     // (after the first copies are in flight, so the two L2 round trips overlap)
@@ -242,24 +250,33 @@ __device__ __noinline__ bool do_update(const BatchView& v, const SchedView& q, c
         const double* As = diag ? Bs + h * UM * KC : Bs + UN * KC;  // diagonal tile: A rows are a slice of B
         // lane c4 takes the 16-byte chunks 2 c4 + ks of a row (a permutation of k shared by A and B): with the
         // 128-byte swizzle the eight lanes of an LDS.128 phase then hit eight different chunk columns
-        // KEEP the loads and the DMMAs of a k-step in separate conditional blocks.  The same loop without them (same
-        // arithmetic, differently scheduled SASS) produced one wrong row / 8x8 block of a tile in ~1 of 10^4 items,
-        // only with two CTAs per SM (profiles/r01_diag_item_bisect.txt; suspected: a fragment register overwritten by
-        // an LDS.128 while a queued DMMA still has to read it).  Re-run tools/stress_check.py after any change here.
+#if AGP_X_SIMPLE
+#define AGP_ACTIVE_IF
+#else
+#define AGP_ACTIVE_IF if (active)
+#endif
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             double2 a[4], b[4];
-            if (active) {
+            AGP_ACTIVE_IF {
 #pragma unroll
                 for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz128(wm * 32 + mb * 8 + g, 2 * c4 + ks));
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz128(wn * 32 + nb * 8 + g, 2 * c4 + ks));
             }
             if (ks == 1) {
+                // Release of the stage.  The LDS above are generic-proxy reads, the next use of the stage is written by the
+                // async proxy (TMA): every lane orders its own reads before the release with a cross-proxy fence, exactly as
+                // CUTLASS does before consumer_release when a TMA-fed buffer is read with ordinary loads.  Without it the
+                // TMA box of chunk ch + NSTAGE can land while a late LDS of chunk ch is still queued behind the co-resident
+                // CTA's shared-memory traffic (round 1's "one wrong row / 8x8 block in 1 of 10^4 items").
+#if !AGP_X_NO_RELEASE_FENCE
+                fence_proxy_async();
+#endif
                 __syncwarp();
-                if (lane == 0) mbar_arrive(s.empty + st);  // this warp holds its last fragments of the stage
+                if (lane == 0) mbar_arrive(s.empty + st);
             }
-            if (active) {
+            AGP_ACTIVE_IF {
 #pragma unroll
                 for (int mb = 0; mb < 4; ++mb)
 #pragma unroll

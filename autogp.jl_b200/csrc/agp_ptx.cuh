@@ -57,6 +57,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_m
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
 // orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// the same for global memory: this thread's generic-proxy stores to global become visible to later async-proxy reads
+// (TMA tensor loads by any CTA, once the usual release / acquire chain has passed)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+// all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 // D(8x8) += A(8x4,row) * B(4x8,col), FP64 tensor core
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

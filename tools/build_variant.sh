@@ -4,12 +4,13 @@
 set -e
 cd "$(dirname "$0")/.."
 NAME=$1; shift
-mkdir -p gpurun_tmp/$NAME
-CS=autogp.jl_b200/csrc
-NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC $*"
-for f in agp_kernels agp_fused agp_api; do $NV -c $CS/$f.cu -o gpurun_tmp/$NAME/$f.o & done
-g++ -O2 -std=c++17 -fPIC -c $CS/agp_program.cpp -o gpurun_tmp/$NAME/agp_program.o
-wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o gpurun_tmp/libagp_$NAME.so gpurun_tmp/$NAME/*.o -lcudart_static -ldl -lrt -lpthread
-rm -rf gpurun_tmp/$NAME
+B=gpurun_tmp/build_$NAME
+rm -rf $B; mkdir -p $B
+cp autogp.jl_b200/csrc/*.cu autogp.jl_b200/csrc/*.cuh autogp.jl_b200/csrc/*.h autogp.jl_b200/csrc/*.cpp autogp.jl_b200/csrc/Makefile $B/
+mkdir -p $B/../../include_link && true
+# the sources include ../../include/agp_b200.h relative to csrc/: give the copy the same view
+mkdir -p gpurun_tmp/include && cp include/agp_b200.h gpurun_tmp/include/ 2>/dev/null || true
+sed -i 's#../../include/agp_b200.h#../include/agp_b200.h#' $B/*.cu $B/*.cpp $B/*.h $B/Makefile
+make -s -C $B -j8 OUT=../libagp_$NAME.so EXTRA="$*" > $B/build.log 2>&1 || { tail -20 $B/build.log; exit 1; }
+rm -rf $B
 echo built gpurun_tmp/libagp_$NAME.so

@@ -6,11 +6,12 @@ read an operand stage with LDS (generic proxy) and released it to the TMA produc
 fence.proxy.async in between, so a late LDS could see the next box.  What has to hold is therefore a property of the
 code, not one particular ptxas schedule:
 
-    in agp_chol_kernel, walking back from every stage release (SYNCS.ARRIVE ... .A1T0 = mbarrier.arrive without
-    expect_tx) a FENCE.VIEW.ASYNC must come before the first LDS, and every UTMALDG (TMA tensor read of L) must be
-    preceded by a FENCE.VIEW.ASYNC within its basic block chain since the last global acquire.
+    in the two phase functions that read TMA-fed stages (update_contract, update_solve), walking back from every
+    stage release (SYNCS.ARRIVE ... .A1T0 = mbarrier.arrive without expect_tx) a FENCE.VIEW.ASYNC must come before
+    the first LDS; both functions must still use TMA tensor copies (UTMALDG); and their main loops must be free of
+    local-memory traffic (spills there cost the round-2 builds up to 2.4x, agp_chol_common.cuh).
 
-    python tools/sass_lint.py [autogp.jl_b200/csrc/agp_fused.o]      exit code 1 on violation
+    python tools/sass_lint.py [object files]      exit code 1 on violation
 """
 import os
 import re
@@ -18,46 +19,79 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEFAULT_OBJ = os.path.join(ROOT, "autogp.jl_b200", "csrc", "agp_fused.o")
+CSRC = os.path.join(ROOT, "autogp.jl_b200", "csrc")
+DEFAULT_OBJS = [os.path.join(CSRC, "agp_chol_contract.o"), os.path.join(CSRC, "agp_chol_solve.o")]
+FUNCS = ("update_contract", "update_solve")
 
 
-def chol_sass(obj):
+def function_sass(obj):
+    """{function name: [instruction text]} for the phase functions found in `obj`."""
     txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
-    f = txt[txt.index("Function : _ZN3agp15agp_chol_kernel"):]
-    nxt = f.find("Function :", 10)
-    f = f[:nxt] if nxt > 0 else f
-    return [m.group(1).strip() for m in (re.search(r"/\*[0-9a-f]{4,5}\*/\s+(.*?);", l) for l in f.split("\n")) if m]
+    out = {}
+    for part in txt.split("Function : ")[1:]:
+        name = part.split("\n", 1)[0].strip()
+        hit = [f for f in FUNCS if f in name]
+        if not hit:
+            continue
+        out[hit[0]] = [(int(m.group(1), 16), m.group(2).strip())
+                       for m in (re.search(r"/\*([0-9a-f]{4,5})\*/\s+(.*?);", l) for l in part.split("\n")) if m]
+    return out
 
 
-def lint(obj=DEFAULT_OBJ):
-    """Returns (n_releases, n_tma_loads, problems)."""
-    ins = chol_sass(obj)
+def lint_function(name, code):
     problems = []
+    addr = [a for a, _ in code]
+    ins = [t for _, t in code]
     releases = [i for i, t in enumerate(ins) if "SYNCS.ARRIVE" in t and "A1T0" in t]
     for i in releases:
         j = i - 1
         while j >= 0 and "FENCE.VIEW.ASYNC" not in ins[j]:
             if re.search(r"\bLDS(\.|\b)", ins[j]):
-                problems.append(f"stage release at instruction {i} ({ins[i]}): LDS at {j} ({ins[j]}) is not fenced from it")
+                problems.append(f"{name}: stage release at instruction {i} ({ins[i]}): LDS at {j} ({ins[j]}) is not fenced from it")
                 break
             if "SYNCS.PHASECHK" in ins[j]:  # reached the wait that opened this stage use without meeting a shared load
                 break
             j -= 1
+        # the main loop = the innermost backward branch around the release: no local-memory instruction inside
+        loop = None
+        for kk in range(i, len(ins)):
+            m = re.search(r"\bBRA(?:\.U)?(?:\s+\S+,)?\s+(0x[0-9a-f]+)", ins[kk])
+            if m and int(m.group(1), 16) <= addr[i]:
+                loop = (int(m.group(1), 16), kk)
+                break
+        if loop is None:
+            problems.append(f"{name}: no loop found around the release at {i}, update this check")
+            continue
+        body = [k for k in range(len(ins)) if loop[0] <= addr[k] and k <= loop[1]]
+        spills = [k for k in body if re.match(r"(@!?U?P\d+ )?(STL|LDL)", ins[k])]
+        if spills:
+            problems.append(f"{name}: {len(spills)} local-memory instruction(s) among the {len(body)} of the main loop around the release at {i} (first: {ins[spills[0]]})")
     tma = [i for i, t in enumerate(ins) if "UTMALDG" in t]
     if not releases:
-        problems.append("no stage release (SYNCS.ARRIVE ... A1T0) found: the kernel's structure changed, update this check")
+        problems.append(f"{name}: no stage release (SYNCS.ARRIVE ... A1T0) found: the function's structure changed, update this check")
     if not tma:
-        problems.append("no UTMALDG found: the operand pipeline no longer uses TMA tensor copies, update this check")
-    n_fence = sum("FENCE.VIEW.ASYNC" in t for t in ins)
-    if n_fence < len(releases) + 1:
-        problems.append(f"only {n_fence} FENCE.VIEW.ASYNC for {len(releases)} releases + the item prologue")
+        problems.append(f"{name}: no UTMALDG found: the operand pipeline no longer uses TMA tensor copies, update this check")
     return len(releases), len(tma), problems
 
 
+def lint(objs=None):
+    """Returns (n_releases, n_tma_loads, problems) over the phase functions."""
+    found, rel, tma, problems = set(), 0, 0, []
+    for obj in (objs or DEFAULT_OBJS):
+        for name, ins in function_sass(obj).items():
+            found.add(name)
+            r, t, p = lint_function(name, ins)
+            rel, tma, problems = rel + r, tma + t, problems + p
+    for f in FUNCS:
+        if f not in found:
+            problems.append(f"{f}: not found in {objs or DEFAULT_OBJS}")
+    return rel, tma, problems
+
+
 if __name__ == "__main__":
-    obj = sys.argv[1] if len(sys.argv) > 1 else DEFAULT_OBJ
-    r, t, problems = lint(obj)
-    print(f"{obj}: {r} stage release(s), {t} UTMALDG, {len(problems)} problem(s)")
+    objs = sys.argv[1:] or DEFAULT_OBJS
+    r, t, problems = lint(objs)
+    print(f"{', '.join(os.path.basename(o) for o in objs)}: {r} stage release(s), {t} UTMALDG, {len(problems)} problem(s)")
     for p in problems:
         print("  " + p)
     sys.exit(1 if problems else 0)

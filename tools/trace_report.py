@@ -7,20 +7,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
-import autogp_oracle as o  # noqa: E402  (workload definition only)
 import autogp.jl_b200 as agp  # noqa: E402
 from autogp.jl_b200 import _lib  # noqa: E402
-
-
-def to_agp(nd):
-    cls = getattr(agp, type(nd).__name__)
-    if isinstance(nd, o.LEAVES):
-        return cls(**nd.__dict__)
-    if isinstance(nd, o.ChangePoint):
-        return cls(to_agp(nd.left), to_agp(nd.right), nd.location, nd.scale)
-    return cls(to_agp(nd.left), to_agp(nd.right))
+from autogp.jl_b200.workloads import synthetic_batch, synthetic_series  # noqa: E402
 
 
 def main():
@@ -28,9 +18,9 @@ def main():
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     order = int(os.environ.get("AGP_ORDER", "3"))
     eng = agp.Engine(0)
-    ts, xs = o.synthetic_series(n)
-    parts = [o.synthetic_particle(p) for p in range(P)]
-    eng.upload([to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
+    ts, xs = synthetic_series(n)
+    nodes, noises = synthetic_batch(P)
+    eng.upload(nodes, noises, ts, xs)
     for _ in range(3):
         eng.run()
     eng.synchronize()
@@ -56,7 +46,7 @@ def main():
         line = f"{names[t]:6s} items {m.sum():6d}  total {tot.sum()/1e3:9.1f} ms*cta  mean {tot.mean():7.1f} us"
         if t == 1:
             w = s[:, 1] - s[:, 0]
-            line += f" | wait {w.mean():6.1f}  work {(s[:,5]-s[:,1]).mean():6.1f}"
+            line += f" | wait {w.mean():6.1f}  work {(s[:,5]-s[:,1]).mean():6.1f} = load {(s[:,2]-s[:,1]).mean():5.1f} + panels {(s[:,3]-s[:,2]).mean():5.1f} + tail {(s[:,5]-s[:,3]).mean():5.1f}"
         else:
             w1 = s[:, 1] - s[:, 0]
             mm = s[:, 2] - s[:, 1]
@@ -73,6 +63,9 @@ def main():
                 kk = items[m, 2] > 0
                 line += f" | (k>0) wait1 {w1[kk].mean():6.1f} mma {mm[kk].mean():6.1f} store {rest[kk].mean():6.1f}"
         print(line)
+        if t == 1 and (st[m][:, 4] != 0).any():  # -DAGP_X_POTF2_CLK=1 builds: clock totals of the micro-panel phases
+            c = st[m][:, 4]
+            print(f"       potf2 clocks per item: P1 (pivot chains) {np.mean(c >> 32):9.0f}  P2 (rank-8 updates) {np.mean(c & 0xffffffff):9.0f}")
     print(f"slots {slots}  busy {busy_total/1e3:.1f} ms*cta  capacity {slots*span/1e3:.1f} ms*cta  occupancy {busy_total/(slots*span):.3f}")
     # per-block-column view of the panels
     print("per block column k: panel items mean us (wait1, mma, gram, waitF, trsm) and the wall-clock window of the column")

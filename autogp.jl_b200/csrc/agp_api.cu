@@ -44,7 +44,7 @@ struct agp_handle {
     const int* d_param_prefix = nullptr;            // [P+1] prefix sums of n_params (inside the input arena)
     BatchView view{};
     agp::TmaMaps tma{};          // TMA descriptors over d_L for the current (pointer, ld, P)
-    double* tma_L = nullptr; double* tma_W = nullptr; int tma_ld = 0; long long tma_rows = 0;
+    double* tma_L = nullptr; int tma_ld = 0; long long tma_rows = 0;
 
     // device workspaces (grow-only)
     double* d_L = nullptr;       size_t cap_L = 0;       // bytes
@@ -310,14 +310,14 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     int rc;
     if ((rc = grow_pinned(h, &h->h_in, &h->cap_hin, in_bytes)) != AGP_OK) return rc;
     if ((rc = grow_device(h, &h->d_in, &h->cap_in, in_bytes)) != AGP_OK) return rc;
-    // work arena: y[P][ld] z[P][ld] cum[P][ld/128][2] dinv[P][ld/128][128][128] (the inverse of every factored
-    // diagonal tile, per block column: the persistent kernel factors column k+1 while column k is still
+    // work arena: y[P][ld] z[P][ld] cum[P][ld/128][2] dinv[P][ld/128][4096] (one set of diagonal-block
+    // inverses per block column: the persistent kernel factors column k+1 while column k is still
     // being solved)
     size_t off_y = 0;
     size_t off_z = off_y + (size_t)P * ld * 8;
     size_t off_cum = off_z + (size_t)P * ld * 8;
     size_t off_dinv = align_up(off_cum + (size_t)P * (ld / TB) * 2 * 8, 256);
-    size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * TB * TB * 8;
+    size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * 4096 * 8;
     if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
     size_t res_bytes = align_up((size_t)P * 8, 16) + (size_t)P * 4;
     if ((rc = grow_device(h, &h->d_res, &h->cap_res, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
@@ -740,10 +740,8 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         AGP_CUDA(h, cudaEventElapsedTime(&kernel_ms[0], h->ev0, h->ev1));
         AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     }
-    if (h->tma_L != v.L || h->tma_ld != h->ld || h->tma_rows != (long long)P * h->ld || h->tma_W != v.dinv) {
-        if (!agp::make_tma_maps(v.L, h->ld, (long long)P * h->ld, v.dinv, (long long)P * nt_stride * TB, &h->tma))
-            return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the factor matrix");
-        h->tma_W = v.dinv;
+    if (h->tma_L != v.L || h->tma_ld != h->ld || h->tma_rows != (long long)P * h->ld) {
+        if (!agp::make_tma_maps(v.L, h->ld, (long long)P * h->ld, &h->tma)) return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the factor matrix");
         h->tma_L = v.L;
         h->tma_ld = h->ld;
         h->tma_rows = (long long)P * h->ld;

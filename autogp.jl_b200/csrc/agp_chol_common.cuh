@@ -1,13 +1,15 @@
-// Shared pieces of the persistent Cholesky kernel (agp_chol_kernel.cu) and its three out-of-line phase functions
-// (agp_chol_contract.cu, agp_chol_solve.cu, agp_chol_potf2.cu).
+// Shared pieces of the persistent Cholesky kernel (agp_chol_kernel.cu: the persistent loop with the DIAG / PANEL items
+// inlined) and the POTF2 item (agp_chol_potf2.cu), which is compiled separately and called through the plain ABI.
 //
-// Why separate translation units: the contraction and the triangular product keep 64 accumulator + 32 fragment
-// registers per thread in flight and fit the 128-register budget of two CTAs per SM with nothing to spare.  Compiled
-// together with the rest of the kernel, ptxas' interprocedural register allocation took registers away from them
-// whenever an unrelated function changed (round 1: "every variant disturbs do_update's register allocation"; round 2:
-// the new POTF2 cost the main loop 100 spill instructions per chunk, 2.4x slower).  As separately compiled functions
-// (relocatable device code, linked by nvlink) each is allocated alone under the plain ABI: callee-saved registers are
-// pushed once per item, the loops are spill-free whatever the other functions look like.
+// Why two translation units: the contraction keeps 64 accumulator + 32 fragment registers per thread in flight and
+// fits the 128-register budget of two CTAs per SM with nothing to spare.  As long as both item functions were
+// out-of-line functions of ONE translation unit, ptxas' interprocedural register allocation took registers away from
+// the contraction whenever the other function changed (round 1: "every variant disturbs do_update's register
+// allocation"; round 2: a rewritten POTF2 cost the main loop 100 spill instructions per chunk, 2.4x slower, whichever
+// way the functions were split or inlined).  With POTF2 behind a true ABI call (relocatable device code, linked by
+// nvlink) the kernel is allocated without knowing it: callee-saved registers are pushed once per POTF2 item (5 % of
+// the items), and the contraction's allocation no longer depends on it.  Measured alternatives: every item function
+// separately compiled: robust too, but 5 % slower (124 KB of register pushes and pops per item and CTA).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -22,12 +24,6 @@
 #endif
 #ifndef AGP_X_POTF2_CLK
 #define AGP_X_POTF2_CLK 0         // diagnostics: clock totals of the two phases of the POTF2 micro-panels into trace slot 4
-#endif
-#ifndef AGP_X_SKIP_SOLVE
-#define AGP_X_SKIP_SOLVE 0        // timing experiment (wrong results): final panels skip the triangular product
-#endif
-#ifndef AGP_X_SKIP_POTF2
-#define AGP_X_SKIP_POTF2 0        // timing experiment (wrong results): POTF2 items load and store but do not factor
 #endif
 #ifndef AGP_X_NO_RELEASE_FENCE
 #define AGP_X_NO_RELEASE_FENCE 0  // drop the cross-proxy fence between a warp's reads of a stage and the stage's release (THE BUG: 1 bad run in 4)
@@ -150,12 +146,6 @@ __device__ __forceinline__ Smem smem_view() {
     return s;
 }
 
-constexpr int XS2 = 130;         // X row stride in the product phase: 2 mod 16 doubles -> the K-permuted LDS.128 of a row pair hit disjoint banks
-constexpr int WST_D = UN * KC;   // one stage of W: 128 rows x 16 columns
-constexpr int XS_OFF = 2 * WST_D;  // X rows sit behind the two W stages
-static_assert(XS_OFF + UM * XS2 <= REGION_D, "two W stages + the X rows must fit in the region");
-constexpr int MODE_DIAG = 1, MODE_H = 2, MODE_GLOBAL = 4;  // contract(): diagonal tile, upper / lower row half, store to L (DIAG, PARTIAL) instead of X
-
 // The item's fields, decoded from the queue entry (every phase function decodes them again instead of receiving them:
 // whatever the caller keeps in registers across a call is taken away from the callee's 128, see above)
 struct ItemFields {
@@ -182,13 +172,8 @@ __device__ __forceinline__ ItemFields decode_item(const SchedView& q, int idx) {
     return f;
 }
 
-// The three phases of the work items, one translation unit each.
-// phase A of a DIAG / PANEL item: dependency waits, contraction, store.  Returns 0: failed (drain), 1: item complete,
-// 2: a final panel, X is in shared memory and phase B follows
-__device__ int update_contract(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx);
-// phase B of a final PANEL item: the triangular product with W = L_kk^{-1}, store, forward solve
-__device__ int update_solve(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx);
-// ITEM_POTF2: Cholesky of the diagonal tile and its inverse
+// ITEM_POTF2: Cholesky of the diagonal tile, inverses of its diagonal 32x32 blocks (agp_chol_potf2.cu; the DIAG / PANEL
+// items are inlined into the kernel's own translation unit)
 __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx);
 
 }  // namespace agp

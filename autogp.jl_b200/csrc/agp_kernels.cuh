@@ -28,7 +28,7 @@ struct BatchView {
     const double* noise;     // [P]
     double* lml;             // [P]
     int* info;               // [P]
-    double* dinv;            // [P][ld/128][128][128] W = L_kk^{-1} of every factored diagonal tile (dense, zeros above the diagonal)
+    double* dinv;            // [P][ld/128][4][32][32] inverses of the diagonal 32x32 blocks of every L_kk
     // rows beyond the factored block (prediction points appended at a tile
     // boundary, see agp_predict_batch) and per-block-column running sums (so a factorisation can be
     // continued from any block column, see agp_lml_run_append)
@@ -94,12 +94,11 @@ void launch_component_fill(const BatchView& v, int P, const ComponentView& cv, c
 void launch_predict_extract(const BatchView& v, int P, const double* noise_pred, double* mean_out, double* cov_out, cudaStream_t s);
 // 2-D TMA descriptors over L viewed as one [P * ld][ld] FP64 matrix: boxes of 16 columns (128 bytes, hardware
 // 128-byte swizzle) x 64 rows (A operand: the item's rows) and x 128 rows (B operand: tile row k)
-// and over the inverted diagonal tiles W viewed as one [w_rows][128] matrix (boxes of 16 columns x 128 rows)
 struct TmaMaps {
-    CUtensorMap a, b, w;
+    CUtensorMap a, b;
 };
 // returns false when the driver refuses a descriptor (reported by the caller)
-bool make_tma_maps(double* L, int ld, long long rows, double* W, long long w_rows, TmaMaps* out);
+bool make_tma_maps(double* L, int ld, long long rows, TmaMaps* out);
 // One launch = the whole batch: Cholesky + solve + logdet for every particle.
 void launch_chol(const BatchView& v, const SchedView& q, const TmaMaps& maps, int ctas, cudaStream_t s);
 cudaError_t configure_fused();

@@ -40,21 +40,27 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
     if (!s.ctl[1]) return false;
     stamp(q, idx, 1);
 
-    // lower triangle -> packed blocks (L2 loads: the tile was written by other CTAs of this launch)
+    // the ten lower 32x32 blocks -> packed blocks: 5120 16-byte L2 loads (the tile was written by other CTAs of this
+    // launch), 20 per thread in two batches of ten, all of a batch in flight (round 1: 64 scalar loads per thread in
+    // eight dependent batches, 11 us of the item's 55)
 #pragma unroll 1
-    for (int base = 0; base < TB * TB; base += FT * 8) {
-        double tmp[8];
+    for (int u0 = 0; u0 < 20; u0 += 10) {
+        double2 tmp[10];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int idx = base + u * FT + tid;
-            int r = idx >> 7, c = idx & (TB - 1);
-            tmp[u] = (c <= r) ? __ldcg(Lp + (long long)(o + r) * ld + o + c) : 0.0;
+        for (int uu = 0; uu < 10; ++uu) {
+            const int e = (u0 + uu) * FT + tid;
+            const int b = e >> 9, w = e & 511, r = w >> 4, c2 = w & 15;
+            const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0, bj = b - bi * (bi + 1) / 2;
+            tmp[uu] = __ldcg(reinterpret_cast<const double2*>(Lp + (long long)(o + bi * 32 + r) * ld + o + bj * 32 + 2 * c2));
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int idx = base + u * FT + tid;
-            int r = idx >> 7, c = idx & (TB - 1);
-            if ((c >> 5) <= (r >> 5)) Ab[blk_off(r >> 5, c >> 5) + (r & 31) * BS + (c & 31)] = tmp[u];
+        for (int uu = 0; uu < 10; ++uu) {
+            const int e = (u0 + uu) * FT + tid;
+            const int b = e >> 9, w = e & 511, r = w >> 4, c2 = w & 15;
+            const bool dg = (b == 0) | (b == 2) | (b == 5) | (b == 9);  // a diagonal block: nothing above the diagonal
+            double* dst = Ab + b * BLK + r * BS + 2 * c2;
+            dst[0] = (dg && 2 * c2 > r) ? 0.0 : tmp[uu].x;
+            dst[1] = (dg && 2 * c2 + 1 > r) ? 0.0 : tmp[uu].y;
         }
     }
     if (tid < TB) ys[tid] = __ldcg(yp + o + tid);

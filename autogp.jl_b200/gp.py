@@ -144,25 +144,42 @@ _LEAF_FIELDS = {
 }
 
 
-def encode_program(node: Node) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Kernel tree -> wire format (ops, param_off, params) of include/agp_b200.h."""
-    ops, offs, params = [], [], []
-    for nd in unroll(node):
-        offs.append(len(params))
+def _encode_into(node: Node, ops: list, offs: list, params: list, p0: int) -> None:
+    """Appends the postfix program of `node` (``unroll`` order, src/GP.jl:111-113); parameter offsets count from `p0`.
+    Iterative: trees are unbounded a priori (max_depth = -1)."""
+    stack = [(node, False)]
+    while stack:
+        nd, seen = stack.pop()
         t = type(nd)
-        if t in _LEAF_FIELDS:
-            code, fields = _LEAF_FIELDS[t]
-            ops.append(code)
-            params.extend(float(getattr(nd, f)) for f in fields)
+        leaf = _LEAF_FIELDS.get(t)
+        if leaf is None and not seen:
+            if not isinstance(nd, BinaryOpNode):
+                raise TypeError(f"not a covariance kernel node: {nd!r}")
+            stack.append((nd, True))
+            stack.append((nd.right, False))
+            stack.append((nd.left, False))
+            continue
+        offs.append(len(params) - p0)
+        if leaf is not None:
+            ops.append(leaf[0])
+            for f in leaf[1]:
+                params.append(float(getattr(nd, f)))
         elif t is Plus:
             ops.append(OP_PLUS)
         elif t is Times:
             ops.append(OP_TIMES)
         elif t is ChangePoint:
             ops.append(OP_CHANGEPOINT)
-            params.extend((float(nd.location), float(nd.scale)))
+            params.append(float(nd.location))
+            params.append(float(nd.scale))
         else:
             raise TypeError(f"not a covariance kernel node: {nd!r}")
+
+
+def encode_program(node: Node) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Kernel tree -> wire format (ops, param_off, params) of include/agp_b200.h."""
+    ops, offs, params = [], [], []
+    _encode_into(node, ops, offs, params, 0)
     return (np.asarray(ops, dtype=np.int32), np.asarray(offs, dtype=np.int32),
             np.asarray(params, dtype=np.float64))
 
@@ -222,16 +239,23 @@ class Engine:
     # ---- site 2 -------------------------------------------------------------------------
     @staticmethod
     def pack_batch(nodes: Sequence[Node], noises: Sequence[float]):
-        progs = [encode_program(nd) for nd in nodes]
-        prog_len = np.asarray([len(p[0]) for p in progs], dtype=np.int32)
-        n_params = np.asarray([len(p[2]) for p in progs], dtype=np.int32)
-        ops = np.concatenate([p[0] for p in progs]) if progs else np.zeros(0, np.int32)
-        offs = np.concatenate([p[1] for p in progs]) if progs else np.zeros(0, np.int32)
-        params = np.concatenate([p[2] for p in progs]) if progs else np.zeros(0, np.float64)
+        """All particles' programs in the wire format of ``agp_lml_upload`` (one flat pass: this runs once per MH step
+        of every particle, inside the end-to-end call)."""
+        ops: List[int] = []
+        offs: List[int] = []
+        params: List[float] = []
+        prog_len: List[int] = []
+        n_params: List[int] = []
+        for node in nodes:
+            o0, p0 = len(ops), len(params)
+            _encode_into(node, ops, offs, params, p0)
+            prog_len.append(len(ops) - o0)
+            n_params.append(len(params) - p0)
         noise = np.ascontiguousarray(noises, dtype=np.float64)
-        if noise.shape[0] != len(progs):
+        if noise.shape[0] != len(prog_len):
             raise ValueError("one noise value per particle")
-        return prog_len, np.ascontiguousarray(ops), np.ascontiguousarray(offs), n_params, np.ascontiguousarray(params), noise
+        return (np.asarray(prog_len, dtype=np.int32), np.asarray(ops, dtype=np.int32), np.asarray(offs, dtype=np.int32),
+                np.asarray(n_params, dtype=np.int32), np.asarray(params, dtype=np.float64), noise)
 
     def lml_batch(self, nodes: Sequence[Node], noises: Sequence[float], ts, xs) -> Tuple[np.ndarray, np.ndarray]:
         """Host buffers in, host results out: one ``agp_lml_batch`` call."""

@@ -43,6 +43,21 @@ def effective_sample_size(log_weights: np.ndarray) -> float:  # inference_smc_an
     return math.exp(-logsumexp(2.0 * lnw))
 
 
+def linear_schedule(n: int, percent: float) -> List[int]:
+    """``Schedule.linear_schedule(n, percent)`` (src/Schedule.jl:24-39): data prefixes growing by about ``n * percent``."""
+    if not (0 < n and 0 < percent < 1):
+        raise ValueError("linear_schedule: need 0 < n and 0 < percent < 1")
+    step = int(round(percent * n))  # Julia's round and Python's both round half to even
+    checkpoints = list(range(step, n + 1, step))
+    remaining = n - checkpoints[-1]
+    if remaining == 0:
+        return checkpoints
+    if remaining < step / 2:
+        checkpoints[-1] = n
+        return checkpoints
+    return checkpoints + [n]
+
+
 def shard_range(P: int, rank: int, world: int):
     """Contiguous block of particles owned by `rank` (sizes differ by at most one)."""
     base, rem = divmod(P, world)

@@ -10,11 +10,18 @@ particle-LMLs/sec at n=2048 x 64 particles, depth-3 Sum(Product(SE,Periodic),Lin
 A step = one pass of the hot path over one batch: Gram build -> Cholesky -> solve -> logdet for
 `--particles` particles per GPU sharing (ts, xs) (+ the single all-gather of log-weights when
 N > 1).  `value` is timed with the batch resident in HBM; `e2e` goes through the C-ABI call with
-host buffers (H2D of programs/ts/xs and D2H of the results inside the timed region).
-Rank 0 prints ONE JSON line.  Nothing here reads /root/reference.
+host buffers (program encoding, H2D of programs/ts/xs and D2H of the results inside the timed region).
+After the headline line's numbers are taken, the rest of BASELINE.json's target is measured into the
+`also` object of the same JSON line: n = 512 and n = 8192 x 64 particles, one LML-gradient and one
+noise-gradient call at n = 2048, and the data-annealing schedule of configs[3] (10 prefixes of
+linear_schedule(2048, 0.10), all-gather + ESS + replicated resample every round) at the launched N.
+Rank 0 prints ONE JSON line.  Nothing here reads /root/reference; the oracle (the checker) is
+imported only by the cpu_baseline leg and by --impl reference.
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,28 +41,19 @@ TREE = "se*per+lin"
 # MEASURED_PEAKS.json uses for bf16); the DMMA issue-rate ceiling is 37.2 TFLOP/s.
 # MEASURED_PEAKS.json itself has no FP64 entry.
 FP64_PEAK_TFLOPS = 35.4
+KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_potf2.cu", "agp_chol_common.cuh")
 
 
-def load_oracle():
-    """The CPU oracle — only for the cpu_baseline / --impl reference legs (never on the product path)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import autogp_oracle as o
-    return o
+def workload_name(n, P):
+    return f"n={n}, {P} particles/GPU, tree Plus(Times(SE,Periodic),Linear), FP64"
 
 
-def workload(o, n, particle_ids):
-    ts, xs = o.synthetic_series(n)
-    parts = [o.synthetic_particle(p, TREE) for p in particle_ids]
-    return ts, xs, parts
-
-
-def to_agp(agp, o, nd):
-    cls = getattr(agp, type(nd).__name__)
-    if isinstance(nd, o.LEAVES):
-        return cls(**nd.__dict__)
-    if isinstance(nd, o.ChangePoint):
-        return cls(to_agp(agp, o, nd.left), to_agp(agp, o, nd.right), nd.location, nd.scale)
-    return cls(to_agp(agp, o, nd.left), to_agp(agp, o, nd.right))
+def kernel_source_md5():
+    h = hashlib.md5()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "autogp.jl_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -108,28 +106,41 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def update_stage_flops(n, tb=128):
-    """Algorithmic flops of the trailing-update (SYRK/GEMM) stage of one n x n Cholesky with block
-    width tb: off-diagonal tiles full, diagonal tiles lower half."""
-    nt = (n + tb - 1) // tb
-    fma = 0.0
-    for k in range(nt):
-        fma += (nt - k - 1) * k * tb ** 3 + k * tb ** 3 / 2
-    return 2.0 * fma
+# ---- the reference's CPU path (oracle port): cpu_baseline leg and --impl reference ---------------------------------
+
+def load_oracle():
+    """The CPU oracle, the checker of this repository: imported ONLY by the cpu_baseline leg and by --impl reference."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import autogp_oracle as o
+    return o
 
 
-def cpu_reference_rate(o, n, n_particles, threads):
-    """The reference's CPU path restated (oracle port): particles in a thread pool like
-    Threads.@threads (src/inference_smc_anneal_data.jl:133); returns (LML/s, seconds)."""
+def cpu_reference_rate(o, n, particle_ids, workers, blas_threads):
+    """The reference's CPU path restated (oracle port): particles in a thread pool like Threads.@threads
+    (src/inference_smc_anneal_data.jl:133), LAPACK with `blas_threads` threads per call; returns (LML/s, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
 
-    ts, xs, parts = workload(o, n, range(n_particles))
-    o.log_marginal_likelihood(*parts[0], ts[:256], xs[:256])  # warm imports / BLAS
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(lambda pr: o.log_marginal_likelihood(pr[0], pr[1], ts, xs), parts))
-    dt = time.perf_counter() - t0
-    return n_particles / dt, dt
+    from threadpoolctl import threadpool_limits
+
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p, TREE) for p in particle_ids]
+    with threadpool_limits(limits=blas_threads):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(lambda pr: o.log_marginal_likelihood(pr[0], pr[1], ts, xs), parts))
+        dt = time.perf_counter() - t0
+    return len(parts) / dt, dt
+
+
+def pick_cpu_threads(o, n, cores):
+    """'All the host threads it can use': the faster of (pool of `cores` workers x 1 LAPACK thread) and (the same pool x
+    `cores` LAPACK threads), probed on `cores` particles each.  torchrun's OMP_NUM_THREADS=1 no longer decides it."""
+    best = None
+    for blas in (1, cores):
+        rate, _ = cpu_reference_rate(o, n, range(cores), cores, blas)
+        if best is None or rate > best[0]:
+            best = (rate, blas)
+    return best[1]
 
 
 def run_reference(args, rank, world):
@@ -137,29 +148,340 @@ def run_reference(args, rank, world):
         return
     o = load_oracle()
     cores = os.cpu_count() or 1
-    sample = max(cores, 8)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_rate(o, args.n, min(sample, 4), cores)
-    steps = max(1, min(args.steps, 5))  # each step = `sample` particles (~2-4 s of CPU); bounded
-    t_tot, done = 0.0, 0
+    n, P = args.n, args.particles
+    o.log_marginal_likelihood(*o.synthetic_particle(0, TREE), *[a[:256] for a in o.synthetic_series(n)])  # warm imports / BLAS
+    blas = pick_cpu_threads(o, n, cores)
+    # a step = the same batch as the CUDA arm's: P particles sharing (ts, xs).  Bounded: the probe above gives the rate,
+    # and the number of steps is capped so that the timed region stays under ~150 s of CPU (the JSON line says so).
+    rate0, _ = cpu_reference_rate(o, n, range(min(P, cores)), cores, blas)
+    est_step = P / rate0
+    steps = max(1, min(args.steps, int(150.0 / max(est_step, 1e-3))))
+    warmup = 1 if args.warmup > 0 else 0
+    for _ in range(warmup):
+        cpu_reference_rate(o, n, range(P), cores, blas)
+    t_tot = 0.0
     for _ in range(steps):
-        _, dt = cpu_reference_rate(o, args.n, sample, cores)
+        _, dt = cpu_reference_rate(o, n, range(P), cores, blas)
         t_tot += dt
-        done += sample
-    value = done / t_tot
+    value = P * steps / t_tot
+    sample = (f"{P} particles per step (the CUDA arm's batch), {steps} of the {args.steps} requested steps"
+              f"{' (capped: ~150 s of CPU)' if steps < args.steps else ''}, pool of {cores} workers x {blas} LAPACK thread(s): "
+              "NumPy Gram with one temporary per op + LAPACK dpotrf/dtrsv = the reference's Julia path restated (Julia is not installed)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": 1e3 * t_tot / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"n={args.n}, {args.particles} particles/GPU, tree Plus(Times(SE,Periodic),Linear), FP64",
-                   "n": args.n, "particles_per_gpu": args.particles, "tree": TREE},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} particles of the same workload per step, {steps} steps, thread pool of {cores} "
-                                   "(NumPy Gram with one temporary per op + LAPACK dpotrf/dtrsv: the reference's Julia path restated; Julia is not installed)"},
+        "config": {"workload": workload_name(n, P) + " (BASELINE.json configs[1])" if n == 2048 and P == 64 else workload_name(n, P),
+                   "n": n, "particles_per_gpu": P, "tree": TREE},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- the CUDA arm ---------------------------------------------------------------------------------------------------
+
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU path)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = f"cuda:{self.local_rank}"
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        import autogp.jl_b200 as agp
+        from autogp.jl_b200 import smc, workloads
+
+        self.agp, self.smc, self.wl = agp, smc, workloads
+        self.eng = agp.Engine(self.local_rank)
+        self.stream = torch.cuda.ExternalStream(self.eng.stream, device=self.local_rank)
+        self.args = args
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_lml(self, P):
+        """The resident batch's P log-weights in HBM as a torch tensor (zero copy)."""
+        ptr, _ = self.eng.device_results()
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (P,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return self.torch.as_tensor(_Wrap(), device=self.dev)
+
+    def batch(self, n, P):
+        ts, xs = self.wl.synthetic_series(n)
+        nodes, noises = self.wl.synthetic_batch(P, TREE, first=self.rank * P)
+        return ts, xs, nodes, noises
+
+    # -- one size: device-resident rate + stage times ---------------------------------------------------------------
+    def size_point(self, n, P, steps, warmup):
+        ts, xs, nodes, noises = self.batch(n, P)
+        self.eng.upload(nodes, noises, ts, xs)
+        for _ in range(warmup):
+            self.eng.run()
+        self.barrier()
+        ms = self.max_over_ranks(self.eng.time_runs(steps)) / steps
+        lml, info = self.eng.fetch()
+        assert np.all(info == 0) and np.all(np.isfinite(lml)), f"n={n}: batch failed to factor"
+        st = [self.eng.stage_times() for _ in range(3)]
+        chol_ms = float(np.median([b for _, b, _ in st]))
+        flops = P * n ** 3 / 3.0
+        return {"workload": workload_name(n, P), "value": self.world * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "chol_kernel_ms": chol_ms, "chol_frac_of_fp64_peak": flops / (chol_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
+                "whole_step_frac_of_fp64_peak": flops / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS}
+
+    # -- gradient calls (SURVEY.md §8 f-1), end to end through the C-ABI ----------------------------------------------
+    def grad_point(self, n, P, reps):
+        ts, xs, nodes, noises = self.batch(n, P)
+        out = {}
+        for name, fn in (("lml_grad_batch", self.eng.lml_grad_batch), ("lml_grad_noise_batch", self.eng.lml_grad_noise_batch)):
+            fn(nodes, noises, ts, xs)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                res = fn(nodes, noises, ts, xs)
+            dt = self.max_over_ranks(time.perf_counter() - t0) / reps
+            assert np.all(res[-1] == 0)
+            out[name] = {"ms_per_call": 1e3 * dt, "gradients_per_s": self.world * P / dt, "calls": reps}
+        out["workload"] = workload_name(n, P) + "; host buffers in and out (what Gen.hmc / the noise move consume per leapfrog step)"
+        return out
+
+    # -- configs[3]: the data-annealing schedule ----------------------------------------------------------------------
+    def schedule_point(self, n, P, passes):
+        """10 rounds of linear_schedule(n, 0.10) (src/Schedule.jl:24-39) as run_smc_anneal_data drives them
+        (src/inference_smc_anneal_data.jl:206-234): re-score every particle on the grown prefix, all-gather the
+        log-weights, ESS, multinomial resampling (replicated from a shared seed) when ESS < P_total / 2.
+        full: every round recomputes the factorisation (the reference's behaviour) and a resampling round re-uploads the
+        permuted programs.  append: the resident factor is continued (agp_lml_run_append), no resampling (a resampled
+        particle would need its parent's factor)."""
+        torch, dist, smc, eng = self.torch, self.dist, self.smc, self.eng
+        ts, xs = self.wl.synthetic_series(n)
+        Ptot = self.world * P
+        all_nodes, all_noises = self.wl.synthetic_batch(Ptot, TREE)
+        sched = smc.linear_schedule(n, 0.10)
+        lo = self.rank * P
+        gathered = torch.empty(Ptot, dtype=torch.float64, device=self.dev)
+        pinned = torch.empty(Ptot, dtype=torch.float64).pin_memory()
+        result = {"workload": f"n={n}, {Ptot} particles over {self.world} GPU(s), prefixes {sched[0]}..{sched[-1]} (BASELINE.json configs[3] shape)",
+                  "rounds_per_pass": len(sched)}
+
+        def one_pass(mode, timed):
+            state = smc.ParticleState(list(all_nodes), list(all_noises))
+            eng.upload(state.nodes[lo:lo + P], state.noises[lo:lo + P], ts, xs)
+            lml_dev = self.device_lml(P)
+            t_dev = t_exch = 0.0
+            resampled = 0
+            self.barrier()
+            t_start = time.perf_counter()
+            for r, n_r in enumerate(sched):
+                t0 = time.perf_counter()
+                eng.set_prefix(n_r)
+                if mode == "append" and r > 0:
+                    eng.run_append()
+                else:
+                    eng.run()
+                if timed == "split":
+                    torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                local, info = eng.fetch()  # D2H of this shard's scores + LAPACK info (what smc_step! needs to raise PosDefException)
+                assert np.all(info == 0), "schedule benchmark: a particle failed to factor"
+                if self.world > 1:
+                    with torch.cuda.stream(self.stream):
+                        dist.all_gather_into_tensor(gathered, lml_dev)
+                        pinned.copy_(gathered, non_blocking=True)
+                    self.stream.synchronize()
+                    scores = pinned.numpy().copy()
+                else:
+                    scores = local
+                state.log_weights = state.log_weights + (scores - state.scores)
+                state.scores = scores
+                if mode == "full" and n_r < sched[-1] and smc.maybe_resample(state, Ptot / 2, seed=1234 + r):
+                    resampled += 1
+                    eng.upload(state.nodes[lo:lo + P], state.noises[lo:lo + P], ts, xs)
+                    lml_dev = self.device_lml(P)
+                t2 = time.perf_counter()
+                t_dev += t1 - t0
+                t_exch += t2 - t1
+            torch.cuda.synchronize()
+            return time.perf_counter() - t_start, t_dev, t_exch, resampled
+
+        for mode in ("full", "append"):
+            one_pass(mode, "total")  # warm: queues for every prefix, NCCL
+            tot = 0.0
+            for _ in range(passes):
+                dt, _, _, resampled = one_pass(mode, "total")
+                tot += dt
+            dt = self.max_over_ranks(tot / passes)
+            _, t_dev, t_exch, _ = one_pass(mode, "split")
+            result[mode] = {"ms_per_pass": 1e3 * dt, "rounds_per_s": len(sched) / dt, "particle_rounds_per_s": Ptot * len(sched) / dt,
+                            "resampling_rounds": resampled, "passes": passes,
+                            "split_pass": {"lml_ms": 1e3 * self.max_over_ranks(t_dev), "exchange_and_host_ms": 1e3 * self.max_over_ranks(t_exch),
+                                           "note": "one extra pass with a device sync after every round's LML: lml = set_prefix + launches + kernels; "
+                                                   "exchange = all-gather of the log-weights + D2H + ESS / resample decision (+ re-upload when resampled)"}}
+        return result
+
+    def run(self):
+        args, torch, dist, eng = self.args, self.torch, self.dist, self.eng
+        rank, world = self.rank, self.world
+        n, P = args.n, args.particles
+        ts, xs, nodes, noises = self.batch(n, P)
+        eng.upload(nodes, noises, ts, xs)
+        lml_dev = self.device_lml(P)
+        gathered = torch.empty(world * P, dtype=torch.float64, device=self.dev)
+
+        def step():
+            eng.run()
+            if world > 1:
+                with torch.cuda.stream(self.stream):
+                    dist.all_gather_into_tensor(gathered, lml_dev)
+
+        # ---- device-resident throughput (`value`) ------------------------------------------------
+        warmup = max(args.warmup, 3)
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.15)
+        launches0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(self.stream)
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        launches = eng.launch_count - launches0 + (args.steps if world > 1 else 0)
+        clocks = sampler.stop() if rank == 0 else None
+        ms_per_step = ms / args.steps
+        value = world * P / (ms_per_step * 1e-3)
+        lml_res, info = eng.fetch()
+        assert np.all(info == 0) and np.all(np.isfinite(lml_res)), "benchmark batch failed to factor"
+
+        # ---- end to end through the public call with host buffers (`e2e`) --------------------------
+        # every step: encode the kernel trees (a new set of programs per MH step in real use), one H2D of the packed
+        # arena, the two launches, one D2H of the results (+ the all-gather and a host read of it when N > 1)
+        e2e_steps = max(5, min(args.steps, 30))
+        for _ in range(3):
+            eng.lml_batch(nodes, noises, ts, xs)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out, _ = eng.lml_batch(nodes, noises, ts, xs)
+            if world > 1:
+                with torch.cuda.stream(self.stream):
+                    dist.all_gather_into_tensor(gathered, lml_dev)
+                float(gathered[0].item())
+        torch.cuda.synchronize()
+        dt = self.max_over_ranks(time.perf_counter() - t0)
+        e2e_value = world * P * e2e_steps / dt
+        ld = -(-n // 128) * 128
+        packed = eng.pack_batch(nodes, noises)
+        n_instr = int(packed[0].sum())
+        h2d = 2 * ld * 8 + 2 * P * 8 + 2 * (P + 1) * 4 + P * 4 + n_instr * 48  # the packed input arena (agp_api.cu: upload_impl)
+        d2h = P * 8 + P * 4
+
+        # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
+        # One step = agp_gramfill_kernel (kernel-tree interpreter -> K tiles in HBM, issue / FP64-pipe bound)
+        # followed by ONE launch of agp_chol_kernel (persistent dataflow kernel: FP64 DMMA contraction,
+        # diagonal Cholesky, panel solves, forward solve, log det), which dominates.  Algorithmic work of
+        # that launch = P * n^3 / 3 flops (SURVEY.md §8d).
+        eng.upload(nodes, noises, ts, xs)
+        st = [eng.stage_times() for _ in range(7)]
+        gram_ms, chol_ms = float(np.median([a for a, _, _ in st])), float(np.median([b for _, b, _ in st]))
+        flops = P * n ** 3 / 3.0
+        achieved = flops / (chol_ms * 1e-3) * 1e-12
+        traffic, traffic_note = None, "no capture on file"
+        tpath = os.path.join(ROOT, "profiles", "chol_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("n") == n and tj.get("particles") == P and tj.get("kernel_source_md5") == kernel_source_md5():
+                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic_note = tj.get("source", "")
+                else:
+                    traffic_note = "the ncu capture on file is of another kernel source or workload"
+            except Exception:
+                pass
+        n_entries = P * (n * (n + 1) / 2.0)
+        roofline = {
+            "bound": "tensor",
+            "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)",
+            "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+            "traffic": traffic, "traffic_source": traffic_note,
+            "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "
+                           "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.2",
+            "launches_per_step": 1, "avg_launch_ms": chol_ms,
+            "algorithmic_flops_per_launch": flops,
+            "gramfill_kernel": {"avg_launch_ms": gram_ms, "entries_per_s": n_entries / (gram_ms * 1e-3),
+                                "hbm_write_GBps": 8.0 * n_entries / (gram_ms * 1e-3) * 1e-9,
+                                "bound": "instruction issue / FP64 pipe (2 exp + 1 sin + 1 division per entry in FP64; ncu: FP64 pipe ~48 % busy, issue slots ~64 %), not HBM"},
+            "whole_step": {"flops": world * flops, "achieved": flops / (ms_per_step * 1e-3) * 1e-12,
+                           "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
+        }
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(n, P) + (" (BASELINE.json configs[1])" if n == 2048 and P == 64 else ""),
+                       "n": n, "particles_per_gpu": P, "tree": TREE, "parallelism": f"particles sharded x{world}",
+                       "l2": f"no flush: working set {P * ld * ld * 8 / 1e9:.2f} GB of factors per GPU exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "includes": "kernel-tree encoding on the host, H2D, both launches, D2H" + (", all-gather + host read" if world > 1 else "")},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+
+        # ---- the rest of BASELINE.json's target, into the same line --------------------------------
+        if not args.no_also:
+            also = {}
+            try:
+                also["n512"] = self.size_point(512, P, steps=50, warmup=5)
+                also["n8192"] = self.size_point(8192, P, steps=3, warmup=1)
+                also["grad_n2048"] = self.grad_point(2048, P, reps=3)
+                also["anneal_schedule_n2048"] = self.schedule_point(2048, P, passes=3)
+            except Exception as e:  # the headline line must survive a failure of the extras
+                also["error"] = f"{type(e).__name__}: {e}"
+            line["also"] = also
+
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            o = load_oracle()
+            cores = os.cpu_count() or 1
+            blas = pick_cpu_threads(o, n, cores)
+            sample = max(2 * cores, 16)
+            rate, secs = cpu_reference_rate(o, n, range(sample), cores, blas)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} particles of the same workload ({secs:.1f} s), pool of {cores} workers x {blas} LAPACK thread(s): "
+                                              "NumPy Gram (one temporary per op, like eval_cov) + LAPACK dpotrf/dtrsv"}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
 
 
 def main():
@@ -171,176 +493,13 @@ def main():
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--particles", type=int, default=64, help="particles per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the other sizes / gradient / schedule measurements")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
-
-    import torch
-    import torch.distributed as dist
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU path)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    import autogp.jl_b200 as agp
-    o = load_oracle()  # workload definition + the CPU baseline leg only
-
-    n, P = args.n, args.particles
-    ts, xs, parts = workload(o, n, range(rank * P, (rank + 1) * P))
-    nodes = [to_agp(agp, o, nd) for nd, _ in parts]
-    noises = [nz for _, nz in parts]
-    eng = agp.Engine(local_rank)
-    packed = eng.pack_batch(nodes, noises)
-    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
-
-    # device-resident results as a torch tensor (zero copy) for the all-gather of log-weights
-    eng.upload_packed(packed, ts, xs)
-    lml_ptr, _ = eng.device_results()
-
-    class _Wrap:
-        __cuda_array_interface__ = {"shape": (P,), "typestr": "<f8", "data": (lml_ptr, False), "version": 2}
-
-    lml_dev = torch.as_tensor(_Wrap(), device=f"cuda:{local_rank}")
-    gathered = torch.empty(world * P, dtype=torch.float64, device=f"cuda:{local_rank}")
-
-    def step():
-        eng.run()
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, lml_dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput (`value`) ------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    launches0 = eng.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count - launches0 + (args.steps if world > 1 else 0)
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * P / (ms_per_step * 1e-3)
-
-    # sanity: results finite and equal to what the C-ABI host path returns
-    lml_res, info = eng.fetch()
-    assert np.all(info == 0) and np.all(np.isfinite(lml_res)), "benchmark batch failed to factor"
-
-    # ---- end to end through the C-ABI with host buffers (`e2e`) ----------------------------------
-    e2e_steps = max(5, min(args.steps, 30))
-    for _ in range(3):
-        eng.lml_batch_packed(packed, ts, xs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out, _ = eng.lml_batch_packed(packed, ts, xs)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, lml_dev)
-            float(gathered[0].item())
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = world * P * e2e_steps / dt
-    ld = -(-n // 128) * 128
-    n_instr = int(packed[0].sum())
-    h2d = 2 * ld * 8 + 2 * P * 8 + 2 * (P + 1) * 4 + P * 4 + n_instr * 48  # the packed input arena (agp_api.cu: upload_impl)
-    d2h = P * 8 + P * 4
-
-    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream ----
-    # One step = agp_gramfill_kernel (kernel-tree interpreter -> K tiles in HBM, issue / FP64-pipe bound)
-    # followed by ONE launch of agp_chol_kernel (persistent dataflow kernel: FP64 DMMA contraction,
-    # diagonal Cholesky, panel solves, forward solve, log det), which dominates.  Algorithmic work of
-    # that launch = P * n^3 / 3 flops.
-    gram_ms, chol_ms = [], []
-    for _ in range(7):
-        a, b, _c = eng.stage_times()
-        gram_ms.append(a), chol_ms.append(b)
-    gram_ms, chol_ms = float(np.median(gram_ms)), float(np.median(chol_ms))
-    flops = P * n ** 3 / 3.0
-    achieved = flops / (chol_ms * 1e-3) * 1e-12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "chol_kernel_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("n") == n and tj.get("particles") == P:
-                traffic = tj.get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    n_entries = P * (n * (n + 1) / 2.0)
-    roofline = {
-        "bound": "tensor",
-        "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)",
-        "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
-        "traffic": traffic,
-        "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "
-                       "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.2",
-        "launches_per_step": 1, "avg_launch_ms": chol_ms,
-        "algorithmic_flops_per_launch": flops,
-        "gramfill_kernel": {"avg_launch_ms": gram_ms, "entries_per_s": n_entries / (gram_ms * 1e-3),
-                            "hbm_write_GBps": 8.0 * n_entries / (gram_ms * 1e-3) * 1e-9,
-                            "bound": "instruction issue / FP64 pipe (2 exp + 1 sin + 1 division per entry in FP64; ncu: FP64 pipe ~48 % busy, issue slots ~64 %), not HBM"},
-        "whole_step": {"flops": world * flops, "achieved": flops / (ms_per_step * 1e-3) * 1e-12,
-                       "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
-    }
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"n={n}, {P} particles/GPU, tree Plus(Times(SE,Periodic),Linear), FP64 (BASELINE.json configs[1])",
-                   "n": n, "particles_per_gpu": P, "tree": TREE, "parallelism": f"particles sharded x{world}",
-                   "l2": f"no flush: working set {P * ld * ld * 8 / 1e9:.2f} GB of factors per GPU exceeds the 126 MB L2"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roofline,
-    }
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        sample = max(2 * cores, 16)
-        rate, secs = cpu_reference_rate(o, n, sample, cores)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{sample} particles of the same workload ({secs:.1f} s), thread pool of {cores}: NumPy Gram "
-                                          "(one temporary per op, like eval_cov) + LAPACK dpotrf/dtrsv"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    Bench(args).run()
 
 
 if __name__ == "__main__":

@@ -67,7 +67,11 @@ struct agp_handle {
     struct Queue {
         int4* d_items = nullptr;
         int n_items = 0;
+        unsigned long long last_use = 0;
     };
+    unsigned long long queue_clock = 0;
+    static constexpr size_t kMaxQueues = 48;  // least recently used queues beyond this are freed (lock-step loops shrink
+                                              // the batch one particle at a time, data annealing walks through every nt)
     std::map<std::tuple<int, int, int, int, int>, Queue> queues;  // (P, nt, nt_total, first row tile, nt_stride)
     int* d_sync = nullptr;   size_t cap_sync = 0;
     int* h_sync = nullptr;   // pinned, 2 ints: queue head, error flag
@@ -689,8 +693,17 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         // pageable source: the copy is staged before the call returns, so `items` may go out of scope
         AGP_CUDA(h, cudaMemcpyAsync(qu.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->queues.size() >= agp_handle::kMaxQueues) {
+            auto lru = h->queues.begin();
+            for (auto jt = h->queues.begin(); jt != h->queues.end(); ++jt)
+                if (jt->second.last_use < lru->second.last_use) lru = jt;
+            AGP_CUDA(h, cudaStreamSynchronize(h->stream));  // a launch that reads it may still be in flight
+            cudaFree(lru->second.d_items);
+            h->queues.erase(lru);
+        }
         it = h->queues.emplace(key, qu).first;
     }
+    it->second.last_use = ++h->queue_clock;
     // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], ppre[P][nt_stride], fdone[P]
     const size_t n_sync = 32 + (size_t)3 * P * nt_stride + P;
     int rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int));

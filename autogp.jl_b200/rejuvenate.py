@@ -105,6 +105,8 @@ class Chains:
     """What the reference keeps in P Gen traces, for the moves of this module."""
     nodes: List[gp.Node]
     z_noise: np.ndarray                       # latent of the noise, [P]
+    fixed_noises: Optional[np.ndarray] = None # infer_noise=False with given noises: the values used as they are ([P];
+                                              # z_noise is then never read: a noise <= JITTER has no latent)
     lml: Optional[np.ndarray] = None          # cached score / gradients of the CURRENT state (None: unknown)
     grad_z: Optional[List[np.ndarray]] = None
     grad_zn: Optional[np.ndarray] = None
@@ -118,13 +120,19 @@ class Chains:
         return len(self.nodes)
 
     def noises(self) -> np.ndarray:
-        return np.array([noise_of(z) for z in self.z_noise])
+        return self.noises_at(np.arange(self.P), self.z_noise)
+
+    def noises_at(self, who, z_noise) -> np.ndarray:
+        """Noise of particles ``who`` at the candidate latents ``z_noise`` (or their fixed noises)."""
+        if self.fixed_noises is not None:
+            return np.asarray(self.fixed_noises, dtype=np.float64)[np.asarray(who, dtype=np.int64)]
+        return np.array([noise_of(z) for z in z_noise])
 
 
-def _evaluate(ch: Chains, nodes, z_list, z_noise, ts, xs, engine, noise_only: bool = False):
+def _evaluate(ch: Chains, who, nodes, z_list, z_noise, ts, xs, engine, noise_only: bool = False):
     """LML and latent-space gradients of the given candidate states: one batched call.  ``noise_only``: the cheaper
     ``agp_lml_grad_noise_batch`` (no K^-1, no kernel-tree walk); the parameter gradients come back as None."""
-    noises = [noise_of(z) for z in z_noise]
+    noises = list(ch.noises_at(who, z_noise))
     ch.n_calls += 1
     ch.n_evals += len(nodes)
     if noise_only:
@@ -143,7 +151,7 @@ def _evaluate(ch: Chains, nodes, z_list, z_noise, ts, xs, engine, noise_only: bo
 def refresh(ch: Chains, ts, xs, engine) -> None:
     """Score and gradient of the current state of every particle (the first ``choice_gradients`` of ``Gen.hmc``)."""
     zs = [latents(nd) for nd in ch.nodes]
-    lml, gz, gzn, ok = _evaluate(ch, ch.nodes, zs, ch.z_noise, ts, xs, engine)
+    lml, gz, gzn, ok = _evaluate(ch, np.arange(ch.P), ch.nodes, zs, ch.z_noise, ts, xs, engine)
     if not ok.all():
         p = int(np.nonzero(~ok)[0][0])
         raise model.PosDefException(1, p)   # the CURRENT state must be scoreable, as in the reference
@@ -219,7 +227,7 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
             zns = np.array([sel[a][0] if alive[a] else zn0[a] for a in range(A)])
         # a noise trajectory needs dLML/dnoise only; its LAST evaluation is a full one so that the cached parameter
         # gradients of an accepted state are current for the parameter move that follows
-        lml, gz, gzn, ok = _evaluate(ch, cand_nodes, zs, zns, ts, xs, engine, noise_only=cheap_noise and step < L - 1)
+        lml, gz, gzn, ok = _evaluate(ch, active, cand_nodes, zs, zns, ts, xs, engine, noise_only=cheap_noise and step < L - 1)
         newly_dead = alive & ~ok
         ch.stats["not_pd"] += int(newly_dead.sum())
         alive &= ok
@@ -330,7 +338,7 @@ def map_optimize_lockstep(ch: Chains, particles, ts, xs, *, engine, max_opt: int
             ok_idx = [i for i, c in enumerate(cands) if c is not None]
             lml = np.full(len(cands), -np.inf)
             if ok_idx:
-                l2, info = engine.lml_batch([cands[i] for i in ok_idx], [noise_of(zns[i]) for i in ok_idx], ts, xs)
+                l2, info = engine.lml_batch([cands[i] for i in ok_idx], list(ch.noises_at([who[i] for i in ok_idx], [zns[i] for i in ok_idx])), ts, xs)
                 ch.n_calls += 1
                 ch.n_evals += len(ok_idx)
                 for j, i in enumerate(ok_idx):
@@ -361,14 +369,14 @@ def map_optimize_lockstep(ch: Chains, particles, ts, xs, *, engine, max_opt: int
         active = nxt
         if active:   # gradients at the new points: one batched call
             nodes = [ch.nodes[p] for p in active]
-            l2, gz, gzn, ok = _evaluate(ch, nodes, [z[p] for p in active], ch.z_noise[active], ts, xs, engine)
+            l2, gz, gzn, ok = _evaluate(ch, active, nodes, [z[p] for p in active], ch.z_noise[active], ts, xs, engine)
             for a, p in enumerate(active):
                 ch.lml[p], ch.grad_z[p], ch.grad_zn[p] = l2[a], gz[a], gzn[a]
     # traces that finished on an accepted step of equal score keep a cache from before that step: refresh lazily
     stale = [p for p in iters if abs((ch.lml[p] + _log_prior(z[p], ch.z_noise[p], infer_noise)) - score[p]) > 0.0]
     if stale:
         nodes = [ch.nodes[p] for p in stale]
-        l2, gz, gzn, ok = _evaluate(ch, nodes, [z[p] for p in stale], ch.z_noise[stale], ts, xs, engine)
+        l2, gz, gzn, ok = _evaluate(ch, stale, nodes, [z[p] for p in stale], ch.z_noise[stale], ts, xs, engine)
         for a, p in enumerate(stale):
             ch.lml[p], ch.grad_z[p], ch.grad_zn[p] = l2[a], gz[a], gzn[a]
     return {p: (iters[p], score[p]) for p in iters}
@@ -393,7 +401,7 @@ def mh_structure_lockstep(ch: Chains, particles, propose: Proposer, ts, xs, *, r
     if len(particles) == 0:
         return np.zeros(0, dtype=bool)
     props = [propose(ch.nodes[p], rngs[p]) for p in particles]
-    noises = [noise_of(ch.z_noise[p]) for p in particles]
+    noises = list(ch.noises_at(particles, ch.z_noise[particles]))
     lml, info = engine.lml_batch([nd for nd, _ in props], noises, ts, xs)
     ch.n_calls += 1
     ch.n_evals += len(props)
@@ -413,7 +421,7 @@ def mh_structure_lockstep(ch: Chains, particles, propose: Proposer, ts, xs, *, r
         # accepted particles only
         idx = particles[accepted]
         nodes = [ch.nodes[p] for p in idx]
-        l2, gz, gzn, ok = _evaluate(ch, nodes, [latents(nd) for nd in nodes], ch.z_noise[idx], ts, xs, engine)
+        l2, gz, gzn, ok = _evaluate(ch, idx, nodes, [latents(nd) for nd in nodes], ch.z_noise[idx], ts, xs, engine)
         for a, p in enumerate(idx):
             ch.lml[p], ch.grad_z[p], ch.grad_zn[p] = l2[a], gz[a], gzn[a]
     return accepted

@@ -166,11 +166,12 @@ def smc_step(state: ParticleState, ts, xs, *, engine: Optional[gp.Engine] = None
 
 def rejuvenate(state: ParticleState, ts, xs, *, n_mcmc: int, n_hmc: int, propose, seed: int,
                engine: Optional[gp.Engine] = None, group=None, hmc_config: Optional[dict] = None,
-               infer_noise: bool = True) -> dict:
+               infer_noise: bool = True, round_index: int = 0) -> dict:
     """Step 4 of ``run_smc_anneal_data`` (src/inference_smc_anneal_data.jl:236-250): ``rejuvenate_particle_structure``
     on every particle.  Each rank rejuvenates ITS shard in lock step on its own GPU (``rejuvenate.py``: one batched call
     per MH proposal / leapfrog step of the whole shard); particle p draws from the random stream (seed, p) whatever
-    rank it lives on, so the result does not depend on the number of GPUs.  The rejuvenated kernels are a few hundred
+    rank it lives on, so the result does not depend on the number of GPUs; ``round_index`` (the SMC round) enters the
+    stream's seed, so a caller that passes the same ``seed`` every round still gets fresh draws.  The rejuvenated kernels are a few hundred
     bytes per particle: one all-gather of them replicates the state for the next resampling step.  MCMC moves leave
     the log-weights alone and replace the trace scores."""
     import torch.distributed as dist
@@ -183,9 +184,16 @@ def rejuvenate(state: ParticleState, ts, xs, *, n_mcmc: int, n_hmc: int, propose
     rank = dist.get_rank(group) if dist_on else 0
     lo, hi = shard_range(P, rank, world)
     eng = engine or gp.default_engine()
-    z_noise = np.array([model.untransform_param("noise", nz - model.JITTER) for nz in state.noises[lo:hi]])
-    ch = rj.Chains(list(state.nodes[lo:hi]), z_noise.copy())
-    rngs = rj.particle_rngs(seed, P)[lo:hi]
+    if infer_noise:
+        bad = [lo + a for a, nz in enumerate(state.noises[lo:hi]) if not nz > model.JITTER]
+        if bad:
+            raise ValueError(f"rejuvenate(infer_noise=True): noise of particle {bad[0]} is not above JITTER = {model.JITTER} "
+                             "(the latent of src/Model.jl:133-134 does not exist); pass infer_noise=False for fixed noises")
+        z_noise = np.array([model.untransform_param("noise", nz - model.JITTER) for nz in state.noises[lo:hi]])
+    else:
+        z_noise = np.zeros(hi - lo)  # never read: the chain's noise is carried through unchanged (below)
+    ch = rj.Chains(list(state.nodes[lo:hi]), z_noise.copy(), fixed_noises=None if infer_noise else np.array(state.noises[lo:hi], dtype=np.float64))
+    rngs = [np.random.default_rng([int(seed), int(round_index), p]) for p in range(lo, hi)]
     stats = rj.rejuvenate_structure_lockstep(ch, n_mcmc, n_hmc, propose, ts, xs, seed=seed, engine=eng, rngs=rngs,
                                              hmc_config=hmc_config, infer_noise=infer_noise) if hi > lo else dict(ch.stats)
     z0 = z_noise

@@ -132,6 +132,26 @@ def cpu_reference_rate(o, n, particle_ids, workers, blas_threads):
     return len(parts) / dt, dt
 
 
+def cpu_fused_rate(o, n, particle_ids, workers):
+    """BASELINE.md §2 context number, NOT the reference's path: fused scalar-C Gram (upper triangle, no n x n temporaries)
+    + LAPACK dpotrf/dtrtrs, one particle per pool worker."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import c_oracle
+    from threadpoolctl import threadpool_limits
+
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p, TREE) for p in particle_ids]
+    progs = [(o.encode_program(nd), nz) for nd, nz in parts]
+    c_oracle.lml_cpu_best(progs[0][0], ts[:64], xs[:64], progs[0][1])
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(lambda pr: c_oracle.lml_cpu_best(pr[0], ts, xs, pr[1], 1), progs))
+        dt = time.perf_counter() - t0
+    return len(parts) / dt, dt
+
+
 def pick_cpu_threads(o, n, cores):
     """'All the host threads it can use': the faster of (pool of `cores` workers x 1 LAPACK thread) and (the same pool x
     `cores` LAPACK threads), probed on `cores` particles each.  torchrun's OMP_NUM_THREADS=1 no longer decides it."""
@@ -477,6 +497,14 @@ class Bench:
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{sample} particles of the same workload ({secs:.1f} s), pool of {cores} workers x {blas} LAPACK thread(s): "
                                               "NumPy Gram (one temporary per op, like eval_cov) + LAPACK dpotrf/dtrsv"}
+            try:
+                frate, fsecs = cpu_fused_rate(o, n, range(sample), cores)
+                line["cpu_baseline"]["context_fused_c"] = {
+                    "value": frate, "unit": UNIT,
+                    "what": f"not the reference's path: fused scalar-C Gram without n x n temporaries + LAPACK, {sample} particles over {cores} workers "
+                            f"({fsecs:.1f} s); scalar libm exp/sin lose to NumPy's SIMD loops what the saved temporaries gain"}
+            except Exception as e:
+                line["cpu_baseline"]["context_fused_c"] = {"error": f"{type(e).__name__}: {e}"}
         if rank == 0:
             print(json.dumps(line), flush=True)
         eng.close()

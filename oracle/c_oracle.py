@@ -22,6 +22,8 @@ def load():
         lib.oracle_gram.restype = None
         lib.oracle_lml.argtypes = [i32p, i32p, C.c_int32, f64p, f64p, f64p, C.c_int32, C.c_double, f64p]
         lib.oracle_lml.restype = C.c_int
+        lib.oracle_gram_upper_cols.argtypes = [i32p, i32p, C.c_int32, f64p, f64p, C.c_int32, C.c_double, C.c_int32, C.c_int32, f64p]
+        lib.oracle_gram_upper_cols.restype = None
         _lib = lib
     return _lib
 
@@ -50,3 +52,36 @@ def lml(program, ts, xs, noise):
     info = load().oracle_lml(_p(ops, C.c_int32), _p(offs, C.c_int32), len(ops), _p(params, C.c_double),
                              _p(ts, C.c_double), _p(xs, C.c_double), len(ts), float(noise), C.byref(out))
     return out.value, info
+
+
+def lml_cpu_best(program, ts, xs, noise, threads=1):
+    """BASELINE.md §2 "CPU-best" context number (not the reference's path): fused Gram (upper triangle, no temporaries,
+    column ranges of equal area over `threads` host threads) + LAPACK dpotrf / dtrtrs from SciPy's OpenBLAS."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from scipy.linalg import cholesky, solve_triangular
+
+    ops, offs, params = program
+    ts = np.ascontiguousarray(ts, dtype=np.float64)
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    params = np.ascontiguousarray(params if len(params) else np.zeros(1), dtype=np.float64)
+    n = len(ts)
+    K = np.zeros((n, n), order="F")
+    lib = load()
+    chunks = 4 * max(threads, 1)
+    cuts = sorted({int(round(n * np.sqrt(c / chunks))) for c in range(chunks + 1)})  # equal triangle area per chunk
+
+    def fill(rng):
+        lib.oracle_gram_upper_cols(_p(ops, C.c_int32), _p(offs, C.c_int32), len(ops), _p(params, C.c_double), _p(ts, C.c_double), n,
+                                   float(noise), rng[0], rng[1], _p(K, C.c_double))
+
+    ranges = list(zip(cuts[:-1], cuts[1:]))
+    if threads > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(fill, ranges))
+    else:
+        for rng in ranges:
+            fill(rng)
+    U = cholesky(K, lower=False, overwrite_a=True, check_finite=False)
+    z = solve_triangular(U, xs, trans="T", lower=False, check_finite=False)
+    return -0.5 * (n * np.log(2.0 * np.pi) + 2.0 * float(np.sum(np.log(np.diag(U))))) - 0.5 * float(z @ z)

@@ -91,6 +91,19 @@ void oracle_gram(const int32_t* ops, const int32_t* off, int32_t m, const double
         }
 }
 
+/* "CPU-best" context baseline, NOT the reference's path: columns [j0, j1) of the upper triangle of
+ * K + noise*I evaluated entry by entry with no n x n temporaries (what one fused dot-broadcast over the whole tree would
+ * give; the reference makes one temporary per node, src/GP.jl:243).  The caller deals column ranges out over host
+ * threads (ctypes releases the GIL; this image has no libgomp) and factors the result with LAPACK. */
+void oracle_gram_upper_cols(const int32_t* ops, const int32_t* off, int32_t m, const double* prm, const double* ts, int32_t n, double noise,
+                            int32_t j0, int32_t j1, double* K) {
+    for (int j = j0; j < j1; ++j) {
+        double* cj = K + (size_t)j * n;
+        for (int i = 0; i <= j; ++i) cj[i] = eval_entry(ops, off, m, prm, ts[i], ts[j], 0);
+        cj[j] += noise;
+    }
+}
+
 /* Upper Cholesky in place on column-major K (only the upper triangle is read), LAPACK info. */
 static int chol_upper(double* K, int n) {
     for (int j = 0; j < n; ++j) {

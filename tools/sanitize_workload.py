@@ -1,0 +1,45 @@
+"""One small invocation of every entry point of the library, for tools/sanitize.sh (compute-sanitizer)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import autogp.jl_b200 as agp  # noqa: E402
+from autogp.jl_b200.workloads import synthetic_particle, synthetic_series  # noqa: E402
+
+
+def main():
+    eng = agp.Engine(0)
+    n, P = 300, 5   # three block columns, ragged last tile
+    ts, xs = synthetic_series(n)
+    parts = [synthetic_particle(p, "se*per+lin" if p % 2 == 0 else "ge+per*lin") for p in range(P)]
+    nodes, noises = [nd for nd, _ in parts], [nz for _, nz in parts]
+    K = eng.gram(nodes[0], noises[0], ts[:100])
+    lml, info = eng.lml_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(K))
+    eng.upload(nodes, noises, ts, xs)
+    eng.set_prefix(140)
+    eng.run()
+    eng.fetch()
+    eng.set_prefix(n)
+    eng.run_append()
+    app, _ = eng.fetch()
+    assert np.array_equal(app, lml)
+    _, grads, gnoise, ginfo = eng.lml_grad_batch(nodes[:2], noises[:2], ts[:200], xs[:200])
+    _, gn2, ninfo = eng.lml_grad_noise_batch(nodes[:2], noises[:2], ts[:200], xs[:200])
+    assert np.all(ginfo == 0) and np.all(ninfo == 0)
+    mean, cov, pinfo = eng.predict_batch(nodes[:2], noises[:2], ts[:200], xs[:200], ts[200:260])
+    m2, var, _ = eng.predict_marginals_batch(nodes[:2], noises[:2], ts[:200], xs[:200], ts[200:260])
+    assert np.all(pinfo == 0) and np.all(np.isfinite(cov)) and np.all(np.isfinite(var))
+    summands = [[parts[0][0].left, parts[0][0].right]]
+    smean, scov, sinfo = eng.predict_sum_batch(summands, noises[:1], ts[:200], xs[:200], ts[200:230])
+    assert sinfo[0] == 0
+    print(f"sanitize workload ok: {eng.launch_count} launches")
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,13 @@ struct agp_handle {
     // persistent dataflow kernel: work queues per batch shape + dependency counters
     int order = 3;        // queue order variant (AGP_ORDER)
     int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
+    // Plain LML runs evaluate the Gram matrix either by a launch of its own in front of the persistent kernel or as GRAM
+    // items of its queue.  Measured (64 particles, profiles/r02_gram_items.txt): items win 5-8 % of the step up to 5 block
+    // columns (n <= 640: the factorisation is a dependency chain there and idle CTAs pick the units up), lose 3-7 % from 8
+    // block columns on (the FP64 pipe is shared: a unit next to a DMMA main loop runs 2.3x slower than next to another unit).
+    int fuse_gram = -1;   // AGP_FUSE_GRAM: -1 = by size (items up to kGramItemsMaxNt block columns), 0 = own launch, 1 = items
+    static constexpr int kGramItemsMaxNt = 5;
+    int gram_lead = 0;    // AGP_GRAM_LEAD: a GRAM item sits this many items ahead of the first reader of its tile half (0: the resident CTAs)
     unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
     int num_sms = 0;
     struct Queue {
@@ -163,6 +170,8 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_ORDER")) h->order = atoi(e);
     if (const char* e = getenv("AGP_WAIT_TIMEOUT_MS")) h->wait_timeout_ns = 1000000ull * (unsigned long long)atoll(e);
     if (const char* e = getenv("AGP_CTAS_PER_SM")) h->ctas_per_sm = atoi(e) >= 1 ? atoi(e) : 1;
+    if (const char* e = getenv("AGP_FUSE_GRAM")) h->fuse_gram = atoi(e) < 0 ? -1 : atoi(e) != 0;
+    if (const char* e = getenv("AGP_GRAM_LEAD")) h->gram_lead = atoi(e) > 0 ? atoi(e) : 0;
     *out = h;
     return AGP_OK;
 }
@@ -598,6 +607,58 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
     }
 }
 
+// Gram units as queue items (ITEM_GRAM, agp_chol_gram.cu).  Takes a schedule of build_queue and (i) gives every DIAG /
+// PANEL item that is the FIRST to touch its tile half (contraction range starting at 0: its accumulators start from
+// minus the Gram tile) a wait for that half's flag, (ii) inserts the Gram unit of the tile half `lead` items ahead of
+// that reader (all units whose reader sits among the first `lead` items open the queue, in reader order).  Producers
+// stay earlier in the queue than their consumers, so in-order popping remains deadlock-free; the units inherit the
+// readers' order, which spreads them over the factorisation in proportion to where tiles are first needed.
+// Flags: one int per (particle, lower tile, half) behind fdone, index relative to SchedView::head (a diagonal tile uses
+// the flag of its first half for both units).
+static int gram_flag_base(int P, int nt_stride) { return 32 + 3 * P * nt_stride + P; }
+static int gram_flag(int P, int nt_stride, int p, int i, int k, int hh) {
+    const int T = nt_stride * (nt_stride + 1) / 2;
+    return gram_flag_base(P, nt_stride) + ((p * T + i * (i + 1) / 2 + k) * 2 + hh);
+}
+static size_t sync_ints(int P, int nt_stride, bool fused) {
+    return 32 + (size_t)3 * P * nt_stride + P + (fused ? (size_t)P * nt_stride * (nt_stride + 1) : 0);
+}
+static void fuse_gram_items(int P, int nt_stride, int lead, std::vector<int4>& items) {
+    const size_t n = items.size() / 2;
+    if (lead < 1) lead = 1;
+    struct G { size_t reader; int4 it, dep; };
+    std::vector<G> grams;
+    for (size_t c = 0; c < n; ++c) {
+        int4& it = items[2 * c];
+        int4& dep = items[2 * c + 1];
+        const int type = it.x & 0xff;
+        if (type == agp::ITEM_POTF2) continue;
+        const int j0 = dep.x & 0xffff;
+        if (j0 != 0 || dep.z >= 0) continue;  // a continuation of an earlier item of the same tile half
+        const int hh = (it.x >> 8) & 1, p = it.y, k = it.z, i = it.w;
+        // a DIAG item reads 16x16 blocks from both row halves of its tile (agp_chol_diag.cu): the two units of a diagonal
+        // tile share one flag and its first readers wait for both
+        const bool dg = type == agp::ITEM_DIAG;
+        const int flag = gram_flag(P, nt_stride, p, i, k, dg ? 0 : hh);
+        dep.z = flag;
+        dep.w = dg ? 2 : 1;
+        grams.push_back({c, make_int4(agp::ITEM_GRAM | (hh << 8), p, k, i), make_int4(0, 0, flag, 0)});
+    }
+    std::vector<int4> out;
+    out.reserve(items.size() + 2 * grams.size());
+    size_t g = 0;
+    for (size_t c = 0; c < n; ++c) {
+        while (g < grams.size() && grams[g].reader <= c + (size_t)lead) {
+            out.push_back(grams[g].it);
+            out.push_back(grams[g].dep);
+            ++g;
+        }
+        out.push_back(items[2 * c]);
+        out.push_back(items[2 * c + 1]);
+    }
+    items.swap(out);
+}
+
 // General schedule (simple block-column order) for the two continuations of a factorisation:
 //   first_row > 0        only tile rows >= first_row are (re)computed: the data prefix grew and rows
 //                        above keep their factor (agp_lml_run_append)
@@ -671,18 +732,31 @@ static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::ve
                 }
 }
 
+// Plain LML run (no appended rows, no continuation, every program fits the item's shared-memory cache): may the Gram units
+// ride in the queue, and does this handle want them to for this size?
+static bool gram_as_items(const agp_handle* h, int first_row) {
+    const BatchView& v = h->view;
+    if (h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.max_prog_len > 64) return false;
+    return h->fuse_gram < 0 ? v.nt <= agp_handle::kGramItemsMaxNt : h->fuse_gram != 0;
+}
+static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : h->ctas_per_sm * h->num_sms; }
+
 static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_ms = nullptr, int first_row = 0) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
     const int nt_total = v.nt_total;
-    auto key = std::make_tuple(P, nt, nt_total, h->aug_identity ? (h->trtri_only ? -2 : -1) : (h->pred_diag_only && first_row == 0 && nt > 0 ? -3 : first_row), nt_stride);
+    // plain LML run (no appended rows, no continuation): the Gram units ride in the queue (agp_chol_gram.cu caches a program in shared memory)
+    const bool fused = gram_as_items(h, first_row);
+    const int lead = gram_items_lead(h);
+    auto key = std::make_tuple(P, nt, nt_total, fused ? -4 : h->aug_identity ? (h->trtri_only ? -2 : -1) : (h->pred_diag_only && first_row == 0 && nt > 0 ? -3 : first_row), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
         if (h->aug_identity) build_queue_inverse(P, nt, nt_stride, h->order, items, !h->trtri_only);
         else if (first_row == 0 && nt_total == nt) build_queue(P, nt, nt_stride, h->order, items);
         else build_queue_general(P, nt, nt_total, first_row, items, h->pred_diag_only);
+        if (fused) fuse_gram_items(P, nt_stride, lead, items);
         agp_handle::Queue qu;
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
@@ -704,8 +778,9 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         it = h->queues.emplace(key, qu).first;
     }
     it->second.last_use = ++h->queue_clock;
-    // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], ppre[P][nt_stride], fdone[P]
-    const size_t n_sync = 32 + (size_t)3 * P * nt_stride + P;
+    // counters: [0] head, [1] error, [32 ..] rowdone[P][nt_stride], diagu[P][nt_stride], ppre[P][nt_stride], fdone[P],
+    // and with Gram items: gram flags [P][nt_stride (nt_stride + 1) / 2][2]
+    const size_t n_sync = sync_ints(P, nt_stride, fused);
     int rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int));
     if (rc != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
@@ -733,7 +808,9 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     q.trace = d_trace;
     q.wait_timeout_ns = h->wait_timeout_ns;
     if (kernel_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    if (h->aug_identity) {
+    if (fused) {
+        h->launches -= 1;  // no Gram launch: the units are items of the persistent kernel
+    } else if (h->aug_identity) {
         // the kernel tree is evaluated over the observation block only; the appended [I 0] rows are plain stores
         BatchView obs = v;
         obs.nt_total = v.nt;
@@ -1083,7 +1160,8 @@ int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     if (h->P == 0 || h->view.n == 0) return 0;
     if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_trace: plain LML batches only");
     AGP_CUDA(h, cudaSetDevice(h->device));
-    const int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0);
+    const bool fused = gram_as_items(h, 0);  // as run_fused decides
+    const int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0) + (fused ? (int64_t)h->P * h->view.nt * (h->view.nt + 1) : 0);
     if (!trace_out) return n_items;
     long long* d_trace = nullptr;
     AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_trace), (size_t)n_items * 8 * sizeof(long long)));
@@ -1119,10 +1197,28 @@ int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap) {
     if (P < 0 || nt < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
-    if (order >= 200) build_queue_inverse(P, nt, 2 * nt, order - 200, items, false);  // factorisation + trtri only (noise gradient)
+    if (order >= 300) {  // plain schedule with the Gram units as items (lead = 8 keeps the replay tests small and strict)
+        build_queue(P, nt, nt, order - 300, items);
+        fuse_gram_items(P, nt, 8, items);
+    } else if (order >= 200) build_queue_inverse(P, nt, 2 * nt, order - 200, items, false);  // factorisation + trtri only (noise gradient)
     else if (order >= 100) build_queue_inverse(P, nt, 2 * nt, order - 100, items);  // identity-augmented schedule, counters laid out for 2 nt
     else build_queue(P, nt, nt, order, items);
     return export_queue(items, items_out, cap);
+}
+
+int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead, int32_t* items_out, int64_t cap) {
+    if (P < 0 || nt < 0 || lead < 1) return AGP_ERR_ARG;
+    std::vector<int4> items;
+    build_queue(P, nt, nt, order, items);
+    fuse_gram_items(P, nt, lead, items);
+    return export_queue(items, items_out, cap);
+}
+
+int agp_gram_items(agp_handle* h, int32_t* fused_out, int32_t* lead_out) {
+    if (!h) return AGP_ERR_ARG;
+    if (fused_out) *fused_out = h->uploaded ? (gram_as_items(h, 0) ? 1 : 0) : h->fuse_gram;
+    if (lead_out) *lead_out = gram_items_lead(h);
+    return AGP_OK;
 }
 
 static int64_t export_queue(const std::vector<int4>& items, int32_t* items_out, int64_t cap) {

@@ -18,10 +18,9 @@
 #include "agp_kernels.cuh"
 #include "agp_ptx.cuh"
 
-// Switches that reproduce the round-1 stage race (profiles/r02_race_experiments.txt, tools/race_variants.sh); all 0 = product.
-#ifndef AGP_X_SIMPLE
-#define AGP_X_SIMPLE 0            // main loop without the `if (active)` blocks: ptxas then places the last LDS of a stage right before the release
-#endif
+// Switches that reproduce the round-1 stage race (profiles/r02_race_experiments.txt); all 0 = product.  (The panel main
+// loop is now the "simple" form of that record — no per-warp `if (active)` blocks, the diagonal tiles have their own item —
+// so AGP_X_NO_RELEASE_FENCE alone brings the failure back.)
 #ifndef AGP_X_POTF2_CLK
 #define AGP_X_POTF2_CLK 0         // diagnostics: clock totals of the two phases of the POTF2 micro-panels into trace slot 4
 #endif
@@ -175,5 +174,9 @@ __device__ __forceinline__ ItemFields decode_item(const SchedView& q, int idx) {
 // ITEM_POTF2: Cholesky of the diagonal tile, inverses of its diagonal 32x32 blocks (agp_chol_potf2.cu; the DIAG / PANEL
 // items are inlined into the kernel's own translation unit)
 __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx);
+// ITEM_DIAG: the lower triangle of a diagonal tile minus its contraction, dealt out as 16x16 blocks (agp_chol_diag.cu)
+__device__ bool do_diag(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx);
+// ITEM_GRAM: one Gram work unit, K(ts_i, ts_k) [+ noise I] into 64 rows of tile (i,k) (agp_chol_gram.cu)
+__device__ bool do_gram(const BatchView& v, const SchedView& q, int idx);
 
 }  // namespace agp

@@ -9,12 +9,15 @@
 // DMMA main loop.  The contraction operands arrive by 2-D TMA tensor copies through a ring of
 // four stages guarded by full/empty mbarriers (no CTA barrier in the main loop).
 //
-// agp_gramfill_kernel runs first: it evaluates every particle's kernel-tree program over the lower
-// 128x128 tiles and leaves K(ts,ts) + noise*I in L (ts slices staged by 1-D TMA bulk copies, all
-// warps of the SM in the FP64-ALU-bound interpreter at once).  The persistent kernel then starts
-// each tile's accumulators from -K, so the Gram work never sits between two DMMA main loops.
+// The Gram matrix K(ts,ts) + noise*I is evaluated tile half by tile half by the kernel-tree interpreter
+// (agp_gram_unit.cuh) and left in L: either by ITEM_GRAM items of this kernel's own queue, popped a few
+// hundred items ahead of the first item that reads the tile (plain LML runs), or by agp_gramfill_kernel in
+// front of this launch (continuations with appended rows).  Every tile's accumulators then start from -K,
+// so the Gram work never sits between two DMMA main loops of one item.
 //
-//   ITEM_DIAG  (p,k,h)    64 rows of the diagonal tile:  K(ts_k,ts_k) + noise I - sum_j L_kj L_kj^T
+//   ITEM_GRAM  (p,k,i,h)  64 rows of tile (i,k)  <-  K(ts_i, ts_k) [+ noise I]
+//   ITEM_DIAG  (p,k,h)    half of the 36 lower 16x16 blocks of the diagonal tile:  K(ts_k,ts_k) + noise I - sum_j L_kj L_kj^T
+//                         (agp_chol_diag.cu)
 //   ITEM_POTF2 (p,k)      Cholesky of the 128x128 diagonal tile (+ observation row): L_kk, z_k,
 //                         log det, z'z, LAPACK info, inverses of the 32x32 diagonal blocks
 //   ITEM_PANEL (p,k,i,h)  64 rows of tile (i,k): K - contraction on FP64 tensor cores, then the
@@ -33,18 +36,17 @@ constexpr int XS = 136;  // X / L_kk-panel row stride: 8 mod 16 doubles -> confl
 static_assert(UM * XS + 4 * 32 * 32 <= REGION_D, "X rows + the solve's ring of four 32x32 operand blocks");
 
 // ------------------------------------------------------------------------------------------
-// ITEM_DIAG / ITEM_PANEL
+// ITEM_PANEL
 // ------------------------------------------------------------------------------------------
-// Contraction range [j0, j1) in block columns.  A finishing item (j1 == k) hands the diagonal tile to
-// potf2 or takes a panel through the triangular solve.  A PARTIAL item only stores: the tile in L
-// receives K - sum_{j<j1}; either a later item with j0 = j1 picks it up from there (the accumulators
-// always start from minus the tile), which takes the long early part of the contraction of the
-// next diagonal tile and of the panel below it off the per-particle critical path.
+// Contraction range [j0, j1) in block columns.  A finishing item (j1 == k) takes the panel through the
+// triangular solve.  A PARTIAL item only stores: the tile in L receives K - sum_{j<j1}; a later item with
+// j0 = j1 picks it up from there (the accumulators always start from minus the tile), which takes the long
+// early part of the contraction of the panel below the next diagonal tile off the per-particle critical path.
 __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx) {
     const Smem s = smem_view();
     const ItemFields f = decode_item(q, idx);
     const int p = f.p, k = f.k, i = f.i, h = f.h, j0 = f.j0, j1 = f.j1, need_k = f.need_k, need_i = f.need_i, extra_flag = f.extra_flag, extra_need = f.extra_need;
-    const bool diag = f.diag, partial = f.partial, yinit = f.yinit;
+    const bool partial = f.partial, yinit = f.yinit;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int row0 = i * TB + h * UM, col0 = k * TB;
@@ -70,17 +72,9 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
     // --- contraction: acc = sum_{j<k} L_ij L_kj^T -----------------------------------------
     const int wm = warp >> 2, wn = warp & 3;  // 2 (m) x 4 (n) warps, warp tile 32x32
     const int g = lane >> 2, c4 = lane & 3;
-    // warp tiles strictly above the diagonal of a diagonal tile are never read
-    const bool active = !diag || (wn * 32 <= h * UM + wm * 32 + 31);
-    // The Gram tile K(ts_i, ts_k) [+ noise I] was written into L by agp_gramfill_kernel.  Block
-    // column 0 needs no contraction: the diagonal tile is already in place and a panel goes
-    // straight to shared memory.  Otherwise the accumulators start from -K, so that after the
-    // contraction  acc = -(K - sum_j L_ij L_kj^T).
-    if (k == 0 && diag) {
-        if (tid < UM) v.y[(long long)p * ld + row0 + tid] = (row0 + tid < v.n) ? v.xs[row0 + tid] : 0.0;
-        signal_done(q.diagu + p * q.nt_stride + k);
-        return true;
-    }
+    // The Gram tile K(ts_i, ts_k) was written into L by a GRAM item or by agp_gramfill_kernel.  Block column 0 needs no
+    // contraction: the panel goes straight to shared memory.  Otherwise the accumulators start from -K, so that after
+    // the contraction  acc = -(K - sum_j L_ij L_kj^T).
     const int nchunk = ((j1 - j0) * TB) / KC;
     // Operand pipeline: one thread issues 2-D TMA tensor copies (B: 128 rows of tile row k, A: the item's 64 rows;
     // 16 columns = 128 bytes per row, hardware 128-byte swizzle) into a ring of NSTAGE stages; full[] carries the
@@ -93,9 +87,9 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
         const int G = G0 + c, st = G % NSTAGE;
         if (G >= NSTAGE && !mbar_wait_bounded(s.empty + st, ((G / NSTAGE) - 1) & 1, q.err, q.wait_timeout_ns)) return;
         double* Bs = stages + st * STAGE_D;
-        mbar_expect_tx(s.full + st, (diag ? UN : UN + UM) * KC * 8);
+        mbar_expect_tx(s.full + st, (UN + UM) * KC * 8);
         tma_load_2d(Bs, &maps.b, ccol + c * KC, brow, s.full + st);
-        if (!diag) tma_load_2d(Bs + UN * KC, &maps.a, ccol + c * KC, arow, s.full + st);
+        tma_load_2d(Bs + UN * KC, &maps.a, ccol + c * KC, arow, s.full + st);
     };
     if (tid == 0) {
         fence_proxy_async_all();  // after the acquire of the dependency counters, before this item's first async-proxy reads of L
@@ -118,29 +112,20 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
         if (tid == 0 && ch + NSTAGE - 1 < nchunk) produce(ch + NSTAGE - 1);
         if (!mbar_wait_bounded(s.full + st, (G / NSTAGE) & 1, q.err, q.wait_timeout_ns)) return false;
         const double* Bs = stages + st * STAGE_D;
-        const double* As = diag ? Bs + h * UM * KC : Bs + UN * KC;  // diagonal tile: A rows are a slice of B
+        const double* As = Bs + UN * KC;
         // lane c4 takes the 16-byte chunks 2 c4 + ks of a row (a permutation of k shared by A and B): with the
         // 128-byte swizzle the eight lanes of an LDS.128 phase then hit eight different chunk columns
-#if AGP_X_SIMPLE
-#define AGP_ACTIVE_IF
-#else
-#define AGP_ACTIVE_IF if (active)
-#endif
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             double2 a[4], b[4];
-            AGP_ACTIVE_IF {
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz128(wm * 32 + mb * 8 + g, 2 * c4 + ks));
+            for (int mb = 0; mb < 4; ++mb) a[mb] = *reinterpret_cast<const double2*>(As + swz128(wm * 32 + mb * 8 + g, 2 * c4 + ks));
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz128(wn * 32 + nb * 8 + g, 2 * c4 + ks));
-            }
-            AGP_ACTIVE_IF {
+            for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(Bs + swz128(wn * 32 + nb * 8 + g, 2 * c4 + ks));
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb)
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
-            }
+                for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
             if (ks == 1) {
                 // Release of the stage.  The LDS above are generic-proxy reads, the next use of the stage is written by the
                 // async proxy (TMA): every lane orders its own reads before the release with a cross-proxy fence, exactly as
@@ -155,42 +140,28 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s.empty + st);
             }
-            AGP_ACTIVE_IF {
 #pragma unroll
-                for (int mb = 0; mb < 4; ++mb)
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                    for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
-            }
+                for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
         }
     }
     if (tid == 0) s.ctl[4] = G0 + nchunk;
     __syncthreads();
     stamp(q, idx, 2);
 
-    // --- X = -acc:  the diagonal tile goes back to L (lower part), a panel stays in shared memory ----
+    // --- X = -acc:  a store-only item writes it back to L, a finishing panel keeps it in shared memory ----
     double* Xs = s.region;            // [UM][XS]
     double* Ls = s.region + UM * XS;  // [32][XS]
-    if (active) {
 #pragma unroll
-        for (int mb = 0; mb < 4; ++mb)
+    for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
-                const double2 x2 = make_double2(-acc[mb][nb][0], -acc[mb][nb][1]);
-                if (!diag && !partial) {
-                    *reinterpret_cast<double2*>(Xs + r * XS + c) = x2;
-                } else {
-                    const int rd = diag ? h * UM + r : TB;  // row inside a diagonal tile: only c <= rd is kept
-                    double* dst = Lp + (long long)(row0 + r) * ld + col0 + c;
-                    if (c + 1 <= rd) *reinterpret_cast<double2*>(dst) = x2;
-                    else if (c <= rd) dst[0] = x2.x;
-                }
-            }
-    }
-    if (diag) {
-        signal_done(q.diagu + p * q.nt_stride + k);
-        return true;
-    }
+        for (int nb = 0; nb < 4; ++nb) {
+            const int r = wm * 32 + mb * 8 + g, c = wn * 32 + nb * 8 + 2 * c4;
+            const double2 x2 = make_double2(-acc[mb][nb][0], -acc[mb][nb][1]);
+            if (!partial) *reinterpret_cast<double2*>(Xs + r * XS + c) = x2;
+            else *reinterpret_cast<double2*>(Lp + (long long)(row0 + r) * ld + col0 + c) = x2;
+        }
     if (partial) {
         signal_done(q.ppre + p * q.nt_stride + i);
         return true;
@@ -343,6 +314,10 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(const __grid_constant__
         stamp(q, idx, 0);
         if (type == ITEM_POTF2) {
             ok = do_potf2(v, q, idx);
+        } else if (type == ITEM_GRAM) {
+            ok = do_gram(v, q, idx);
+        } else if (type == ITEM_DIAG) {
+            ok = do_diag(v, q, maps, idx);
         } else {
             ok = do_update(v, q, maps, idx);
         }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "agp_eval.cuh"
+#include "agp_gram_unit.cuh"
 #include "agp_kernels.cuh"
 #include "agp_ptx.cuh"
 
@@ -49,10 +50,7 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
     const int k = t - i * (i + 1) / 2;
-    const bool diag = (i == k);
     const int row0 = i * TB + h * UM, col0 = k * TB;
-    const int ld = v.ld;
-    double* __restrict__ Lp = v.L + (long long)p * v.mat_stride;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -74,61 +72,7 @@ __global__ void __launch_bounds__(FT, MINB) agp_gramfill_kernel(BatchView v, int
     mbar_wait(&bar, 0);
     __syncthreads();
 
-    const int need = v.prog_need[p];
-    const double noise = v.noise[p];
-    const int n = v.n;
-    const int c = tid & (UN - 1), rbase = tid >> 7;
-    const int gc = col0 + c;
-    const double tcol = ts_c[c];
-    const bool plain = !diag && row0 + UM <= n && col0 + UN <= n;
-    const bool no_kernel_rows = v.aug_identity && row0 >= v.nt * TB;
-#pragma unroll 1
-    for (int eb = 0; eb < 32 / E; ++eb) {
-        double t1[E], t2[E], val[E];
-        const int rlast = rbase + 2 * (E * eb + E - 1);
-        // nothing to evaluate: the strictly-upper part of a diagonal tile (zeros), and every appended row of an
-        // identity-augmented batch ([I 0]: agp_lml_grad_batch — three quarters of that matrix)
-        const bool skip = (diag && c > rlast + h * UM) || no_kernel_rows;
-        if (!skip) {
-#pragma unroll
-            for (int j = 0; j < E; ++j) {
-                t1[j] = tcol;  // upper-triangle element (gc, gr): gc <= gr
-                t2[j] = ts_r[rbase + 2 * (E * eb + j)];
-            }
-            if (LONGPROG) eval_entries<E>(v.prog + poff, pm, need, t1, t2, 0, val);
-            else eval_entries<E>(prog_s, pm, need, t1, t2, 0, val);
-        }
-        if (plain) {
-            // interior tile (all rows and columns are observations, no diagonal): nothing to decide per entry
-            double* dst = Lp + (long long)(row0 + rbase + 2 * E * eb) * ld + gc;
-#pragma unroll
-            for (int j = 0; j < E; ++j) dst[(long long)(2 * j) * ld] = val[j];
-            continue;
-        }
-#pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int r = rbase + 2 * (E * eb + j);
-            const int gr = row0 + r;
-            // rows/columns: [0, n) observations | [n, nt*TB) padding | [nt*TB, nt*TB + n_pred) appended
-            // prediction points | padding.  Padding rows are independent unit-variance dummies
-            // (identity block: log 1 = 0 in the log det, 0 in the quadratic form).
-            double out = 0.0;
-            if (!(diag && c > r + h * UM)) {
-                const int lt = v.nt * TB;
-                if (gr < n) {  // gc <= gr < n
-                    out = val[j];
-                    if (gr == gc) out = out + noise;  // + noise*I, src/GP.jl:667
-                } else if (v.aug_identity && gr >= lt) {
-                    out = (gr - lt == gc) ? 1.0 : 0.0;  // [I 0]: the appended rows solve to L^{-T}, -K^{-1}, -alpha
-                } else if (gr >= lt && gr < lt + v.n_pred && (gc < n || gc >= lt)) {
-                    out = val[j];  // K(t, t*) and K(t*, t*), no noise (src/GP.jl:743-747)
-                } else {
-                    out = (gr == gc) ? 1.0 : 0.0;
-                }
-            }
-            Lp[(long long)gr * ld + gc] = out;
-        }
-    }
+    gram_unit<E, LONGPROG>(v, p, i, k, h, ts_r, ts_c, prog_s, tid);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -49,7 +49,10 @@ struct BatchView {
 //   two operand tile rows); for a continuation item, the index (relative to SchedView::head) and
 //   value of the counter its predecessor bumps; POTF2 carries in extra_need how many DIAG items
 //   finish its tile.
-enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_PARTIAL = 1 << 9, ITEM_YINIT = 1 << 10 };
+//   ITEM_GRAM: {ITEM_GRAM | h << 8, particle, block column k, tile row i}, {0, 0, flag, 0}: the Gram unit of that tile
+//   half; bumps counter `flag` (relative to SchedView::head), which the first PANEL item of the tile half carries as
+//   its extra_flag with extra_need = 1 (the two units of a diagonal tile bump one flag, its first DIAG items need 2).
+enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_GRAM = 3, ITEM_PARTIAL = 1 << 9, ITEM_YINIT = 1 << 10 };
 
 struct SchedView {
     const int4* items;  // in-order queue (2 x int4 per item): every item's producers sit earlier in the list

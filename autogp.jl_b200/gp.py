@@ -469,6 +469,12 @@ class Engine:
             self._check(rc)
         return stamps
 
+    def gram_items(self) -> Tuple[bool, int]:
+        """(Gram units run as items of the persistent kernel's queue, their lead in items): agp_gram_items."""
+        a, b = C.c_int32(), C.c_int32()
+        self._check(self._lib.agp_gram_items(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), int(b.value)
+
     def synchronize(self) -> None:
         self._check(self._lib.agp_synchronize(self._h))
 

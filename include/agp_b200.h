@@ -243,6 +243,14 @@ int agp_lml_stage_times(agp_handle* h, float* stage_ms);
  * total item count.  tests/test_abi_host.py replays the queue against the kernel's wait rules and
  * checks that no item ever waits for a later one (the scheduler's deadlock-freedom argument). */
 int64_t agp_queue_build(int32_t P, int32_t nt, int32_t order, int32_t* items_out, int64_t cap);
+/* The schedule agp_lml_run uses for a plain batch: agp_queue_build's items plus one ITEM_GRAM item per lower tile half
+ * (the kernel-tree evaluation of src/GP.jl:666-668 as work items of the same queue), each `lead` items ahead of the
+ * first item that reads its tile half; those readers carry the unit's flag as a wait.  `order` as above (0..3). */
+int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead, int32_t* items_out, int64_t cap);
+/* Diagnostics: whether agp_lml_run evaluates the Gram matrix of the resident batch as queue items (AGP_FUSE_GRAM: -1 = by
+ * size, the default: up to 5 block columns; 0 = never; 1 = whenever possible) and with which lead (AGP_GRAM_LEAD,
+ * default: the number of resident CTAs).  Without a resident batch *fused_out receives the AGP_FUSE_GRAM setting. */
+int agp_gram_items(agp_handle* h, int32_t* fused_out, int32_t* lead_out);
 /* Same for the continuation schedules: tile rows >= first_row only (agp_lml_run_append) and
  * nt_total - nt tile rows of prediction points below the factored block (agp_predict_batch). */
 int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t first_row,

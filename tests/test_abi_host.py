@@ -129,16 +129,19 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True):
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False):
     """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
     counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
     every tile an item reads must be final, and the items must tile every contraction exactly.
     first_col(i): first block column with a non-zero tile in tile row i (0 except for the rows of
     the inverse schedule)."""
-    DIAG, POTF2, PANEL, PARTIAL, YINIT = 0, 1, 2, 1 << 9, 1 << 10
+    DIAG, POTF2, PANEL, GRAM, PARTIAL, YINIT = 0, 1, 2, 3, 1 << 9, 1 << 10
     first_col = first_col or (lambda i: 0)
     nts = nt_total  # the builders lay the counters out for nt_stride = nt_total
-    counters = np.zeros(32 + 3 * P * nts + P, dtype=np.int64)
+    n_tiles = nts * (nts + 1) // 2
+    counters = np.zeros(32 + 3 * P * nts + P + 2 * P * n_tiles, dtype=np.int64)
+    gflag = lambda p, i, k, h: 32 + 3 * P * nts + P + ((p * n_tiles + i * (i + 1) // 2 + k) * 2 + h)
+    n_gram, gram_done = 0, set()
     rowdone = lambda p, i: 32 + p * nts + i
     diagu = lambda p, k: 32 + P * nts + p * nts + k
     ppre = lambda p, i: 32 + 2 * P * nts + p * nts + i
@@ -155,6 +158,15 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
         t, h, partial, yinit = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL), bool(x & YINIT)
         j0, j1, need_k, need_i = f4 & 0xFFFF, f4 >> 16, f5 & 0xFFFF, f5 >> 16
         assert 0 <= p < P and 0 <= k < nt_total
+        if t == GRAM:   # Gram unit of tile half (i, k, h): bumps that half's flag, exactly once, before its reader
+            assert gram_items and k <= i < nt and (p, i, k, h) not in gram_done
+            # the two units of a diagonal tile share the flag of its first half (a DIAG item reads blocks of both halves)
+            assert flag == gflag(p, i, k, 0 if i == k else h) and counters[flag] == (len({(p, i, k, 0), (p, i, k, 1)} & gram_done) if i == k else 0)
+            assert (p, i, k, h) not in covered and (i != k or (p, i, k, 1 - h) not in covered)
+            gram_done.add((p, i, k, h))
+            counters[flag] += 1
+            n_gram += 1
+            continue
         if t == POTF2:
             assert k < nt and counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
             assert counters[fdone(p)] == k          # block columns are factored in order
@@ -167,9 +179,16 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
         covered[(p, i, k, h)] = j1
         # the kernel's waits
         assert counters[rowdone(p, k)] >= need_k and (t == DIAG or counters[rowdone(p, i)] >= need_i)
-        if flag >= 0:
+        first_touch = gram_items and j0 == 0 and start == 0
+        if first_touch:   # the accumulators start from minus the Gram tile half: its unit must be done
+            if t == DIAG:
+                assert flag == gflag(p, k, k, 0) and need == 2 and counters[flag] == 2
+            else:
+                assert flag == gflag(p, i, k, h) and need == 1 and counters[flag] == 1
+        elif flag >= 0:
             assert flag == (diagu(p, k) if t == DIAG else ppre(p, i)) and counters[flag] >= need
-        assert (flag >= 0) == (j0 > start)
+        if not first_touch:
+            assert (flag >= 0) == (j0 > start)
         # what it reads is final
         for j in range(j0, j1):
             assert final.get((p, k, j), 0) == 2 and final.get((p, i, j), 0) == 2, (t, p, k, i, j)
@@ -188,6 +207,7 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
             assert counters[fdone(p)] >= k + 1      # L_kk ready for the triangular solve
             counters[rowdone(p, i)] += 1
             final[(p, i, k)] = final.get((p, i, k), 0) + 1
+    assert n_gram == (P * nt * (nt + 1) if gram_items else 0)   # every lower tile half exactly once
     for p in range(P):
         assert counters[fdone(p)] == nt
         for i in range(first_row, nt_total):
@@ -215,6 +235,28 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     buf = np.zeros((n_items, 8), dtype=np.int32)
     assert lib.agp_queue_build(P, nt, order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
     _replay_queue(buf, P, nt, nt, 0)
+
+
+@pytest.mark.parametrize("order", [0, 2, 3])
+@pytest.mark.parametrize("P,nt", [(1, 1), (3, 2), (2, 5), (5, 16), (2, 23)])
+def test_work_queue_with_gram_items_replay(P, nt, order):
+    """The plain schedule with the Gram units as queue items (ITEM_GRAM, csrc/agp_chol_gram.cu): every lower tile half is
+    evaluated exactly once, before the first item that reads it, and that item waits for the unit's flag; stripped of the
+    GRAM items and of those waits the queue is the plain one."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    n_items = lib.agp_queue_build(P, nt, 300 + order, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    assert lib.agp_queue_build(P, nt, 300 + order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
+    _replay_queue(buf, P, nt, nt, 0, gram_items=True)
+    n_plain = lib.agp_queue_build(P, nt, order, None, 0)
+    plain = np.zeros((n_plain, 8), dtype=np.int32)
+    lib.agp_queue_build(P, nt, order, plain.ctypes.data_as(C.POINTER(C.c_int32)), n_plain)
+    rest = buf[(buf[:, 0] & 0xFF) != 3].copy()
+    assert n_items - n_plain == P * nt * (nt + 1) and rest.shape == plain.shape
+    first = (plain[:, 6] < 0) & ((plain[:, 0] & 0xFF) != 1) & ((plain[:, 4] & 0xFFFF) == 0)
+    assert np.array_equal(rest[~first], plain[~first]) and np.array_equal(rest[first][:, :6], plain[first][:, :6])
 
 
 @pytest.mark.parametrize("P,nt,nt_total,first_row", [(2, 4, 4, 2), (3, 6, 6, 5), (1, 3, 3, 0), (2, 4, 6, 0), (1, 1, 2, 0),

@@ -414,6 +414,38 @@ def test_scheduler_stress_repeated_runs_are_bitwise_stable(engine):
     assert np.all(got == got[0])
 
 
+def test_gram_items_equal_the_separate_gram_launch_whatever_their_lead(monkeypatch):
+    """The Gram units as items of the persistent kernel's queue (csrc/agp_chol_gram.cu) run the code of the separate
+    agp_gramfill_kernel launch, so the LMLs must be bitwise the same — also with a lead of 1 or 5 items, where the first
+    readers of a tile really wait for the unit's flag (a lead that small found the missing wait of the diagonal-tile
+    item for the other row half of its tile)."""
+    import autogp.jl_b200 as agp
+
+    def run(fuse, lead, cases):
+        monkeypatch.setenv("AGP_FUSE_GRAM", "1" if fuse else "0")
+        monkeypatch.setenv("AGP_GRAM_LEAD", str(lead))
+        eng = agp.Engine(0)
+        out = []
+        for n, P in cases:
+            ts, xs = o.synthetic_series(n)
+            parts = [o.synthetic_particle(p, "se*per+lin" if p % 2 == 0 else "ge+per*lin") for p in range(P)]
+            for _ in range(3):
+                lml, info = gpu_lmls(eng, parts, ts, xs)
+                assert np.all(info == 0) and eng.gram_items()[0] == bool(fuse)
+                out.append(lml.copy())
+        eng.close()
+        return out
+
+    cases = [(100, 3), (300, 70), (512, 64), (1100, 40), (2048, 24)]
+    want = run(False, 0, cases)
+    ref = oracle_lmls([o.synthetic_particle(p, "se*per+lin" if p % 2 == 0 else "ge+per*lin") for p in range(2)], *o.synthetic_series(300))
+    assert H.rel_err(want[3][:2], ref) <= LML_RTOL_TIGHT
+    for lead in (1, 5, 148, 0):
+        got = run(True, lead, cases)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b), lead
+
+
 # ---- §8 f-2: block-append continuation of the factorisation ------------------------------------
 
 def test_lml_block_append_is_bitwise_the_full_recompute(engine):

@@ -6,7 +6,8 @@ read an operand stage with LDS (generic proxy) and released it to the TMA produc
 fence.proxy.async in between, so a late LDS could see the next box.  What has to hold is therefore a property of the
 code, not one particular ptxas schedule:
 
-    in the function that reads TMA-fed stages (agp_chol_kernel in agp_chol_kernel.o), walking back from every
+    in the functions that read TMA-fed stages (agp_chol_kernel in agp_chol_kernel.o: the panel item; do_diag in
+    agp_chol_diag.o: the diagonal-tile item), walking back from every
     stage release (SYNCS.ARRIVE ... .A1T0 = mbarrier.arrive without expect_tx) a FENCE.VIEW.ASYNC must come before
     the first LDS; the function must still use TMA tensor copies (UTMALDG); and its main loop must be free of
     local-memory traffic (spills there cost the round-2 builds up to 2.4x, agp_chol_common.cuh).
@@ -20,8 +21,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "autogp.jl_b200", "csrc")
-DEFAULT_OBJS = [os.path.join(CSRC, "agp_chol_kernel.o")]
-FUNCS = ("agp_chol_kernel",)
+DEFAULT_OBJS = [os.path.join(CSRC, "agp_chol_kernel.o"), os.path.join(CSRC, "agp_chol_diag.o")]
+FUNCS = ("agp_chol_kernel", "do_diag")  # the functions that read TMA-fed operand stages (panel item inlined in the kernel; diagonal-tile item)
 
 
 def function_sass(obj):

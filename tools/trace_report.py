@@ -29,7 +29,11 @@ def main():
     nt = -(-n // 128)
     lib = _lib.load()
     items = np.zeros((st.shape[0], 8), dtype=np.int32)
-    lib.agp_queue_build(P, nt, order, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0])
+    fused, lead = eng.gram_items()
+    if fused:
+        assert lib.agp_queue_build_gram(P, nt, order, lead, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0]) == st.shape[0]
+    else:
+        assert lib.agp_queue_build(P, nt, order, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0]) == st.shape[0]
     typ = items[:, 0] & 0xFF
     t0 = st[:, 0].min()
     t_end = st[:, 5].max()
@@ -38,6 +42,13 @@ def main():
     names = {0: "DIAG", 1: "POTF2", 2: "PANEL"}
     slots = len(np.unique(st[:, 7]))
     busy_total = 0.0
+    if fused:
+        m = typ == 3
+        s = st[m].astype(np.float64) * 1e-3
+        tot = s[:, 5] - s[:, 0]
+        busy_total += tot.sum()
+        print(f"GRAM   items {m.sum():6d}  total {tot.sum()/1e3:9.1f} ms*cta  mean {tot.mean():7.1f} us  (lead {lead}); window [{(s[:,0].min()-t0*1e-3):8.0f}, {(s[:,5].max()-t0*1e-3):8.0f}] us")
+        # waits of the first readers for their Gram flag: inside wait1 of DIAG / PANEL items below
     for t in (0, 1, 2):
         m = typ == t
         s = st[m].astype(np.float64) * 1e-3

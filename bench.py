@@ -266,7 +266,10 @@ class Bench:
         st = [self.eng.stage_times() for _ in range(3)]
         chol_ms = float(np.median([b for _, b, _ in st]))
         flops = P * n ** 3 / 3.0
+        fused, lead = self.eng.gram_items()
         return {"workload": workload_name(n, P), "value": self.world * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "gram_units": f"items of the persistent kernel's queue (lead {lead}): one launch per step, chol_kernel_ms is that launch, timed "
+                              "with an event pair and a host sync around it" if fused else "own launch in front of the persistent kernel",
                 "chol_kernel_ms": chol_ms, "chol_frac_of_fp64_peak": flops / (chol_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
                 "whole_step_frac_of_fp64_peak": flops / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS}
 

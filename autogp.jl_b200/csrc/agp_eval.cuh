@@ -46,6 +46,15 @@ struct RegStack {
 #pragma unroll
         for (int e = 0; e < E; ++e) s[0][e] = v[e];
     }
+    // remove the top entry into r
+    __device__ __forceinline__ void pop(double (&r)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = s[0][e];
+#pragma unroll
+        for (int i = 0; i < D - 1; ++i)
+#pragma unroll
+            for (int e = 0; e < E; ++e) s[i][e] = s[i + 1][e];
+    }
     // replace the two top entries by r
     __device__ __forceinline__ void reduce(const double (&r)[E]) {
 #pragma unroll
@@ -475,4 +484,283 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The same derivative with a LIFO tape instead of per-node arrays (round 2).  The version above keeps the value, the
+// adjoint and three leaf intermediates of EVERY node in dynamically indexed per-thread arrays: 75 local-memory
+// instructions per covariance entry, FP64 pipe 20 % busy (profiles/r01_ncu_launches_grad_v8.csv).  A
+// postfix program is a tree, so both sweeps are stack machines:
+//   forward   the operand stack of eval_program (D shift registers); a node pushes onto the TAPE only what its own
+//             backward step needs: SE its exponential; GE its power and exponential; Periodic sin, cos, exponential;
+//             Times its two operand values; ChangePoint its operand values and the two tanh — nothing for Constant,
+//             Linear, WhiteNoise, Plus;
+//   backward  the program read from its last node to its first visits every node after its parent and the subtree of the
+//             operand that was evaluated LAST before the one evaluated first — the mirror image of the forward order — so
+//             the adjoints live on a register stack of the same depth D (same recurrence as the Sethi-Ullman need of the
+//             forward sweep) and the tape is popped in exactly the reverse order of the pushes.
+// Tape traffic for Plus(Times(SE, Periodic), Linear): 6 pushes + 6 pops per entry.
+// ------------------------------------------------------------------------------------------
+constexpr int AGP_GRAD_TAPE = 4 * AGP_GRAD_MAX_NODES;  // a node pushes at most four values
+
+template <int D, int E, class Acc>
+__device__ __forceinline__ void eval_program_grad(const AgpInstr* __restrict__ prog, int m, const double (&t1)[E], const double (&t2)[E],
+                                                  const double (&seed)[E], Acc&& acc) {
+    double tape[AGP_GRAD_TAPE][E];
+    int tp = 0;
+    RegStack<D, E> st;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int e = 0; e < E; ++e) st.s[i][e] = 0.0;
+    double dx[E], adx[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        dx[e] = t1[e] - t2[e];
+        adx[e] = fabs(dx[e]);
+    }
+    auto tpush = [&](const double (&x)[E]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) tape[tp][e] = x[e];
+        ++tp;
+    };
+    auto tpop = [&](double (&x)[E]) {
+        --tp;
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = tape[tp][e];
+    };
+#pragma unroll 1
+    for (int q = 0; q < m; ++q) {
+        const int op = prog[q].op & 0xff;
+        const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        double v[E];
+        if (op >= AGP_I_PLUS) {
+            if (op == AGP_I_PLUS) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = st.s[1][e] + st.s[0][e];
+            } else if (op == AGP_I_TIMES) {
+                tpush(st.s[1]);
+                tpush(st.s[0]);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = st.s[1][e] * st.s[0][e];
+            } else {  // ChangePoint; the SWAP form has its right-hand kernel on s[1]
+                double th1[E], th2[E];
+                tpush(op == AGP_I_CP ? st.s[1] : st.s[0]);  // k_left
+                tpush(op == AGP_I_CP ? st.s[0] : st.s[1]);  // k_right
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    th1[e] = tanh((a - t1[e]) / b);
+                    th2[e] = tanh((a - t2[e]) / b);
+                    const double kl = (op == AGP_I_CP) ? st.s[1][e] : st.s[0][e], kr = (op == AGP_I_CP) ? st.s[0][e] : st.s[1][e];
+                    const double g1 = 0.5 * (1.0 + th1[e]), g2 = 0.5 * (1.0 + th2[e]);
+                    v[e] = (g1 * g2) * kl + ((1.0 - g1) * (1.0 - g2)) * kr;
+                }
+                tpush(th1);
+                tpush(th2);
+            }
+            st.reduce(v);
+            continue;
+        }
+        switch (op) {
+            case AGP_I_CONST:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = a;
+                break;
+            case AGP_I_LINEAR:
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b + c * ((t1[e] - a) * (t2[e] - a));
+                break;
+            case AGP_I_SE: {
+                double xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) xin[e] = ((-0.5 * dx[e]) * dx[e]) / a;
+                exp_v<E>(xin, e1);
+                tpush(e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = b * e1[e];
+                break;
+            }
+            case AGP_I_GE: {
+                double w[E], xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    w[e] = pow(adx[e] / a, b);
+                    xin[e] = -w[e];
+                }
+                exp_v<E>(xin, e1);
+                tpush(w);
+                tpush(e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * e1[e];
+                break;
+            }
+            case AGP_I_PER: {
+                double sn[E], cs[E], xin[E], e1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    sincos(a * adx[e], &sn[e], &cs[e]);
+                    xin[e] = b * (sn[e] * sn[e]);
+                }
+                exp_v<E>(xin, e1);
+                tpush(sn);
+                tpush(cs);
+                tpush(e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = c * e1[e];
+                break;
+            }
+            default:  // AGP_I_WN
+#pragma unroll
+                for (int e = 0; e < E; ++e) v[e] = (t1[e] == t2[e]) ? a : 0.0;
+                break;
+        }
+        st.push(v);
+    }
+    // backward sweep: the adjoint stack starts with the seed on the root
+    RegStack<D, E> ad;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int e = 0; e < E; ++e) ad.s[i][e] = 0.0;
+    ad.push(seed);
+#pragma unroll 1
+    for (int q = m - 1; q >= 0; --q) {
+        const int op = prog[q].op & 0xff, off = prog[q].pad;
+        const double a = prog[q].a, b = prog[q].b, c = prog[q].c;
+        double g[E];
+        ad.pop(g);
+        switch (op) {
+            case AGP_I_CONST: {
+                double s0 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) s0 += g[e];
+                acc(off, s0);
+                break;
+            }
+            case AGP_I_WN: {
+                double s0 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) s0 += (t1[e] == t2[e]) ? g[e] : 0.0;
+                acc(off, s0);
+                break;
+            }
+            case AGP_I_LINEAR: {  // bias + amp (t1 - c0)(t2 - c0): params (intercept c0, bias, amplitude)
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double u1 = t1[e] - a, u2 = t2[e] - a;
+                    s0 += g[e] * (-c * (u1 + u2));
+                    s1 += g[e];
+                    s2 += g[e] * (u1 * u2);
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
+                break;
+            }
+            case AGP_I_SE: {  // amp exp(-dx^2 / (2 l^2)): params (lengthscale l, amplitude); a = l^2, d = l
+                const double al = a * prog[q].d;
+                double e1[E], s0 = 0.0, s1 = 0.0;
+                tpop(e1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    s0 += g[e] * ((b * e1[e]) * (dx[e] * dx[e]) / al);
+                    s1 += g[e] * e1[e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                break;
+            }
+            case AGP_I_GE: {  // amp exp(-(|dx| / l)^gamma): params (l, gamma, amp)
+                double e1[E], w[E], s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                tpop(e1);
+                tpop(w);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double u = adx[e] / a, val = c * e1[e];
+                    s0 += g[e] * (val * b * w[e] / a);
+                    s1 += (u > 0.0) ? g[e] * (-val * w[e] * log(u)) : 0.0;
+                    s2 += g[e] * e1[e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
+                break;
+            }
+            case AGP_I_PER: {  // amp exp(b s^2), s = sin(a |dx|), a = pi / p, b = -2 / l^2: params (l, p, amp); d = l, reserved = p
+                const double dbdl = -2.0 * b / prog[q].d;       // db/dl = 4 / l^3 = -2 b / l
+                const double dadp = -a / prog[q].reserved;      // da/dp = -pi / p^2 = -a / p
+                double e1[E], cs[E], sn[E], s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                tpop(e1);
+                tpop(cs);
+                tpop(sn);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double val = c * e1[e];
+                    s0 += g[e] * (val * (sn[e] * sn[e]) * dbdl);
+                    s1 += g[e] * (val * b * 2.0 * sn[e] * cs[e] * adx[e] * dadp);
+                    s2 += g[e] * e1[e];
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                acc(off + 2, s2);
+                break;
+            }
+            case AGP_I_PLUS:
+                ad.push(g);  // the operand evaluated first ...
+                ad.push(g);  // ... and, on top, the operand evaluated last: its subtree is what the sweep meets next
+                break;
+            case AGP_I_TIMES: {
+                double v0[E], v1[E], g1[E], g0[E];
+                tpop(v0);
+                tpop(v1);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    g1[e] = g[e] * v0[e];
+                    g0[e] = g[e] * v1[e];
+                }
+                ad.push(g1);
+                ad.push(g0);
+                break;
+            }
+            default: {  // ChangePoint: params (location, scale)
+                double th2[E], th1[E], kr[E], kl[E], gl[E], gr[E], s0 = 0.0, s1 = 0.0;
+                tpop(th2);
+                tpop(th1);
+                tpop(kr);
+                tpop(kl);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double u1 = (a - t1[e]) / b, u2 = (a - t2[e]) / b;
+                    const double s1g = 0.5 * (1.0 + th1[e]), s2g = 0.5 * (1.0 + th2[e]);
+                    const double dg1 = 0.5 * (1.0 - th1[e] * th1[e]) / b, dg2 = 0.5 * (1.0 - th2[e] * th2[e]) / b;  // d sigma / d location
+                    gl[e] = g[e] * (s1g * s2g);
+                    gr[e] = g[e] * ((1.0 - s1g) * (1.0 - s2g));
+                    const double dk1 = s2g * kl[e] - (1.0 - s2g) * kr[e], dk2 = s1g * kl[e] - (1.0 - s1g) * kr[e];  // dk / d sigma(t1), d sigma(t2)
+                    s0 += g[e] * (dk1 * dg1 + dk2 * dg2);
+                    s1 += g[e] * (-(dk1 * dg1 * u1 + dk2 * dg2 * u2));
+                }
+                acc(off, s0);
+                acc(off + 1, s1);
+                // the operand on s[0] in the forward sweep was evaluated last: its adjoint goes on top
+                if (op == AGP_I_CP) {
+                    ad.push(gl);
+                    ad.push(gr);
+                } else {
+                    ad.push(gr);
+                    ad.push(gl);
+                }
+                break;
+            }
+        }
+    }
+}
+
+// dispatch on the operand-stack depth the program needs, as eval_entries does
+template <int E, class Acc>
+__device__ __forceinline__ void eval_entries_grad_tape(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E],
+                                                       const double (&t2)[E], const double (&seed)[E], Acc&& acc) {
+    if (need <= 2) eval_program_grad<2, E>(prog, m, t1, t2, seed, acc);
+    else if (need <= 4) eval_program_grad<4, E>(prog, m, t1, t2, seed, acc);
+    else eval_program_grad<AGP_MAX_STACK, E>(prog, m, t1, t2, seed, acc);
+}
 }  // namespace agp

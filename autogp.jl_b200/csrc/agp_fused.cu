@@ -28,6 +28,9 @@ constexpr int PROG_SMEM = 64;
 #ifndef AGP_GRAD_E
 #define AGP_GRAD_E 2
 #endif
+#ifndef AGP_GRAD_ARRAYS
+#define AGP_GRAD_ARRAYS 0  // 1: the round-1 reverse-mode interpreter (per-node arrays) instead of the tape form, for A/B builds
+#endif
 #ifndef AGP_GF_MINB
 #define AGP_GF_MINB 2
 #endif
@@ -120,8 +123,11 @@ void launch_predict_extract(const BatchView& v, int P, const double* noise_pred,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __restrict__ param_off, double* __restrict__ partial) {
     __shared__ AgpInstr prog_s[PROG_SMEM];
+#if AGP_GRAD_ARRAYS
     __shared__ unsigned char opa_s[PROG_SMEM], opb_s[PROG_SMEM];
+#endif
     __shared__ double red[FT / 32][AGP_GRAD_MAX_PARAMS + 1];
+    __shared__ double ts_rs[UM], nal_rs[UM];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = blockIdx.y;
     const int t = blockIdx.x >> 1, h = blockIdx.x & 1;
@@ -141,37 +147,66 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
         for (int w = tid; w < pm * AGP_INSTR_DOUBLES; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
     }
     __syncthreads();
+#if AGP_GRAD_ARRAYS
     if (tid == 0) grad_operands(prog_s, pm, opa_s, opb_s);
     __syncthreads();
+#else
+    const int need = v.prog_need[p];
+#endif
     const int np = param_off[p + 1] - param_off[p];  // host guarantees np <= AGP_GRAD_MAX_PARAMS
     double g[AGP_GRAD_MAX_PARAMS + 1];
     for (int j = 0; j <= np; ++j) g[j] = 0.0;
     const int c = tid & (UN - 1), rbase = tid >> 7;
     const int gc = col0 + c;
+    // the unit's row time points and -alpha entries: read once per CTA
+    if (tid < UM) {
+        const int gr = row0 + tid;
+        ts_rs[tid] = (gr < n) ? v.ts[gr] : 0.0;
+        nal_rs[tid] = (gr < n) ? nal[gr] : 0.0;
+    }
+    __syncthreads();
     if (gc < n) {
         const double tcol = v.ts[gc];
         const double nac = nal[gc];
         constexpr int GE_ = AGP_GRAD_E;  // entries per interpreter pass
-#pragma unroll 1
-        for (int e0 = 0; e0 < 32; e0 += GE_) {
-            double t1[GE_], t2[GE_], wgt[GE_];
-            bool any = false;
+        // -K^{-1} entries of a pass are loaded one pass ahead: their DRAM latency (the two most stalled instructions of
+        // the first tape version, 10 % of all samples each) hides behind the interpreter
+        auto load_kinv = [&](int e0, double (&kin)[GE_]) {
 #pragma unroll
             for (int u = 0; u < GE_; ++u) {
                 const int gr = row0 + rbase + 2 * (e0 + u);
+                kin[u] = (gr < n && gc <= gr) ? Lp[(long long)(lt + gr) * ld + lt + gc] : 0.0;
+            }
+        };
+        double kin[GE_];
+        load_kinv(0, kin);
+#pragma unroll 1
+        for (int e0 = 0; e0 < 32; e0 += GE_) {
+            double t1[GE_], t2[GE_], wgt[GE_], knext[GE_];
+            if (e0 + GE_ < 32) load_kinv(e0 + GE_, knext);
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < GE_; ++u) {
+                const int r = rbase + 2 * (e0 + u), gr = row0 + r;
                 const bool ok = gr < n && gc <= gr;
                 t1[u] = tcol;
-                t2[u] = ok ? v.ts[gr] : tcol;  // an entry outside the lower triangle runs as a (k(t,t), weight 0) dummy
+                t2[u] = ok ? ts_rs[r] : tcol;  // an entry outside the lower triangle runs as a (k(t,t), weight 0) dummy
                 double A = 0.0;
                 if (ok) {
-                    A = nal[gr] * nac + Lp[(long long)(lt + gr) * ld + lt + gc];
+                    A = nal_rs[r] * nac + kin[u];
                     if (gr == gc) g[np] += A;  // dK/dnoise = I
                 }
                 wgt[u] = ok ? ((gr == gc) ? A : 2.0 * A) : 0.0;  // off-diagonal entries count twice (symmetry)
                 any = any || ok;
             }
+#pragma unroll
+            for (int u = 0; u < GE_; ++u) kin[u] = knext[u];
             if (!any) continue;
+#if AGP_GRAD_ARRAYS
             eval_entries_grad<GE_>(prog_s, pm, opa_s, opb_s, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
+#else
+            eval_entries_grad_tape<GE_>(prog_s, pm, need, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
+#endif
         }
     }
     for (int j = 0; j <= np; ++j) {

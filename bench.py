@@ -41,7 +41,7 @@ TREE = "se*per+lin"
 # MEASURED_PEAKS.json uses for bf16); the DMMA issue-rate ceiling is 37.2 TFLOP/s.
 # MEASURED_PEAKS.json itself has no FP64 entry.
 FP64_PEAK_TFLOPS = 35.4
-KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_potf2.cu", "agp_chol_common.cuh")
+KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_diag.cu", "agp_chol_potf2.cu", "agp_chol_gram.cu", "agp_chol_common.cuh")
 
 
 def workload_name(n, P):

@@ -333,7 +333,12 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     size_t work_bytes = off_dinv + (size_t)P * (ld / TB) * 4096 * 8;
     if ((rc = grow_device(h, &h->d_work, &h->cap_work, work_bytes)) != AGP_OK) return rc;
     size_t res_bytes = align_up((size_t)P * 8, 16) + (size_t)P * 4;
-    if ((rc = grow_device(h, &h->d_res, &h->cap_res, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
+    {
+        const size_t cap_before = h->cap_res;
+        if ((rc = grow_device(h, &h->d_res, &h->cap_res, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
+        // a fresh block: the fetch copies lml[P] | pad | info[P] in one piece, the pad bytes are never written by a kernel
+        if (h->cap_res != cap_before) AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, h->cap_res, h->stream));
+    }
     if ((rc = grow_pinned(h, &h->h_res, &h->cap_hres, res_bytes > 0 ? res_bytes : 16)) != AGP_OK) return rc;
     size_t L_bytes = (size_t)P * ld * ld * 8;
     if ((rc = grow_device(h, &h->d_L, &h->cap_L, L_bytes > 0 ? L_bytes : 16)) != AGP_OK) return rc;

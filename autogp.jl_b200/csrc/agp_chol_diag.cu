@@ -153,6 +153,7 @@ __device__ bool do_diag(const BatchView& v, const SchedView& q, const TmaMaps& m
             }
         }
     }
+    __syncthreads();  // orders every thread's read of ctl[4] above before this write for tools that do not model mbarriers
     if (tid == 0) s.ctl[4] = G0 + nchunk;
     stamp(q, idx, 2);
 

@@ -146,8 +146,10 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
                 for (int nb = 0; nb < 4; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
         }
     }
+    __syncthreads();  // every warp is done with the operand stages: X overwrites them below
+    // (behind the barrier rather than in front of it: the item's first read of ctl[4] is ordered before this write by the
+    // stage barriers alone — nchunk is 0 or >= 8 > NSTAGE — which compute-sanitizer's racecheck does not model)
     if (tid == 0) s.ctl[4] = G0 + nchunk;
-    __syncthreads();
     stamp(q, idx, 2);
 
     // --- X = -acc:  a store-only item writes it back to L, a finishing panel keeps it in shared memory ----

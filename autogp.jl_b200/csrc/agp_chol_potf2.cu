@@ -19,6 +19,11 @@ static_assert(10 * BLK <= REGION_D, "packed diagonal tile must fit in the region
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_off(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * BLK; }
 
+// The named barriers of this item are reached by the factoring warps and by the inverting warp from different places of
+// the code.  PTX allows that (bar.sync is per warp), compute-sanitizer's synccheck reports "divergent thread(s) in block"
+// unless all of them execute the SAME barrier instruction: one out-of-line copy serves every call site.
+__device__ __noinline__ void potf2_bar(int id, int count) { named_bar_sync(id, count); }
+
 __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
     const Smem s = smem_view();
     const int p = __ldg(&q.items[2 * idx].y), k = __ldg(&q.items[2 * idx].z), need_diag = __ldg(&q.items[2 * idx + 1].w);
@@ -74,7 +79,7 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
         for (int jb = 0; jb < 4; ++jb) {
             const int j0 = jb * 32;
             const double* Dg = Ab + blk_off(jb, jb);
-            named_bar_sync(1, FT);  // diagonal block jb is final
+            potf2_bar(1, FT);  // diagonal block jb is final
             if (want_dinv) {
                 // inverse of the diagonal block, lane = column of the inverse
                 double x[32];
@@ -103,19 +108,33 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) a[c] = rowp[c];
                 int bad = 0;
+                // Software-pipelined over the columns: as soon as column j is scaled, column j + 1 receives its update, and
+                // the NEXT pivot (shuffle -> test -> rsqrt: ~130 of the 353 clocks a column took when this chain ran after
+                // the whole rank-1 update) is computed while the remaining 30 - j updates of column j are issued.  Same
+                // operations on the same operands in the same order per entry: bitwise the unpipelined loop.
+                double d = __shfl_sync(0xffffffffu, a[0], 0);
+                if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
+                    bad = o + j0 + 1;
+                    d = 1.0;
+                }
+                double inv = rsqrt(d);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    double d = __shfl_sync(0xffffffffu, a[j], j);
-                    if (!(d > 0.0)) {  // also catches NaN; LAPACK dpotrf: info = j (1-based)
-                        if (bad == 0) bad = o + j0 + j + 1;
-                        d = 1.0;
-                    }
-                    const double inv = rsqrt(d);
                     const double l = (lane == j) ? d * inv : a[j] * inv;
                     a[j] = l;
                     if (lane == 0) Ri[j0 + j] = inv;
+                    if (j + 1 < 32) {
+                        const double l1 = __shfl_sync(0xffffffffu, l, j + 1);
+                        a[j + 1] = fma(-l, l1, a[j + 1]);
+                        d = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                        if (!(d > 0.0)) {
+                            if (bad == 0) bad = o + j0 + j + 2;
+                            d = 1.0;
+                        }
+                        inv = rsqrt(d);
+                    }
 #pragma unroll
-                    for (int c = j + 1; c < 32; ++c) {
+                    for (int c = j + 2; c < 32; ++c) {
                         const double lc = __shfl_sync(0xffffffffu, l, c);
                         a[c] = fma(-l, lc, a[c]);
                     }
@@ -126,7 +145,7 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
                     if (c <= lane) roww[c] = a[c];
                 if (lane == 0 && bad != 0 && s.ctl[2] == 0) s.ctl[2] = bad;
             }
-            named_bar_sync(1, FT);
+            potf2_bar(1, FT);
             // ---- phase 2: rows below the block, one thread per row (threads 32..) -----------
             const int R = TB + 1 - (j0 + 32);  // rows j0+32 .. 128 (row 128 = y)
             if (tid >= 32 && tid - 32 < R) {
@@ -145,7 +164,7 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) rowp[c] = a[c];
             }
-            named_bar_sync(2, WORKERS);
+            potf2_bar(2, WORKERS);
             // ---- phase 3: trailing update  A[i][c] -= sum_m L[i][m] L[c][m]  (DMMA) ---------
             const int T = TB - (j0 + 32);  // trailing rows/cols inside the tile
             if (T > 0) {
@@ -188,7 +207,7 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
                     }
                 }
             }
-            named_bar_sync(3, WORKERS);
+            potf2_bar(3, WORKERS);
         }
     }
     __syncthreads();

@@ -19,7 +19,12 @@ def main():
     nodes, noises = [nd for nd, _ in parts], [nz for _, nz in parts]
     K = eng.gram(nodes[0], noises[0], ts[:100])
     lml, info = eng.lml_batch(nodes, noises, ts, xs)
-    assert np.all(info == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(K))
+    assert np.all(info == 0) and np.all(np.isfinite(lml)) and np.all(np.isfinite(K)) and eng.gram_items()[0] is True
+    # seven block columns: the Gram fill as its own launch, look-ahead items, the right-looking tail (n = 300 above: three
+    # block columns, the Gram units as queue items)
+    ts7, xs7 = synthetic_series(800)
+    lml7, info7 = eng.lml_batch(nodes[:3], noises[:3], ts7, xs7)
+    assert np.all(info7 == 0) and np.all(np.isfinite(lml7)) and eng.gram_items()[0] is False
     eng.upload(nodes, noises, ts, xs)
     eng.set_prefix(140)
     eng.run()

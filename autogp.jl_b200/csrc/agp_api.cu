@@ -494,23 +494,31 @@ static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vect
     for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);
     for (int p = 0; p < P; ++p) b.potf2(p, 0);
     struct T { int p, i, k, j1; };
-    for (int k = 0; k < nt - 1; ++k) {
-        for (int p = 0; p < P; ++p) b.tile(p, k + 1, k, k);  // panels of tile row k+1 first
+    // Particle groups: within a block column the schedule below is emitted group by group (AGP_PGROUP particles each), so
+    // that the items in flight at any time belong to few particles and the B operand of a particle — tile row k, read by
+    // every panel item of the column — stays in L2 between them.  With all particles in one group (the round-1 order)
+    // consecutive items belong to different particles and 296 resident items touch all 64 B panels plus their own A panels.
+    int pg = P;
+    if (const char* e = getenv("AGP_PGROUP")) pg = std::max(1, atoi(e));
+    for (int k = 0; k < nt - 1; ++k)
+      for (int p0 = 0; p0 < P; p0 += pg) {
+        const int p1 = std::min(P, p0 + pg);
+        for (int p = p0; p < p1; ++p) b.tile(p, k + 1, k, k);  // panels of tile row k+1 first
         if (k < ks) {
             std::vector<T> la;  // look-ahead store-only items over [0,k)
             if (split(k + 1) && k >= 1)
-                for (int p = 0; p < P; ++p) {
+                for (int p = p0; p < p1; ++p) {
                     la.push_back({p, k + 1, k + 1, k});
                     if (k + 2 < nt) la.push_back({p, k + 2, k + 1, k});
                 }
             if (k + 1 == ks && k >= 1)  // the switch: the rest of the trailing triangle
-                for (int p = 0; p < P; ++p)
+                for (int p = p0; p < p1; ++p)
                     for (int c = k + 1; c < nt; ++c)
                         for (int i = c; i < nt; ++i)
                             if (!(split(k + 1) && c == k + 1 && (i == k + 1 || i == k + 2))) la.push_back({p, i, c, k});
             std::vector<T> bulk;
             for (int i = k + 2; i < nt; ++i)
-                for (int p = 0; p < P; ++p) bulk.push_back({p, i, k, k});
+                for (int p = p0; p < p1; ++p) bulk.push_back({p, i, k, k});
             // the look-ahead items, DIAG(k+1) and POTF2(k+1) are interleaved into the bulk of column k at these
             // fractions (tuned with tools/queue_sim.py, confirmed on the device: profiles/r01_order_tuning.txt)
             const size_t nb = bulk.size();
@@ -518,20 +526,20 @@ static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vect
             for (size_t a = 0; a < c0; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
             for (const T& a : la) b.tile(a.p, a.i, a.k, a.j1);
             for (size_t a = c0; a < c1; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
-            for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
+            for (int p = p0; p < p1; ++p) b.tile(p, k + 1, k + 1, k + 1);
             for (size_t a = c1; a < c2; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
-            for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+            for (int p = p0; p < p1; ++p) b.potf2(p, k + 1);
             for (size_t a = c2; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].j1);
         } else {
-            for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
-            for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+            for (int p = p0; p < p1; ++p) b.tile(p, k + 1, k + 1, k + 1);
+            for (int p = p0; p < p1; ++p) b.potf2(p, k + 1);
             for (int i = k + 2; i < nt; ++i)
-                for (int p = 0; p < P; ++p) b.tile(p, i, k, k);
+                for (int p = p0; p < p1; ++p) b.tile(p, i, k, k);
             for (int c = k + 2; c < nt; ++c)
                 for (int i = c; i < nt; ++i)
-                    for (int p = 0; p < P; ++p) b.tile(p, i, c, k + 1);
+                    for (int p = p0; p < p1; ++p) b.tile(p, i, c, k + 1);
         }
-    }
+      }
 }
 
 static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int4>& items) {

@@ -74,9 +74,10 @@ def main():
                 kk = items[m, 2] > 0
                 line += f" | (k>0) wait1 {w1[kk].mean():6.1f} mma {mm[kk].mean():6.1f} store {rest[kk].mean():6.1f}"
         print(line)
-        if t == 1 and (st[m][:, 4] != 0).any():  # -DAGP_X_POTF2_CLK=1 builds: clock totals of the micro-panel phases
+        if t == 1 and (st[m][:, 4] != 0).any():  # clocks thread 0 spent in the three phases of the item's steps
             c = st[m][:, 4]
-            print(f"       potf2 clocks per item: P1 (pivot chains) {np.mean(c >> 32):9.0f}  P2 (rank-8 updates) {np.mean(c & 0xffffffff):9.0f}")
+            p1, p2, p3 = ((c >> 42) & 0x1fffff) * 16, ((c >> 21) & 0x1fffff) * 16, (c & 0x1fffff) * 16
+            print(f"       potf2 clocks per item: phase 1 (diagonal block, warp 0) {np.mean(p1):8.0f}  phase 2 (row substitution) {np.mean(p2):8.0f}  phase 3 (DMMA update) {np.mean(p3):8.0f}")
     print(f"slots {slots}  busy {busy_total/1e3:.1f} ms*cta  capacity {slots*span/1e3:.1f} ms*cta  occupancy {busy_total/(slots*span):.3f}")
     # per-block-column view of the panels
     print("per block column k: panel items mean us (wait1, mma, gram, waitF, trsm) and the wall-clock window of the column")

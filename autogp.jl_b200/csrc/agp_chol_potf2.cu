@@ -255,10 +255,18 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx) {
     __syncthreads();
     stamp(q, idx, 3);
 
-    // write L_kk (lower, row-major; strictly-upper zeroed so the tile is a clean factor)
-    for (int idx = tid; idx < TB * TB; idx += FT) {
-        int r = idx >> 7, c = idx & (TB - 1);
-        Lp[(long long)(o + r) * ld + o + c] = (c <= r) ? Ab[blk_off(r >> 5, c >> 5) + (r & 31) * BS + (c & 31)] : 0.0;
+    // write L_kk: the ten lower 32x32 blocks as 16-byte stores, 20 per thread (the strictly upper part of the diagonal
+    // blocks zeroed, so the tile is a clean factor; the six blocks above the diagonal hold the Gram fill's zeros and no item
+    // ever writes them).  This store sits on every particle's critical path: POTF2 -> panel solve -> next diagonal tile.
+#pragma unroll 4
+    for (int u = 0; u < 20; ++u) {
+        const int e = u * FT + tid;
+        const int b = e >> 9, w = e & 511, r = w >> 4, c2 = w & 15;
+        const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0, bj = b - bi * (bi + 1) / 2;
+        const double* src = Ab + b * BLK + r * BS + 2 * c2;
+        const bool dg = bi == bj;
+        const double2 val = make_double2((dg && 2 * c2 > r) ? 0.0 : src[0], (dg && 2 * c2 + 1 > r) ? 0.0 : src[1]);
+        *reinterpret_cast<double2*>(Lp + (long long)(o + bi * 32 + r) * ld + o + bj * 32 + 2 * c2) = val;
     }
     // z_k, sum z^2, sum log L_jj
     if (tid < TB) {

@@ -1,0 +1,432 @@
+// Error-free int8 split of the long contractions of the blocked Cholesky onto tcgen05.mma kind::i8 (sm_100a).
+// Interface and the arithmetic of the scheme: agp_ozaki.cuh.  Three kernels:
+//
+//   agp_ozaki_rowscale_kernel   per row r of every particle: e_r = ceil(log2 sqrt(K_rr)) from the Gram diagonal
+//   agp_ozaki_slice_kernel      finished tiles of L -> eight int8 digit planes (what the FP64 tile costs in bytes)
+//   agp_ozaki_update_kernel     T_ik -= sum_{j < c0} L_ij L_kj^T for every lower tile of block columns [c0, c1):
+//                               one CTA per SM, warp-specialised:
+//                                 warp 0   TMA producer: digit-plane boxes (128-byte swizzle) into a ring of A slots
+//                                          and a double-buffered B chunk, full / empty mbarriers
+//                                 warp 1   one thread issues tcgen05.mma.cta_group::1.kind::i8 M128 N64 K32; the eight
+//                                          weight groups g = p + q live in TMEM columns [64 g, 64 g + 64); stages are
+//                                          released by tcgen05.commit
+//                                 warps 2-5  epilogue: tcgen05.ld of the eight int32 sums, exact recombination in
+//                                          int64 -> FP64, scale by 2^(e_i + e_k), subtract from the tile in L
+//
+// Reference semantics: the products are part of dpotrf as called by PDMats for `mvnormal` (src/Model.jl:136).
+#include "agp_ozaki.cuh"
+
+#include <math.h>
+
+#include "agp_ptx.cuh"
+
+namespace agp {
+
+namespace {
+
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_NA = 6;                          // A ring slots
+constexpr uint32_t OZ_A_BYTES = 128 * 128;        // one digit plane of a 128-row tile, 128 bytes of k
+constexpr uint32_t OZ_BQ_BYTES = 64 * 128;        // one digit plane of the item's 64 B rows
+constexpr uint32_t OZ_B_BYTES = OZ_SLICES * OZ_BQ_BYTES;
+constexpr uint32_t OZ_OFF_A = 2 * OZ_B_BYTES;
+constexpr uint32_t OZ_OFF_BAR = OZ_OFF_A + OZ_NA * OZ_A_BYTES;
+constexpr int OZ_SMEM = (int)OZ_OFF_BAR + 256;
+static_assert(OZ_SMEM <= 227 * 1024, "one CTA per SM");
+
+// K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups of 1024 bytes (stride byte offset), version 1
+__device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::i8: D = S32 (c_format 2), A and B signed 8 bit, both K-major, N = 64, M = 128
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long oz_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
+// mbarrier wait that cannot hang the device (same policy as the persistent kernel's waits)
+__device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* err, unsigned long long limit_ns) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return true;
+        if ((spins & 1023u) == 1023u) {
+            if (ld_relaxed_gpu(err) != 0) return false;
+            const unsigned long long now = oz_timer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > limit_ns) {
+                atomicExch(err, 2);
+                return false;
+            }
+        }
+    }
+}
+
+#ifndef OZ_STATS
+#define OZ_STATS 0
+#endif
+#if OZ_STATS
+__device__ long long oz_stats[8];  // MMA thread: total, wait B, wait A, wait TMEM free; epilogue warp 2: total busy; items
+#define OZ_T0() const long long t_s_ = clock64()
+#define OZ_ACC(slot) oz_acc_[slot] += clock64() - t_s_
+#else
+#define OZ_T0()
+#define OZ_ACC(slot)
+#endif
+
+struct OzItem {
+    int p, i, k, h;
+};
+// items of one launch: particle-major, then block column, then tile row, the two 64-column halves adjacent (they share A)
+__device__ __forceinline__ OzItem oz_decode(int idx, int per_p, int c0, int nt) {
+    OzItem it;
+    it.p = idx / per_p;
+    int r = idx - it.p * per_p;
+    int k = c0;
+    for (;;) {
+        const int cnt = 2 * (nt - k);
+        if (r < cnt) break;
+        r -= cnt;
+        ++k;
+    }
+    it.k = k;
+    it.i = k + (r >> 1);
+    it.h = r & 1;
+    return it;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const __grid_constant__ OzakiParams prm, const __grid_constant__ OzakiMaps maps) {
+    extern __shared__ __align__(1024) unsigned char oz_smem[];
+    unsigned char* Bs = oz_smem;
+    unsigned char* As = oz_smem + OZ_OFF_A;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + OZ_OFF_BAR);
+    uint64_t* a_full = bars;              // [OZ_NA]
+    uint64_t* a_empty = bars + OZ_NA;     // [OZ_NA]
+    uint64_t* b_full = bars + 2 * OZ_NA;  // [2]
+    uint64_t* b_empty = b_full + 2;       // [2]
+    uint64_t* acc_full = b_empty + 2;     // MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 1;   // epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = prm.c0, nt = prm.nt, P = prm.P, ld = prm.ld;
+    int per_p = 0;
+    for (int k = c0; k < prm.c1; ++k) per_p += 2 * (nt - k);
+    const int n_items = per_p * P;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b) : "memory");
+        for (int s = 0; s < OZ_NA; ++s) {
+            mbar_init(a_full + s, 1);
+            mbar_init(a_empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(b_full + s, 1);
+            mbar_init(b_empty + s, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer ------------------------------------------------------------------------
+            int an = 0, bn = 0;
+            bool ok = true;
+            for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x) {
+                const OzItem it = oz_decode(idx, per_p, c0, nt);
+                const int brow = it.p * ld + it.k * 128 + it.h * 64, arow = it.p * ld + it.i * 128;
+                for (int c = 0; c < c0 && ok; ++c) {
+                    const int buf = bn & 1;
+                    if (bn >= 2) ok = oz_wait(b_empty + buf, ((bn >> 1) - 1) & 1, prm.err, prm.wait_timeout_ns);
+                    if (!ok) break;
+                    mbar_expect_tx(b_full + buf, OZ_B_BYTES);
+#pragma unroll
+                    for (int q = 0; q < OZ_SLICES; ++q)
+                        tma_load_2d(Bs + buf * OZ_B_BYTES + q * OZ_BQ_BYTES, &maps.b, c * 128, q * P * ld + brow, b_full + buf);
+                    ++bn;
+                    for (int ps = OZ_SLICES - 1; ps >= 0; --ps) {
+                        const int slot = an % OZ_NA, n = an / OZ_NA;
+                        if (n >= 1) ok = oz_wait(a_empty + slot, (n - 1) & 1, prm.err, prm.wait_timeout_ns);
+                        if (!ok) break;
+                        mbar_expect_tx(a_full + slot, OZ_A_BYTES);
+                        tma_load_2d(As + slot * OZ_A_BYTES, &maps.a, c * 128, ps * P * ld + arow, a_full + slot);
+                        ++an;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----------------------------------------------------------------------
+            // One thread feeds the tensor pipe: its own instruction stream has to stay well below the 48 clocks an
+            // M128 N64 K32 instruction takes (shared-memory operand reads: 6 KB at 128 B/clk), so the 36 x 4
+            // instructions of a chunk are straight-line code, descriptors are advanced by integer adds on their
+            // address field, and ring positions are counters with wrap, not divisions.
+            int a_slot = 0, a_par = 0, bn = 0, t = 0;
+            bool ok = true;
+            const uint64_t da0 = oz_desc(smem_u32(As)), db0 = oz_desc(smem_u32(Bs));
+#if OZ_STATS
+            long long oz_acc_[4] = {0, 0, 0, 0};
+            const long long t_all_ = clock64();
+#endif
+            for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x, ++t) {
+                {
+                    OZ_T0();
+                    if (t >= 1) ok = oz_wait(acc_empty, (t - 1) & 1, prm.err, prm.wait_timeout_ns);  // the previous item's sums have left TMEM
+                    OZ_ACC(3);
+                }
+                if (!ok) break;
+                tc_fence_after();
+                for (int c = 0; c < c0 && ok; ++c) {
+                    const int buf = bn & 1;
+                    {
+                        OZ_T0();
+                        ok = oz_wait(b_full + buf, (bn >> 1) & 1, prm.err, prm.wait_timeout_ns);
+                        OZ_ACC(1);
+                    }
+                    if (!ok) break;
+                    const uint64_t db = db0 + (uint64_t)(buf * (OZ_B_BYTES >> 4));
+                    const uint32_t first = (c == 0) ? 0u : 1u;
+#pragma unroll
+                    for (int ps = OZ_SLICES - 1; ps >= 0; --ps) {
+                        {
+                            OZ_T0();
+                            ok = oz_wait(a_full + a_slot, a_par, prm.err, prm.wait_timeout_ns);
+                            OZ_ACC(2);
+                        }
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint64_t da = da0 + (uint64_t)(a_slot * (int)(OZ_A_BYTES >> 4));
+#pragma unroll
+                        for (int q = 0; q + ps < OZ_SLICES; ++q) {
+                            const uint32_t d = tmem + (uint32_t)(ps + q) * 64u;
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                oz_mma(d, da + 2 * k4, db + (uint64_t)(q * (int)(OZ_BQ_BYTES >> 4) + 2 * k4), (q == 0 && k4 == 0) ? first : 1u);
+                        }
+                        oz_commit(a_empty + a_slot);  // the slot is free once the instructions above have read it
+                        if (++a_slot == OZ_NA) a_slot = 0, a_par ^= 1;
+                    }
+                    if (!ok) break;
+                    oz_commit(b_empty + buf);
+                    ++bn;
+                }
+                if (ok) oz_commit(acc_full);
+            }
+#if OZ_STATS
+            atomicAdd((unsigned long long*)&oz_stats[0], (unsigned long long)(clock64() - t_all_));
+            for (int e = 1; e < 4; ++e) atomicAdd((unsigned long long*)&oz_stats[e], (unsigned long long)oz_acc_[e]);
+            atomicAdd((unsigned long long*)&oz_stats[5], (unsigned long long)t);
+#endif
+        }
+    } else {
+        // ---- epilogue: thread = one row of the 128 x 64 output --------------------------------------
+        const int ew = warp & 3;  // the TMEM lanes [32 ew, 32 ew + 32) are the ones this warp may read
+        const int row = ew * 32 + lane;
+        int t = 0;
+        bool ok = true;
+        for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x, ++t) {
+            const OzItem it = oz_decode(idx, per_p, c0, nt);
+            const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
+            const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + it.h * 64);
+            double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + it.h * 64;
+            const int cmax = (it.i == it.k) ? row - it.h * 64 : 63;  // diagonal tile: the strict upper triangle keeps its Gram values
+            // the tile row is fetched while the tensor pipe still works on the item: 64 doubles in registers
+            double2 tv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
+            ok = oz_wait(acc_full, t & 1, prm.err, prm.wait_timeout_ns);
+            if (!ok) break;
+            tc_fence_after();
+#if OZ_STATS
+            const long long t_epi_ = clock64();
+#endif
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+                uint32_t a[OZ_SLICES][8];
+                const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(cb * 8);
+#pragma unroll
+                for (int g = 0; g < OZ_SLICES; ++g) tmem_ld8(taddr + (uint32_t)g * 64u, a[g]);
+                tmem_ld_wait();
+                double out[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // exact in int64: |sum| < 2^31 per group
+                    const long long t0 = ((long long)(int)a[0][j] << 14) + ((long long)(int)a[1][j] << 7) + (long long)(int)a[2][j];
+                    const long long t1 = ((long long)(int)a[3][j] << 14) + ((long long)(int)a[4][j] << 7) + (long long)(int)a[5][j];
+                    const long long t2 = ((long long)(int)a[6][j] << 7) + (long long)(int)a[7][j];
+                    // weights: group g carries 2^(-12 - 7 g)
+                    double val = (double)t2 * 0x1p-61;
+                    val = fma((double)t1, 0x1p-47, val);
+                    val = fma((double)t0, 0x1p-26, val);
+                    const double scj = __ldg(sc + 2 * (cb * 8 + j));
+                    const double tin = (j & 1) ? tv[cb * 4 + (j >> 1)].y : tv[cb * 4 + (j >> 1)].x;
+                    out[j] = tin - val * (sr * scj);
+                }
+                if (cb * 8 + 7 <= cmax) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) reinterpret_cast<double2*>(Trow + cb * 8)[e] = make_double2(out[2 * e], out[2 * e + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cb * 8 + j <= cmax) Trow[cb * 8 + j] = out[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+#if OZ_STATS
+            if (tid == 64) atomicAdd((unsigned long long*)&oz_stats[4], (unsigned long long)(clock64() - t_epi_));
+#endif
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
+}
+
+// ---- row scales -----------------------------------------------------------------------------------
+__global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P, double* __restrict__ rscale) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (long long)P * ld) return;
+    const int p = (int)(w / ld), r = (int)(w - (long long)p * ld);
+    const double kd = L[(long long)p * mat_stride + (long long)r * ld + r];
+    int e = 0;
+    if (kd > 0.0 && kd < 1e300) {
+        int ex;
+        frexp(kd, &ex);        // kd = m 2^ex, 1/2 <= m < 1: sqrt(kd) < 2^(ex / 2)
+        e = (ex + 1) >> 1;     // ceil(ex / 2)
+    }
+    rscale[2 * w] = ldexp(1.0, e);
+    rscale[2 * w + 1] = ldexp(1.0, 55 - e);
+}
+
+// ---- digit planes ---------------------------------------------------------------------------------
+// One CTA = one 128 x 128 tile of L; a warp walks rows, lane = 4 consecutive columns: every plane receives 128
+// contiguous bytes per row.  The entry is rounded once to 55 bits below its row scale, v = rint(x 2^(55 - e)), and
+// v = sum_p a_p 128^(7 - p) is peeled into balanced base-128 digits from the bottom (integer arithmetic: exact).
+__global__ void __launch_bounds__(256) agp_ozaki_slice_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P,
+                                                              const double* __restrict__ rscale, int8_t* __restrict__ S, int c0, int ncol, int r0) {
+    const int p = blockIdx.z, i = r0 + blockIdx.y, j = c0 + blockIdx.x;
+    (void)ncol;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long plane = (long long)P * ld * ld;
+    for (int rr = warp; rr < 128; rr += 8) {
+        const int r = i * 128 + rr;
+        const double f = __ldg(rscale + 2 * ((long long)p * ld + r) + 1);
+        const double* src = L + (long long)p * mat_stride + (long long)r * ld + j * 128 + lane * 4;
+        const double2 x01 = __ldcs(reinterpret_cast<const double2*>(src));
+        const double2 x23 = __ldcs(reinterpret_cast<const double2*>(src) + 1);
+        long long v[4] = {__double2ll_rn(x01.x * f), __double2ll_rn(x01.y * f), __double2ll_rn(x23.x * f), __double2ll_rn(x23.y * f)};
+        int8_t* dst = S + ((long long)p * ld + r) * ld + j * 128 + lane * 4;
+#pragma unroll
+        for (int q = OZ_SLICES - 1; q >= 0; --q) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                long long d;
+                if (q > 0) {
+                    d = ((v[e] + 64) & 127) - 64;  // balanced digit in [-64, 63]
+                    v[e] = (v[e] - d) >> 7;        // exact
+                } else {
+                    d = v[e] < -127 ? -127 : (v[e] > 127 ? 127 : v[e]);  // |x| <= 2^e: the leading digit is within +-65
+                }
+                word |= ((uint32_t)(d & 0xff)) << (8 * e);
+            }
+            *reinterpret_cast<uint32_t*>(dst + (long long)q * plane) = word;
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s) {
+    const long long n = (long long)P * ld;
+    if (n <= 0) return;
+    agp_ozaki_rowscale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, mat_stride, ld, P, rscale);
+}
+
+void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
+                        cudaStream_t s) {
+    if (c1 <= c0 || r0 >= nt || P <= 0) return;
+    dim3 grid(c1 - c0, nt - r0, P);
+    agp_ozaki_slice_kernel<<<grid, 256, 0, s>>>(L, mat_stride, ld, P, rscale, S, c0, c1 - c0, r0);
+}
+
+void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s) {
+    long long per_p = 0;
+    for (int k = prm.c0; k < prm.c1; ++k) per_p += 2 * (prm.nt - k);
+    const long long n_items = per_p * prm.P;
+    if (n_items <= 0 || prm.c0 <= 0) return;
+    if (ctas > n_items) ctas = (int)n_items;
+    agp_ozaki_update_kernel<<<ctas, OZ_THREADS, OZ_SMEM, s>>>(prm, maps);
+}
+
+cudaError_t configure_ozaki() { return cudaFuncSetAttribute(agp_ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM); }
+
+bool make_ozaki_maps(int8_t* S, int ld, int P, OzakiMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)OZ_SLICES * (cuuint64_t)P * (cuuint64_t)ld};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld};
+    const cuuint32_t box_a[2] = {128, 128}, box_b[2] = {128, 64}, estr[2] = {1, 1};
+    const CUresult r1 = encode(&out->a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r2 = encode(&out->b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, S, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+}
+
+}  // namespace agp

@@ -1,0 +1,45 @@
+// Error-free int8 split of the factorisation's long contractions onto the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM) — interface of agp_ozaki.cu.
+//
+// tcgen05.mma has no f64 kind, so the FP64 tensor path of sm_100a is DMMA (mma.sync m8n8k4) at 64 FMA/clk/SM.  The
+// int8 kind runs at 8192 MAC/clk/SM.  An FP64 product  sum_j L_ij L_kj^T  is rebuilt from exact integer products:
+// every row of L is scaled by a power of two known BEFORE the factorisation (|L_ij| <= sqrt(K_ii) <= 2^e_i), the scaled
+// entry is cut into eight signed 7-bit digits  x = sum_p a_p 2^(-6-7p)  (|a_p| <= 64: 55 bits below the row scale), and
+// the 36 digit-plane products with p + q <= 7 are accumulated EXACTLY in int32, one accumulator per weight
+// g = p + q (8 accumulators x 64 columns = the SM's 512 TMEM columns), over the WHOLE contraction depth.  The eight
+// integer sums are recombined once per output tile in FP64.  Error of the scheme on the benchmark factor: 2.9e-14 of
+// the largest entry for a 1920-deep contraction (plain FP64 accumulation: 1.2e-14; tools/ozaki_accuracy.py).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace agp {
+
+constexpr int OZ_SLICES = 8;
+
+struct OzakiMaps {
+    CUtensorMap a, b;  // digit planes viewed as one [8 P ld][ld] byte matrix: boxes of 128 bytes x 128 rows (A) / x 64 rows (B), 128-byte swizzle
+};
+
+struct OzakiParams {
+    double* L;             // [P][ld][ld] the factor / running Schur complement (row-major lower)
+    long long mat_stride;  // ld * ld
+    int ld, nt, P;
+    const double* rscale;  // [P][ld][2]: row scale 2^e, digit factor 2^(55 - e)
+    int c0, c1;            // tiles (i, k), c0 <= k < c1, k <= i < nt:  T_ik -= sum_{j < c0} L_ij L_kj^T
+    int* err;              // raised when a barrier wait times out (never in a correct run)
+    unsigned long long wait_timeout_ns;
+};
+
+// rscale[p][r] <- power-of-two bound of sqrt(K_rr), read from the diagonal of L right after the Gram fill
+void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s);
+// digit planes of the tiles (i, j), c0 <= j < c1, r0 <= i < nt (all 128 rows, 128 columns each)
+void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
+                        cudaStream_t s);
+// the contraction over block columns [0, c0) of every lower tile of block columns [c0, c1), subtracted in place
+void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s);
+bool make_ozaki_maps(int8_t* S, int ld, int P, OzakiMaps* out);
+cudaError_t configure_ozaki();
+
+}  // namespace agp

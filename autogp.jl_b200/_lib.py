@@ -19,7 +19,7 @@ EXPORTS = (
     "agp_lml_batch", "agp_lml_upload", "agp_lml_run", "agp_lml_fetch",
     "agp_lml_device_results", "agp_lml_set_prefix",
     "agp_stream", "agp_synchronize", "agp_launch_count", "agp_lml_time", "agp_lml_stage_times",
-    "agp_queue_build", "agp_queue_build_general", "agp_queue_build_gram", "agp_gram_items", "agp_lml_trace",
+    "agp_queue_build", "agp_set_hybrid", "agp_dev_overlap_probe", "agp_hybrid_info", "agp_queue_build_hybrid", "agp_queue_build_general", "agp_queue_build_gram", "agp_gram_items", "agp_lml_trace",
     "agp_lml_run_append", "agp_predict_batch", "agp_predict_marginals_batch", "agp_predict_sum_batch", "agp_queue_build_marginals", "agp_lml_grad_batch", "agp_lml_grad_noise_batch", "agp_lml_copy_factor",
 )
 
@@ -88,6 +88,14 @@ def load() -> C.CDLL:
     lib.agp_queue_build.restype = C.c_int64
     lib.agp_queue_build_gram.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64]
     lib.agp_queue_build_gram.restype = C.c_int64
+    lib.agp_set_hybrid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.agp_set_hybrid.restype = C.c_int
+    lib.agp_hybrid_info.argtypes = [vp, i32p, i32p, C.POINTER(C.c_float)]
+    lib.agp_hybrid_info.restype = C.c_int
+    lib.agp_queue_build_hybrid.argtypes = [C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int32]
+    lib.agp_queue_build_hybrid.restype = C.c_int64
+    lib.agp_dev_overlap_probe.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
+    lib.agp_dev_overlap_probe.restype = C.c_int
     lib.agp_gram_items.argtypes = [C.c_void_p, i32p, i32p]
     lib.agp_gram_items.restype = C.c_int
     lib.agp_queue_build_general.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64]

@@ -16,6 +16,7 @@
 
 #include "../../include/agp_b200.h"
 #include "agp_kernels.cuh"
+#include "agp_ozaki.cuh"
 #include "agp_program.h"
 
 using agp::BatchView;
@@ -71,10 +72,25 @@ struct agp_handle {
     int gram_lead = 0;    // AGP_GRAM_LEAD: a GRAM item sits this many items ahead of the first reader of its tile half (0: the resident CTAs)
     unsigned long long wait_timeout_ns = 2000000000ull;  // AGP_WAIT_TIMEOUT_MS (raise under profilers that replay slowly)
     int num_sms = 0;
+    // Hybrid factorisation (agp_ozaki.cu): the block columns are grouped into super-columns of `oz_width`; the contraction
+    // of a super-column's tiles over ALL earlier block columns runs as exact int8 digit-plane products on tcgen05
+    // (one launch per super-column), the persistent DMMA kernel then factors the super-column (contractions inside it
+    // only).  Plain LML runs from `oz_min_nt` block columns on.
+    int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
+    int oz_width = 4;      // AGP_OZ_W
+    int oz_min_nt = 8;     // AGP_OZ_MIN_NT
+    int oz_variant = 3;    // AGP_OZ_KERNEL: 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one pass
+    bool force_plain = false;  // diagnostics that index the single-launch schedule (agp_lml_trace)
+    int8_t* d_S = nullptr;     size_t cap_S = 0;       // digit planes [8][P][ld][ld]
+    double* d_rscale = nullptr; size_t cap_rscale = 0;  // [P][ld][2]
+    agp::OzakiMaps ozmaps{};
+    int8_t* oz_S = nullptr; int oz_ld = 0, oz_P = 0;
+    float hybrid_ms[4] = {0.f, 0.f, 0.f, 0.f};  // last agp_lml_stage_times of a hybrid run: Gram, DMMA segments, int8 updates, digit planes
     struct Queue {
         int4* d_items = nullptr;
         int n_items = 0;
         unsigned long long last_use = 0;
+        std::vector<int> seg;  // hybrid schedule: first item of every super-column's segment (+ the total at the end)
     };
     unsigned long long queue_clock = 0;
     static constexpr size_t kMaxQueues = 48;  // least recently used queues beyond this are freed (lock-step loops shrink
@@ -172,6 +188,15 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_CTAS_PER_SM")) h->ctas_per_sm = atoi(e) >= 1 ? atoi(e) : 1;
     if (const char* e = getenv("AGP_FUSE_GRAM")) h->fuse_gram = atoi(e) < 0 ? -1 : atoi(e) != 0;
     if (const char* e = getenv("AGP_GRAM_LEAD")) h->gram_lead = atoi(e) > 0 ? atoi(e) : 0;
+    if (const char* e = getenv("AGP_OZAKI")) h->oz_mode = atoi(e) < 0 ? -1 : atoi(e) != 0;
+    if (const char* e = getenv("AGP_OZ_W")) h->oz_width = std::max(1, atoi(e));
+    if (const char* e = getenv("AGP_OZ_MIN_NT")) h->oz_min_nt = std::max(2, atoi(e));
+    if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 0 || atoi(e) == 2) ? atoi(e) : 3;
+    if (agp::configure_ozaki() != cudaSuccess) {
+        cudaGetLastError();
+        agp_destroy(h);
+        return AGP_ERR_CUDA;
+    }
     *out = h;
     return AGP_OK;
 }
@@ -190,6 +215,8 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_pred);
     cudaFree(h->d_comp);
     cudaFree(h->d_grad);
+    cudaFree(h->d_S);
+    cudaFree(h->d_rscale);
     for (auto& kv : h->queues) cudaFree(kv.second.d_items);
     cudaFreeHost(h->h_sync);
     cudaFreeHost(h->h_gin);
@@ -620,6 +647,53 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
     }
 }
 
+// Hybrid schedule (agp_ozaki.cu): block columns in super-columns of W.  Segment s covers block columns [c0, c1) =
+// [s W, min(nt, (s + 1) W)) and is ONE launch of the persistent kernel; before it (s >= 1) the int8 update kernel has
+// brought every lower tile of those block columns to coverage c0 (T_ik = K_ik - sum_{j < c0} L_ij L_kj^T), so the
+// segment's items contract over [c0, k) only: DIAG(k)[c0, k), POTF2(k), PANEL(k, i)[c0, k) + solve for every i > k.
+// Inside a segment the order is the look-ahead order of the single-launch schedule (panels of tile row k + 1 first,
+// DIAG(k + 1) / POTF2(k + 1) interleaved into the bulk of column k).  The dependency counters are NOT reset between
+// the segments (rowdone / fdone / diagu keep counting), only the queue head is.
+static void build_queue_hybrid(int P, int nt, int nt_stride, int W, std::vector<int4>& items, std::vector<int>& seg) {
+    items.clear();
+    seg.clear();
+    TileState b(P, nt, nt_stride, &items);
+    double pos_diag = 1.0 / 3, pos_potf2 = 0.5;
+    if (const char* e = getenv("AGP_OZ_POS")) sscanf(e, "%lf,%lf", &pos_diag, &pos_potf2);  // developer A/B
+    struct T { int p, i, k; };
+    for (int c0 = 0; c0 < nt; c0 += W) {
+        const int c1 = std::min(nt, c0 + W);
+        seg.push_back((int)(items.size() / 2));
+        if (c0 == 0) {
+            for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);  // starts the forward solve: y_0 = xs
+        } else {
+            for (int p = 0; p < P; ++p)
+                for (int k = c0; k < c1; ++k)
+                    for (int i = k; i < nt; ++i) b.cov[((size_t)p * nt + i) * nt + k] = c0;  // the int8 update
+        }
+        for (int p = 0; p < P; ++p) b.potf2(p, c0);  // s >= 1: the diagonal tile needs no DIAG item (no contraction left)
+        for (int k = c0; k < c1; ++k) {
+            if (k + 1 < nt)
+                for (int p = 0; p < P; ++p) b.tile(p, k + 1, k, k);  // panels of tile row k + 1 first
+            std::vector<T> bulk;
+            for (int i = k + 2; i < nt; ++i)
+                for (int p = 0; p < P; ++p) bulk.push_back({p, i, k});
+            const size_t nb = bulk.size();
+            if (k + 1 < c1) {
+                const size_t a1 = (size_t)(pos_diag * nb), a2 = std::max(a1, (size_t)(pos_potf2 * nb));
+                for (size_t a = 0; a < a1; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
+                for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
+                for (size_t a = a1; a < a2; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
+                for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+                for (size_t a = a2; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
+            } else {
+                for (size_t a = 0; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
+            }
+        }
+    }
+    seg.push_back((int)(items.size() / 2));
+}
+
 // Gram units as queue items (ITEM_GRAM, agp_chol_gram.cu).  Takes a schedule of build_queue and (i) gives every DIAG /
 // PANEL item that is the FIRST to touch its tile half (contraction range starting at 0: its accumulators start from
 // minus the Gram tile) a wait for that half's flag, (ii) inserts the Gram unit of the tile half `lead` items ahead of
@@ -754,7 +828,17 @@ static bool gram_as_items(const agp_handle* h, int first_row) {
 }
 static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : h->ctas_per_sm * h->num_sms; }
 
+// Plain LML run with at least two super-columns: does this handle factor it through the hybrid schedule?
+static bool use_hybrid(const agp_handle* h, int first_row) {
+    const BatchView& v = h->view;
+    if (h->force_plain || h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.nt <= h->oz_width) return false;
+    return h->oz_mode < 0 ? v.nt >= h->oz_min_nt : h->oz_mode != 0;
+}
+
+static int run_hybrid(agp_handle* h, float* kernel_ms);
+
 static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_ms = nullptr, int first_row = 0) {
+    if (d_trace == nullptr && use_hybrid(h, first_row)) return run_hybrid(h, kernel_ms);
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
@@ -859,6 +943,118 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
     h->n_factored = v.n;
     h->factor_clean = false;
     return check_launch(h, "chol");
+}
+
+// Hybrid factorisation: Gram fill, row scales, then per super-column  [digit planes of the previous super-column's
+// panels -> int8 update of this super-column's tiles ->] one launch of the persistent kernel over the segment.
+static int run_hybrid(agp_handle* h, float* kernel_ms) {
+    const BatchView& v = h->view;
+    const int P = h->P, nt = v.nt, ld = h->ld;
+    const int nt_stride = ld / TB;
+    const int W = h->oz_width;
+    auto key = std::make_tuple(P, nt, nt, -5 - W, nt_stride);
+    auto it = h->queues.find(key);
+    if (it == h->queues.end()) {
+        std::vector<int4> items;
+        agp_handle::Queue qu;
+        build_queue_hybrid(P, nt, nt_stride, W, items, qu.seg);
+        qu.n_items = (int)(items.size() / 2);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, AGP_ERR_NOMEM, std::string("work queue allocation failed: ") + cudaGetErrorString(e));
+        }
+        AGP_CUDA(h, cudaMemcpyAsync(qu.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->queues.size() >= agp_handle::kMaxQueues) {
+            auto lru = h->queues.begin();
+            for (auto jt = h->queues.begin(); jt != h->queues.end(); ++jt)
+                if (jt->second.last_use < lru->second.last_use) lru = jt;
+            cudaFree(lru->second.d_items);
+            h->queues.erase(lru);
+        }
+        it = h->queues.emplace(key, qu).first;
+    }
+    it->second.last_use = ++h->queue_clock;
+    const agp_handle::Queue& qu = it->second;
+    int rc;
+    if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld * ld)) != AGP_OK) return rc;
+    if ((rc = grow_device(h, &h->d_rscale, &h->cap_rscale, (size_t)P * ld * 16)) != AGP_OK) return rc;
+    if (h->oz_S != h->d_S || h->oz_ld != ld || h->oz_P != P) {
+        if (!agp::make_ozaki_maps(h->d_S, ld, P, &h->ozmaps)) return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the digit planes");
+        h->oz_S = h->d_S;
+        h->oz_ld = ld;
+        h->oz_P = P;
+    }
+    const size_t n_sync = sync_ints(P, nt_stride, false);
+    if ((rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int))) != AGP_OK) return rc;
+    AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
+    if (h->tma_L != v.L || h->tma_ld != ld || h->tma_rows != (long long)P * ld) {
+        if (!agp::make_tma_maps(v.L, ld, (long long)P * ld, &h->tma)) return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the factor matrix");
+        h->tma_L = v.L;
+        h->tma_ld = ld;
+        h->tma_rows = (long long)P * ld;
+    }
+    SchedView q;
+    q.head = h->d_sync;
+    q.err = h->d_sync + 1;
+    q.rowdone = h->d_sync + 32;
+    q.diagu = q.rowdone + (size_t)P * nt_stride;
+    q.ppre = q.diagu + (size_t)P * nt_stride;
+    q.fdone = q.ppre + (size_t)P * nt_stride;
+    q.nt_stride = nt_stride;
+    q.trace = nullptr;
+    q.wait_timeout_ns = h->wait_timeout_ns;
+    // stage timing (agp_lml_stage_times): every stage bracketed by events and a synchronisation, so the four sums are
+    // per-kernel times, not a pipelined step time
+    float acc_ms[4] = {0.f, 0.f, 0.f, 0.f};
+    auto tic = [&]() -> int {
+        if (kernel_ms) AGP_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        return AGP_OK;
+    };
+    auto toc = [&](int slot) -> int {
+        if (!kernel_ms) return AGP_OK;
+        float ms = 0.f;
+        AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        AGP_CUDA(h, cudaEventSynchronize(h->ev1));
+        AGP_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        acc_ms[slot] += ms;
+        return AGP_OK;
+    };
+    if ((rc = tic()) != AGP_OK) return rc;
+    agp::launch_gramfill(v, P, 0, h->stream);
+    agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream);
+    h->launches += 2;
+    if ((rc = toc(0)) != AGP_OK) return rc;
+    const int n_seg = (int)qu.seg.size() - 1;
+    for (int s = 0; s < n_seg; ++s) {
+        const int c0 = s * W, c1 = std::min(nt, c0 + W);
+        if (s > 0) {
+            if ((rc = tic()) != AGP_OK) return rc;
+            agp::launch_ozaki_slice(v.L, v.mat_stride, ld, nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
+            if ((rc = toc(3)) != AGP_OK) return rc;
+            if ((rc = tic()) != AGP_OK) return rc;
+            agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, c0, c1, q.err, h->wait_timeout_ns};
+            agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, h->oz_variant);
+            if ((rc = toc(2)) != AGP_OK) return rc;
+            AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, sizeof(int), h->stream));  // the queue head; the dependency counters keep counting
+            h->launches += 2;
+        }
+        if ((rc = tic()) != AGP_OK) return rc;
+        q.items = qu.d_items + 2 * (size_t)qu.seg[s];
+        q.n_items = qu.seg[s + 1] - qu.seg[s];
+        agp::launch_chol(v, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
+        h->launches += 1;
+        if ((rc = toc(1)) != AGP_OK) return rc;
+    }
+    if (kernel_ms) {
+        kernel_ms[0] = acc_ms[0];
+        kernel_ms[1] = acc_ms[1] + acc_ms[2] + acc_ms[3];
+        for (int e = 0; e < 4; ++e) h->hybrid_ms[e] = acc_ms[e];
+    }
+    h->n_factored = v.n;
+    h->factor_clean = false;
+    return check_launch(h, "hybrid factorisation");
 }
 
 static int run_impl(agp_handle* h, float* kernel_ms) {
@@ -1179,7 +1375,7 @@ int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     long long* d_trace = nullptr;
     AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_trace), (size_t)n_items * 8 * sizeof(long long)));
     cudaMemsetAsync(d_trace, 0, (size_t)n_items * 8 * sizeof(long long), h->stream);
-    int rc = run_fused(h, d_trace);
+    int rc = run_fused(h, d_trace);  // (a traced run always takes the single-launch schedule)
     if (rc == AGP_OK) {
         int64_t m = n_items < cap_items ? n_items : cap_items;
         cudaError_t e = cudaMemcpyAsync(trace_out, d_trace, (size_t)m * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
@@ -1225,6 +1421,104 @@ int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead,
     build_queue(P, nt, nt, order, items);
     fuse_gram_items(P, nt, lead, items);
     return export_queue(items, items_out, cap);
+}
+
+int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t* items_out, int64_t cap, int32_t* seg_out, int32_t seg_cap) {
+    if (P < 0 || nt < 1 || width < 1) return AGP_ERR_ARG;
+    std::vector<int4> items;
+    std::vector<int> seg;
+    build_queue_hybrid(P, nt, nt, width, items, seg);
+    if (seg_out)
+        for (size_t e = 0; e < seg.size() && (int32_t)e < seg_cap; ++e) seg_out[e] = seg[e];
+    return export_queue(items, items_out, cap);
+}
+
+int agp_set_hybrid(agp_handle* h, int32_t mode, int32_t width, int32_t min_nt) {
+    if (!h || width < 1 || min_nt < 2) return AGP_ERR_ARG;
+    h->oz_mode = mode < 0 ? -1 : (mode != 0);
+    h->oz_width = width;
+    h->oz_min_nt = min_nt;
+    return AGP_OK;
+}
+
+int agp_hybrid_info(agp_handle* h, int32_t* active_out, int32_t* width_out, float* stage_ms4) {
+    if (!h) return AGP_ERR_ARG;
+    if (active_out) *active_out = h->uploaded ? (use_hybrid(h, 0) ? 1 : 0) : h->oz_mode;
+    if (width_out) *width_out = h->oz_width;
+    if (stage_ms4)
+        for (int e = 0; e < 4; ++e) stage_ms4[e] = h->hybrid_ms[e];
+    return AGP_OK;
+}
+
+// Experiment (profiles/r02_overlap_probe.txt): do the FP64 persistent kernel and the int8 update kernel share an SM well?
+// Times the single-launch FP64 step of the resident batch with `ctas_per_sm` CTAs per SM, `reps` int8 update launches
+// (block columns [c0, c0 + 4), writing into a scratch matrix) on a second stream, and both at once.
+// ms_out: {FP64 alone, int8 alone, FP64 with int8 next to it, int8 with FP64 next to it}.
+int agp_dev_overlap_probe(agp_handle* h, int32_t ctas_per_sm, int32_t variant, int32_t c0, int32_t reps, float* ms_out) {
+    if (!h || !ms_out || reps < 1) return AGP_ERR_ARG;
+    if (!h->uploaded || h->aug_identity || h->view.nt_total != h->view.nt || h->view.nt < c0 + 1 || c0 < 1)
+        return fail(h, AGP_ERR_STATE, "agp_dev_overlap_probe: needs a resident plain batch with more than c0 block columns");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    const BatchView& v = h->view;
+    const int P = h->P, ld = h->ld, nt = v.nt;
+    int rc;
+    if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld * ld)) != AGP_OK) return rc;
+    if ((rc = grow_device(h, &h->d_rscale, &h->cap_rscale, (size_t)P * ld * 16)) != AGP_OK) return rc;
+    if (!agp::make_ozaki_maps(h->d_S, ld, P, &h->ozmaps)) return fail(h, AGP_ERR_CUDA, "tensor map");
+    h->oz_S = h->d_S, h->oz_ld = ld, h->oz_P = P;
+    double* scratch = nullptr;
+    AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&scratch), (size_t)P * ld * ld * 8));
+    cudaStream_t s2;
+    cudaEvent_t a0, a1, b0, b1;
+    AGP_CUDA(h, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cudaEventCreate(&a0), cudaEventCreate(&a1), cudaEventCreate(&b0), cudaEventCreate(&b1);
+    AGP_CUDA(h, cudaMemsetAsync(h->d_S, 1, (size_t)agp::OZ_SLICES * P * ld * ld, h->stream));
+    AGP_CUDA(h, cudaMemsetAsync(scratch, 0, (size_t)P * ld * ld * 8, h->stream));
+    const int saved_ctas = h->ctas_per_sm, saved_mode = h->oz_mode;
+    h->ctas_per_sm = ctas_per_sm;
+    h->oz_mode = 0;
+    rc = run_fused(h);  // warm-up, queue build, row scales need the Gram diagonal
+    agp::launch_gramfill(v, P, 0, h->stream);
+    agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream);
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    int* d_err2 = nullptr;
+    AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_err2), 4));
+    AGP_CUDA(h, cudaMemset(d_err2, 0, 4));
+    agp::OzakiParams prm{scratch, v.mat_stride, ld, nt, P, h->d_rscale, c0, std::min(nt, c0 + 4), d_err2, h->wait_timeout_ns};
+    auto int8_burst = [&]() {
+        for (int r = 0; r < reps; ++r) agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, s2, variant);
+    };
+    for (int pass = 0; pass < 2 && rc == AGP_OK; ++pass) {
+        // alone
+        cudaEventRecord(a0, h->stream);
+        rc = run_fused(h);
+        cudaEventRecord(a1, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaEventRecord(b0, s2);
+        int8_burst();
+        cudaEventRecord(b1, s2);
+        cudaStreamSynchronize(s2);
+        cudaEventElapsedTime(&ms_out[0], a0, a1);
+        cudaEventElapsedTime(&ms_out[1], b0, b1);
+        // together
+        cudaEventRecord(b0, s2);
+        cudaEventRecord(a0, h->stream);
+        int8_burst();
+        if (rc == AGP_OK) rc = run_fused(h);
+        cudaEventRecord(a1, h->stream);
+        cudaEventRecord(b1, s2);
+        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(s2);
+        cudaEventElapsedTime(&ms_out[2], a0, a1);
+        cudaEventElapsedTime(&ms_out[3], b0, b1);
+    }
+    h->ctas_per_sm = saved_ctas;
+    h->oz_mode = saved_mode;
+    cudaFree(scratch);
+    cudaFree(d_err2);
+    cudaStreamDestroy(s2);
+    cudaEventDestroy(a0), cudaEventDestroy(a1), cudaEventDestroy(b0), cudaEventDestroy(b1);
+    return rc;
 }
 
 int agp_gram_items(agp_handle* h, int32_t* fused_out, int32_t* lead_out) {

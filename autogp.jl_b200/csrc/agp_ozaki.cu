@@ -25,14 +25,21 @@ namespace agp {
 namespace {
 
 constexpr int OZ_THREADS = 192;
-constexpr int OZ_NA = 6;                          // A ring slots
 constexpr uint32_t OZ_A_BYTES = 128 * 128;        // one digit plane of a 128-row tile, 128 bytes of k
 constexpr uint32_t OZ_BQ_BYTES = 64 * 128;        // one digit plane of the item's 64 B rows
 constexpr uint32_t OZ_B_BYTES = OZ_SLICES * OZ_BQ_BYTES;
-constexpr uint32_t OZ_OFF_A = 2 * OZ_B_BYTES;
-constexpr uint32_t OZ_OFF_BAR = OZ_OFF_A + OZ_NA * OZ_A_BYTES;
-constexpr int OZ_SMEM = (int)OZ_OFF_BAR + 256;
+// shared-memory image: NBUF chunk buffers for B, a ring of NA slots for A, the barriers
+template <int NA, int NBUF>
+struct OzLayout {
+    static constexpr uint32_t OFF_A = NBUF * OZ_B_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_A + NA * OZ_A_BYTES;
+    static constexpr int SMEM = (int)OFF_BAR + 256;
+};
+constexpr int OZ_NA = 6, OZ_NBUF = 2;   // the product kernel: one CTA per SM
+constexpr int OZ_SMEM = OzLayout<OZ_NA, OZ_NBUF>::SMEM;
 static_assert(OZ_SMEM <= 227 * 1024, "one CTA per SM");
+constexpr int OZ_NA_S = 3, OZ_NBUF_S = 1;  // small variant (experiments: co-residency with one CTA of the FP64 kernel)
+constexpr int OZ_SMEM_S = OzLayout<OZ_NA_S, OZ_NBUF_S>::SMEM;
 
 // K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups of 1024 bytes (stride byte offset), version 1
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
@@ -130,15 +137,16 @@ __device__ __forceinline__ OzItem oz_decode(int idx, int per_p, int c0, int nt) 
 
 }  // namespace
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const __grid_constant__ OzakiParams prm, const __grid_constant__ OzakiMaps maps) {
+template <int OZ_NA, int OZ_NBUF, int MINB>
+__global__ void __launch_bounds__(OZ_THREADS, MINB) agp_ozaki_update_kernel(const __grid_constant__ OzakiParams prm, const __grid_constant__ OzakiMaps maps) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
     unsigned char* Bs = oz_smem;
-    unsigned char* As = oz_smem + OZ_OFF_A;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + OZ_OFF_BAR);
+    unsigned char* As = oz_smem + OzLayout<OZ_NA, OZ_NBUF>::OFF_A;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + OzLayout<OZ_NA, OZ_NBUF>::OFF_BAR);
     uint64_t* a_full = bars;              // [OZ_NA]
     uint64_t* a_empty = bars + OZ_NA;     // [OZ_NA]
-    uint64_t* b_full = bars + 2 * OZ_NA;  // [2]
-    uint64_t* b_empty = b_full + 2;       // [2]
+    uint64_t* b_full = bars + 2 * OZ_NA;  // [OZ_NBUF]
+    uint64_t* b_empty = b_full + 2;       // [OZ_NBUF]
     uint64_t* acc_full = b_empty + 2;     // MMA -> epilogue
     uint64_t* acc_empty = acc_full + 1;   // epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const _
             mbar_init(a_full + s, 1);
             mbar_init(a_empty + s, 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < OZ_NBUF; ++s) {
             mbar_init(b_full + s, 1);
             mbar_init(b_empty + s, 1);
         }
@@ -182,8 +190,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const _
                 const OzItem it = oz_decode(idx, per_p, c0, nt);
                 const int brow = it.p * ld + it.k * 128 + it.h * 64, arow = it.p * ld + it.i * 128;
                 for (int c = 0; c < c0 && ok; ++c) {
-                    const int buf = bn & 1;
-                    if (bn >= 2) ok = oz_wait(b_empty + buf, ((bn >> 1) - 1) & 1, prm.err, prm.wait_timeout_ns);
+                    const int buf = bn % OZ_NBUF;
+                    if (bn >= OZ_NBUF) ok = oz_wait(b_empty + buf, ((bn / OZ_NBUF) - 1) & 1, prm.err, prm.wait_timeout_ns);
                     if (!ok) break;
                     mbar_expect_tx(b_full + buf, OZ_B_BYTES);
 #pragma unroll
@@ -224,10 +232,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const _
                 if (!ok) break;
                 tc_fence_after();
                 for (int c = 0; c < c0 && ok; ++c) {
-                    const int buf = bn & 1;
+                    const int buf = bn % OZ_NBUF;
                     {
                         OZ_T0();
-                        ok = oz_wait(b_full + buf, (bn >> 1) & 1, prm.err, prm.wait_timeout_ns);
+                        ok = oz_wait(b_full + buf, (bn / OZ_NBUF) & 1, prm.err, prm.wait_timeout_ns);
                         OZ_ACC(1);
                     }
                     if (!ok) break;
@@ -331,6 +339,402 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) agp_ozaki_update_kernel(const _
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
 }
 
+// ---- second generation: 128-column accumulators, two passes over the weight groups, optional CTA pairs ------------
+// An M128 N64 instruction re-reads its 4 KB A operand from shared memory every 32 tensor clocks: 6 KB per instruction at
+// 128 B/clk = 48 clocks (profiles/r02_i8_shape_probe.txt) — the N = 64 kernel above is bound by shared-memory operand
+// reads at 65 % of the int8 rate.  Here an accumulator is 128 columns wide, so only FOUR weight groups fit into TMEM and
+// a tile takes two passes over the contraction: groups 0..3 (10 digit-plane products per 128-deep chunk: 4 planes of
+// either operand), then groups 4..7 (26 products, all planes); each pass ends with its own recombination and
+// read-modify-write of the tile.  With G = 2 two CTAs of a cluster (an SM pair) work on the tiles (i, k) and (i + 1, k):
+// tcgen05.mma.cta_group::2 (M = 256) reads each CTA's own A rows and HALF of the 128 B rows from either CTA's shared
+// memory — 6 KB per 64 clocks and SM instead of 8 — issued by the leader CTA for both; the operands arrive by
+// cta_group::2 TMA loads that signal the leader's barriers, stages are released in both CTAs by multicast commits.
+template <int G>
+struct Oz2 {
+    static constexpr int NA = (G == 2) ? 8 : 6;    // A ring: one digit plane of 128 rows x 128 bytes per slot
+    static constexpr int NB = (G == 2) ? 10 : 7;   // B ring: one digit plane of 128 / G rows per slot
+    static constexpr uint32_t A_BYTES = 128 * 128;
+    static constexpr uint32_t B_BYTES = 128 * 128 / G;
+    static constexpr uint32_t OFF_B = NA * A_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_B + NB * B_BYTES;
+    static constexpr int SMEM = (int)OFF_BAR + 512;
+    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | (((128u * G) >> 4) << 24);
+};
+static_assert(Oz2<1>::SMEM <= 227 * 1024 && Oz2<2>::SMEM <= 227 * 1024, "one CTA per SM");
+
+template <int G>
+__device__ __forceinline__ void oz2_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    if constexpr (G == 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(da), "l"(db), "r"(Oz2<1>::IDESC), "r"(accumulate), "r"(0u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(da), "l"(db), "r"(Oz2<2>::IDESC), "r"(accumulate), "r"(0u)
+            : "memory");
+    }
+}
+template <int G>
+__device__ __forceinline__ void oz2_commit(uint64_t* bar) {
+    if constexpr (G == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        // arrives on the barrier at this offset in BOTH CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    }
+}
+// TMA tensor load whose completion bytes go to the LEADER CTA's barrier (cta_group::2); leader_bar is a shared::cluster address
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tensor_map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(tensor_map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// one lane of a converged warp (the MMA warp runs its control flow on all 32 lanes so that descriptors and barrier
+// addresses stay warp-uniform — uniform registers, no per-thread election loop around every tcgen05 instruction)
+__device__ __forceinline__ uint32_t oz_elect_one() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 %%rx;\n"
+        ".reg .pred %%px;\n"
+        "     elect.sync %%rx|%%px, %2;\n"
+        "@%%px mov.s32 %1, 1;\n"
+        "     mov.s32 %0, %%rx;\n"
+        "}\n"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFF));
+    return pred;
+}
+
+struct Oz2Item {
+    int p, i, k;
+    bool valid;
+};
+// units of one launch (a unit = one tile, or with G = 2 the tiles (i, k) and (i + 1, k) of a CTA pair): particle-major,
+// then block column, then tile rows
+template <int G>
+__device__ __forceinline__ int oz2_units_per_particle(int c0, int c1, int nt) {
+    int n = 0;
+    for (int k = c0; k < c1; ++k) n += (nt - k + G - 1) / G;
+    return n;
+}
+template <int G>
+__device__ __forceinline__ Oz2Item oz2_decode(int unit, int per_p, int c0, int nt, int rank) {
+    Oz2Item it;
+    it.p = unit / per_p;
+    int r = unit - it.p * per_p;
+    int k = c0;
+    for (;;) {
+        const int cnt = (nt - k + G - 1) / G;
+        if (r < cnt) break;
+        r -= cnt;
+        ++k;
+    }
+    it.k = k;
+    it.i = k + r * G + rank;
+    it.valid = it.i < nt;
+    if (!it.valid) it.i = nt - 1;  // odd number of tile rows: the pair's second CTA repeats the last tile and stores nothing
+    return it;
+}
+
+// the MMA instructions of one 128-deep chunk of one pass; PASS 0: weight groups 0..3, PASS 1: groups 4..7
+template <int G, int PASS>
+__device__ __forceinline__ bool oz2_chunk(uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty, uint64_t da0, uint64_t db0,
+                                          uint32_t tmem, uint32_t first, int& a_slot, int& a_par, int& b_slot, int& b_par, const OzakiParams& prm
+#if OZ_STATS
+                                          , long long* oz_acc_
+#endif
+                                          ) {
+    constexpr int NA = Oz2<G>::NA, NB = Oz2<G>::NB;
+    constexpr int PMAX = PASS ? 7 : 3, GMIN = PASS ? 4 : 0;
+    // ring positions of this chunk's B planes: plane q sits in slot (b_slot + q) mod NB
+    uint64_t dbq[PMAX + 1];
+    int bs[PMAX + 1];
+#pragma unroll
+    for (int q = 0; q <= PMAX; ++q) {
+        int s = b_slot + q;
+        if (s >= NB) s -= NB;
+        bs[q] = s;
+        dbq[q] = db0 + (uint64_t)(s * (int)(Oz2<G>::B_BYTES >> 4));
+    }
+#pragma unroll
+    for (int p = PMAX; p >= 0; --p) {
+        const int qn = PMAX - p;  // the plane of B that is new at this step
+        {
+            const int par = (b_slot + qn >= NB) ? (b_par ^ 1) : b_par;
+            OZ_T0();
+            if (!oz_wait(b_full + bs[qn], par, prm.err, prm.wait_timeout_ns)) return false;
+            OZ_ACC(1);
+        }
+        {
+            OZ_T0();
+            if (!oz_wait(a_full + a_slot, a_par, prm.err, prm.wait_timeout_ns)) return false;
+            OZ_ACC(2);
+        }
+        tc_fence_after();
+        const uint64_t da = da0 + (uint64_t)(a_slot * (int)(Oz2<G>::A_BYTES >> 4));
+        if (oz_elect_one()) {
+#pragma unroll
+            for (int q = (GMIN - p > 0 ? GMIN - p : 0); q <= PMAX - p; ++q) {
+                const uint32_t d = tmem + (uint32_t)((p + q) & 3) * 128u;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) oz2_mma<G>(d, da + 2 * k4, dbq[q] + 2 * k4, (q == 0 && k4 == 0) ? first : 1u);
+            }
+            oz2_commit<G>(a_empty + a_slot);
+            // planes of B whose last product was in this step
+            if (PASS == 1 && p >= 1 && p <= 4) oz2_commit<G>(b_empty + bs[4 - p]);
+            if (p == 0) {
+#pragma unroll
+                for (int q = (PASS ? 4 : 0); q <= PMAX; ++q) oz2_commit<G>(b_empty + bs[q]);
+            }
+        }
+        __syncwarp();
+        if (++a_slot == NA) a_slot = 0, a_par ^= 1;
+    }
+    b_slot += PMAX + 1;
+#pragma unroll
+    for (int w = 0; w < 2; ++w)  // PMAX + 1 may exceed the ring: up to two trips
+        if (b_slot >= NB) b_slot -= NB, b_par ^= 1;
+    return true;
+}
+
+constexpr int OZ2_THREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+template <int G>
+__global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const __grid_constant__ OzakiParams prm, const __grid_constant__ OzakiMaps maps) {
+    using Lay = Oz2<G>;
+    constexpr int NA = Lay::NA, NB = Lay::NB;
+    extern __shared__ __align__(1024) unsigned char oz_smem[];
+    unsigned char* As = oz_smem;
+    unsigned char* Bs = oz_smem + Lay::OFF_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + Lay::OFF_BAR);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + NA;
+    uint64_t* b_full = a_empty + NA;
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* acc_full = b_empty + NB;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = prm.c0, nt = prm.nt, P = prm.P, ld = prm.ld;
+    uint32_t rank = 0;
+    if constexpr (G == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    const int per_p = oz2_units_per_particle<G>(c0, prm.c1, nt);
+    const int n_units = per_p * P;
+    const int unit0 = blockIdx.x / G, unit_stride = gridDim.x / G;
+
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b) : "memory");
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(a_full + s, 1);
+            mbar_init(a_empty + s, 1);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(b_full + s, 1);
+            mbar_init(b_empty + s, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8 * G);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        if constexpr (G == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+        }
+    }
+    tc_fence_before();
+    if constexpr (G == 2) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer (either CTA loads its own A rows and its share of the B rows) ------------------------
+            int a_slot = 0, a_n = 0, b_slot = 0, b_n = 0;  // ring position, completed trips round the ring
+            bool ok = true;
+            for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
+                const Oz2Item it = oz2_decode<G>(unit, per_p, c0, nt, (int)rank);
+                const int arow = it.p * ld + it.i * 128, brow = it.p * ld + it.k * 128 + (int)rank * (128 / G);
+                for (int pass = 0; pass < 2 && ok; ++pass) {
+                    const int pmax = pass ? 7 : 3;
+                    for (int c = 0; c < c0 && ok; ++c) {
+                        for (int p = pmax; p >= 0; --p) {
+                            const int q = pmax - p;
+                            if (b_n >= 1) ok = oz_wait(b_empty + b_slot, (b_n - 1) & 1, prm.err, prm.wait_timeout_ns);
+                            if (!ok) break;
+                            if constexpr (G == 1) {
+                                mbar_expect_tx(b_full + b_slot, Lay::B_BYTES);
+                                tma_load_2d(Bs + b_slot * Lay::B_BYTES, &maps.a, c * 128, q * P * ld + brow, b_full + b_slot);
+                            } else {
+                                if (rank == 0) mbar_expect_tx(b_full + b_slot, 2 * Lay::B_BYTES);
+                                tma_load_2d_pair(Bs + b_slot * Lay::B_BYTES, &maps.b, c * 128, q * P * ld + brow, map_to_cta(smem_u32(b_full + b_slot), 0));
+                            }
+                            if (++b_slot == NB) b_slot = 0, ++b_n;
+                            if (a_n >= 1) ok = oz_wait(a_empty + a_slot, (a_n - 1) & 1, prm.err, prm.wait_timeout_ns);
+                            if (!ok) break;
+                            if constexpr (G == 1) {
+                                mbar_expect_tx(a_full + a_slot, Lay::A_BYTES);
+                                tma_load_2d(As + a_slot * Lay::A_BYTES, &maps.a, c * 128, p * P * ld + arow, a_full + a_slot);
+                            } else {
+                                if (rank == 0) mbar_expect_tx(a_full + a_slot, 2 * Lay::A_BYTES);
+                                tma_load_2d_pair(As + a_slot * Lay::A_BYTES, &maps.a, c * 128, p * P * ld + arow, map_to_cta(smem_u32(a_full + a_slot), 0));
+                            }
+                            if (++a_slot == NA) a_slot = 0, ++a_n;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ---- MMA issuer (the leader CTA issues for the pair; all 32 lanes run the control flow, one issues) ------------------------------------------------
+            int a_slot = 0, a_par = 0, b_slot = 0, b_par = 0, use = 0;
+            bool ok = true;
+            const uint64_t da0 = oz_desc(smem_u32(As)), db0 = oz_desc(smem_u32(Bs));
+#if OZ_STATS
+            long long oz_acc_[4] = {0, 0, 0, 0};
+            const long long t_all_ = clock64();
+#define OZ_EXTRA , oz_acc_
+#else
+#define OZ_EXTRA
+#endif
+            for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
+                for (int pass = 0; pass < 2 && ok; ++pass, ++use) {
+                    {
+                        OZ_T0();
+                        if (use >= 1) ok = oz_wait(acc_empty, (use - 1) & 1, prm.err, prm.wait_timeout_ns);  // the previous sums have left TMEM
+                        OZ_ACC(3);
+                    }
+                    if (!ok) break;
+                    tc_fence_after();
+                    for (int c = 0; c < c0 && ok; ++c) {
+                        const uint32_t first = (c == 0) ? 0u : 1u;
+                        ok = pass ? oz2_chunk<G, 1>(a_full, a_empty, b_full, b_empty, da0, db0, tmem, first, a_slot, a_par, b_slot, b_par, prm OZ_EXTRA)
+                                  : oz2_chunk<G, 0>(a_full, a_empty, b_full, b_empty, da0, db0, tmem, first, a_slot, a_par, b_slot, b_par, prm OZ_EXTRA);
+                    }
+                    if (ok && oz_elect_one()) oz2_commit<G>(acc_full);
+                    __syncwarp();
+                }
+            }
+#if OZ_STATS
+            if (lane == 0) {
+                atomicAdd((unsigned long long*)&oz_stats[0], (unsigned long long)(clock64() - t_all_));
+                for (int e = 1; e < 4; ++e) atomicAdd((unsigned long long*)&oz_stats[e], (unsigned long long)oz_acc_[e]);
+                atomicAdd((unsigned long long*)&oz_stats[5], (unsigned long long)(use / 2));
+            }
+#endif
+        }
+    } else {
+        // ---- epilogue: eight warps, thread = 64 columns of one row of this CTA's 128 x 128 tile -------------------
+        // The tile row segment is fetched into registers while the tensor pipe works on pass 0, receives the high-order
+        // groups after pass 0 and the low-order groups after pass 1, and is stored once.  (Reading the sums out of TMEM
+        // is the floor of an epilogue: 256 KB per pass at 64 B/clk.)
+        const int ew = warp & 3;          // the TMEM lanes [32 ew, 32 ew + 32) are the ones this warp may read
+        const int hh = (warp - 2) >> 2;   // column half
+        const int row = ew * 32 + lane;
+        const uint32_t acc_empty_leader = (G == 2) ? map_to_cta(smem_u32(acc_empty), 0) : 0u;
+        int use = 0;
+        bool ok = true;
+        for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
+            const Oz2Item it = oz2_decode<G>(unit, per_p, c0, nt, (int)rank);
+            const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
+            const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + hh * 64);
+            double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + hh * 64;
+            const int cmax = !it.valid ? -1 : (it.i == it.k) ? row - hh * 64 : 63;  // diagonal tile: the strict upper triangle keeps its Gram values
+            double2 tv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const double w = pass ? 0x1p-61 : 0x1p-33;  // the last group of the pass carries 2^(-12 - 7 g), g = 3 / 7
+                ok = ok && oz_wait(acc_full, (use + pass) & 1, prm.err, prm.wait_timeout_ns);
+                if (!ok) break;
+                tc_fence_after();
+#if OZ_STATS
+                const long long t_epi_ = clock64();
+#endif
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb) {
+                    uint32_t a[4][8];
+                    const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(hh * 64 + cb * 8);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)g * 128u, a[g]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        // exact in int64: |sum| < 2^31 per group
+                        const long long t = ((long long)(int)a[0][j] << 21) + ((long long)(int)a[1][j] << 14) + ((long long)(int)a[2][j] << 7) + (long long)(int)a[3][j];
+                        const double scj = __ldg(sc + 2 * (cb * 8 + j));
+                        const double v = ((double)t * w) * (sr * scj);
+                        if (j & 1) tv[cb * 4 + (j >> 1)].y -= v;
+                        else tv[cb * 4 + (j >> 1)].x -= v;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (G == 1) mbar_arrive(acc_empty);
+                    else mbar_arrive_cluster(acc_empty_leader);
+                }
+#if OZ_STATS
+                if (tid == 64 && rank == 0) atomicAdd((unsigned long long*)&oz_stats[4], (unsigned long long)(clock64() - t_epi_));
+#endif
+            }
+            use += 2;
+            if (!ok) break;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+                if (cb * 8 + 7 <= cmax) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) reinterpret_cast<double2*>(Trow + cb * 8)[e] = tv[cb * 4 + e];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (cb * 8 + j <= cmax) Trow[cb * 8 + j] = (j & 1) ? tv[cb * 4 + (j >> 1)].y : tv[cb * 4 + (j >> 1)].x;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    if constexpr (G == 2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 0) {
+        if constexpr (G == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
+    }
+}
+
 // ---- row scales -----------------------------------------------------------------------------------
 __global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P, double* __restrict__ rscale) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,16 +802,41 @@ void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, i
     agp_ozaki_slice_kernel<<<grid, 256, 0, s>>>(L, mat_stride, ld, P, rscale, S, c0, c1 - c0, r0);
 }
 
-void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s) {
+void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant) {
     long long per_p = 0;
     for (int k = prm.c0; k < prm.c1; ++k) per_p += 2 * (prm.nt - k);
     const long long n_items = per_p * prm.P;
     if (n_items <= 0 || prm.c0 <= 0) return;
-    if (ctas > n_items) ctas = (int)n_items;
-    agp_ozaki_update_kernel<<<ctas, OZ_THREADS, OZ_SMEM, s>>>(prm, maps);
+    if (variant < 2 && ctas > n_items) ctas = (int)n_items;
+    if (variant == 2) {
+        agp_ozaki_update2_kernel<1><<<ctas, OZ2_THREADS, Oz2<1>::SMEM, s>>>(prm, maps);
+    } else if (variant == 3) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ctas & ~1), 1, 1);
+        cfg.blockDim = dim3(OZ2_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = Oz2<2>::SMEM;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, agp_ozaki_update2_kernel<2>, prm, maps);
+    } else if (variant == 1) agp_ozaki_update_kernel<OZ_NA_S, OZ_NBUF_S, 2><<<ctas, OZ_THREADS, OZ_SMEM_S, s>>>(prm, maps);
+    else agp_ozaki_update_kernel<OZ_NA, OZ_NBUF, 1><<<ctas, OZ_THREADS, OZ_SMEM, s>>>(prm, maps);
 }
 
-cudaError_t configure_ozaki() { return cudaFuncSetAttribute(agp_ozaki_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM); }
+cudaError_t configure_ozaki() {
+    cudaError_t e = cudaFuncSetAttribute(agp_ozaki_update_kernel<OZ_NA, OZ_NBUF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(agp_ozaki_update_kernel<OZ_NA_S, OZ_NBUF_S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_S);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(agp_ozaki_update2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2<1>::SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(agp_ozaki_update2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2<2>::SMEM);
+}
 
 bool make_ozaki_maps(int8_t* S, int ld, int P, OzakiMaps* out) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

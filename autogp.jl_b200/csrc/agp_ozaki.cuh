@@ -38,7 +38,8 @@ void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P,
 void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
                         cudaStream_t s);
 // the contraction over block columns [0, c0) of every lower tile of block columns [c0, c1), subtracted in place
-void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s);
+// variant 0: the product kernel (one CTA per SM); 1: small shared-memory image (experiments)
+void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant = 0);
 bool make_ozaki_maps(int8_t* S, int ld, int P, OzakiMaps* out);
 cudaError_t configure_ozaki();
 

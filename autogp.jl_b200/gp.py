@@ -475,6 +475,20 @@ class Engine:
         self._check(self._lib.agp_gram_items(self._h, C.byref(a), C.byref(b)))
         return bool(a.value), int(b.value)
 
+    def set_hybrid(self, mode: int = -1, width: int = 4, min_nt: int = 8) -> None:
+        """Hybrid factorisation of plain LML runs (agp_set_hybrid): the long contractions as exact int8 digit-plane
+        products on tcgen05, super-columns of `width` block columns; mode -1 = from `min_nt` block columns on, 0 = never,
+        1 = whenever the batch has more than `width` block columns."""
+        self._check(self._lib.agp_set_hybrid(self._h, int(mode), int(width), int(min_nt)))
+
+    def hybrid_info(self) -> Tuple[bool, int, Tuple[float, float, float, float]]:
+        """(the resident batch takes the hybrid schedule, super-column width, stage times of the last stage_times()
+        call on a hybrid run: Gram + row scales, persistent-kernel segments, int8 updates, digit planes) in ms."""
+        a, w = C.c_int32(), C.c_int32()
+        ms = (C.c_float * 4)()
+        self._check(self._lib.agp_hybrid_info(self._h, C.byref(a), C.byref(w), ms))
+        return a.value > 0, int(w.value), tuple(float(x) for x in ms)
+
     def synchronize(self) -> None:
         self._check(self._lib.agp_synchronize(self._h))
 

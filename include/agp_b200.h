@@ -258,6 +258,32 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
 /* ... and of agp_predict_marginals_batch (first_row = 0, only the diagonal tiles of the trailing block). */
 int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32_t* items_out, int64_t cap);
 
+/* Hybrid factorisation of plain LML runs (csrc/agp_ozaki.cu).  From `min_nt` block columns on (default 8: n >= 897) the
+ * block columns are grouped into super-columns of `width` (default 4); before a super-column is factored, the contraction
+ * of its tiles over ALL earlier block columns — the long sums of dpotrf's trailing update, which is what PDMats runs for
+ * the mvnormal of src/Model.jl:136 — is computed by exact int8 digit-plane products on the 5th-generation tensor cores
+ * (tcgen05.mma kind::i8, int32 accumulators in TMEM; tcgen05 has no f64 kind), the persistent FP64 kernel then does the
+ * contractions inside the super-column, POTF2 and the panel solves.  Rows are scaled by a power of two >= sqrt(K_ii)
+ * (an a-priori bound on |L_ij|) and cut into eight signed 7-bit digits; products below 2^-61 of the row scales are
+ * dropped: the contraction error is of the order of FP64 accumulation (measured: tests/test_gpu_parity.py).
+ * mode: -1 = by size (default), 0 = never (every run takes the single-launch FP64 schedule), 1 = whenever the batch has
+ * more than `width` block columns.  Environment: AGP_OZAKI, AGP_OZ_W, AGP_OZ_MIN_NT. */
+int agp_set_hybrid(agp_handle* h, int32_t mode, int32_t width, int32_t min_nt);
+/* Diagnostics: whether agp_lml_run takes the hybrid schedule for the resident batch (without one: the mode), the
+ * super-column width, and the per-stage device times (ms) of the last agp_lml_stage_times call on a hybrid run:
+ * {Gram fill + row scales, persistent-kernel segments, int8 update launches, digit-plane launches}.  Any pointer may be NULL. */
+int agp_hybrid_info(agp_handle* h, int32_t* active_out, int32_t* width_out, float* stage_ms4);
+/* The hybrid schedule as agp_queue_build exports it, plus the first item of every super-column's segment (seg_out
+ * receives up to seg_cap entries: one per segment and the total item count).  Contractions over block columns below a
+ * segment's first one are the int8 kernel's, the items start at j0 = that column. */
+int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t* items_out, int64_t cap, int32_t* seg_out, int32_t seg_cap);
+
+/* Experiment behind DESIGN.md's co-residency note: the single-launch FP64 step of the resident batch with `ctas_per_sm`
+ * CTAs per SM, `reps` int8 update launches over block columns [c0, c0 + 4) on a second stream (variant 0: the product
+ * kernel, 1: the small shared-memory image that fits next to one FP64 CTA), alone and at the same time.
+ * ms_out[4] = {FP64 alone, int8 alone, FP64 next to int8, int8 next to FP64}. */
+int agp_dev_overlap_probe(agp_handle* h, int32_t ctas_per_sm, int32_t variant, int32_t c0, int32_t reps, float* ms_out);
+
 /* Diagnostics: one traced run of the resident batch.  trace_out receives 8 int64 per work item
  * (queue order): globaltimer ns at {pop, producers ready, contraction done, Gram done, L_kk
  * ready, item done}, then SM id and CTA id.  Returns the item count (trace_out may be NULL to

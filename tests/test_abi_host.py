@@ -129,7 +129,7 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False):
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False, segments=None, width=0):
     """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
     counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
     every tile an item reads must be final, and the items must tile every contraction exactly.
@@ -154,7 +154,24 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                 final[(p, i, j)] = 2
         counters[fdone(p)] = first_row
     covered, n_diag, stored = {}, {}, set()
-    for x, p, k, i, f4, f5, flag, need in buf.tolist():
+    seg_first = {int(a): s_ for s_, a in enumerate(segments[:-1])} if segments is not None else {}
+    seg_base = {}   # (p, i, k, h) -> block columns [0, base) were contracted by the int8 update kernel
+    for idx_, (x, p, k, i, f4, f5, flag, need) in enumerate(buf.tolist()):
+        if idx_ in seg_first and seg_first[idx_] > 0:
+            # hybrid schedule: a new launch starts here.  Between the launches the int8 kernel brings every lower tile of
+            # the super-column's block columns to coverage c0 — everything it reads must be final, nothing it writes
+            # may have been touched, and all earlier items are complete (kernel boundary).
+            c0_ = seg_first[idx_] * width
+            for pp in range(P):
+                assert counters[fdone(pp)] == c0_
+                for ii in range(c0_, nt):
+                    assert all(final.get((pp, ii, j), 0) == 2 for j in range(c0_)), (pp, ii)
+                    for kk in range(c0_, min(nt, c0_ + width)):
+                        if kk <= ii:
+                            for hh in (0, 1):
+                                assert (pp, ii, kk, hh) not in covered
+                                covered[(pp, ii, kk, hh)] = c0_
+                                seg_base[(pp, ii, kk, hh)] = c0_
         t, h, partial, yinit = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL), bool(x & YINIT)
         j0, j1, need_k, need_i = f4 & 0xFFFF, f4 >> 16, f5 & 0xFFFF, f5 >> 16
         assert 0 <= p < P and 0 <= k < nt_total
@@ -169,6 +186,8 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
             continue
         if t == POTF2:
             assert k < nt and counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
+            if segments is not None and k > 0:   # the diagonal tile is complete: DIAG items or the int8 update
+                assert all(covered.get((p, k, k, hh)) == k for hh in (0, 1)), (p, k)
             assert counters[fdone(p)] == k          # block columns are factored in order
             counters[fdone(p)] += 1
             continue
@@ -187,7 +206,7 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                 assert flag == gflag(p, i, k, h) and need == 1 and counters[flag] == 1
         elif flag >= 0:
             assert flag == (diagu(p, k) if t == DIAG else ppre(p, i)) and counters[flag] >= need
-        if not first_touch:
+        if not first_touch and (p, i, k, h) not in seg_base:
             assert (flag >= 0) == (j0 > start)
         # what it reads is final
         for j in range(j0, j1):
@@ -235,6 +254,23 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     buf = np.zeros((n_items, 8), dtype=np.int32)
     assert lib.agp_queue_build(P, nt, order, buf.ctypes.data_as(C.POINTER(C.c_int32)), n_items) == n_items
     _replay_queue(buf, P, nt, nt, 0)
+
+
+@pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (5, 16, 4), (2, 16, 2), (2, 23, 4), (1, 9, 3)])
+def test_hybrid_schedule_replay(P, nt, width):
+    """The super-column schedule of the hybrid factorisation (agp_queue_build_hybrid): every segment is a launch of
+    its own, the int8 update between two launches covers block columns [0, c0) of the next super-column's tiles, and the
+    items inside a segment obey the same wait rules as the single-launch schedule."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    i32p = C.POINTER(C.c_int32)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, None, 0, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
+    assert lib.agp_queue_build_hybrid(P, nt, width, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert seg[0] == 0 and seg[-1] == n_items and np.all(np.diff(seg) > 0)
+    _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width)
 
 
 @pytest.mark.parametrize("order", [0, 2, 3])

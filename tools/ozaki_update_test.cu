@@ -98,8 +98,10 @@ int main(int argc, char** argv) {
             printf("tensor map encode failed\n");
             return 1;
         }
+        for (int variant : {0, 2, 3}) {
+        CK(cudaMemcpy(dL, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
         agp::OzakiParams prm{dL, ms, ld, nt, P, dR, c0, c1, d_err, 2000000000ull};
-        agp::launch_ozaki_update(prm, maps, sms, 0);
+        agp::launch_ozaki_update(prm, maps, sms, 0, variant);
         CK(cudaDeviceSynchronize());
         int err = 0;
         CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
@@ -128,9 +130,10 @@ int main(int argc, char** argv) {
                     worst = fmax(worst, fabs((double)((long double)out[o] - ref)));
                     worst_fp64 = fmax(worst_fp64, fabs((double)((long double)(T[o] - s64) - ref)));
                 }
-        printf("(2) update, P = %d, nt = %d, block columns [%d, %d), depth %d: err flag %d, max |T| = %.3f, max error int8 path = %.3e, "
+        printf("(2) variant %d: update, P = %d, nt = %d, block columns [%d, %d), depth %d: err flag %d, max |T| = %.3f, max error int8 path = %.3e, "
                "FP64 fma chain = %.3e; %lld entries outside the target region changed\n",
-               P, nt, c0, c1, c0 * 128, err, maxres, worst, worst_fp64, touched_wrong);
+               variant, P, nt, c0, c1, c0 * 128, err, maxres, worst, worst_fp64, touched_wrong);
+        }
         cudaFree(dL);
         cudaFree(dR);
         cudaFree(dS);
@@ -158,14 +161,15 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int W : {2, 4}) {
+        for (int variant : {0, 2, 3})
+        for (int W : {4}) {
             double total_ms = 0, total_slice = 0, total_flop = 0;
             for (int c0 = W; c0 < nt; c0 += W) {
                 const int c1 = (c0 + W < nt) ? c0 + W : nt;
                 agp::OzakiParams prm{dL, ms, ld, nt, P, dR, c0, c1, d_err, 2000000000ull};
-                agp::launch_ozaki_update(prm, maps, sms, 0);  // warm
+                agp::launch_ozaki_update(prm, maps, sms, 0, variant);  // warm
                 CK(cudaEventRecord(e0));
-                agp::launch_ozaki_update(prm, maps, sms, 0);
+                agp::launch_ozaki_update(prm, maps, sms, 0, variant);
                 CK(cudaEventRecord(e1));
                 CK(cudaDeviceSynchronize());
                 float t = 0;
@@ -186,20 +190,21 @@ int main(int argc, char** argv) {
                 total_slice += ts;
                 total_flop += flop;
             }
-            printf("(3) P = %d, n = %d, W = %d: all updates %.3f ms (%.1f FP64-equivalent TFLOP/s), all slicing %.3f ms\n", P, ld, W, total_ms,
+            printf("(3) variant %d: P = %d, n = %d, W = %d: all updates %.3f ms (%.1f FP64-equivalent TFLOP/s), all slicing %.3f ms\n", variant, P, ld, W, total_ms,
                    total_flop / (total_ms * 1e-3) * 1e-12, total_slice);
         }
 #if OZ_STATS
-        for (int c0 : {2, 8, 14}) {
+        for (int variant : {0, 2, 3})
+        for (int c0 : {4, 8, 12}) {
             long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st[8];
             CK(cudaMemcpyToSymbol(agp::oz_stats, z, sizeof(z)));
-            agp::OzakiParams prm{dL, ms, ld, nt, P, dR, c0, c0 + 2, d_err, 2000000000ull};
-            agp::launch_ozaki_update(prm, maps, sms, 0);
+            agp::OzakiParams prm{dL, ms, ld, nt, P, dR, c0, c0 + 4, d_err, 2000000000ull};
+            agp::launch_ozaki_update(prm, maps, sms, 0, variant);
             CK(cudaDeviceSynchronize());
             CK(cudaMemcpyFromSymbol(st, agp::oz_stats, sizeof(st)));
             const double it = (double)st[5];
-            printf("    stats c0 = %d: per item (clocks): MMA thread total %.0f, wait B %.0f, wait A %.0f, wait TMEM free %.0f; epilogue %.0f; ideal tensor time %d\n", c0,
-                   st[0] / it, st[1] / it, st[2] / it, st[3] / it, st[4] / it, c0 * 144 * 32);
+            printf("    stats variant %d c0 = %d: per unit (clocks): MMA thread total %.0f, wait B %.0f, wait A %.0f, wait TMEM free %.0f; epilogue (all passes) %.0f; ideal tensor time %d\n", variant, c0,
+                   st[0] / it, st[1] / it, st[2] / it, st[3] / it, st[4] / it, c0 * 144 * (variant ? 64 : 32));
         }
 #endif
         int err = 0;

@@ -77,8 +77,9 @@ struct agp_handle {
     // (one launch per super-column), the persistent DMMA kernel then factors the super-column (contractions inside it
     // only).  Plain LML runs from `oz_min_nt` block columns on.
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
-    int oz_width = 4;      // AGP_OZ_W
-    int oz_min_nt = 8;     // AGP_OZ_MIN_NT
+    int oz_width = 0;      // AGP_OZ_W (0 = by size)
+    int oz_min_nt = 16;    // AGP_OZ_MIN_NT
+    bool oz_ride = false;  // AGP_OZ_RIDE: Gram units as items of the segments' queues (measured slower, see run_hybrid)
     int oz_variant = 3;    // AGP_OZ_KERNEL: 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one pass
     bool force_plain = false;  // diagnostics that index the single-launch schedule (agp_lml_trace)
     int8_t* d_S = nullptr;     size_t cap_S = 0;       // digit planes [8][P][ld][ld]
@@ -189,8 +190,9 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_FUSE_GRAM")) h->fuse_gram = atoi(e) < 0 ? -1 : atoi(e) != 0;
     if (const char* e = getenv("AGP_GRAM_LEAD")) h->gram_lead = atoi(e) > 0 ? atoi(e) : 0;
     if (const char* e = getenv("AGP_OZAKI")) h->oz_mode = atoi(e) < 0 ? -1 : atoi(e) != 0;
-    if (const char* e = getenv("AGP_OZ_W")) h->oz_width = std::max(1, atoi(e));
+    if (const char* e = getenv("AGP_OZ_W")) h->oz_width = std::max(0, atoi(e));
     if (const char* e = getenv("AGP_OZ_MIN_NT")) h->oz_min_nt = std::max(2, atoi(e));
+    if (const char* e = getenv("AGP_OZ_RIDE")) h->oz_ride = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 0 || atoi(e) == 2) ? atoi(e) : 3;
     if (agp::configure_ozaki() != cudaSuccess) {
         cudaGetLastError();
@@ -654,16 +656,50 @@ static void build_queue(int P, int nt, int nt_stride, int order, std::vector<int
 // Inside a segment the order is the look-ahead order of the single-launch schedule (panels of tile row k + 1 first,
 // DIAG(k + 1) / POTF2(k + 1) interleaved into the bulk of column k).  The dependency counters are NOT reset between
 // the segments (rowdone / fdone / diagu keep counting), only the queue head is.
-static void build_queue_hybrid(int P, int nt, int nt_stride, int W, std::vector<int4>& items, std::vector<int>& seg) {
+static int gram_flag(int P, int nt_stride, int p, int i, int k, int hh);
+static void fuse_gram_items(int P, int nt_stride, int lead, std::vector<int4>& items);
+
+// gram_lead > 0: the Gram units ride in the queue as well (ITEM_GRAM).  Segment 0 carries the units of its own tiles `lead`
+// items ahead of their first readers (fuse_gram_items, as in the single-launch schedule), the diagonal tiles of ALL later
+// super-columns (the row scales of the digit planes are read off the Gram diagonal right after segment 0) and the other
+// tiles of super-column 1; segment s >= 1 carries the tiles of super-column s + 1.  Nothing in a segment reads the units
+// that ride for a later super-column, so they need no flag wait — the launch boundary orders them — and they are dealt
+// out behind the POTF2 items of the segment's block columns, where the CTAs that hold no POTF2 item would otherwise
+// spin on the factor of the diagonal tile.
+static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lead, std::vector<int4>& items, std::vector<int>& seg) {
     items.clear();
     seg.clear();
-    TileState b(P, nt, nt_stride, &items);
+    std::vector<int4> cur;
+    TileState b(P, nt, nt_stride, &cur);
     double pos_diag = 1.0 / 3, pos_potf2 = 0.5;
     if (const char* e = getenv("AGP_OZ_POS")) sscanf(e, "%lf,%lf", &pos_diag, &pos_potf2);  // developer A/B
     struct T { int p, i, k; };
+    auto gram_unit = [&](std::vector<int4>& out, int p, int i, int k, int hh) {
+        out.push_back(make_int4(agp::ITEM_GRAM | (hh << 8), p, k, i));
+        out.push_back(make_int4(0, 0, gram_flag(P, nt_stride, p, i, k, i == k ? 0 : hh), 0));
+    };
     for (int c0 = 0; c0 < nt; c0 += W) {
         const int c1 = std::min(nt, c0 + W);
-        seg.push_back((int)(items.size() / 2));
+        cur.clear();
+        std::vector<int4> ride;  // Gram units of later super-columns that ride in this segment
+        if (gram_lead > 0 && c1 < nt) {
+            if (c0 == 0)
+                for (int c = c1; c < nt; ++c)
+                    for (int p = 0; p < P; ++p)
+                        for (int hh = 0; hh < 2; ++hh) gram_unit(ride, p, c, c, hh);
+            for (int k = c1; k < std::min(nt, c1 + W); ++k)
+                for (int i = k + 1; i < nt; ++i)
+                    for (int p = 0; p < P; ++p)
+                        for (int hh = 0; hh < 2; ++hh) gram_unit(ride, p, i, k, hh);
+        }
+        size_t ride_pos = 0;
+        auto deal = [&](int j) {  // behind the POTF2 items of the segment's j-th block column
+            const size_t hi = (ride.size() / 2) * (size_t)(j + 1) / (size_t)(c1 - c0);
+            for (; ride_pos < hi; ++ride_pos) {
+                cur.push_back(ride[2 * ride_pos]);
+                cur.push_back(ride[2 * ride_pos + 1]);
+            }
+        };
         if (c0 == 0) {
             for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);  // starts the forward solve: y_0 = xs
         } else {
@@ -672,6 +708,7 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, std::vector<
                     for (int i = k; i < nt; ++i) b.cov[((size_t)p * nt + i) * nt + k] = c0;  // the int8 update
         }
         for (int p = 0; p < P; ++p) b.potf2(p, c0);  // s >= 1: the diagonal tile needs no DIAG item (no contraction left)
+        deal(0);
         for (int k = c0; k < c1; ++k) {
             if (k + 1 < nt)
                 for (int p = 0; p < P; ++p) b.tile(p, k + 1, k, k);  // panels of tile row k + 1 first
@@ -685,11 +722,16 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, std::vector<
                 for (int p = 0; p < P; ++p) b.tile(p, k + 1, k + 1, k + 1);
                 for (size_t a = a1; a < a2; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
                 for (int p = 0; p < P; ++p) b.potf2(p, k + 1);
+                deal(k + 1 - c0);
                 for (size_t a = a2; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
             } else {
                 for (size_t a = 0; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
             }
         }
+        deal(c1 - c0 - 1);
+        if (gram_lead > 0 && c0 == 0) fuse_gram_items(P, nt_stride, gram_lead, cur);
+        seg.push_back((int)(items.size() / 2));
+        items.insert(items.end(), cur.begin(), cur.end());
     }
     seg.push_back((int)(items.size() / 2));
 }
@@ -828,11 +870,15 @@ static bool gram_as_items(const agp_handle* h, int first_row) {
 }
 static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : h->ctas_per_sm * h->num_sms; }
 
+// Super-column width: AGP_OZ_W / agp_set_hybrid, or by size (measured, 64 particles: n = 2048: 4 best, 6.72 ms against
+// 6.81 with 3 and 6.98 with 2; n = 4096: 2..4 within 0.5 %; n = 8192: 3 best, 205 ms against 207 / 208 with 2 / 4)
+static int hybrid_width(const agp_handle* h, int nt) { return h->oz_width > 0 ? h->oz_width : (nt >= 48 ? 3 : 4); }
+
 // Plain LML run with at least two super-columns: does this handle factor it through the hybrid schedule?
 static bool use_hybrid(const agp_handle* h, int first_row) {
     const BatchView& v = h->view;
-    if (h->force_plain || h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.nt <= h->oz_width) return false;
-    return h->oz_mode < 0 ? v.nt >= h->oz_min_nt : h->oz_mode != 0;
+    if (h->force_plain || h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
+    return h->oz_mode < 0 ? (v.nt >= h->oz_min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 
 static int run_hybrid(agp_handle* h, float* kernel_ms);
@@ -951,13 +997,18 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt, ld = h->ld;
     const int nt_stride = ld / TB;
-    const int W = h->oz_width;
-    auto key = std::make_tuple(P, nt, nt, -5 - W, nt_stride);
+    const int W = hybrid_width(h, nt);
+    // The Gram units can ride in the segments' queues (every program must fit the item's shared-memory cache).  Measured and
+    // NOT the default (profiles/r02_hybrid.txt): n = 2048 x 64 7.15 ms against 6.72 with the Gram launch in front, n = 8192
+    // 204 against 198 ms — next to a DMMA item a unit's DFMAs wait for the shared FP64 datapath, and the units that ride
+    // behind the POTF2 items slow exactly the chain the segment is bound by.  AGP_OZ_RIDE=1 enables it.
+    const bool ride = h->oz_ride && v.max_prog_len <= 64 && h->fuse_gram != 0;
+    auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
         agp_handle::Queue qu;
-        build_queue_hybrid(P, nt, nt_stride, W, items, qu.seg);
+        build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg);
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
         if (e != cudaSuccess) {
@@ -986,7 +1037,7 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
         h->oz_ld = ld;
         h->oz_P = P;
     }
-    const size_t n_sync = sync_ints(P, nt_stride, false);
+    const size_t n_sync = sync_ints(P, nt_stride, ride);
     if ((rc = grow_device(h, &h->d_sync, &h->cap_sync, n_sync * sizeof(int))) != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, n_sync * sizeof(int), h->stream));
     if (h->tma_L != v.L || h->tma_ld != ld || h->tma_rows != (long long)P * ld) {
@@ -1021,14 +1072,22 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
         acc_ms[slot] += ms;
         return AGP_OK;
     };
-    if ((rc = tic()) != AGP_OK) return rc;
-    agp::launch_gramfill(v, P, 0, h->stream);
-    agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream);
-    h->launches += 2;
-    if ((rc = toc(0)) != AGP_OK) return rc;
+    if (!ride) {
+        if ((rc = tic()) != AGP_OK) return rc;
+        agp::launch_gramfill(v, P, 0, h->stream);
+        h->launches += 1;
+        if ((rc = toc(0)) != AGP_OK) return rc;
+    }
     const int n_seg = (int)qu.seg.size() - 1;
     for (int s = 0; s < n_seg; ++s) {
         const int c0 = s * W, c1 = std::min(nt, c0 + W);
+        if (s == 1) {
+            // every diagonal tile of K is in place (Gram launch, or the units that rode in segment 0): row scales
+            if ((rc = tic()) != AGP_OK) return rc;
+            agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream);
+            h->launches += 1;
+            if ((rc = toc(0)) != AGP_OK) return rc;
+        }
         if (s > 0) {
             if ((rc = tic()) != AGP_OK) return rc;
             agp::launch_ozaki_slice(v.L, v.mat_stride, ld, nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
@@ -1423,18 +1482,18 @@ int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead,
     return export_queue(items, items_out, cap);
 }
 
-int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t* items_out, int64_t cap, int32_t* seg_out, int32_t seg_cap) {
-    if (P < 0 || nt < 1 || width < 1) return AGP_ERR_ARG;
+int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t* items_out, int64_t cap, int32_t* seg_out, int32_t seg_cap) {
+    if (P < 0 || nt < 1 || width < 1 || gram_lead < 0) return AGP_ERR_ARG;
     std::vector<int4> items;
     std::vector<int> seg;
-    build_queue_hybrid(P, nt, nt, width, items, seg);
+    build_queue_hybrid(P, nt, nt, width, gram_lead, items, seg);
     if (seg_out)
         for (size_t e = 0; e < seg.size() && (int32_t)e < seg_cap; ++e) seg_out[e] = seg[e];
     return export_queue(items, items_out, cap);
 }
 
 int agp_set_hybrid(agp_handle* h, int32_t mode, int32_t width, int32_t min_nt) {
-    if (!h || width < 1 || min_nt < 2) return AGP_ERR_ARG;
+    if (!h || width < 0 || min_nt < 2) return AGP_ERR_ARG;
     h->oz_mode = mode < 0 ? -1 : (mode != 0);
     h->oz_width = width;
     h->oz_min_nt = min_nt;
@@ -1444,7 +1503,7 @@ int agp_set_hybrid(agp_handle* h, int32_t mode, int32_t width, int32_t min_nt) {
 int agp_hybrid_info(agp_handle* h, int32_t* active_out, int32_t* width_out, float* stage_ms4) {
     if (!h) return AGP_ERR_ARG;
     if (active_out) *active_out = h->uploaded ? (use_hybrid(h, 0) ? 1 : 0) : h->oz_mode;
-    if (width_out) *width_out = h->oz_width;
+    if (width_out) *width_out = hybrid_width(h, h->uploaded ? h->view.nt : 16);
     if (stage_ms4)
         for (int e = 0; e < 4; ++e) stage_ms4[e] = h->hybrid_ms[e];
     return AGP_OK;

@@ -435,30 +435,36 @@ struct Oz2Item {
     int p, i, k;
     bool valid;
 };
-// units of one launch (a unit = one tile, or with G = 2 the tiles (i, k) and (i + 1, k) of a CTA pair): particle-major,
-// then block column, then tile rows
+// units of one launch (a unit = one tile, or with G = 2 the tiles (i0, k) and (i0 + 1, k) of a CTA pair): particle-major,
+// then tile rows (pairs aligned at c0), the block columns of the super-column innermost — the units that run at the same
+// time then read the same A rows, and the B rows of the few block columns stay in L2.  A tile above the diagonal
+// (i0 < k <= i0 + 1) or below the matrix is computed and not stored.
 template <int G>
 __device__ __forceinline__ int oz2_units_per_particle(int c0, int c1, int nt) {
     int n = 0;
-    for (int k = c0; k < c1; ++k) n += (nt - k + G - 1) / G;
+    for (int i0 = c0; i0 < nt; i0 += G) {
+        const int kc = i0 + G - c0;  // block columns c0 .. i0 + G - 1 have a tile on or below the diagonal in this row group
+        n += kc < c1 - c0 ? kc : c1 - c0;
+    }
     return n;
 }
 template <int G>
-__device__ __forceinline__ Oz2Item oz2_decode(int unit, int per_p, int c0, int nt, int rank) {
+__device__ __forceinline__ Oz2Item oz2_decode(int unit, int per_p, int c0, int c1, int nt, int rank) {
     Oz2Item it;
     it.p = unit / per_p;
     int r = unit - it.p * per_p;
-    int k = c0;
+    int i0 = c0;
     for (;;) {
-        const int cnt = (nt - k + G - 1) / G;
-        if (r < cnt) break;
-        r -= cnt;
-        ++k;
+        int kc = i0 + G - c0;
+        kc = kc < c1 - c0 ? kc : c1 - c0;
+        if (r < kc) break;
+        r -= kc;
+        i0 += G;
     }
-    it.k = k;
-    it.i = k + r * G + rank;
-    it.valid = it.i < nt;
-    if (!it.valid) it.i = nt - 1;  // odd number of tile rows: the pair's second CTA repeats the last tile and stores nothing
+    it.k = c0 + r;
+    it.i = i0 + rank;
+    it.valid = it.i < nt && it.i >= it.k;
+    if (it.i >= nt) it.i = nt - 1;  // stay inside the matrix; nothing is stored
     return it;
 }
 
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             int a_slot = 0, a_n = 0, b_slot = 0, b_n = 0;  // ring position, completed trips round the ring
             bool ok = true;
             for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
-                const Oz2Item it = oz2_decode<G>(unit, per_p, c0, nt, (int)rank);
+                const Oz2Item it = oz2_decode<G>(unit, per_p, c0, prm.c1, nt, (int)rank);
                 const int arow = it.p * ld + it.i * 128, brow = it.p * ld + it.k * 128 + (int)rank * (128 / G);
                 for (int pass = 0; pass < 2 && ok; ++pass) {
                     const int pmax = pass ? 7 : 3;
@@ -667,7 +673,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
         int use = 0;
         bool ok = true;
         for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
-            const Oz2Item it = oz2_decode<G>(unit, per_p, c0, nt, (int)rank);
+            const Oz2Item it = oz2_decode<G>(unit, per_p, c0, prm.c1, nt, (int)rank);
             const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
             const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + hh * 64);
             double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + hh * 64;

@@ -41,7 +41,11 @@ TREE = "se*per+lin"
 # MEASURED_PEAKS.json uses for bf16); the DMMA issue-rate ceiling is 37.2 TFLOP/s.
 # MEASURED_PEAKS.json itself has no FP64 entry.
 FP64_PEAK_TFLOPS = 35.4
-KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_diag.cu", "agp_chol_potf2.cu", "agp_chol_gram.cu", "agp_chol_common.cuh")
+KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_diag.cu", "agp_chol_potf2.cu", "agp_chol_gram.cu", "agp_chol_common.cuh", "agp_ozaki.cu")
+# dense int8 tensor rate measured on this pool (profiles/r02_i8_probe.txt, r02_i8_shape_probe.txt): one M128 N128 K32
+# tcgen05.mma kind::i8 per 64.0 clocks and SM = 8192 MAC/clk/SM = 4117 TOP/s at the clocks of that run
+INT8_PEAK_TOPS = 4117.0
+INT8_PRODUCTS = 36  # digit-plane products per FP64 product (8 planes, p + q <= 7)
 
 
 def workload_name(n, P):
@@ -267,11 +271,36 @@ class Bench:
         chol_ms = float(np.median([b for _, b, _ in st]))
         flops = P * n ** 3 / 3.0
         fused, lead = self.eng.gram_items()
-        return {"workload": workload_name(n, P), "value": self.world * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        hyb_on, hyb_w, hyb_ms = self.eng.hybrid_info()
+        extra = {}
+        if hyb_on:
+            extra["hybrid"] = self.hybrid_record(n, P, hyb_w, hyb_ms)
+            self.eng.set_hybrid(0)
+            self.eng.run()
+            self.barrier()
+            extra["fp64_single_launch_ms_per_step"] = self.max_over_ranks(self.eng.time_runs(max(2, steps // 2))) / max(2, steps // 2)
+            self.eng.set_hybrid(-1)
+        return {**extra, "workload": workload_name(n, P), "value": self.world * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
                 "gram_units": f"items of the persistent kernel's queue (lead {lead}): one launch per step, chol_kernel_ms is that launch, timed "
                               "with an event pair and a host sync around it" if fused else "own launch in front of the persistent kernel",
                 "chol_kernel_ms": chol_ms, "chol_frac_of_fp64_peak": flops / (chol_ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS,
                 "whole_step_frac_of_fp64_peak": flops / (ms * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS}
+
+    def hybrid_record(self, n, P, width, stage_ms):
+        """Stage times of a hybrid step (agp_hybrid_info; each stage bracketed by events and a sync) and the int8 kernel's rate."""
+        nt = -(-n // 128)
+        mac = 0.0   # multiply-accumulates of the int8 updates in FP64 terms: tile (i, k) of super-column [c0, c1) over depth c0
+        for c0 in range(width, nt, width):
+            for k in range(c0, min(nt, c0 + width)):
+                mac += (nt - k) * 128.0 * 128.0 * (c0 * 128.0)
+        int8_tops = 2.0 * INT8_PRODUCTS * P * mac / (stage_ms[2] * 1e-3) * 1e-12 if stage_ms[2] > 0 else None
+        return {"super_column_width": width, "gram_and_row_scales_ms": stage_ms[0], "fp64_segments_ms": stage_ms[1], "int8_updates_ms": stage_ms[2],
+                "digit_planes_ms": stage_ms[3],
+                "share_of_flops_on_int8": 2.0 * mac / (n ** 3 / 3.0) if n % 128 == 0 else None,
+                "int8_kernel": {"kernel": "agp_ozaki_update2_kernel<2> (tcgen05.mma.cta_group::2.kind::i8, TMEM accumulators, CTA pairs)",
+                                "achieved": int8_tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, 36 digit-plane products per FP64 product)",
+                                "frac": None if int8_tops is None else int8_tops / INT8_PEAK_TOPS,
+                                "fp64_equivalent_tflops": None if int8_tops is None else int8_tops / INT8_PRODUCTS}}
 
     # -- gradient calls (SURVEY.md §8 f-1), end to end through the C-ABI ----------------------------------------------
     def grad_point(self, n, P, reps):
@@ -449,14 +478,24 @@ class Bench:
             except Exception:
                 pass
         n_entries = P * (n * (n + 1) / 2.0)
+        hyb_on, hyb_w, hyb_ms = eng.hybrid_info()
+        n_launch = 1
+        kernel_name = "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)"
+        if hyb_on:
+            n_seg = -(-(-(-n // 128)) // hyb_w)
+            n_launch = 3 * n_seg - 2
+            kernel_name = (f"the factorisation as {n_launch} launches: {n_seg} segments of agp_chol_kernel (FP64 DMMA: potf2, panel solves, contractions inside a "
+                           f"super-column of {hyb_w} block columns), {n_seg - 1} x agp_ozaki_update2_kernel (the contractions over all earlier block columns as exact "
+                           f"int8 digit-plane products on tcgen05, kind::i8) and {n_seg - 1} x agp_ozaki_slice_kernel; avg_launch_ms = their sum")
+            traffic, traffic_note = None, "no capture of the multi-launch factorisation on file"
         roofline = {
             "bound": "tensor",
-            "kernel": "agp_chol_kernel (persistent: FP64 DMMA contraction + potf2 + panel solve + forward solve)",
+            "kernel": kernel_name,
             "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
             "traffic": traffic, "traffic_source": traffic_note,
             "peak_source": "measured on this pool: cuBLAS DGEMM 8192^3 sustained (profiles/r01_fp64_lib_probe.txt); "
                            "MEASURED_PEAKS.json has no FP64 entry; DMMA issue ceiling 37.2",
-            "launches_per_step": 1, "avg_launch_ms": chol_ms,
+            "launches_per_step": n_launch, "avg_launch_ms": chol_ms,
             "algorithmic_flops_per_launch": flops,
             "gramfill_kernel": {"avg_launch_ms": gram_ms, "entries_per_s": n_entries / (gram_ms * 1e-3),
                                 "hbm_write_GBps": 8.0 * n_entries / (gram_ms * 1e-3) * 1e-9,
@@ -465,6 +504,16 @@ class Bench:
                            "frac": flops / (ms_per_step * 1e-3) * 1e-12 / FP64_PEAK_TFLOPS, "unit": "TFLOP/s per GPU"},
         }
 
+        if hyb_on:
+            roofline["hybrid"] = self.hybrid_record(n, P, hyb_w, hyb_ms)
+            roofline["note"] = ("peak is the FP64 tensor (DMMA) peak; a frac above the FP64 segments' share is possible because the long contractions "
+                                "run on the int8 tensor path at FP64-grade accuracy (error-free digit-plane split)")
+            eng.set_hybrid(0)
+            eng.run()
+            self.barrier()
+            k = max(3, args.steps // 4)
+            roofline["fp64_single_launch_ms_per_step"] = self.max_over_ranks(eng.time_runs(k)) / k
+            eng.set_hybrid(-1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

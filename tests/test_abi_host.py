@@ -162,6 +162,8 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
             # the super-column's block columns to coverage c0 — everything it reads must be final, nothing it writes
             # may have been touched, and all earlier items are complete (kernel boundary).
             c0_ = seg_first[idx_] * width
+            if gram_items and seg_first[idx_] == 1:   # the row scales are read off the Gram diagonal after the first segment
+                assert all((pp, c, c, hh) in gram_done for pp in range(P) for c in range(nt) for hh in (0, 1))
             for pp in range(P):
                 assert counters[fdone(pp)] == c0_
                 for ii in range(c0_, nt):
@@ -170,6 +172,7 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                         if kk <= ii:
                             for hh in (0, 1):
                                 assert (pp, ii, kk, hh) not in covered
+                                assert not gram_items or (pp, ii, kk, hh) in gram_done   # the update subtracts from the Gram tile
                                 covered[(pp, ii, kk, hh)] = c0_
                                 seg_base[(pp, ii, kk, hh)] = c0_
         t, h, partial, yinit = x & 0xFF, (x >> 8) & 1, bool(x & PARTIAL), bool(x & YINIT)
@@ -256,8 +259,9 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     _replay_queue(buf, P, nt, nt, 0)
 
 
+@pytest.mark.parametrize("gram_lead", [0, 1, 8, 296])
 @pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (5, 16, 4), (2, 16, 2), (2, 23, 4), (1, 9, 3)])
-def test_hybrid_schedule_replay(P, nt, width):
+def test_hybrid_schedule_replay(P, nt, width, gram_lead):
     """The super-column schedule of the hybrid factorisation (agp_queue_build_hybrid): every segment is a launch of
     its own, the int8 update between two launches covers block columns [0, c0) of the next super-column's tiles, and the
     items inside a segment obey the same wait rules as the single-launch schedule."""
@@ -265,12 +269,12 @@ def test_hybrid_schedule_replay(P, nt, width):
 
     lib = _lib.load()
     i32p = C.POINTER(C.c_int32)
-    n_items = lib.agp_queue_build_hybrid(P, nt, width, None, 0, None, 0)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, gram_lead, None, 0, None, 0)
     buf = np.zeros((n_items, 8), dtype=np.int32)
     seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
-    assert lib.agp_queue_build_hybrid(P, nt, width, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert lib.agp_queue_build_hybrid(P, nt, width, gram_lead, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
     assert seg[0] == 0 and seg[-1] == n_items and np.all(np.diff(seg) > 0)
-    _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width)
+    _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width, gram_items=gram_lead > 0)
 
 
 @pytest.mark.parametrize("order", [0, 2, 3])

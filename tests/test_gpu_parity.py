@@ -422,6 +422,7 @@ def test_gram_items_equal_the_separate_gram_launch_whatever_their_lead(monkeypat
     import autogp.jl_b200 as agp
 
     def run(fuse, lead, cases):
+        monkeypatch.setenv("AGP_OZAKI", "0")   # the two Gram paths of the single-launch FP64 schedule (the hybrid schedule has its own tests)
         monkeypatch.setenv("AGP_FUSE_GRAM", "1" if fuse else "0")
         monkeypatch.setenv("AGP_GRAM_LEAD", str(lead))
         eng = agp.Engine(0)
@@ -607,7 +608,14 @@ def test_lml_gradient_full_size_directional_derivative(engine):
         fd = (f_up[0] - f_dn[0]) / (2 * hstep)
         an = float(np.dot(grads[p], d) + gnoise[p] * dn)
         assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (p, fd, an)
-    assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
+    # the gradient call factors the augmented matrix on the FP64 schedule; a plain batch of this size takes the hybrid
+    # schedule (int8 digit-plane contractions, tests/test_hybrid_gpu.py): equal to 1e-11, and to 1e-13 with the hybrid off
+    assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-11
+    engine.set_hybrid(0)
+    try:
+        assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
+    finally:
+        engine.set_hybrid(-1)
 
 
 @pytest.mark.parametrize("n", [1, 77, 128, 300, 1000])
@@ -652,8 +660,14 @@ def test_noise_only_gradient_full_size_and_edge_cases(engine):
         dn, _ = engine.lml_batch([nodes[p]], [noises[p] * (1 - hstep)], ts, xs)
         fd = (up[0] - dn[0]) / (2 * hstep * noises[p])
         assert abs(fd - gn[p]) <= 1e-5 * max(1.0, abs(fd)), (p, fd, gn[p])
-    # a plain LML batch after the augmented one is unaffected by the leftover state
-    assert np.array_equal(engine.lml_batch(nodes, noises, ts, xs)[0], lml)
+    # a plain LML batch after the augmented one is unaffected by the leftover state (bitwise on the same FP64 schedule;
+    # by default a plain batch of this size takes the hybrid schedule: equal to 1e-11)
+    assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-11
+    engine.set_hybrid(0)
+    try:
+        assert np.array_equal(engine.lml_batch(nodes, noises, ts, xs)[0], lml)
+    finally:
+        engine.set_hybrid(-1)
     # empty data, failed factorisation, and no program-size limit on this path
     lml, gn, info = engine.lml_grad_noise_batch([agp.SquaredExponential(0.3, 1.0)], [0.1], ts[:0], xs[:0])
     assert lml[0] == 0.0 and gn[0] == 0.0 and info[0] == 0

@@ -1,0 +1,121 @@
+"""GPU suite of the hybrid factorisation (csrc/agp_ozaki.cu): the long contractions of the blocked Cholesky as exact
+int8 digit-plane products on tcgen05 (kind::i8, TMEM accumulators), the rest on the FP64 persistent kernel.
+
+Stated tolerances.  The scheme rounds every entry of L once at 2^-55 of a per-row power-of-two bound of sqrt(K_ii) and
+drops digit products below 2^-61 of the two row scales, so the error of a contraction is ABSOLUTE in units of
+sqrt(K_ii K_kk) (about sqrt(depth) 2^-55), where FP64 accumulation rounds relative to the running sum.  Observed on these
+cases: factor entries within 3e-14 of the FP64 schedule's (relative to max |L|), LML within 2e-13 (n <= 2300, these
+trees), 1.4e-11 at n = 4096 and 9.4e-10 at n = 8192 over the 64 benchmark particles (tools/hybrid_check.py) — against
+the north_star bound 1e-8.  Asserted here: 1e-10 against the FP64 schedule and the oracle up to n = 2300, 1e-8 at
+n = 8192.
+"""
+import numpy as np
+import pytest
+
+import autogp_oracle as o
+import c_oracle
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TREES = ["se*per+lin", "ge+per*lin", "se+wn", "cp(lin,se)", "se*per+lin"]
+
+
+def _batch(n, P):
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(p, TREES[p % len(TREES)]) for p in range(P)]
+    return ts, xs, parts, [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+
+
+@pytest.fixture()
+def eng():
+    import autogp.jl_b200 as agp
+
+    e = agp.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("n,width", [(300, 1), (640, 2), (1100, 4), (1100, 3), (1153, 2), (2048, 4), (2300, 5)])
+def test_hybrid_matches_the_fp64_schedule_and_the_oracle(eng, n, width):
+    """Forced on (mode 1) at ragged sizes, odd numbers of tile rows (the second CTA of a pair idles on the last row),
+    every width: LML and factor against the single-launch FP64 schedule and the oracle."""
+    ts, xs, parts, nodes, noises = _batch(n, 5)
+    eng.set_hybrid(0)
+    lml0, info0 = eng.lml_batch(nodes, noises, ts, xs)
+    assert not eng.hybrid_info()[0]
+    L0 = eng.factor(1)
+    eng.set_hybrid(1, width, 2)
+    lml1, info1 = eng.lml_batch(nodes, noises, ts, xs)
+    assert eng.hybrid_info()[0] and eng.hybrid_info()[1] == width
+    L1 = eng.factor(1)
+    assert np.all(info0 == 0) and np.all(info1 == 0)
+    assert np.max(np.abs(lml1 - lml0) / np.abs(lml0)) <= 1e-10
+    ref = np.array([o.log_marginal_likelihood(nd, nz, ts, xs) for nd, nz in parts[:2]])
+    assert np.max(np.abs(lml1[:2] - ref) / np.abs(ref)) <= 1e-10
+    assert np.max(np.abs(L1 - L0)) <= 1e-12 * np.max(np.abs(L0))
+    # deterministic: integer sums are exact, the FP64 items run the same arithmetic per tile
+    again, _ = eng.lml_batch(nodes, noises, ts, xs)
+    assert np.array_equal(again, lml1)
+
+
+def test_hybrid_is_chosen_by_size_and_can_be_switched_off(eng):
+    """Default: plain LML runs from 16 block columns on (n >= 1921); continuations and augmented batches never."""
+    ts, xs, parts, nodes, noises = _batch(2048, 3)
+    eng.upload(nodes, noises, ts, xs)
+    assert eng.hybrid_info()[0]
+    eng.run()
+    lml_h, info = eng.fetch()
+    assert np.all(info == 0)
+    eng.set_prefix(1500)
+    assert not eng.hybrid_info()[0]
+    eng.set_prefix(2048)
+    eng.set_hybrid(0)
+    assert not eng.hybrid_info()[0]
+    eng.run()
+    lml_f, _ = eng.fetch()
+    assert np.max(np.abs(lml_h - lml_f) / np.abs(lml_f)) <= 1e-10
+    # a data-annealing continuation of a hybrid factor (agp_lml_run_append) is the FP64 schedule on top of it
+    eng.set_hybrid(-1)
+    eng.set_prefix(1930)
+    eng.run()
+    got, info = eng.fetch()
+    assert np.all(info == 0) and eng.hybrid_info()[0]
+    eng.set_prefix(2048)
+    eng.run_append()
+    app, info = eng.fetch()
+    assert np.all(info == 0)
+    assert np.max(np.abs(app - lml_f) / np.abs(lml_f)) <= 1e-10
+
+
+def test_hybrid_reports_a_failed_factorisation_like_the_fp64_schedule(eng):
+    """A matrix that is not positive definite: the LAPACK info of the FP64 schedule, NaN score, the other particles of
+    the batch unharmed (digit planes of NaN / huge entries are garbage bytes, never a hang)."""
+    n = 700
+    ts, xs = o.synthetic_series(n)
+    tsd = ts.copy()
+    tsd[500] = tsd[10]          # duplicate time point + zero noise: singular leading minor in the fourth block column
+    cases = [(o.SquaredExponential(0.5, 1.0), 0.0), (o.SquaredExponential(0.1, 1.0), 0.1), (o.Constant(1.0), -2.0)]
+    nodes, noises = [H.to_agp(k) for k, _ in cases], [nz for _, nz in cases]
+    eng.set_hybrid(0)
+    lml0, info0 = eng.lml_batch(nodes, noises, tsd, xs)
+    eng.set_hybrid(1, 2, 2)
+    lml1, info1 = eng.lml_batch(nodes, noises, tsd, xs)
+    assert eng.hybrid_info()[0]
+    assert info1[1] == 0 and info1[2] == info0[2] == 1 and info0[0] != 0
+    # the singular minor's pivot is pure rounding noise: the hybrid schedule may or may not see it as non-positive
+    assert np.isnan(lml1[2]) and (np.isnan(lml1[0]) if info1[0] != 0 else np.isfinite(lml1[0]))
+    assert abs(lml1[1] - lml0[1]) <= 1e-10 * abs(lml0[1])
+    ref_info = c_oracle.lml(o.encode_program(cases[0][0]), tsd, xs, 0.0)[1]
+    assert ref_info != 0
+
+
+def test_hybrid_full_size_n8192(eng):
+    """configs[2] shape with the default settings (hybrid by size): against the oracle at the north_star tolerance."""
+    n = 8192
+    ts, xs = o.synthetic_series(n)
+    parts = [o.synthetic_particle(3), o.synthetic_particle(7)]
+    got, info = eng.lml_batch([H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
+    assert eng.hybrid_info()[0] and np.all(info == 0)
+    ref = o.log_marginal_likelihood(*parts[1], ts, xs)
+    assert abs(got[1] - ref) <= 1e-8 * abs(ref)

@@ -92,7 +92,7 @@ def load() -> C.CDLL:
     lib.agp_set_hybrid.restype = C.c_int
     lib.agp_hybrid_info.argtypes = [vp, i32p, i32p, C.POINTER(C.c_float)]
     lib.agp_hybrid_info.restype = C.c_int
-    lib.agp_queue_build_hybrid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int32]
+    lib.agp_queue_build_hybrid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64, i32p, C.c_int32]
     lib.agp_queue_build_hybrid.restype = C.c_int64
     lib.agp_dev_overlap_probe.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]
     lib.agp_dev_overlap_probe.restype = C.c_int

@@ -79,6 +79,7 @@ struct agp_handle {
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
     int oz_min_nt = 16;    // AGP_OZ_MIN_NT
+    bool oz_aug = true;    // AGP_OZ_AUG: the identity-augmented batches of the gradient calls take the hybrid schedule too
     bool oz_ride = false;  // AGP_OZ_RIDE: Gram units as items of the segments' queues (measured slower, see run_hybrid)
     int oz_variant = 3;    // AGP_OZ_KERNEL: 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one pass
     bool force_plain = false;  // diagnostics that index the single-launch schedule (agp_lml_trace)
@@ -193,6 +194,7 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_OZ_W")) h->oz_width = std::max(0, atoi(e));
     if (const char* e = getenv("AGP_OZ_MIN_NT")) h->oz_min_nt = std::max(2, atoi(e));
     if (const char* e = getenv("AGP_OZ_RIDE")) h->oz_ride = atoi(e) != 0;
+    if (const char* e = getenv("AGP_OZ_AUG")) h->oz_aug = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 0 || atoi(e) == 2) ? atoi(e) : 3;
     if (agp::configure_ozaki() != cudaSuccess) {
         cudaGetLastError();
@@ -480,10 +482,19 @@ struct QueueLayout {
 //          too few tiles for all CTAs: their per-particle critical path then no longer waits for
 //          contractions that could have been done earlier.
 struct TileState {
-    int P, nt, nt_stride;
+    int P, nt, nt_stride, nrows;  // nrows = nt, or 2 nt with the appended rows of an identity-augmented batch (tile row nt + a is
+                                  // structurally zero left of block column a: its coverage starts there)
     std::vector<int> cov, n_ppre, n_diag;  // coverage per tile, partial / diag item counts
     std::vector<int4>* items;
-    TileState(int P_, int nt_, int nts, std::vector<int4>* it) : P(P_), nt(nt_), nt_stride(nts), cov((size_t)P_ * nt_ * nt_, 0), n_ppre((size_t)P_ * nt_, 0), n_diag((size_t)P_ * nt_, 0), items(it) {}
+    TileState(int P_, int nt_, int nts, std::vector<int4>* it, int nrows_ = 0)
+        : P(P_), nt(nt_), nt_stride(nts), nrows(nrows_ > nt_ ? nrows_ : nt_), cov((size_t)P_ * (nrows_ > nt_ ? nrows_ : nt_) * nt_, 0),
+          n_ppre((size_t)P_ * (nrows_ > nt_ ? nrows_ : nt_), 0), n_diag((size_t)P_ * nt_, 0), items(it) {
+        for (int p = 0; p < P; ++p)
+            for (int i = nt; i < nrows; ++i)
+                for (int k = 0; k < nt; ++k) cov[((size_t)p * nrows + i) * nt + k] = i - nt;
+    }
+    int fc(int i) const { return i >= nt ? i - nt : 0; }
+    int& coverage(int p, int i, int k) { return cov[((size_t)p * nrows + i) * nt + k]; }
     int flag_diagu(int p, int k) const { return 32 + P * nt_stride + p * nt_stride + k; }
     int flag_ppre(int p, int i) const { return 32 + 2 * P * nt_stride + p * nt_stride + i; }
     void potf2(int p, int k) {
@@ -492,8 +503,8 @@ struct TileState {
     }
     // advance tile (i,k) to coverage j1 (final when j1 == k): both row halves
     void tile(int p, int i, int k, int j1) {
-        int& c = cov[((size_t)p * nt + i) * nt + k];
-        const int j0 = c;
+        int& c = coverage(p, i, k);
+        const int j0 = c, f = fc(i);
         const bool fin = j1 == k;
         for (int h = 0; h < 2; ++h) {
             if (i == k) {
@@ -501,13 +512,13 @@ struct TileState {
                 items->push_back(make_int4(agp::ITEM_DIAG | (h << 8) | (fin ? 0 : agp::ITEM_PARTIAL), p, k, i));
                 items->push_back(make_int4(j0 | (j1 << 16), 2 * j1, j0 > 0 ? flag_diagu(p, k) : -1, j0 > 0 ? cnt : 0));
             } else {
-                const int cnt = n_ppre[(size_t)p * nt + i];
-                items->push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (fin ? 0 : agp::ITEM_PARTIAL) | (k == 0 ? agp::ITEM_YINIT : 0), p, k, i));
-                items->push_back(make_int4(j0 | (j1 << 16), (2 * j1) | ((2 * j1) << 16), j0 > 0 ? flag_ppre(p, i) : -1, j0 > 0 ? cnt : 0));
+                const int cnt = n_ppre[(size_t)p * nrows + i];
+                items->push_back(make_int4(agp::ITEM_PANEL | (h << 8) | (fin ? 0 : agp::ITEM_PARTIAL) | (k == f ? agp::ITEM_YINIT : 0), p, k, i));
+                items->push_back(make_int4(j0 | (j1 << 16), (2 * j1) | ((2 * (j1 - f)) << 16), j0 > f ? flag_ppre(p, i) : -1, j0 > f ? cnt : 0));
             }
         }
         if (i == k) n_diag[(size_t)p * nt + k] += 2;
-        else if (!fin) n_ppre[(size_t)p * nt + i] += 2;
+        else if (!fin) n_ppre[(size_t)p * nrows + i] += 2;
         c = j1;
     }
 };
@@ -666,11 +677,15 @@ static void fuse_gram_items(int P, int nt_stride, int lead, std::vector<int4>& i
 // that ride for a later super-column, so they need no flag wait — the launch boundary orders them — and they are dealt
 // out behind the POTF2 items of the segment's block columns, where the CTAs that hold no POTF2 item would otherwise
 // spin on the factor of the diagonal tile.
-static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lead, std::vector<int4>& items, std::vector<int>& seg) {
+// aug: the identity-augmented batch of the gradient calls (tile rows nt + a hold [I 0] and end as rows of L^{-T}): the
+// panels of the appended rows ride in the bulk of their block column, their contraction over [a, c0) is the int8 kernel's
+// like everyone else's; the lauum pass (-K^{-1} into the trailing tiles) has no FP64 items at all — one int8 launch after
+// the last segment.
+static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lead, std::vector<int4>& items, std::vector<int>& seg, bool aug = false) {
     items.clear();
     seg.clear();
     std::vector<int4> cur;
-    TileState b(P, nt, nt_stride, &cur);
+    TileState b(P, nt, nt_stride, &cur, aug ? 2 * nt : nt);
     double pos_diag = 1.0 / 3, pos_potf2 = 0.5;
     if (const char* e = getenv("AGP_OZ_POS")) sscanf(e, "%lf,%lf", &pos_diag, &pos_potf2);  // developer A/B
     struct T { int p, i, k; };
@@ -704,8 +719,10 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lea
             for (int p = 0; p < P; ++p) b.tile(p, 0, 0, 0);  // starts the forward solve: y_0 = xs
         } else {
             for (int p = 0; p < P; ++p)
-                for (int k = c0; k < c1; ++k)
-                    for (int i = k; i < nt; ++i) b.cov[((size_t)p * nt + i) * nt + k] = c0;  // the int8 update
+                for (int k = c0; k < c1; ++k) {
+                    for (int i = k; i < nt; ++i) b.coverage(p, i, k) = c0;  // the int8 update
+                    for (int a = 0; aug && a < c0; ++a) b.coverage(p, nt + a, k) = c0;
+                }
         }
         for (int p = 0; p < P; ++p) b.potf2(p, c0);  // s >= 1: the diagonal tile needs no DIAG item (no contraction left)
         deal(0);
@@ -715,6 +732,8 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lea
             std::vector<T> bulk;
             for (int i = k + 2; i < nt; ++i)
                 for (int p = 0; p < P; ++p) bulk.push_back({p, i, k});
+            for (int a = 0; aug && a <= k; ++a)
+                for (int p = 0; p < P; ++p) bulk.push_back({p, nt + a, k});
             const size_t nb = bulk.size();
             if (k + 1 < c1) {
                 const size_t a1 = (size_t)(pos_diag * nb), a2 = std::max(a1, (size_t)(pos_potf2 * nb));
@@ -877,7 +896,8 @@ static int hybrid_width(const agp_handle* h, int nt) { return h->oz_width > 0 ? 
 // Plain LML run with at least two super-columns: does this handle factor it through the hybrid schedule?
 static bool use_hybrid(const agp_handle* h, int first_row) {
     const BatchView& v = h->view;
-    if (h->force_plain || h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
+    if (h->force_plain || first_row != 0 || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
+    if (h->aug_identity ? (!h->oz_aug || v.nt_total != 2 * v.nt) : v.nt_total != v.nt) return false;
     return h->oz_mode < 0 ? (v.nt >= h->oz_min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 
@@ -1002,13 +1022,14 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     // NOT the default (profiles/r02_hybrid.txt): n = 2048 x 64 7.15 ms against 6.72 with the Gram launch in front, n = 8192
     // 204 against 198 ms — next to a DMMA item a unit's DFMAs wait for the shared FP64 datapath, and the units that ride
     // behind the POTF2 items slow exactly the chain the segment is bound by.  AGP_OZ_RIDE=1 enables it.
-    const bool ride = h->oz_ride && v.max_prog_len <= 64 && h->fuse_gram != 0;
-    auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0), nt_stride);
+    const bool aug = h->aug_identity;  // gradient calls: [I 0] rows appended (tile rows nt .. 2 nt), agp_lml_grad_batch / _noise_batch
+    const bool ride = !aug && h->oz_ride && v.max_prog_len <= 64 && h->fuse_gram != 0;
+    auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0) - (aug ? 2000 : 0), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
         agp_handle::Queue qu;
-        build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg);
+        build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg, aug);
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
         if (e != cudaSuccess) {
@@ -1074,27 +1095,40 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     };
     if (!ride) {
         if ((rc = tic()) != AGP_OK) return rc;
-        agp::launch_gramfill(v, P, 0, h->stream);
+        if (aug) {
+            // the kernel tree is evaluated over the observation block only; the appended [I 0] rows are plain stores
+            BatchView obs = v;
+            obs.nt_total = v.nt;
+            agp::launch_gramfill(obs, P, 0, h->stream);
+            agp::launch_augfill(v, P, h->stream);
+            h->launches += 1;
+        } else {
+            agp::launch_gramfill(v, P, 0, h->stream);
+        }
         h->launches += 1;
         if ((rc = toc(0)) != AGP_OK) return rc;
     }
+    const int oz_variant = (aug && h->oz_variant < 2) ? 3 : h->oz_variant;  // appended rows: second-generation kernels only
     const int n_seg = (int)qu.seg.size() - 1;
     for (int s = 0; s < n_seg; ++s) {
         const int c0 = s * W, c1 = std::min(nt, c0 + W);
         if (s == 1) {
             // every diagonal tile of K is in place (Gram launch, or the units that rode in segment 0): row scales
             if ((rc = tic()) != AGP_OK) return rc;
-            agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream);
+            agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream, nt * TB, aug ? v.noise : nullptr);
             h->launches += 1;
             if ((rc = toc(0)) != AGP_OK) return rc;
         }
         if (s > 0) {
             if ((rc = tic()) != AGP_OK) return rc;
-            agp::launch_ozaki_slice(v.L, v.mat_stride, ld, nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
+            // digit planes of the previous super-column's finished panels: tile rows below it, and (aug) the appended rows
+            // nt + a, a <= c0 (row a = j + 1 is structurally zero at block column j: zero planes, read by the pair of row a - 1)
+            agp::launch_ozaki_slice(v.L, v.mat_stride, ld, aug ? nt + std::min(nt, c0 + 1) : nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
             if ((rc = toc(3)) != AGP_OK) return rc;
             if ((rc = tic()) != AGP_OK) return rc;
-            agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, c0, c1, q.err, h->wait_timeout_ns};
-            agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, h->oz_variant);
+            agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, c0, c1, q.err, h->wait_timeout_ns, 0, 0, 0, 0, 0};
+            if (aug) prm.r_lo = c0, prm.r_hi = nt + c0, prm.k_lo = c0, prm.k_hi = c1, prm.chi = c0;  // appended rows a < c0 over [a, c0)
+            agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, oz_variant);
             if ((rc = toc(2)) != AGP_OK) return rc;
             AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, sizeof(int), h->stream));  // the queue head; the dependency counters keep counting
             h->launches += 2;
@@ -1105,6 +1139,20 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
         agp::launch_chol(v, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
         h->launches += 1;
         if ((rc = toc(1)) != AGP_OK) return rc;
+    }
+    if (aug && !h->trtri_only) {
+        // lauum pass: -K^{-1}[a][b] = 0 - sum_{j >= a} L^{-T}[a][j] L^{-T}[b][j]^T into the trailing tile (nt + a, nt + b), b <= a — a pure
+        // contraction over block columns [a, nt): all of it on the int8 path, after the planes of the last super-column's
+        // appended panels are cut
+        const int cl = (n_seg - 1) * W;
+        if ((rc = tic()) != AGP_OK) return rc;
+        agp::launch_ozaki_slice(v.L, v.mat_stride, ld, 2 * nt, P, h->d_rscale, h->d_S, cl, nt, nt, h->stream);
+        if ((rc = toc(3)) != AGP_OK) return rc;
+        if ((rc = tic()) != AGP_OK) return rc;
+        agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, 0, 0, q.err, h->wait_timeout_ns, nt, 2 * nt, nt, 2 * nt, nt};
+        agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, oz_variant);
+        if ((rc = toc(2)) != AGP_OK) return rc;
+        h->launches += 2;
     }
     if (kernel_ms) {
         kernel_ms[0] = acc_ms[0];
@@ -1482,11 +1530,12 @@ int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead,
     return export_queue(items, items_out, cap);
 }
 
-int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t* items_out, int64_t cap, int32_t* seg_out, int32_t seg_cap) {
-    if (P < 0 || nt < 1 || width < 1 || gram_lead < 0) return AGP_ERR_ARG;
+int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t augmented, int32_t* items_out, int64_t cap, int32_t* seg_out,
+                               int32_t seg_cap) {
+    if (P < 0 || nt < 1 || width < 1 || gram_lead < 0 || (augmented && gram_lead > 0)) return AGP_ERR_ARG;
     std::vector<int4> items;
     std::vector<int> seg;
-    build_queue_hybrid(P, nt, nt, width, gram_lead, items, seg);
+    build_queue_hybrid(P, nt, augmented ? 2 * nt : nt, width, gram_lead, items, seg, augmented != 0);
     if (seg_out)
         for (size_t e = 0; e < seg.size() && (int32_t)e < seg_cap; ++e) seg_out[e] = seg[e];
     return export_queue(items, items_out, cap);

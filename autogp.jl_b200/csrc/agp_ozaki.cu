@@ -431,40 +431,45 @@ __device__ __forceinline__ uint32_t oz_elect_one() {
     return pred;
 }
 
-struct Oz2Item {
-    int p, i, k;
-    bool valid;
-};
 // units of one launch (a unit = one tile, or with G = 2 the tiles (i0, k) and (i0 + 1, k) of a CTA pair): particle-major,
 // then tile rows (pairs aligned at c0), the block columns of the super-column innermost — the units that run at the same
 // time then read the same A rows, and the B rows of the few block columns stay in L2.  A tile above the diagonal
 // (i0 < k <= i0 + 1) or below the matrix is computed and not stored.
+__device__ __forceinline__ int oz2_fc(int r, int nt) { return r >= nt ? r - nt : 0; }
 template <int G>
-__device__ __forceinline__ int oz2_units_per_particle(int c0, int c1, int nt) {
-    int n = 0;
-    for (int i0 = c0; i0 < nt; i0 += G) {
-        const int kc = i0 + G - c0;  // block columns c0 .. i0 + G - 1 have a tile on or below the diagonal in this row group
-        n += kc < c1 - c0 ? kc : c1 - c0;
-    }
-    return n;
+__device__ __forceinline__ int oz2_kcount(int i0, const OzakiParams& prm) {
+    int kc = i0 + G - prm.k_lo;  // tile rows k_lo .. i0 + G - 1 have a tile on or below the diagonal in this row group
+    kc = kc < prm.k_hi - prm.k_lo ? kc : prm.k_hi - prm.k_lo;
+    return kc > 0 ? kc : 0;
 }
 template <int G>
-__device__ __forceinline__ Oz2Item oz2_decode(int unit, int per_p, int c0, int c1, int nt, int rank) {
-    Oz2Item it;
+__device__ __forceinline__ int oz2_units_per_particle(const OzakiParams& prm) {
+    int n = 0;
+    for (int i0 = prm.r_lo; i0 < prm.r_hi; i0 += G) n += oz2_kcount<G>(i0, prm);
+    return n;
+}
+struct Oz2Unit {
+    int p, i, k, clo;
+    bool valid;
+};
+template <int G>
+__device__ __forceinline__ Oz2Unit oz2_decode(int unit, int per_p, const OzakiParams& prm, int rank) {
+    Oz2Unit it;
     it.p = unit / per_p;
     int r = unit - it.p * per_p;
-    int i0 = c0;
+    int i0 = prm.r_lo;
     for (;;) {
-        int kc = i0 + G - c0;
-        kc = kc < c1 - c0 ? kc : c1 - c0;
+        const int kc = oz2_kcount<G>(i0, prm);
         if (r < kc) break;
         r -= kc;
         i0 += G;
     }
-    it.k = c0 + r;
+    it.k = prm.k_lo + r;
     it.i = i0 + rank;
-    it.valid = it.i < nt && it.i >= it.k;
-    if (it.i >= nt) it.i = nt - 1;  // stay inside the matrix; nothing is stored
+    it.valid = it.i < prm.r_hi && it.i >= it.k;
+    if (it.i >= prm.r_hi) it.i = prm.r_hi - 1;  // stay inside the matrix; nothing is stored
+    const int fi = oz2_fc(i0, prm.nt), fk = oz2_fc(it.k, prm.nt);
+    it.clo = fi > fk ? fi : fk;  // the same for both CTAs of a pair: the leader issues for both
     return it;
 }
 
@@ -547,10 +552,10 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c0 = prm.c0, nt = prm.nt, P = prm.P, ld = prm.ld;
+    const int P = prm.P, ld = prm.ld;
     uint32_t rank = 0;
     if constexpr (G == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
-    const int per_p = oz2_units_per_particle<G>(c0, prm.c1, nt);
+    const int per_p = oz2_units_per_particle<G>(prm);
     const int n_units = per_p * P;
     const int unit0 = blockIdx.x / G, unit_stride = gridDim.x / G;
 
@@ -590,11 +595,11 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             int a_slot = 0, a_n = 0, b_slot = 0, b_n = 0;  // ring position, completed trips round the ring
             bool ok = true;
             for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
-                const Oz2Item it = oz2_decode<G>(unit, per_p, c0, prm.c1, nt, (int)rank);
+                const Oz2Unit it = oz2_decode<G>(unit, per_p, prm, (int)rank);
                 const int arow = it.p * ld + it.i * 128, brow = it.p * ld + it.k * 128 + (int)rank * (128 / G);
                 for (int pass = 0; pass < 2 && ok; ++pass) {
                     const int pmax = pass ? 7 : 3;
-                    for (int c = 0; c < c0 && ok; ++c) {
+                    for (int c = it.clo; c < prm.chi && ok; ++c) {
                         for (int p = pmax; p >= 0; --p) {
                             const int q = pmax - p;
                             if (b_n >= 1) ok = oz_wait(b_empty + b_slot, (b_n - 1) & 1, prm.err, prm.wait_timeout_ns);
@@ -636,6 +641,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
 #define OZ_EXTRA
 #endif
             for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
+                const int clo = oz2_decode<G>(unit, per_p, prm, 0).clo;
                 for (int pass = 0; pass < 2 && ok; ++pass, ++use) {
                     {
                         OZ_T0();
@@ -644,8 +650,8 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
                     }
                     if (!ok) break;
                     tc_fence_after();
-                    for (int c = 0; c < c0 && ok; ++c) {
-                        const uint32_t first = (c == 0) ? 0u : 1u;
+                    for (int c = clo; c < prm.chi && ok; ++c) {
+                        const uint32_t first = (c == clo) ? 0u : 1u;
                         ok = pass ? oz2_chunk<G, 1>(a_full, a_empty, b_full, b_empty, da0, db0, tmem, first, a_slot, a_par, b_slot, b_par, prm OZ_EXTRA)
                                   : oz2_chunk<G, 0>(a_full, a_empty, b_full, b_empty, da0, db0, tmem, first, a_slot, a_par, b_slot, b_par, prm OZ_EXTRA);
                     }
@@ -673,7 +679,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
         int use = 0;
         bool ok = true;
         for (int unit = unit0; unit < n_units && ok; unit += unit_stride) {
-            const Oz2Item it = oz2_decode<G>(unit, per_p, c0, prm.c1, nt, (int)rank);
+            const Oz2Unit it = oz2_decode<G>(unit, per_p, prm, (int)rank);
             const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
             const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + hh * 64);
             double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + hh * 64;
@@ -742,16 +748,29 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
 }
 
 // ---- row scales -----------------------------------------------------------------------------------
-__global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P, double* __restrict__ rscale) {
+__global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P, double* __restrict__ rscale,
+                                          int ld_obs, const double* __restrict__ noise) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= (long long)P * ld) return;
     const int p = (int)(w / ld), r = (int)(w - (long long)p * ld);
-    const double kd = L[(long long)p * mat_stride + (long long)r * ld + r];
     int e = 0;
-    if (kd > 0.0 && kd < 1e300) {
-        int ex;
-        frexp(kd, &ex);        // kd = m 2^ex, 1/2 <= m < 1: sqrt(kd) < 2^(ex / 2)
-        e = (ex + 1) >> 1;     // ceil(ex / 2)
+    if (r >= ld_obs) {
+        // appended row of an identity-augmented batch: it ends as a row of L^{-T}, |entries| <= sqrt((K^{-1})_rr) <= 1 / sqrt(noise);
+        // one extra bit for kernel matrices that are PSD only up to rounding; padding columns hold 1
+        const double nz = noise[p];
+        if (nz > 0.0 && nz < 1e300) {
+            int ex;
+            frexp(1.0 / nz, &ex);
+            e = (ex + 1) >> 1;
+        }
+        e = (e > 0 ? e : 0) + 1;
+    } else {
+        const double kd = L[(long long)p * mat_stride + (long long)r * ld + r];
+        if (kd > 0.0 && kd < 1e300) {
+            int ex;
+            frexp(kd, &ex);        // kd = m 2^ex, 1/2 <= m < 1: sqrt(kd) < 2^(ex / 2)
+            e = (ex + 1) >> 1;     // ceil(ex / 2)
+        }
     }
     rscale[2 * w] = ldexp(1.0, e);
     rscale[2 * w + 1] = ldexp(1.0, 55 - e);
@@ -795,10 +814,10 @@ __global__ void __launch_bounds__(256) agp_ozaki_slice_kernel(const double* __re
 }
 
 // ---- host side --------------------------------------------------------------------------------------
-void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s) {
+void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s, int ld_obs, const double* noise) {
     const long long n = (long long)P * ld;
     if (n <= 0) return;
-    agp_ozaki_rowscale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, mat_stride, ld, P, rscale);
+    agp_ozaki_rowscale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(L, mat_stride, ld, P, rscale, noise ? ld_obs : (1 << 30), noise);
 }
 
 void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
@@ -808,11 +827,15 @@ void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, i
     agp_ozaki_slice_kernel<<<grid, 256, 0, s>>>(L, mat_stride, ld, P, rscale, S, c0, c1 - c0, r0);
 }
 
-void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant) {
+void launch_ozaki_update(const OzakiParams& prm_in, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant) {
+    OzakiParams prm = prm_in;
+    if (prm.r_hi <= prm.r_lo) {  // plain form: lower tiles of block columns [c0, c1) over [0, c0)
+        prm.r_lo = prm.c0, prm.r_hi = prm.nt, prm.k_lo = prm.c0, prm.k_hi = prm.c1, prm.chi = prm.c0;
+    }
+    if (prm.r_hi <= prm.r_lo || prm.k_hi <= prm.k_lo || prm.chi <= 0 || prm.P <= 0) return;
     long long per_p = 0;
     for (int k = prm.c0; k < prm.c1; ++k) per_p += 2 * (prm.nt - k);
     const long long n_items = per_p * prm.P;
-    if (n_items <= 0 || prm.c0 <= 0) return;
     if (variant < 2 && ctas > n_items) ctas = (int)n_items;
     if (variant == 2) {
         agp_ozaki_update2_kernel<1><<<ctas, OZ2_THREADS, Oz2<1>::SMEM, s>>>(prm, maps);

@@ -30,10 +30,18 @@ struct OzakiParams {
     int c0, c1;            // tiles (i, k), c0 <= k < c1, k <= i < nt:  T_ik -= sum_{j < c0} L_ij L_kj^T
     int* err;              // raised when a barrier wait times out (never in a correct run)
     unsigned long long wait_timeout_ns;
+    // generalised form (second-generation kernels): tile rows r_lo <= i < r_hi against tile rows k_lo <= k < k_hi, k <= i,
+    // contraction over block columns [max(fc(i), fc(k)), chi), fc(r) = r - nt for the appended rows r >= nt of an
+    // identity-augmented batch (their tiles left of block column r - nt are structurally zero), else 0
+    // (all zero: the plain form above)
+    int r_lo, r_hi, k_lo, k_hi, chi;
 };
 
 // rscale[p][r] <- power-of-two bound of sqrt(K_rr), read from the diagonal of L right after the Gram fill
-void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s);
+// rows >= ld_obs (appended [I 0] rows of an identity-augmented batch, which end as rows of L^{-T}): bound 1 / sqrt(noise),
+// since sum_j (L^{-1})_jr^2 = (K^{-1})_rr <= 1 / lambda_min(K) <= 1 / noise for K = (PSD kernel matrix) + noise I
+void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P, double* rscale, cudaStream_t s, int ld_obs = 1 << 30,
+                           const double* noise = nullptr);
 // digit planes of the tiles (i, j), c0 <= j < c1, r0 <= i < nt (all 128 rows, 128 columns each)
 void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
                         cudaStream_t s);

@@ -277,9 +277,12 @@ int agp_hybrid_info(agp_handle* h, int32_t* active_out, int32_t* width_out, floa
  * receives up to seg_cap entries: one per segment and the total item count).  Contractions over block columns below a
  * segment's first one are the int8 kernel's, the items start at j0 = that column.  gram_lead > 0: with the Gram units as
  * ITEM_GRAM items (segment 0: its own tiles `gram_lead` items ahead of their readers, all later diagonal tiles and
- * super-column 1; segment s: super-column s + 1), 0: the Gram matrix comes from a launch of its own. */
-int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t* items_out, int64_t cap, int32_t* seg_out,
-                               int32_t seg_cap);
+ * super-column 1; segment s: super-column s + 1), 0: the Gram matrix comes from a launch of its own.  augmented != 0: the
+ * schedule of the gradient calls (counters laid out for 2 nt tile rows): the panels of the appended rows nt + a ride in the
+ * bulk of their block column with contraction ranges starting at max(a, first block column of the segment); the lauum pass
+ * has no items (one int8 launch after the last segment). */
+int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t augmented, int32_t* items_out, int64_t cap,
+                               int32_t* seg_out, int32_t seg_cap);
 
 /* Experiment behind DESIGN.md's co-residency note: the single-launch FP64 step of the resident batch with `ctas_per_sm`
  * CTAs per SM, `reps` int8 update launches over block columns [c0, c0 + 4) on a second stream (variant 0: the product

@@ -129,7 +129,7 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False, segments=None, width=0):
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False, segments=None, width=0, aug=False):
     """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
     counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
     every tile an item reads must be final, and the items must tile every contraction exactly.
@@ -166,8 +166,8 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                 assert all((pp, c, c, hh) in gram_done for pp in range(P) for c in range(nt) for hh in (0, 1))
             for pp in range(P):
                 assert counters[fdone(pp)] == c0_
-                for ii in range(c0_, nt):
-                    assert all(final.get((pp, ii, j), 0) == 2 for j in range(c0_)), (pp, ii)
+                for ii in range(c0_, nt + (c0_ if aug else 0)):   # (aug: and the appended rows nt + a, a < c0, over [a, c0))
+                    assert all(final.get((pp, ii, j), 0) == 2 for j in range(first_col(ii), c0_)), (pp, ii)
                     for kk in range(c0_, min(nt, c0_ + width)):
                         if kk <= ii:
                             for hh in (0, 1):
@@ -259,6 +259,23 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     _replay_queue(buf, P, nt, nt, 0)
 
 
+@pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (3, 16, 4), (2, 16, 3), (1, 9, 2)])
+def test_hybrid_schedule_of_the_gradient_calls_replay(P, nt, width):
+    """The identity-augmented batch on the hybrid schedule: the panels of the appended rows nt + a (rows of L^{-T}) in
+    the segments, their contraction over [a, c0) on the int8 path; no FP64 item touches the trailing block (the lauum
+    pass is one int8 launch)."""
+    from autogp.jl_b200 import _lib
+
+    lib = _lib.load()
+    i32p = C.POINTER(C.c_int32)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, 0, 1, None, 0, None, 0)
+    buf = np.zeros((n_items, 8), dtype=np.int32)
+    seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
+    assert lib.agp_queue_build_hybrid(P, nt, width, 0, 1, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert seg[0] == 0 and seg[-1] == n_items
+    _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0, expect_trailing=False, segments=seg.tolist(), width=width, aug=True)
+
+
 @pytest.mark.parametrize("gram_lead", [0, 1, 8, 296])
 @pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (5, 16, 4), (2, 16, 2), (2, 23, 4), (1, 9, 3)])
 def test_hybrid_schedule_replay(P, nt, width, gram_lead):
@@ -269,10 +286,10 @@ def test_hybrid_schedule_replay(P, nt, width, gram_lead):
 
     lib = _lib.load()
     i32p = C.POINTER(C.c_int32)
-    n_items = lib.agp_queue_build_hybrid(P, nt, width, gram_lead, None, 0, None, 0)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, gram_lead, 0, None, 0, None, 0)
     buf = np.zeros((n_items, 8), dtype=np.int32)
     seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
-    assert lib.agp_queue_build_hybrid(P, nt, width, gram_lead, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert lib.agp_queue_build_hybrid(P, nt, width, gram_lead, 0, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
     assert seg[0] == 0 and seg[-1] == n_items and np.all(np.diff(seg) > 0)
     _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width, gram_items=gram_lead > 0)
 

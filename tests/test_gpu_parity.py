@@ -608,12 +608,14 @@ def test_lml_gradient_full_size_directional_derivative(engine):
         fd = (f_up[0] - f_dn[0]) / (2 * hstep)
         an = float(np.dot(grads[p], d) + gnoise[p] * dn)
         assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (p, fd, an)
-    # the gradient call factors the augmented matrix on the FP64 schedule; a plain batch of this size takes the hybrid
-    # schedule (int8 digit-plane contractions, tests/test_hybrid_gpu.py): equal to 1e-11, and to 1e-13 with the hybrid off
+    # at this size both calls take the hybrid schedule (int8 digit-plane contractions, tests/test_hybrid_gpu.py); the LML of
+    # the gradient call equals the plain batch's to 1e-11 there and to 1e-13 on the FP64 schedule
     assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-11
     engine.set_hybrid(0)
     try:
-        assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
+        lml_f = engine.lml_grad_batch(nodes, noises, ts, xs)[0]
+        assert H.rel_err(lml_f, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-13
+        assert H.rel_err(lml_f, lml) <= 1e-11
     finally:
         engine.set_hybrid(-1)
 
@@ -660,12 +662,13 @@ def test_noise_only_gradient_full_size_and_edge_cases(engine):
         dn, _ = engine.lml_batch([nodes[p]], [noises[p] * (1 - hstep)], ts, xs)
         fd = (up[0] - dn[0]) / (2 * hstep * noises[p])
         assert abs(fd - gn[p]) <= 1e-5 * max(1.0, abs(fd)), (p, fd, gn[p])
-    # a plain LML batch after the augmented one is unaffected by the leftover state (bitwise on the same FP64 schedule;
-    # by default a plain batch of this size takes the hybrid schedule: equal to 1e-11)
+    # a plain LML batch after the augmented one is unaffected by the leftover state (at this size both take the hybrid
+    # schedule: equal to 1e-11; bitwise on the FP64 schedule)
     assert H.rel_err(lml, engine.lml_batch(nodes, noises, ts, xs)[0]) <= 1e-11
     engine.set_hybrid(0)
     try:
-        assert np.array_equal(engine.lml_batch(nodes, noises, ts, xs)[0], lml)
+        lml_f = engine.lml_grad_noise_batch(nodes, noises, ts, xs)[0]
+        assert np.array_equal(engine.lml_batch(nodes, noises, ts, xs)[0], lml_f)
     finally:
         engine.set_hybrid(-1)
     # empty data, failed factorisation, and no program-size limit on this path

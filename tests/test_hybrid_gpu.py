@@ -110,6 +110,29 @@ def test_hybrid_reports_a_failed_factorisation_like_the_fp64_schedule(eng):
     assert ref_info != 0
 
 
+@pytest.mark.parametrize("n,width", [(300, 1), (700, 2), (1100, 3), (1153, 4), (2048, 4)])
+def test_hybrid_gradient_calls_match_the_fp64_schedule(eng, n, width):
+    """agp_lml_grad_batch / agp_lml_grad_noise_batch on the hybrid schedule (the identity-augmented matrix: factorisation,
+    trtri and lauum contractions on the int8 path; bound of the appended rows 1 / sqrt(noise)) against the FP64 schedule:
+    LML, dLML/dparams, dLML/dnoise.  The gradients are sums of n^2 products of -K^{-1} entries with kernel derivatives:
+    agreement to 1e-8 of the gradient's scale."""
+    ts, xs, parts, nodes, noises = _batch(n, 4)
+    eng.set_hybrid(0)
+    lml0, g0, gn0, info0 = eng.lml_grad_batch(nodes, noises, ts, xs)
+    lmln0, gnn0, infon0 = eng.lml_grad_noise_batch(nodes, noises, ts, xs)
+    eng.set_hybrid(1, width, 2)
+    lml1, g1, gn1, info1 = eng.lml_grad_batch(nodes, noises, ts, xs)
+    lmln1, gnn1, infon1 = eng.lml_grad_noise_batch(nodes, noises, ts, xs)
+    assert np.all(info0 == 0) and np.all(info1 == 0) and np.all(infon1 == 0)
+    assert np.max(np.abs(lml1 - lml0) / np.abs(lml0)) <= 1e-10 and np.max(np.abs(lmln1 - lml0) / np.abs(lml0)) <= 1e-10
+    for p in range(len(nodes)):
+        scale = max(1.0, float(np.max(np.abs(g0[p]))) if len(g0[p]) else 1.0, abs(gn0[p]))
+        assert np.max(np.abs(np.asarray(g1[p]) - np.asarray(g0[p]))) <= 1e-8 * scale, (p, g1[p], g0[p])
+        assert abs(gn1[p] - gn0[p]) <= 1e-8 * scale and abs(gnn1[p] - gnn0[p]) <= 1e-8 * scale, (p, gn1[p], gn0[p], gnn1[p])
+    again = eng.lml_grad_batch(nodes, noises, ts, xs)
+    assert all(np.array_equal(a, b) for a, b in zip(g1, again[1])) and np.array_equal(gn1, again[2])
+
+
 def test_hybrid_full_size_n8192(eng):
     """configs[2] shape with the default settings (hybrid by size): against the oracle at the north_star tolerance."""
     n = 8192

@@ -80,6 +80,11 @@ struct agp_handle {
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
     int oz_min_nt = 16;    // AGP_OZ_MIN_NT
     bool oz_aug = true;    // AGP_OZ_AUG: the identity-augmented batches of the gradient calls take the hybrid schedule too
+    // AGP_OZ_SLICE_ITEMS=1: digit planes cut by SLICE items of the segments' queues instead of launches between them.  Built,
+    // replay- and GPU-tested, measured and NOT the default: n = 2048 x 64 6.80 against 6.71 ms, n = 8192 203.9 against 201.9 ms,
+    // gradient call 19.8 against 19.3 ms — the segments grow by more than the launches cost (the items' HBM traffic and
+    // dependency polls sit next to the panel items the segment is bound by).
+    bool oz_slice_items = false;
     bool oz_ride = false;  // AGP_OZ_RIDE: Gram units as items of the segments' queues (measured slower, see run_hybrid)
     int oz_variant = 3;    // AGP_OZ_KERNEL: 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one pass
     bool force_plain = false;  // diagnostics that index the single-launch schedule (agp_lml_trace)
@@ -195,6 +200,7 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_OZ_MIN_NT")) h->oz_min_nt = std::max(2, atoi(e));
     if (const char* e = getenv("AGP_OZ_RIDE")) h->oz_ride = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_AUG")) h->oz_aug = atoi(e) != 0;
+    if (const char* e = getenv("AGP_OZ_SLICE_ITEMS")) h->oz_slice_items = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 0 || atoi(e) == 2) ? atoi(e) : 3;
     if (agp::configure_ozaki() != cudaSuccess) {
         cudaGetLastError();
@@ -681,7 +687,10 @@ static void fuse_gram_items(int P, int nt_stride, int lead, std::vector<int4>& i
 // panels of the appended rows ride in the bulk of their block column, their contraction over [a, c0) is the int8 kernel's
 // like everyone else's; the lauum pass (-K^{-1} into the trailing tiles) has no FP64 items at all — one int8 launch after
 // the last segment.
-static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lead, std::vector<int4>& items, std::vector<int>& seg, bool aug = false) {
+// slice_items: the int8 digit planes of a block column's finished panels (the rows later int8 launches read: below the
+// super-column, and the appended rows) are cut by SLICE items of the segment itself, one block column behind the panels.
+static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lead, std::vector<int4>& items, std::vector<int>& seg, bool aug = false,
+                               bool slice_items = false, bool with_lauum = true) {
     items.clear();
     seg.clear();
     std::vector<int4> cur;
@@ -707,6 +716,22 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lea
                     for (int p = 0; p < P; ++p)
                         for (int hh = 0; hh < 2; ++hh) gram_unit(ride, p, i, k, hh);
         }
+        auto slices_of_column = [&](int k) {
+            if (!slice_items) return;
+            auto push = [&](int p, int i, int need_i) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    cur.push_back(make_int4(agp::ITEM_SLICE | (hh << 8), p, k, i));
+                    cur.push_back(make_int4(0, (need_i > 0 ? need_i : 0) << 16, -1, 0));
+                }
+            };
+            for (int i = c1; i < nt; ++i)
+                for (int p = 0; p < P; ++p) push(p, i, 2 * (k + 1));
+            // appended rows nt + a: tile (nt + a, k) is final after k - a + 1 panels of that row; a = k + 1 is structurally
+            // zero there (zero planes, read by the CTA pair of row a - 1).  The last super-column's are read by the lauum pass only.
+            if (aug && (c1 < nt || with_lauum))
+                for (int a = 0; a < std::min(nt, c1 + 1); ++a)
+                    for (int p = 0; p < P; ++p) push(p, nt + a, 2 * (k - a + 1));
+        };
         size_t ride_pos = 0;
         auto deal = [&](int j) {  // behind the POTF2 items of the segment's j-th block column
             const size_t hi = (ride.size() / 2) * (size_t)(j + 1) / (size_t)(c1 - c0);
@@ -746,7 +771,9 @@ static void build_queue_hybrid(int P, int nt, int nt_stride, int W, int gram_lea
             } else {
                 for (size_t a = 0; a < nb; ++a) b.tile(bulk[a].p, bulk[a].i, bulk[a].k, bulk[a].k);
             }
+            if (k > c0) slices_of_column(k - 1);
         }
+        slices_of_column(c1 - 1);
         deal(c1 - c0 - 1);
         if (gram_lead > 0 && c0 == 0) fuse_gram_items(P, nt_stride, gram_lead, cur);
         seg.push_back((int)(items.size() / 2));
@@ -780,7 +807,7 @@ static void fuse_gram_items(int P, int nt_stride, int lead, std::vector<int4>& i
         int4& it = items[2 * c];
         int4& dep = items[2 * c + 1];
         const int type = it.x & 0xff;
-        if (type == agp::ITEM_POTF2) continue;
+        if (type == agp::ITEM_POTF2 || type == agp::ITEM_SLICE) continue;
         const int j0 = dep.x & 0xffff;
         if (j0 != 0 || dep.z >= 0) continue;  // a continuation of an earlier item of the same tile half
         const int hh = (it.x >> 8) & 1, p = it.y, k = it.z, i = it.w;
@@ -1024,12 +1051,15 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     // behind the POTF2 items slow exactly the chain the segment is bound by.  AGP_OZ_RIDE=1 enables it.
     const bool aug = h->aug_identity;  // gradient calls: [I 0] rows appended (tile rows nt .. 2 nt), agp_lml_grad_batch / _noise_batch
     const bool ride = !aug && h->oz_ride && v.max_prog_len <= 64 && h->fuse_gram != 0;
-    auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0) - (aug ? 2000 : 0), nt_stride);
+    // digit planes cut by launches between the segments (default) or by SLICE items of the segments (AGP_OZ_SLICE_ITEMS=1)
+    const bool slice_items = h->oz_slice_items && !ride;
+    const bool lauum = aug && !h->trtri_only;
+    auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0) - (aug ? 2000 : 0) - (slice_items ? 4000 : 0) - (lauum ? 8000 : 0), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
         std::vector<int4> items;
         agp_handle::Queue qu;
-        build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg, aug);
+        build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg, aug, slice_items, lauum);
         qu.n_items = (int)(items.size() / 2);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
         if (e != cudaSuccess) {
@@ -1110,9 +1140,20 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     }
     const int oz_variant = (aug && h->oz_variant < 2) ? 3 : h->oz_variant;  // appended rows: second-generation kernels only
     const int n_seg = (int)qu.seg.size() - 1;
+    BatchView vq = v;  // what the persistent kernel sees: + the digit-plane buffers for its SLICE items
+    vq.oz_S = reinterpret_cast<signed char*>(h->d_S);
+    vq.oz_rscale = h->d_rscale;
+    vq.oz_plane = (long long)P * ld * ld;
+    if (slice_items) {
+        // the Gram diagonal is in place (launch above): row scales before the first segment
+        if ((rc = tic()) != AGP_OK) return rc;
+        agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream, nt * TB, aug ? v.noise : nullptr);
+        h->launches += 1;
+        if ((rc = toc(0)) != AGP_OK) return rc;
+    }
     for (int s = 0; s < n_seg; ++s) {
         const int c0 = s * W, c1 = std::min(nt, c0 + W);
-        if (s == 1) {
+        if (s == 1 && !slice_items) {
             // every diagonal tile of K is in place (Gram launch, or the units that rode in segment 0): row scales
             if ((rc = tic()) != AGP_OK) return rc;
             agp::launch_ozaki_rowscale(v.L, v.mat_stride, ld, P, h->d_rscale, h->stream, nt * TB, aug ? v.noise : nullptr);
@@ -1120,39 +1161,45 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
             if ((rc = toc(0)) != AGP_OK) return rc;
         }
         if (s > 0) {
-            if ((rc = tic()) != AGP_OK) return rc;
-            // digit planes of the previous super-column's finished panels: tile rows below it, and (aug) the appended rows
-            // nt + a, a <= c0 (row a = j + 1 is structurally zero at block column j: zero planes, read by the pair of row a - 1)
-            agp::launch_ozaki_slice(v.L, v.mat_stride, ld, aug ? nt + std::min(nt, c0 + 1) : nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
-            if ((rc = toc(3)) != AGP_OK) return rc;
+            if (!slice_items) {
+                if ((rc = tic()) != AGP_OK) return rc;
+                // digit planes of the previous super-column's finished panels: tile rows below it, and (aug) the appended rows
+                // nt + a, a <= c0 (row a = j + 1 is structurally zero at block column j: zero planes, read by the pair of row a - 1)
+                agp::launch_ozaki_slice(v.L, v.mat_stride, ld, aug ? nt + std::min(nt, c0 + 1) : nt, P, h->d_rscale, h->d_S, c0 - W, c0, c0, h->stream);
+                h->launches += 1;
+                if ((rc = toc(3)) != AGP_OK) return rc;
+            }
             if ((rc = tic()) != AGP_OK) return rc;
             agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, c0, c1, q.err, h->wait_timeout_ns, 0, 0, 0, 0, 0};
             if (aug) prm.r_lo = c0, prm.r_hi = nt + c0, prm.k_lo = c0, prm.k_hi = c1, prm.chi = c0;  // appended rows a < c0 over [a, c0)
             agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, oz_variant);
             if ((rc = toc(2)) != AGP_OK) return rc;
             AGP_CUDA(h, cudaMemsetAsync(h->d_sync, 0, sizeof(int), h->stream));  // the queue head; the dependency counters keep counting
-            h->launches += 2;
+            h->launches += 1;
         }
         if ((rc = tic()) != AGP_OK) return rc;
         q.items = qu.d_items + 2 * (size_t)qu.seg[s];
         q.n_items = qu.seg[s + 1] - qu.seg[s];
-        agp::launch_chol(v, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
+        agp::launch_chol(vq, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
         h->launches += 1;
         if ((rc = toc(1)) != AGP_OK) return rc;
     }
-    if (aug && !h->trtri_only) {
+    if (lauum) {
         // lauum pass: -K^{-1}[a][b] = 0 - sum_{j >= a} L^{-T}[a][j] L^{-T}[b][j]^T into the trailing tile (nt + a, nt + b), b <= a — a pure
         // contraction over block columns [a, nt): all of it on the int8 path, after the planes of the last super-column's
         // appended panels are cut
         const int cl = (n_seg - 1) * W;
-        if ((rc = tic()) != AGP_OK) return rc;
-        agp::launch_ozaki_slice(v.L, v.mat_stride, ld, 2 * nt, P, h->d_rscale, h->d_S, cl, nt, nt, h->stream);
-        if ((rc = toc(3)) != AGP_OK) return rc;
+        if (!slice_items) {
+            if ((rc = tic()) != AGP_OK) return rc;
+            agp::launch_ozaki_slice(v.L, v.mat_stride, ld, 2 * nt, P, h->d_rscale, h->d_S, cl, nt, nt, h->stream);
+            h->launches += 1;
+            if ((rc = toc(3)) != AGP_OK) return rc;
+        }
         if ((rc = tic()) != AGP_OK) return rc;
         agp::OzakiParams prm{v.L, v.mat_stride, ld, nt, P, h->d_rscale, 0, 0, q.err, h->wait_timeout_ns, nt, 2 * nt, nt, 2 * nt, nt};
         agp::launch_ozaki_update(prm, h->ozmaps, h->num_sms, h->stream, oz_variant);
         if ((rc = toc(2)) != AGP_OK) return rc;
-        h->launches += 2;
+        h->launches += 1;
     }
     if (kernel_ms) {
         kernel_ms[0] = acc_ms[0];
@@ -1533,9 +1580,11 @@ int64_t agp_queue_build_gram(int32_t P, int32_t nt, int32_t order, int32_t lead,
 int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t augmented, int32_t* items_out, int64_t cap, int32_t* seg_out,
                                int32_t seg_cap) {
     if (P < 0 || nt < 1 || width < 1 || gram_lead < 0 || (augmented && gram_lead > 0)) return AGP_ERR_ARG;
+    const bool slice_items = (augmented & 2) != 0;  // bit 1: with the SLICE items
+    augmented &= 1;
     std::vector<int4> items;
     std::vector<int> seg;
-    build_queue_hybrid(P, nt, augmented ? 2 * nt : nt, width, gram_lead, items, seg, augmented != 0);
+    build_queue_hybrid(P, nt, augmented ? 2 * nt : nt, width, gram_lead, items, seg, augmented != 0, slice_items, true);
     if (seg_out)
         for (size_t e = 0; e < seg.size() && (int32_t)e < seg_cap; ++e) seg_out[e] = seg[e];
     return export_queue(items, items_out, cap);

@@ -178,5 +178,7 @@ __device__ bool do_potf2(const BatchView& v, const SchedView& q, int idx);
 __device__ bool do_diag(const BatchView& v, const SchedView& q, const TmaMaps& maps, int idx);
 // ITEM_GRAM: one Gram work unit, K(ts_i, ts_k) [+ noise I] into 64 rows of tile (i,k) (agp_chol_gram.cu)
 __device__ bool do_gram(const BatchView& v, const SchedView& q, int idx);
+// ITEM_SLICE: int8 digit planes of a finished tile half for the hybrid schedule (agp_chol_slice.cu)
+__device__ bool do_slice(const BatchView& v, const SchedView& q, int idx);
 
 }  // namespace agp

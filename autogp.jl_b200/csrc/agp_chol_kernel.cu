@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(FT, 2) agp_chol_kernel(const __grid_constant__
             ok = do_potf2(v, q, idx);
         } else if (type == ITEM_GRAM) {
             ok = do_gram(v, q, idx);
+        } else if (type == ITEM_SLICE) {
+            ok = do_slice(v, q, idx);
         } else if (type == ITEM_DIAG) {
             ok = do_diag(v, q, maps, idx);
         } else {

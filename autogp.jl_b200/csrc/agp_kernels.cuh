@@ -37,6 +37,10 @@ struct BatchView {
     double* cum;             // [P][ld/TB][2] running (sum log L_ii, sum z_i^2) after each block column
     int aug_identity;        // appended rows carry [I 0] instead of kernel values: their Schur complement is -K^{-1}
                              // and their forward-solve entries are -alpha (agp_lml_grad_batch)
+    // hybrid schedule (agp_ozaki.cu), for the SLICE items of the persistent kernel
+    signed char* oz_S;       // digit planes [8][P][ld][ld]
+    const double* oz_rscale; // [P][ld][2] row scale, digit factor
+    long long oz_plane;      // bytes between two planes = P ld ld
 };
 
 // ---- persistent dataflow scheduler (agp_fused.cu) ------------------------------------------
@@ -52,7 +56,9 @@ struct BatchView {
 //   ITEM_GRAM: {ITEM_GRAM | h << 8, particle, block column k, tile row i}, {0, 0, flag, 0}: the Gram unit of that tile
 //   half; bumps counter `flag` (relative to SchedView::head), which the first PANEL item of the tile half carries as
 //   its extra_flag with extra_need = 1 (the two units of a diagonal tile bump one flag, its first DIAG items need 2).
-enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_GRAM = 3, ITEM_PARTIAL = 1 << 9, ITEM_YINIT = 1 << 10 };
+//   ITEM_SLICE: {ITEM_SLICE | h << 8, particle, block column k, tile row i}, {0, need_i << 16, -1, 0}: the int8 digit planes of that
+//   finished tile half (hybrid schedule); waits for rowdone[p][i] >= need_i, nobody in the launch waits for it.
+enum { ITEM_DIAG = 0, ITEM_POTF2 = 1, ITEM_PANEL = 2, ITEM_GRAM = 3, ITEM_SLICE = 4, ITEM_PARTIAL = 1 << 9, ITEM_YINIT = 1 << 10 };
 
 struct SchedView {
     const int4* items;  // in-order queue (2 x int4 per item): every item's producers sit earlier in the list

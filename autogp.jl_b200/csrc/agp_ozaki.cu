@@ -18,6 +18,7 @@
 
 #include <math.h>
 
+#include "agp_ozaki_digits.cuh"
 #include "agp_ptx.cuh"
 
 namespace agp {
@@ -685,8 +686,14 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + hh * 64;
             const int cmax = !it.valid ? -1 : (it.i == it.k) ? row - hh * 64 : 63;  // diagonal tile: the strict upper triangle keeps its Gram values
             double2 tv[32];
+            // (only what will be stored back is read: the strict upper triangle of a diagonal tile is never written by the
+            // Gram fill, and a pair's idle CTA has nothing to read)
 #pragma unroll
-            for (int e = 0; e < 32; ++e) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
+            for (int e = 0; e < 32; ++e) {
+                if (2 * e + 1 <= cmax) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
+                else if (2 * e <= cmax) tv[e] = make_double2(__ldcg(Trow + 2 * e), 0.0);
+                else tv[e] = make_double2(0.0, 0.0);
+            }
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const double w = pass ? 0x1p-61 : 0x1p-33;  // the last group of the pass carries 2^(-12 - 7 g), g = 3 / 7
@@ -792,24 +799,7 @@ __global__ void __launch_bounds__(256) agp_ozaki_slice_kernel(const double* __re
         const double* src = L + (long long)p * mat_stride + (long long)r * ld + j * 128 + lane * 4;
         const double2 x01 = __ldcs(reinterpret_cast<const double2*>(src));
         const double2 x23 = __ldcs(reinterpret_cast<const double2*>(src) + 1);
-        long long v[4] = {__double2ll_rn(x01.x * f), __double2ll_rn(x01.y * f), __double2ll_rn(x23.x * f), __double2ll_rn(x23.y * f)};
-        int8_t* dst = S + ((long long)p * ld + r) * ld + j * 128 + lane * 4;
-#pragma unroll
-        for (int q = OZ_SLICES - 1; q >= 0; --q) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                long long d;
-                if (q > 0) {
-                    d = ((v[e] + 64) & 127) - 64;  // balanced digit in [-64, 63]
-                    v[e] = (v[e] - d) >> 7;        // exact
-                } else {
-                    d = v[e] < -127 ? -127 : (v[e] > 127 ? 127 : v[e]);  // |x| <= 2^e: the leading digit is within +-65
-                }
-                word |= ((uint32_t)(d & 0xff)) << (8 * e);
-            }
-            *reinterpret_cast<uint32_t*>(dst + (long long)q * plane) = word;
-        }
+        oz_store_digits4(x01.x, x01.y, x23.x, x23.y, f, S + ((long long)p * ld + r) * ld + j * 128 + lane * 4, plane);
     }
 }
 

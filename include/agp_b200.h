@@ -280,7 +280,8 @@ int agp_hybrid_info(agp_handle* h, int32_t* active_out, int32_t* width_out, floa
  * super-column 1; segment s: super-column s + 1), 0: the Gram matrix comes from a launch of its own.  augmented != 0: the
  * schedule of the gradient calls (counters laid out for 2 nt tile rows): the panels of the appended rows nt + a ride in the
  * bulk of their block column with contraction ranges starting at max(a, first block column of the segment); the lauum pass
- * has no items (one int8 launch after the last segment). */
+ * has no items (one int8 launch after the last segment).  augmented & 2: with the ITEM_SLICE items (type 4: the int8
+ * digit planes of a finished tile half, field 5 >> 16 = the rowdone value of its tile row it waits for). */
 int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gram_lead, int32_t augmented, int32_t* items_out, int64_t cap,
                                int32_t* seg_out, int32_t seg_cap);
 

@@ -129,13 +129,15 @@ def test_weight_consumers_match_oracle():
     assert np.array_equal(smc.resample_indices(lw, 11), smc.resample_indices(lw, 11))
 
 
-def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False, segments=None, width=0, aug=False):
+def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_trailing=True, gram_items=False, segments=None, width=0, aug=False,
+                  slice_items=False):
     """Sequential replay of a work queue with the kernel's own wait rules (agp_fused.cu).  Every
     counter wait must already be satisfied by EARLIER items (deadlock-freedom of in-order popping),
     every tile an item reads must be final, and the items must tile every contraction exactly.
     first_col(i): first block column with a non-zero tile in tile row i (0 except for the rows of
     the inverse schedule)."""
-    DIAG, POTF2, PANEL, GRAM, PARTIAL, YINIT = 0, 1, 2, 3, 1 << 9, 1 << 10
+    DIAG, POTF2, PANEL, GRAM, SLICE, PARTIAL, YINIT = 0, 1, 2, 3, 4, 1 << 9, 1 << 10
+    sliced = set()
     first_col = first_col or (lambda i: 0)
     nts = nt_total  # the builders lay the counters out for nt_stride = nt_total
     n_tiles = nts * (nts + 1) // 2
@@ -168,6 +170,8 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                 assert counters[fdone(pp)] == c0_
                 for ii in range(c0_, nt + (c0_ if aug else 0)):   # (aug: and the appended rows nt + a, a < c0, over [a, c0))
                     assert all(final.get((pp, ii, j), 0) == 2 for j in range(first_col(ii), c0_)), (pp, ii)
+                    if slice_items:   # what the int8 launch reads: planes from the first non-zero tile on, and one zero tile before it
+                        assert all((pp, ii, j, hh) in sliced for j in range(max(first_col(ii) - 1, 0), c0_) for hh in (0, 1)), (pp, ii)
                     for kk in range(c0_, min(nt, c0_ + width)):
                         if kk <= ii:
                             for hh in (0, 1):
@@ -186,6 +190,12 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
             gram_done.add((p, i, k, h))
             counters[flag] += 1
             n_gram += 1
+            continue
+        if t == SLICE:   # digit planes of a finished tile half: its tile row has finished the panels up to block column k
+            assert slice_items and k < nt and k < i < nt_total and (p, i, k, h) not in sliced and flag == -1
+            assert counters[rowdone(p, i)] >= need_i and need_i == max(0, 2 * (k - first_col(i) + 1))
+            assert final.get((p, i, k), 0) == 2 or k < first_col(i)
+            sliced.add((p, i, k, h))
             continue
         if t == POTF2:
             assert k < nt and counters[diagu(p, k)] >= need and need == n_diag.get((p, k), 0), (p, k, need)
@@ -242,6 +252,7 @@ def _replay_queue(buf, P, nt, nt_total, first_row, first_col=None, expect_traili
                         assert (p, i, k, h) not in covered
                     elif first_col(k) <= first_col(i):
                         assert covered[(p, i, k, h)] == nt and (p, i, k, h) in stored   # trailing (Schur complement) tile
+    return sliced
 
 
 @pytest.mark.parametrize("order", [0, 1, 2, 3])
@@ -259,8 +270,9 @@ def test_work_queue_replay_never_waits_for_a_later_item(P, nt, order):
     _replay_queue(buf, P, nt, nt, 0)
 
 
+@pytest.mark.parametrize("slices", [0, 1])
 @pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (3, 16, 4), (2, 16, 3), (1, 9, 2)])
-def test_hybrid_schedule_of_the_gradient_calls_replay(P, nt, width):
+def test_hybrid_schedule_of_the_gradient_calls_replay(P, nt, width, slices):
     """The identity-augmented batch on the hybrid schedule: the panels of the appended rows nt + a (rows of L^{-T}) in
     the segments, their contraction over [a, c0) on the int8 path; no FP64 item touches the trailing block (the lauum
     pass is one int8 launch)."""
@@ -268,15 +280,18 @@ def test_hybrid_schedule_of_the_gradient_calls_replay(P, nt, width):
 
     lib = _lib.load()
     i32p = C.POINTER(C.c_int32)
-    n_items = lib.agp_queue_build_hybrid(P, nt, width, 0, 1, None, 0, None, 0)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, 0, 1 + 2 * slices, None, 0, None, 0)
     buf = np.zeros((n_items, 8), dtype=np.int32)
     seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
-    assert lib.agp_queue_build_hybrid(P, nt, width, 0, 1, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert lib.agp_queue_build_hybrid(P, nt, width, 0, 1 + 2 * slices, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
     assert seg[0] == 0 and seg[-1] == n_items
-    _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0, expect_trailing=False, segments=seg.tolist(), width=width, aug=True)
+    sliced = _replay_queue(buf, P, nt, 2 * nt, 0, first_col=lambda i: i - nt if i >= nt else 0, expect_trailing=False, segments=seg.tolist(), width=width,
+                           aug=True, slice_items=bool(slices))
+    if slices:   # the lauum launch after the last segment reads every appended row from one tile before its first non-zero one
+        assert all((p, nt + a, j, hh) in sliced for p in range(P) for a in range(nt) for j in range(max(a - 1, 0), nt) for hh in (0, 1))
 
 
-@pytest.mark.parametrize("gram_lead", [0, 1, 8, 296])
+@pytest.mark.parametrize("gram_lead", [0, 1, 8, 296, -1])
 @pytest.mark.parametrize("P,nt,width", [(1, 2, 1), (3, 5, 2), (2, 8, 4), (5, 16, 4), (2, 16, 2), (2, 23, 4), (1, 9, 3)])
 def test_hybrid_schedule_replay(P, nt, width, gram_lead):
     """The super-column schedule of the hybrid factorisation (agp_queue_build_hybrid): every segment is a launch of
@@ -286,12 +301,14 @@ def test_hybrid_schedule_replay(P, nt, width, gram_lead):
 
     lib = _lib.load()
     i32p = C.POINTER(C.c_int32)
-    n_items = lib.agp_queue_build_hybrid(P, nt, width, gram_lead, 0, None, 0, None, 0)
+    slices = 2 if gram_lead < 0 else 0   # (-1: the default schedule — Gram launch in front, SLICE items in the segments)
+    gram_lead = max(gram_lead, 0)
+    n_items = lib.agp_queue_build_hybrid(P, nt, width, gram_lead, slices, None, 0, None, 0)
     buf = np.zeros((n_items, 8), dtype=np.int32)
     seg = np.zeros((nt + width - 1) // width + 1, dtype=np.int32)
-    assert lib.agp_queue_build_hybrid(P, nt, width, gram_lead, 0, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
+    assert lib.agp_queue_build_hybrid(P, nt, width, gram_lead, slices, buf.ctypes.data_as(i32p), n_items, seg.ctypes.data_as(i32p), len(seg)) == n_items
     assert seg[0] == 0 and seg[-1] == n_items and np.all(np.diff(seg) > 0)
-    _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width, gram_items=gram_lead > 0)
+    _replay_queue(buf, P, nt, nt, 0, segments=seg.tolist(), width=width, gram_items=gram_lead > 0, slice_items=slices > 0)
 
 
 @pytest.mark.parametrize("order", [0, 2, 3])

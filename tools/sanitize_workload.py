@@ -42,6 +42,16 @@ def main():
     summands = [[parts[0][0].left, parts[0][0].right]]
     smean, scov, sinfo = eng.predict_sum_batch(summands, noises[:1], ts[:200], xs[:200], ts[200:230])
     assert sinfo[0] == 0
+    # the hybrid schedule, forced on at small sizes: int8 tcgen05 update kernel (CTA pairs; odd numbers of tile rows), digit
+    # planes, row scales, the FP64 segments; then the gradient calls on it (appended rows, lauum pass on the int8 path)
+    eng.set_hybrid(1, 2, 2)
+    ts5, xs5 = synthetic_series(600)
+    lml5, info5 = eng.lml_batch(nodes[:3], noises[:3], ts5, xs5)
+    assert eng.hybrid_info()[0] and np.all(info5 == 0) and np.all(np.isfinite(lml5))
+    _, hg, hgn, hinfo = eng.lml_grad_batch(nodes[:2], noises[:2], ts5[:400], xs5[:400])
+    _, hgn2, hinfo2 = eng.lml_grad_noise_batch(nodes[:2], noises[:2], ts5[:400], xs5[:400])
+    assert np.all(hinfo == 0) and np.all(hinfo2 == 0) and np.all(np.isfinite(hgn)) and np.all(np.isfinite(hgn2))
+    eng.set_hybrid(-1)
     print(f"sanitize workload ok: {eng.launch_count} launches")
     eng.close()
 

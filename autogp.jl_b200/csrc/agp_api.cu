@@ -79,6 +79,11 @@ struct agp_handle {
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
     int oz_min_nt = 16;    // AGP_OZ_MIN_NT
+    double min_noise = 0.0;  // smallest noise of the resident batch (NaN counts as -1)
+    // The appended rows of an identity-augmented batch are scaled by the a-priori bound 1 / sqrt(noise) (agp_ozaki.cuh); a noise
+    // far below the smallest eigenvalue the kernel itself provides (a WhiteNoise node with noise ~ 0) makes that bound loose and
+    // costs digits: below this value the gradient calls keep the FP64 schedule.  The reference never goes below its JITTER = 1e-5.
+    static constexpr double kAugMinNoise = 1e-9;
     bool oz_aug = true;    // AGP_OZ_AUG: the identity-augmented batches of the gradient calls take the hybrid schedule too
     // AGP_OZ_SLICE_ITEMS=1: digit planes cut by SLICE items of the segments' queues instead of launches between them.  Built,
     // replay- and GPU-tested, measured and NOT the default: n = 2048 x 64 6.80 against 6.71 ms, n = 8192 203.9 against 201.9 ms,
@@ -88,6 +93,7 @@ struct agp_handle {
     bool oz_ride = false;  // AGP_OZ_RIDE: Gram units as items of the segments' queues (measured slower, see run_hybrid)
     int oz_variant = 3;    // AGP_OZ_KERNEL: 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one pass
     bool force_plain = false;  // diagnostics that index the single-launch schedule (agp_lml_trace)
+    bool oz_nomem = false;     // the digit planes did not fit into device memory once: this handle stays on the FP64 schedule
     int8_t* d_S = nullptr;     size_t cap_S = 0;       // digit planes [8][P][ld][ld]
     double* d_rscale = nullptr; size_t cap_rscale = 0;  // [P][ld][2]
     agp::OzakiMaps ozmaps{};
@@ -393,6 +399,8 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
         pp[0] = 0;
         for (int p = 0; p < P; ++p) pp[p + 1] = pp[p] + n_params[p];
     }
+    h->min_noise = 1e300;
+    for (int p = 0; p < P; ++p) h->min_noise = (noise[p] == noise[p] && noise[p] < h->min_noise) ? noise[p] : (noise[p] == noise[p] ? h->min_noise : -1.0);
     if (P > 0) {
         memcpy(h->h_in + off_noise, noise, (size_t)P * 8);
         memcpy(h->h_in + off_npred, noise_pred ? noise_pred : noise, (size_t)P * 8);  // default: noise_pred = noise (src/GP.jl:738)
@@ -924,7 +932,8 @@ static int hybrid_width(const agp_handle* h, int nt) { return h->oz_width > 0 ? 
 static bool use_hybrid(const agp_handle* h, int first_row) {
     const BatchView& v = h->view;
     if (h->force_plain || first_row != 0 || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
-    if (h->aug_identity ? (!h->oz_aug || v.nt_total != 2 * v.nt) : v.nt_total != v.nt) return false;
+    if (h->aug_identity ? (!h->oz_aug || v.nt_total != 2 * v.nt || !(h->min_noise >= agp_handle::kAugMinNoise)) : v.nt_total != v.nt) return false;
+    if (h->oz_nomem) return false;
     return h->oz_mode < 0 ? (v.nt >= h->oz_min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 
@@ -1080,7 +1089,13 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
     it->second.last_use = ++h->queue_clock;
     const agp_handle::Queue& qu = it->second;
     int rc;
-    if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld * ld)) != AGP_OK) return rc;
+    if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld * ld)) != AGP_OK) {
+        if (rc != AGP_ERR_NOMEM) return rc;
+        // the digit planes are as large as the factors themselves: without room for them the FP64 schedule does the job
+        h->oz_nomem = true;
+        h->err.clear();
+        return run_fused(h, nullptr, kernel_ms);
+    }
     if ((rc = grow_device(h, &h->d_rscale, &h->cap_rscale, (size_t)P * ld * 16)) != AGP_OK) return rc;
     if (h->oz_S != h->d_S || h->oz_ld != ld || h->oz_P != P) {
         if (!agp::make_ozaki_maps(h->d_S, ld, P, &h->ozmaps)) return fail(h, AGP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the digit planes");

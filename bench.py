@@ -488,6 +488,17 @@ class Bench:
                            f"super-column of {hyb_w} block columns), {n_seg - 1} x agp_ozaki_update2_kernel (the contractions over all earlier block columns as exact "
                            f"int8 digit-plane products on tcgen05, kind::i8) and {n_seg - 1} x agp_ozaki_slice_kernel; avg_launch_ms = their sum")
             traffic, traffic_note = None, "no capture of the multi-launch factorisation on file"
+            hpath = os.path.join(ROOT, "profiles", "hybrid_traffic.json")
+            if os.path.exists(hpath):
+                try:
+                    tj = json.load(open(hpath))
+                    if tj.get("n") == n and tj.get("particles") == P and tj.get("kernel_source_md5") == kernel_source_md5():
+                        traffic = tj.get("dram_bytes_per_step")
+                        traffic_note = tj.get("source", "")
+                    else:
+                        traffic_note = "the ncu capture on file is of another kernel source or workload"
+                except Exception:
+                    pass
         roofline = {
             "bound": "tensor",
             "kernel": kernel_name,

@@ -133,6 +133,25 @@ def test_hybrid_gradient_calls_match_the_fp64_schedule(eng, n, width):
     assert all(np.array_equal(a, b) for a, b in zip(g1, again[1])) and np.array_equal(gn1, again[2])
 
 
+def test_hybrid_gradient_keeps_the_fp64_schedule_when_the_noise_bound_is_useless(eng):
+    """The appended rows' scale is the a-priori bound 1 / sqrt(noise); with a noise far below what the kernel itself puts on the
+    diagonal (a WhiteNoise node, noise ~ 0) that bound would cost the digits: such a batch stays on the FP64 schedule."""
+    n = 700
+    ts, xs = o.synthetic_series(n)
+    nd = H.to_agp(o.synthetic_particle(0, "se+wn")[0])
+    eng.set_hybrid(0)
+    ref = eng.lml_grad_batch([nd], [1e-12], ts, xs)
+    eng.set_hybrid(1, 2, 2)
+    got = eng.lml_grad_batch([nd], [1e-12], ts, xs)
+    assert not eng.hybrid_info()[0] and got[3][0] == 0
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1][0], ref[1][0]) and np.array_equal(got[2], ref[2])
+    eng.lml_grad_batch([nd], [1e-3], ts, xs)
+    assert eng.hybrid_info()[0]
+    # the plain LML of the same batch has no such restriction (its row scales come from the Gram diagonal)
+    eng.lml_batch([nd], [1e-12], ts, xs)
+    assert eng.hybrid_info()[0]
+
+
 def test_hybrid_full_size_n8192(eng):
     """configs[2] shape with the default settings (hybrid by size): against the oracle at the north_star tolerance."""
     n = 8192

@@ -937,10 +937,10 @@ static bool use_hybrid(const agp_handle* h, int first_row) {
     return h->oz_mode < 0 ? (v.nt >= h->oz_min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 
-static int run_hybrid(agp_handle* h, float* kernel_ms);
+static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace = nullptr);
 
 static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_ms = nullptr, int first_row = 0) {
-    if (d_trace == nullptr && use_hybrid(h, first_row)) return run_hybrid(h, kernel_ms);
+    if (use_hybrid(h, first_row)) return run_hybrid(h, kernel_ms, d_trace);
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt;
     const int nt_stride = h->ld / TB;
@@ -1049,7 +1049,7 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
 
 // Hybrid factorisation: Gram fill, row scales, then per super-column  [digit planes of the previous super-column's
 // panels -> int8 update of this super-column's tiles ->] one launch of the persistent kernel over the segment.
-static int run_hybrid(agp_handle* h, float* kernel_ms) {
+static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt, ld = h->ld;
     const int nt_stride = ld / TB;
@@ -1195,6 +1195,7 @@ static int run_hybrid(agp_handle* h, float* kernel_ms) {
         if ((rc = tic()) != AGP_OK) return rc;
         q.items = qu.d_items + 2 * (size_t)qu.seg[s];
         q.n_items = qu.seg[s + 1] - qu.seg[s];
+        q.trace = d_trace ? d_trace + 8 * (long long)qu.seg[s] : nullptr;
         agp::launch_chol(vq, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
         h->launches += 1;
         if ((rc = toc(1)) != AGP_OK) return rc;
@@ -1539,12 +1540,18 @@ int64_t agp_lml_trace(agp_handle* h, int64_t* trace_out, int64_t cap_items) {
     if (h->n_pred > 0) return fail(h, AGP_ERR_STATE, "agp_lml_trace: plain LML batches only");
     AGP_CUDA(h, cudaSetDevice(h->device));
     const bool fused = gram_as_items(h, 0);  // as run_fused decides
-    const int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0) + (fused ? (int64_t)h->P * h->view.nt * (h->view.nt + 1) : 0);
+    int64_t n_items = agp_queue_build(h->P, h->view.nt, h->order, nullptr, 0) + (fused ? (int64_t)h->P * h->view.nt * (h->view.nt + 1) : 0);
+    if (use_hybrid(h, 0)) {  // the segments of the hybrid schedule, items in agp_queue_build_hybrid order (default switches)
+        std::vector<int4> items;
+        std::vector<int> seg;
+        build_queue_hybrid(h->P, h->view.nt, h->ld / TB, hybrid_width(h, h->view.nt), 0, items, seg, false, h->oz_slice_items && !h->oz_ride, true);
+        n_items = (int64_t)items.size() / 2;
+    }
     if (!trace_out) return n_items;
     long long* d_trace = nullptr;
     AGP_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&d_trace), (size_t)n_items * 8 * sizeof(long long)));
     cudaMemsetAsync(d_trace, 0, (size_t)n_items * 8 * sizeof(long long), h->stream);
-    int rc = run_fused(h, d_trace);  // (a traced run always takes the single-launch schedule)
+    int rc = run_fused(h, d_trace);
     if (rc == AGP_OK) {
         int64_t m = n_items < cap_items ? n_items : cap_items;
         cudaError_t e = cudaMemcpyAsync(trace_out, d_trace, (size_t)m * 8 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);

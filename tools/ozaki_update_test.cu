@@ -102,6 +102,7 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(dL, T.data(), T.size() * 8, cudaMemcpyHostToDevice));
         agp::OzakiParams prm{dL, ms, ld, nt, P, dR, c0, c1, d_err, 2000000000ull};
         agp::launch_ozaki_update(prm, maps, sms, 0, variant);
+        CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
         int err = 0;
         CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));

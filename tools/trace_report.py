@@ -30,7 +30,22 @@ def main():
     lib = _lib.load()
     items = np.zeros((st.shape[0], 8), dtype=np.int32)
     fused, lead = eng.gram_items()
-    if fused:
+    hyb, width, _ = eng.hybrid_info()
+    seg = None
+    if hyb:   # the segments of the hybrid schedule: stamps of all launches in one array, items in agp_queue_build_hybrid order
+        fused = False
+        seg = np.zeros(-(-nt // width) + 1, dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        assert lib.agp_queue_build_hybrid(P, nt, width, 0, 0, items.ctypes.data_as(i32p), st.shape[0], seg.ctypes.data_as(i32p), len(seg)) == st.shape[0]
+        print(f"hybrid schedule, super-column width {width}: segments start at items {seg.tolist()}")
+        for s_ in range(len(seg) - 1):
+            a, b = seg[s_], seg[s_ + 1]
+            w = st[a:b]
+            busy = (w[:, 5] - w[:, 0]).sum() * 1e-3
+            span_s = (w[:, 5].max() - w[:, 0].min()) * 1e-3
+            slots_s = len(np.unique(w[:, 7]))
+            print(f"  segment {s_}: items {b - a:6d}  span {span_s:8.0f} us  busy {busy / 1e3:8.1f} ms*cta  occupancy {busy / (slots_s * span_s):.3f}")
+    elif fused:
         assert lib.agp_queue_build_gram(P, nt, order, lead, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0]) == st.shape[0]
     else:
         assert lib.agp_queue_build(P, nt, order, items.ctypes.data_as(C.POINTER(C.c_int32)), st.shape[0]) == st.shape[0]

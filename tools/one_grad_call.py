@@ -1,5 +1,7 @@
+"""Two agp_lml_grad_batch calls at n = 2048 x 64 (the second one warm) — run under `ncu --metrics gpu__time_duration.sum` for the launch
+list of a gradient call on the hybrid schedule (profiles/r02_ncu_launches_grad_hybrid.csv)."""
 import os, sys
-ROOT='/root/repo'
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'oracle'))
 import autogp_oracle as o
 import autogp.jl_b200 as agp

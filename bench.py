@@ -300,6 +300,8 @@ class Bench:
                 "int8_kernel": {"kernel": "agp_ozaki_update2_kernel<2> (tcgen05.mma.cta_group::2.kind::i8, TMEM accumulators, CTA pairs)",
                                 "achieved": int8_tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, 36 digit-plane products per FP64 product)",
                                 "frac": None if int8_tops is None else int8_tops / INT8_PEAK_TOPS,
+                                "peak_source": "measured on this pool: tcgen05.mma kind::i8 issue rate with operands resident in shared memory, 8192 MAC/clk/SM "
+                                               "at 1965 MHz (profiles/r02_i8_probe.txt); 2 x MEASURED_PEAKS.json's dense bf16 burst figure would be 3326",
                                 "fp64_equivalent_tflops": None if int8_tops is None else int8_tops / INT8_PRODUCTS}}
 
     # -- gradient calls, end to end through the C-ABI ----------------------------------------------

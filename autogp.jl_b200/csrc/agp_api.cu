@@ -79,6 +79,8 @@ struct agp_handle {
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
     int oz_min_nt = 16;    // AGP_OZ_MIN_NT
+    int oz_min_nt_aug = 12;  // AGP_OZ_MIN_NT_AUG: the gradient calls gain earlier (three passes of contractions, the lauum pass all int8): measured
+                             // n = 1280 7.46 -> 7.61 ms, 1536 11.49 -> 10.85, 1792 16.78 -> 14.76, 2048 23.6 -> 19.3 (64 particles)
     double min_noise = 0.0;  // smallest noise of the resident batch (NaN counts as -1)
     // The appended rows of an identity-augmented batch are scaled by the a-priori bound 1 / sqrt(noise) (agp_ozaki.cuh); a noise
     // far below the smallest eigenvalue the kernel itself provides (a WhiteNoise node with noise ~ 0) makes that bound loose and
@@ -204,6 +206,7 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_OZAKI")) h->oz_mode = atoi(e) < 0 ? -1 : atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_W")) h->oz_width = std::max(0, atoi(e));
     if (const char* e = getenv("AGP_OZ_MIN_NT")) h->oz_min_nt = std::max(2, atoi(e));
+    if (const char* e = getenv("AGP_OZ_MIN_NT_AUG")) h->oz_min_nt_aug = std::max(2, atoi(e));
     if (const char* e = getenv("AGP_OZ_RIDE")) h->oz_ride = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_AUG")) h->oz_aug = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_SLICE_ITEMS")) h->oz_slice_items = atoi(e) != 0;
@@ -934,7 +937,8 @@ static bool use_hybrid(const agp_handle* h, int first_row) {
     if (h->force_plain || first_row != 0 || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
     if (h->aug_identity ? (!h->oz_aug || v.nt_total != 2 * v.nt || !(h->min_noise >= agp_handle::kAugMinNoise)) : v.nt_total != v.nt) return false;
     if (h->oz_nomem) return false;
-    return h->oz_mode < 0 ? (v.nt >= h->oz_min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
+    const int min_nt = h->aug_identity ? std::min(h->oz_min_nt, h->oz_min_nt_aug) : h->oz_min_nt;
+    return h->oz_mode < 0 ? (v.nt >= min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 
 static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace = nullptr);

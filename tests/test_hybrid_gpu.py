@@ -60,7 +60,8 @@ def test_hybrid_matches_the_fp64_schedule_and_the_oracle(eng, n, width):
 
 
 def test_hybrid_is_chosen_by_size_and_can_be_switched_off(eng):
-    """Default: plain LML runs from 16 block columns on (n >= 1921); continuations and augmented batches never."""
+    """Default: plain LML runs from 16 block columns on (n >= 1921), the gradient calls from 12 (n >= 1409); continuations
+    (set_prefix + run_append) and predictive batches never."""
     ts, xs, parts, nodes, noises = _batch(2048, 3)
     eng.upload(nodes, noises, ts, xs)
     assert eng.hybrid_info()[0]
@@ -75,6 +76,13 @@ def test_hybrid_is_chosen_by_size_and_can_be_switched_off(eng):
     eng.run()
     lml_f, _ = eng.fetch()
     assert np.max(np.abs(lml_h - lml_f) / np.abs(lml_f)) <= 1e-10
+    ts_g, xs_g = o.synthetic_series(1536)
+    eng.set_hybrid(-1)
+    _, _, _, ginfo = eng.lml_grad_batch(nodes[:2], noises[:2], ts_g, xs_g)
+    assert eng.hybrid_info()[0] and np.all(ginfo == 0)
+    eng.lml_grad_batch(nodes[:2], noises[:2], ts_g[:1300], xs_g[:1300])
+    assert not eng.hybrid_info()[0]
+    eng.upload(nodes, noises, ts, xs)
     # a data-annealing continuation of a hybrid factor (agp_lml_run_append) is the FP64 schedule on top of it
     eng.set_hybrid(-1)
     eng.set_prefix(1930)

@@ -8,7 +8,7 @@ import autogp_oracle as o
 import autogp.jl_b200 as agp
 from tools.dev_check import to_agp
 eng=agp.Engine(0)
-n,P=2048,64
+n,P=(int(sys.argv[1]) if len(sys.argv)>1 else 2048),64
 ts,xs=o.synthetic_series(n)
 parts=[o.synthetic_particle(p) for p in range(P)]
 nodes,noises=[to_agp(nd) for nd,_ in parts],[nz for _,nz in parts]

@@ -670,9 +670,12 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
         }
     } else {
         // ---- epilogue: eight warps, thread = 64 columns of one row of this CTA's 128 x 128 tile -------------------
-        // The tile row segment is fetched into registers while the tensor pipe works on pass 0, receives the high-order
-        // groups after pass 0 and the low-order groups after pass 1, and is stored once.  (Reading the sums out of TMEM
-        // is the floor of an epilogue: 256 KB per pass at 64 B/clk.)
+        // While the tensor pipe waits (after either pass): the four integer sums of every entry leave TMEM and are combined
+        // exactly in int64; pass 0 keeps them as one FP64 number per entry in registers, pass 1 folds its own onto them
+        // (one fma: t0 + t1 2^-28, the only rounding before the final subtraction), then the accumulators are handed back.
+        // Next to the following unit's products: scale by the two rows' powers of two and subtract from the tile row in L
+        // (read-modify-write; the row was prefetched into L2 when the unit started).  Reading the sums out of TMEM is the
+        // floor of the first part: 256 KB per pass at 64 B/clk.
         const int ew = warp & 3;          // the TMEM lanes [32 ew, 32 ew + 32) are the ones this warp may read
         const int hh = (warp - 2) >> 2;   // column half
         const int row = ew * 32 + lane;
@@ -684,19 +687,16 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
             const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + hh * 64);
             double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + hh * 64;
-            const int cmax = !it.valid ? -1 : (it.i == it.k) ? row - hh * 64 : 63;  // diagonal tile: the strict upper triangle keeps its Gram values
-            double2 tv[32];
-            // (only what will be stored back is read: the strict upper triangle of a diagonal tile is never written by the
-            // Gram fill, and a pair's idle CTA has nothing to read)
+            // only what is stored back is read: the strict upper triangle of a diagonal tile keeps its Gram values (it is never
+            // written by the Gram fill), and a pair's idle CTA has nothing to do
+            const int cmax = !it.valid ? -1 : (it.i == it.k) ? row - hh * 64 : 63;
+            if (cmax >= 0) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                if (2 * e + 1 <= cmax) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
-                else if (2 * e <= cmax) tv[e] = make_double2(__ldcg(Trow + 2 * e), 0.0);
-                else tv[e] = make_double2(0.0, 0.0);
+                for (int e = 0; e < 4; ++e) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Trow + 16 * e));
             }
+            double d[64];
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                const double w = pass ? 0x1p-61 : 0x1p-33;  // the last group of the pass carries 2^(-12 - 7 g), g = 3 / 7
                 ok = ok && oz_wait(acc_full, (use + pass) & 1, prm.err, prm.wait_timeout_ns);
                 if (!ok) break;
                 tc_fence_after();
@@ -714,10 +714,8 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
                     for (int j = 0; j < 8; ++j) {
                         // exact in int64: |sum| < 2^31 per group
                         const long long t = ((long long)(int)a[0][j] << 21) + ((long long)(int)a[1][j] << 14) + ((long long)(int)a[2][j] << 7) + (long long)(int)a[3][j];
-                        const double scj = __ldg(sc + 2 * (cb * 8 + j));
-                        const double v = ((double)t * w) * (sr * scj);
-                        if (j & 1) tv[cb * 4 + (j >> 1)].y -= v;
-                        else tv[cb * 4 + (j >> 1)].x -= v;
+                        if (pass == 0) d[cb * 8 + j] = (double)t;                       // groups 0..3: weight 2^-33 for the last one
+                        else d[cb * 8 + j] = fma((double)t, 0x1p-28, d[cb * 8 + j]);    // groups 4..7: 2^-61 = 2^-33 2^-28
                     }
                 }
                 tc_fence_before();
@@ -732,16 +730,31 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             }
             use += 2;
             if (!ok) break;
+            const double w = 0x1p-33 * sr;  // exact: powers of two
+            if (cmax >= 63) {
+                double2 cur[4], nxt[4];
 #pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                if (cb * 8 + 7 <= cmax) {
+                for (int e = 0; e < 4; ++e) cur[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) reinterpret_cast<double2*>(Trow + cb * 8)[e] = tv[cb * 4 + e];
-                } else {
+                for (int cb = 0; cb < 8; ++cb) {
+                    if (cb < 7) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (cb * 8 + j <= cmax) Trow[cb * 8 + j] = (j & 1) ? tv[cb * 4 + (j >> 1)].y : tv[cb * 4 + (j >> 1)].x;
+                        for (int e = 0; e < 4; ++e) nxt[e] = __ldcg(reinterpret_cast<const double2*>(Trow + cb * 8 + 8) + e);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double s0 = w * __ldg(sc + 2 * (cb * 8 + 2 * e)), s1 = w * __ldg(sc + 2 * (cb * 8 + 2 * e + 1));
+                        cur[e].x = fma(-d[cb * 8 + 2 * e], s0, cur[e].x);
+                        cur[e].y = fma(-d[cb * 8 + 2 * e + 1], s1, cur[e].y);
+                        reinterpret_cast<double2*>(Trow + cb * 8)[e] = cur[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
                 }
+            } else if (cmax >= 0) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c <= cmax) Trow[c] = fma(-d[c], w * __ldg(sc + 2 * c), __ldcg(Trow + c));
             }
         }
     }

@@ -297,7 +297,7 @@ class Bench:
         return {"super_column_width": width, "gram_and_row_scales_ms": stage_ms[0], "fp64_segments_ms": stage_ms[1], "int8_updates_ms": stage_ms[2],
                 "digit_planes_ms": stage_ms[3],
                 "share_of_flops_on_int8": 2.0 * mac / (n ** 3 / 3.0) if n % 128 == 0 else None,
-                "int8_kernel": {"kernel": "agp_ozaki_update2_kernel<2> (tcgen05.mma.cta_group::2.kind::i8, TMEM accumulators, CTA pairs)",
+                "int8_kernel": {"kernel": "agp_ozaki_update2_kernel (tcgen05.mma kind::i8, TMEM accumulators; one CTA per unit below 24 block columns, CTA pairs with cta_group::2 from there on)",
                                 "achieved": int8_tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, 36 digit-plane products per FP64 product)",
                                 "frac": None if int8_tops is None else int8_tops / INT8_PEAK_TOPS,
                                 "peak_source": "measured on this pool: tcgen05.mma kind::i8 issue rate with operands resident in shared memory, 8192 MAC/clk/SM "

@@ -22,3 +22,15 @@ def test_every_stage_release_is_fenced_from_the_loads_before_it():
     releases, tma_loads, problems = sass_lint.lint(OBJS)
     assert releases >= 2 and tma_loads >= 3
     assert problems == []
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_int8_update_kernels_are_on_the_tcgen05_path():
+    """The hybrid schedule's int8 kernels really use the 5th-generation tensor path (UTCIMMA with TMEM accumulators, UTCBAR,
+    LDTM, UTMALDG; .2CTA in the pair variant) and issue a product's k-steps back to back."""
+    obj = os.path.join(ROOT, "autogp.jl_b200", "csrc", "agp_ozaki.o")
+    if not os.path.exists(obj):
+        pytest.skip("agp_ozaki.o not built (python -c 'import __graft_entry__ as g; g.build()')")
+    import sass_lint
+
+    assert sass_lint.lint_int8(obj) == []

@@ -12,6 +12,11 @@ code, not one particular ptxas schedule:
     the first LDS; the function must still use TMA tensor copies (UTMALDG); and its main loop must be free of
     local-memory traffic (spills there cost the round-2 builds up to 2.4x, agp_chol_common.cuh).
 
+    and, for the hybrid schedule's int8 kernel (agp_ozaki_update2_kernel in agp_ozaki.o): the 5th-generation tensor path must
+    really be there — UTCIMMA (tcgen05.mma kind::i8; .2CTA for the pair variant), UTCBAR (tcgen05.commit), LDTM (tcgen05.ld),
+    UTMALDG (TMA tensor loads) — and the MMA issue sequence must be free of per-instruction election loops (no BRA between two
+    UTCIMMA of a product's four k-steps: with the issue loop inside `if (lane == 0)` ptxas emitted one, 79 instead of 64 clocks).
+
     python tools/sass_lint.py [object files]      exit code 1 on violation
 """
 import os
@@ -75,6 +80,31 @@ def lint_function(name, code):
     return len(releases), len(tma), problems
 
 
+def lint_int8(obj=None):
+    """Problems of the int8 update kernels in agp_ozaki.o (see the module docstring)."""
+    obj = obj or os.path.join(CSRC, "agp_ozaki.o")
+    txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    problems, seen = [], 0
+    for part in txt.split("Function : ")[1:]:
+        name = part.split("\n", 1)[0].strip()
+        if "agp_ozaki_update2_kernel" not in name:
+            continue
+        seen += 1
+        pair = "ILi2E" in name
+        ins = [m.group(1).strip() for m in (re.search(r"/\*[0-9a-f]{4,5}\*/\s+(.*?);", l) for l in part.split("\n")) if m]
+        for op in (("UTCIMMA.2CTA" if pair else "UTCIMMA"), "UTCBAR", "LDTM", "UTMALDG"):
+            if not any(op in t for t in ins):
+                problems.append(f"{name}: no {op} in the SASS")
+        mma = [i for i, t in enumerate(ins) if "UTCIMMA" in t]
+        # the four k-steps of a digit-plane product are issued back to back: at most a handful of uniform-register instructions between them
+        runs = sum(1 for a, b in zip(mma, mma[1:]) if b - a <= 6)
+        if mma and runs < len(mma) // 2:
+            problems.append(f"{name}: only {runs} of {len(mma)} UTCIMMA are issued back to back (per-instruction election loop?)")
+    if seen < 2:
+        problems.append(f"agp_ozaki_update2_kernel<1> / <2>: {seen} of 2 found in {obj}")
+    return problems
+
+
 def lint(objs=None):
     """Returns (n_releases, n_tma_loads, problems) over the phase functions."""
     found, rel, tma, problems = set(), 0, 0, []
@@ -92,6 +122,10 @@ def lint(objs=None):
 if __name__ == "__main__":
     objs = sys.argv[1:] or DEFAULT_OBJS
     r, t, problems = lint(objs)
+    if not sys.argv[1:]:
+        p8 = lint_int8()
+        print(f"agp_ozaki.o: int8 update kernels, {len(p8)} problem(s)")
+        problems += p8
     print(f"{', '.join(os.path.basename(o) for o in objs)}: {r} stage release(s), {t} UTMALDG, {len(problems)} problem(s)")
     for p in problems:
         print("  " + p)

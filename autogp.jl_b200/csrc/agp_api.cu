@@ -78,7 +78,8 @@ struct agp_handle {
     // only).  Plain LML runs from `oz_min_nt` block columns on.
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
-    int oz_min_nt = 16;    // AGP_OZ_MIN_NT
+    int oz_min_nt = 14;    // AGP_OZ_MIN_NT (measured, 64 particles, FP64 single launch -> hybrid: n = 1536 3.59 -> 3.61 ms, 1664 4.36 -> 4.30,
+                           // 1792 5.26 -> 5.05, 1920 6.25 -> 5.80, 2048 7.31 -> 6.54)
     int oz_min_nt_aug = 12;  // AGP_OZ_MIN_NT_AUG: the gradient calls gain earlier (three passes of contractions, the lauum pass all int8): measured
                              // n = 1280 7.46 -> 7.61 ms, 1536 11.49 -> 10.85, 1792 16.78 -> 14.76, 2048 23.6 -> 19.3 (64 particles)
     double min_noise = 0.0;  // smallest noise of the resident batch (NaN counts as -1)

@@ -259,7 +259,7 @@ int64_t agp_queue_build_general(int32_t P, int32_t nt, int32_t nt_total, int32_t
 int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32_t* items_out, int64_t cap);
 
 /* Hybrid factorisation of plain LML runs and of the gradient calls (csrc/agp_ozaki.cu).  From `min_nt` block columns on
- * (default 16: n >= 1921) the block columns are grouped into super-columns of `width` (0 = by size, the default: 4, and 3
+ * (default 14: n >= 1665) the block columns are grouped into super-columns of `width` (0 = by size, the default: 4, and 3
  * from 48 block columns on); before a super-column is factored, the contraction
  * of its tiles over ALL earlier block columns — the long sums of dpotrf's trailing update, which is what PDMats runs for
  * the mvnormal of src/Model.jl:136 — is computed by exact int8 digit-plane products on the 5th-generation tensor cores

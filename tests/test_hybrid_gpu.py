@@ -60,7 +60,7 @@ def test_hybrid_matches_the_fp64_schedule_and_the_oracle(eng, n, width):
 
 
 def test_hybrid_is_chosen_by_size_and_can_be_switched_off(eng):
-    """Default: plain LML runs from 16 block columns on (n >= 1921), the gradient calls from 12 (n >= 1409); continuations
+    """Default: plain LML runs from 14 block columns on (n >= 1665), the gradient calls from 12 (n >= 1409); continuations
     (set_prefix + run_append) and predictive batches never."""
     ts, xs, parts, nodes, noises = _batch(2048, 3)
     eng.upload(nodes, noises, ts, xs)

@@ -94,8 +94,7 @@ struct agp_handle {
     // dependency polls sit next to the panel items the segment is bound by).
     bool oz_slice_items = false;
     bool oz_ride = false;  // AGP_OZ_RIDE: Gram units as items of the segments' queues (measured slower, see run_hybrid)
-    // AGP_OZ_KERNEL: -1 = by size, 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA, 0 = N = 64, one
-    // pass.  By size (measured, 64 particles): one CTA per unit below 24 block columns (n = 2048: 6.56 against 6.69 ms per step, gradient
+    // AGP_OZ_KERNEL: -1 = by size, 3 = CTA pairs (cta_group::2, 128-column accumulators, two passes), 2 = the same per CTA.  By size (measured, 64 particles): one CTA per unit below 24 block columns (n = 2048: 6.56 against 6.69 ms per step, gradient
     // call 18.7 against 19.1 ms — twice as many units in flight, no idle half pair on odd row counts), pairs from there on (n = 4096: 32.2
     // against 32.7 ms, n = 8192: int8 updates 128.5 against 135.8 ms — the shared-memory operand traffic of the long contractions)
     int oz_variant = -1;
@@ -215,7 +214,7 @@ int agp_create(int device, agp_handle** out) {
     if (const char* e = getenv("AGP_OZ_RIDE")) h->oz_ride = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_AUG")) h->oz_aug = atoi(e) != 0;
     if (const char* e = getenv("AGP_OZ_SLICE_ITEMS")) h->oz_slice_items = atoi(e) != 0;
-    if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 0 || atoi(e) == 2 || atoi(e) == 3) ? atoi(e) : -1;
+    if (const char* e = getenv("AGP_OZ_KERNEL")) h->oz_variant = (atoi(e) == 2 || atoi(e) == 3) ? atoi(e) : -1;
     if (agp::configure_ozaki() != cudaSuccess) {
         cudaGetLastError();
         agp_destroy(h);
@@ -1162,8 +1161,7 @@ static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
         h->launches += 1;
         if ((rc = toc(0)) != AGP_OK) return rc;
     }
-    int oz_variant = h->oz_variant < 0 ? (nt >= 24 ? 3 : 2) : h->oz_variant;
-    if (aug && oz_variant < 2) oz_variant = 2;  // appended rows: second-generation kernels only
+    const int oz_variant = h->oz_variant < 0 ? (nt >= 24 ? 3 : 2) : h->oz_variant;
     const int n_seg = (int)qu.seg.size() - 1;
     BatchView vq = v;  // what the persistent kernel sees: + the digit-plane buffers for its SLICE items
     vq.oz_S = reinterpret_cast<signed char*>(h->d_S);

@@ -1,17 +1,13 @@
 // Error-free int8 split of the long contractions of the blocked Cholesky onto tcgen05.mma kind::i8 (sm_100a).
 // Interface and the arithmetic of the scheme: agp_ozaki.cuh.  Three kernels:
 //
-//   agp_ozaki_rowscale_kernel   per row r of every particle: e_r = ceil(log2 sqrt(K_rr)) from the Gram diagonal
-//   agp_ozaki_slice_kernel      finished tiles of L -> eight int8 digit planes (what the FP64 tile costs in bytes)
-//   agp_ozaki_update_kernel     T_ik -= sum_{j < c0} L_ij L_kj^T for every lower tile of block columns [c0, c1):
-//                               one CTA per SM, warp-specialised:
-//                                 warp 0   TMA producer: digit-plane boxes (128-byte swizzle) into a ring of A slots
-//                                          and a double-buffered B chunk, full / empty mbarriers
-//                                 warp 1   one thread issues tcgen05.mma.cta_group::1.kind::i8 M128 N64 K32; the eight
-//                                          weight groups g = p + q live in TMEM columns [64 g, 64 g + 64); stages are
-//                                          released by tcgen05.commit
-//                                 warps 2-5  epilogue: tcgen05.ld of the eight int32 sums, exact recombination in
-//                                          int64 -> FP64, scale by 2^(e_i + e_k), subtract from the tile in L
+//   agp_ozaki_rowscale_kernel   per row r of every particle: e_r = ceil(log2 sqrt(K_rr)) from the Gram diagonal (appended rows of
+//                               the gradient calls: from the noise)
+//   agp_ozaki_slice_kernel      finished tiles of L -> seven int8 digit planes
+//   agp_ozaki_update2_kernel    T_ik -= sum_j L_ij L_kj^T over the block columns left of a super-column, for every lower tile of it:
+//                               warp-specialised (TMA producer, one MMA-issuing warp, eight epilogue warps), 128-column int32
+//                               accumulators in TMEM, two passes over the weight groups, per CTA (<1>) or per CTA pair (<2>,
+//                               tcgen05.mma.cta_group::2) — described at the kernel
 //
 // Reference semantics: the products are part of dpotrf as called by PDMats for `mvnormal` (src/Model.jl:136).
 #include "agp_ozaki.cuh"
@@ -25,42 +21,9 @@ namespace agp {
 
 namespace {
 
-constexpr int OZ_THREADS = 192;
-constexpr uint32_t OZ_A_BYTES = 128 * 128;        // one digit plane of a 128-row tile, 128 bytes of k
-constexpr uint32_t OZ_BQ_BYTES = 64 * 128;        // one digit plane of the item's 64 B rows
-constexpr uint32_t OZ_B_BYTES = OZ_SLICES * OZ_BQ_BYTES;
-// shared-memory image: NBUF chunk buffers for B, a ring of NA slots for A, the barriers
-template <int NA, int NBUF>
-struct OzLayout {
-    static constexpr uint32_t OFF_A = NBUF * OZ_B_BYTES;
-    static constexpr uint32_t OFF_BAR = OFF_A + NA * OZ_A_BYTES;
-    static constexpr int SMEM = (int)OFF_BAR + 256;
-};
-constexpr int OZ_NA = 6, OZ_NBUF = 2;   // the product kernel: one CTA per SM
-constexpr int OZ_SMEM = OzLayout<OZ_NA, OZ_NBUF>::SMEM;
-static_assert(OZ_SMEM <= 227 * 1024, "one CTA per SM");
-constexpr int OZ_NA_S = 3, OZ_NBUF_S = 1;  // small variant (experiments: co-residency with one CTA of the FP64 kernel)
-constexpr int OZ_SMEM_S = OzLayout<OZ_NA_S, OZ_NBUF_S>::SMEM;
-
 // K-major operand tile, rows of 128 bytes, SWIZZLE_128B: 8-row groups of 1024 bytes (stride byte offset), version 1
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::i8: D = S32 (c_format 2), A and B signed 8 bit, both K-major, N = 64, M = 128
-constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void oz_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -115,241 +78,16 @@ __device__ long long oz_stats[8];  // MMA thread: total, wait B, wait A, wait TM
 #define OZ_ACC(slot)
 #endif
 
-struct OzItem {
-    int p, i, k, h;
-};
-// items of one launch: particle-major, then block column, then tile row, the two 64-column halves adjacent (they share A)
-__device__ __forceinline__ OzItem oz_decode(int idx, int per_p, int c0, int nt) {
-    OzItem it;
-    it.p = idx / per_p;
-    int r = idx - it.p * per_p;
-    int k = c0;
-    for (;;) {
-        const int cnt = 2 * (nt - k);
-        if (r < cnt) break;
-        r -= cnt;
-        ++k;
-    }
-    it.k = k;
-    it.i = k + (r >> 1);
-    it.h = r & 1;
-    return it;
-}
-
-}  // namespace
-
-template <int OZ_NA, int OZ_NBUF, int MINB>
-__global__ void __launch_bounds__(OZ_THREADS, MINB) agp_ozaki_update_kernel(const __grid_constant__ OzakiParams prm, const __grid_constant__ OzakiMaps maps) {
-    extern __shared__ __align__(1024) unsigned char oz_smem[];
-    unsigned char* Bs = oz_smem;
-    unsigned char* As = oz_smem + OzLayout<OZ_NA, OZ_NBUF>::OFF_A;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + OzLayout<OZ_NA, OZ_NBUF>::OFF_BAR);
-    uint64_t* a_full = bars;              // [OZ_NA]
-    uint64_t* a_empty = bars + OZ_NA;     // [OZ_NA]
-    uint64_t* b_full = bars + 2 * OZ_NA;  // [OZ_NBUF]
-    uint64_t* b_empty = b_full + 2;       // [OZ_NBUF]
-    uint64_t* acc_full = b_empty + 2;     // MMA -> epilogue
-    uint64_t* acc_empty = acc_full + 1;   // epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c0 = prm.c0, nt = prm.nt, P = prm.P, ld = prm.ld;
-    int per_p = 0;
-    for (int k = c0; k < prm.c1; ++k) per_p += 2 * (nt - k);
-    const int n_items = per_p * P;
-
-    if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a) : "memory");
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b) : "memory");
-        for (int s = 0; s < OZ_NA; ++s) {
-            mbar_init(a_full + s, 1);
-            mbar_init(a_empty + s, 1);
-        }
-        for (int s = 0; s < OZ_NBUF; ++s) {
-            mbar_init(b_full + s, 1);
-            mbar_init(b_empty + s, 1);
-        }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
-        mbar_fence_init();
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---- producer ------------------------------------------------------------------------
-            int an = 0, bn = 0;
-            bool ok = true;
-            for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x) {
-                const OzItem it = oz_decode(idx, per_p, c0, nt);
-                const int brow = it.p * ld + it.k * 128 + it.h * 64, arow = it.p * ld + it.i * 128;
-                for (int c = 0; c < c0 && ok; ++c) {
-                    const int buf = bn % OZ_NBUF;
-                    if (bn >= OZ_NBUF) ok = oz_wait(b_empty + buf, ((bn / OZ_NBUF) - 1) & 1, prm.err, prm.wait_timeout_ns);
-                    if (!ok) break;
-                    mbar_expect_tx(b_full + buf, OZ_B_BYTES);
-#pragma unroll
-                    for (int q = 0; q < OZ_SLICES; ++q)
-                        tma_load_2d(Bs + buf * OZ_B_BYTES + q * OZ_BQ_BYTES, &maps.b, c * 128, q * P * ld + brow, b_full + buf);
-                    ++bn;
-                    for (int ps = OZ_SLICES - 1; ps >= 0; --ps) {
-                        const int slot = an % OZ_NA, n = an / OZ_NA;
-                        if (n >= 1) ok = oz_wait(a_empty + slot, (n - 1) & 1, prm.err, prm.wait_timeout_ns);
-                        if (!ok) break;
-                        mbar_expect_tx(a_full + slot, OZ_A_BYTES);
-                        tma_load_2d(As + slot * OZ_A_BYTES, &maps.a, c * 128, ps * P * ld + arow, a_full + slot);
-                        ++an;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer ----------------------------------------------------------------------
-            // One thread feeds the tensor pipe: its own instruction stream has to stay well below the 48 clocks an
-            // M128 N64 K32 instruction takes (shared-memory operand reads: 6 KB at 128 B/clk), so the 36 x 4
-            // instructions of a chunk are straight-line code, descriptors are advanced by integer adds on their
-            // address field, and ring positions are counters with wrap, not divisions.
-            int a_slot = 0, a_par = 0, bn = 0, t = 0;
-            bool ok = true;
-            const uint64_t da0 = oz_desc(smem_u32(As)), db0 = oz_desc(smem_u32(Bs));
-#if OZ_STATS
-            long long oz_acc_[4] = {0, 0, 0, 0};
-            const long long t_all_ = clock64();
-#endif
-            for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x, ++t) {
-                {
-                    OZ_T0();
-                    if (t >= 1) ok = oz_wait(acc_empty, (t - 1) & 1, prm.err, prm.wait_timeout_ns);  // the previous item's sums have left TMEM
-                    OZ_ACC(3);
-                }
-                if (!ok) break;
-                tc_fence_after();
-                for (int c = 0; c < c0 && ok; ++c) {
-                    const int buf = bn % OZ_NBUF;
-                    {
-                        OZ_T0();
-                        ok = oz_wait(b_full + buf, (bn / OZ_NBUF) & 1, prm.err, prm.wait_timeout_ns);
-                        OZ_ACC(1);
-                    }
-                    if (!ok) break;
-                    const uint64_t db = db0 + (uint64_t)(buf * (OZ_B_BYTES >> 4));
-                    const uint32_t first = (c == 0) ? 0u : 1u;
-#pragma unroll
-                    for (int ps = OZ_SLICES - 1; ps >= 0; --ps) {
-                        {
-                            OZ_T0();
-                            ok = oz_wait(a_full + a_slot, a_par, prm.err, prm.wait_timeout_ns);
-                            OZ_ACC(2);
-                        }
-                        if (!ok) break;
-                        tc_fence_after();
-                        const uint64_t da = da0 + (uint64_t)(a_slot * (int)(OZ_A_BYTES >> 4));
-#pragma unroll
-                        for (int q = 0; q + ps < OZ_SLICES; ++q) {
-                            const uint32_t d = tmem + (uint32_t)(ps + q) * 64u;
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)
-                                oz_mma(d, da + 2 * k4, db + (uint64_t)(q * (int)(OZ_BQ_BYTES >> 4) + 2 * k4), (q == 0 && k4 == 0) ? first : 1u);
-                        }
-                        oz_commit(a_empty + a_slot);  // the slot is free once the instructions above have read it
-                        if (++a_slot == OZ_NA) a_slot = 0, a_par ^= 1;
-                    }
-                    if (!ok) break;
-                    oz_commit(b_empty + buf);
-                    ++bn;
-                }
-                if (ok) oz_commit(acc_full);
-            }
-#if OZ_STATS
-            atomicAdd((unsigned long long*)&oz_stats[0], (unsigned long long)(clock64() - t_all_));
-            for (int e = 1; e < 4; ++e) atomicAdd((unsigned long long*)&oz_stats[e], (unsigned long long)oz_acc_[e]);
-            atomicAdd((unsigned long long*)&oz_stats[5], (unsigned long long)t);
-#endif
-        }
-    } else {
-        // ---- epilogue: thread = one row of the 128 x 64 output --------------------------------------
-        const int ew = warp & 3;  // the TMEM lanes [32 ew, 32 ew + 32) are the ones this warp may read
-        const int row = ew * 32 + lane;
-        int t = 0;
-        bool ok = true;
-        for (int idx = blockIdx.x; idx < n_items && ok; idx += gridDim.x, ++t) {
-            const OzItem it = oz_decode(idx, per_p, c0, nt);
-            const double sr = __ldg(prm.rscale + 2 * ((long long)it.p * ld + it.i * 128 + row));
-            const double* sc = prm.rscale + 2 * ((long long)it.p * ld + it.k * 128 + it.h * 64);
-            double* Trow = prm.L + (long long)it.p * prm.mat_stride + (long long)(it.i * 128 + row) * ld + it.k * 128 + it.h * 64;
-            const int cmax = (it.i == it.k) ? row - it.h * 64 : 63;  // diagonal tile: the strict upper triangle keeps its Gram values
-            // the tile row is fetched while the tensor pipe still works on the item: 64 doubles in registers
-            double2 tv[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) tv[e] = __ldcg(reinterpret_cast<const double2*>(Trow) + e);
-            ok = oz_wait(acc_full, t & 1, prm.err, prm.wait_timeout_ns);
-            if (!ok) break;
-            tc_fence_after();
-#if OZ_STATS
-            const long long t_epi_ = clock64();
-#endif
-#pragma unroll
-            for (int cb = 0; cb < 8; ++cb) {
-                uint32_t a[OZ_SLICES][8];
-                const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(cb * 8);
-#pragma unroll
-                for (int g = 0; g < OZ_SLICES; ++g) tmem_ld8(taddr + (uint32_t)g * 64u, a[g]);
-                tmem_ld_wait();
-                double out[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // exact in int64: |sum| < 2^31 per group
-                    const long long t0 = ((long long)(int)a[0][j] << 14) + ((long long)(int)a[1][j] << 7) + (long long)(int)a[2][j];
-                    const long long t1 = ((long long)(int)a[3][j] << 14) + ((long long)(int)a[4][j] << 7) + (long long)(int)a[5][j];
-                    const long long t2 = ((long long)(int)a[6][j] << 7) + (long long)(int)a[7][j];
-                    // weights: group g carries 2^(-12 - 7 g)
-                    double val = (double)t2 * 0x1p-61;
-                    val = fma((double)t1, 0x1p-47, val);
-                    val = fma((double)t0, 0x1p-26, val);
-                    const double scj = __ldg(sc + 2 * (cb * 8 + j));
-                    const double tin = (j & 1) ? tv[cb * 4 + (j >> 1)].y : tv[cb * 4 + (j >> 1)].x;
-                    out[j] = tin - val * (sr * scj);
-                }
-                if (cb * 8 + 7 <= cmax) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) reinterpret_cast<double2*>(Trow + cb * 8)[e] = make_double2(out[2 * e], out[2 * e + 1]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (cb * 8 + j <= cmax) Trow[cb * 8 + j] = out[j];
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
-#if OZ_STATS
-            if (tid == 64) atomicAdd((unsigned long long*)&oz_stats[4], (unsigned long long)(clock64() - t_epi_));
-#endif
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
-}
-
-// ---- second generation: 128-column accumulators, two passes over the weight groups, optional CTA pairs ------------
-// An M128 N64 instruction re-reads its 4 KB A operand from shared memory every 32 tensor clocks: 6 KB per instruction at
-// 128 B/clk = 48 clocks (profiles/r02_i8_shape_probe.txt) — the N = 64 kernel above is bound by shared-memory operand
-// reads at 65 % of the int8 rate.  Here an accumulator is 128 columns wide, so only FOUR weight groups fit into TMEM and
-// a tile takes two passes over the contraction: groups 0..3 (10 digit-plane products per 128-deep chunk: 4 planes of
-// either operand), then groups 4..7 (26 products, all planes); each pass ends with its own recombination and
-// read-modify-write of the tile.  With G = 2 two CTAs of a cluster (an SM pair) work on the tiles (i, k) and (i + 1, k):
-// tcgen05.mma.cta_group::2 (M = 256) reads each CTA's own A rows and HALF of the 128 B rows from either CTA's shared
-// memory — 6 KB per 64 clocks and SM instead of 8 — issued by the leader CTA for both; the operands arrive by
-// cta_group::2 TMA loads that signal the leader's barriers, stages are released in both CTAs by multicast commits.
+// ---- the update kernel: 128-column accumulators, two passes over the weight groups, optional CTA pairs -------------
+// An M128 instruction re-reads its 4 KB A operand from shared memory whatever N is: N = 64 costs 49.5 clocks instead of 32
+// (6 KB at 128 B/clk, profiles/r02_i8_shape_probe.txt; the first generation of this kernel — N = 64, one accumulator per
+// weight group, one pass — was bound by that at 65 % of the int8 rate).  Here an accumulator is 128 columns wide, so FOUR
+// weight groups fit into TMEM and a tile takes two passes over the contraction: groups 0..3 (10 digit-plane products per
+// 128-deep chunk: planes 0..3 of either operand), then groups 4..6 (18 products, all seven planes).  With G = 2 two CTAs of a
+// cluster (an SM pair) work on the tiles (i, k) and (i + 1, k): tcgen05.mma.cta_group::2 (M = 256) reads each CTA's own A rows
+// and HALF of the 128 B rows from either CTA's shared memory — 6 KB per 64 clocks and SM instead of 8 — issued by the leader
+// CTA for both; the operands arrive by cta_group::2 TMA loads that signal the leader's barriers, stages are released in both
+// CTAs by multicast commits.
 template <int G>
 struct Oz2 {
     static constexpr int NA = (G == 2) ? 8 : 6;    // A ring: one digit plane of 128 rows x 128 bytes per slot
@@ -474,7 +212,7 @@ __device__ __forceinline__ Oz2Unit oz2_decode(int unit, int per_p, const OzakiPa
     return it;
 }
 
-// the MMA instructions of one 128-deep chunk of one pass; PASS 0: weight groups 0..3, PASS 1: groups 4..7
+// the MMA instructions of one 128-deep chunk of one pass; PASS 0: weight groups 0..3, PASS 1: groups 4..6
 template <int G, int PASS>
 __device__ __forceinline__ bool oz2_chunk(uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty, uint64_t da0, uint64_t db0,
                                           uint32_t tmem, uint32_t first, int& a_slot, int& a_par, int& b_slot, int& b_par, const OzakiParams& prm
@@ -483,7 +221,8 @@ __device__ __forceinline__ bool oz2_chunk(uint64_t* a_full, uint64_t* a_empty, u
 #endif
                                           ) {
     constexpr int NA = Oz2<G>::NA, NB = Oz2<G>::NB;
-    constexpr int PMAX = PASS ? 7 : 3, GMIN = PASS ? 4 : 0;
+    constexpr int PMAX = PASS ? OZ_SLICES - 1 : 3, GMIN = PASS ? 4 : 0;
+    static_assert(OZ_SLICES == 7, "pass structure: groups 0..3 | 4..6");
     // ring positions of this chunk's B planes: plane q sits in slot (b_slot + q) mod NB
     uint64_t dbq[PMAX + 1];
     int bs[PMAX + 1];
@@ -534,6 +273,8 @@ __device__ __forceinline__ bool oz2_chunk(uint64_t* a_full, uint64_t* a_empty, u
         if (b_slot >= NB) b_slot -= NB, b_par ^= 1;
     return true;
 }
+
+}  // namespace
 
 constexpr int OZ2_THREADS = 320;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 template <int G>
@@ -599,7 +340,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
                 const Oz2Unit it = oz2_decode<G>(unit, per_p, prm, (int)rank);
                 const int arow = it.p * ld + it.i * 128, brow = it.p * ld + it.k * 128 + (int)rank * (128 / G);
                 for (int pass = 0; pass < 2 && ok; ++pass) {
-                    const int pmax = pass ? 7 : 3;
+                    const int pmax = pass ? OZ_SLICES - 1 : 3;
                     for (int c = it.clo; c < prm.chi && ok; ++c) {
                         for (int p = pmax; p >= 0; --p) {
                             const int q = pmax - p;
@@ -672,7 +413,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
         // ---- epilogue: eight warps, thread = 64 columns of one row of this CTA's 128 x 128 tile -------------------
         // While the tensor pipe waits (after either pass): the four integer sums of every entry leave TMEM and are combined
         // exactly in int64; pass 0 keeps them as one FP64 number per entry in registers, pass 1 folds its own onto them
-        // (one fma: t0 + t1 2^-28, the only rounding before the final subtraction), then the accumulators are handed back.
+        // (one fma: t0 + t1 2^-24, the only rounding before the final subtraction), then the accumulators are handed back.
         // Next to the following unit's products: scale by the two rows' powers of two and subtract from the tile row in L
         // (read-modify-write; the row was prefetched into L2 when the unit started).  Reading the sums out of TMEM is the
         // floor of the first part: 256 KB per pass at 64 B/clk.
@@ -708,14 +449,18 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
                     uint32_t a[4][8];
                     const uint32_t taddr = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)(hh * 64 + cb * 8);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) tmem_ld8(taddr + (uint32_t)g * 128u, a[g]);
+                    for (int g = 0; g < (pass ? 3 : 4); ++g) tmem_ld8(taddr + (uint32_t)g * 128u, a[g]);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        // exact in int64: |sum| < 2^31 per group
-                        const long long t = ((long long)(int)a[0][j] << 21) + ((long long)(int)a[1][j] << 14) + ((long long)(int)a[2][j] << 7) + (long long)(int)a[3][j];
-                        if (pass == 0) d[cb * 8 + j] = (double)t;                       // groups 0..3: weight 2^-33 for the last one
-                        else d[cb * 8 + j] = fma((double)t, 0x1p-28, d[cb * 8 + j]);    // groups 4..7: 2^-61 = 2^-33 2^-28
+                        // exact in int64 (|sum| < 2^31 per group); group g carries the weight 2^(-14 - 8 g)
+                        if (pass == 0) {
+                            const long long t = ((long long)(int)a[0][j] << 24) + ((long long)(int)a[1][j] << 16) + ((long long)(int)a[2][j] << 8) + (long long)(int)a[3][j];
+                            d[cb * 8 + j] = (double)t;                                    // groups 0..3, in units of 2^-38
+                        } else {
+                            const long long t = ((long long)(int)a[0][j] << 16) + ((long long)(int)a[1][j] << 8) + (long long)(int)a[2][j];
+                            d[cb * 8 + j] = fma((double)t, 0x1p-24, d[cb * 8 + j]);       // groups 4..6, in units of 2^-62 = 2^-38 2^-24
+                        }
                     }
                 }
                 tc_fence_before();
@@ -730,7 +475,7 @@ __global__ void __launch_bounds__(OZ2_THREADS, 1) agp_ozaki_update2_kernel(const
             }
             use += 2;
             if (!ok) break;
-            const double w = 0x1p-33 * sr;  // exact: powers of two
+            const double w = 0x1p-38 * sr;  // exact: powers of two
             if (cmax >= 63) {
                 double2 cur[4], nxt[4];
 #pragma unroll
@@ -790,6 +535,8 @@ __global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long lon
             int ex;
             frexp(kd, &ex);        // kd = m 2^ex, 1/2 <= m < 1: sqrt(kd) < 2^(ex / 2)
             e = (ex + 1) >> 1;     // ceil(ex / 2)
+            // seven balanced base-256 digits reach 0.996 of the scale: keep |L_ij| <= sqrt(K_rr) below 0.99 of it
+            if (kd > 0.98 * ldexp(1.0, 2 * e)) e += 1;
         }
     }
     rscale[2 * w] = ldexp(1.0, e);
@@ -798,8 +545,7 @@ __global__ void agp_ozaki_rowscale_kernel(const double* __restrict__ L, long lon
 
 // ---- digit planes ---------------------------------------------------------------------------------
 // One CTA = one 128 x 128 tile of L; a warp walks rows, lane = 4 consecutive columns: every plane receives 128
-// contiguous bytes per row.  The entry is rounded once to 55 bits below its row scale, v = rint(x 2^(55 - e)), and
-// v = sum_p a_p 128^(7 - p) is peeled into balanced base-128 digits from the bottom (integer arithmetic: exact).
+// contiguous bytes per row (digits: agp_ozaki_digits.cuh).
 __global__ void __launch_bounds__(256) agp_ozaki_slice_kernel(const double* __restrict__ L, long long mat_stride, int ld, int P,
                                                               const double* __restrict__ rscale, int8_t* __restrict__ S, int c0, int ncol, int r0) {
     const int p = blockIdx.z, i = r0 + blockIdx.y, j = c0 + blockIdx.x;
@@ -836,13 +582,9 @@ void launch_ozaki_update(const OzakiParams& prm_in, const OzakiMaps& maps, int c
         prm.r_lo = prm.c0, prm.r_hi = prm.nt, prm.k_lo = prm.c0, prm.k_hi = prm.c1, prm.chi = prm.c0;
     }
     if (prm.r_hi <= prm.r_lo || prm.k_hi <= prm.k_lo || prm.chi <= 0 || prm.P <= 0) return;
-    long long per_p = 0;
-    for (int k = prm.c0; k < prm.c1; ++k) per_p += 2 * (prm.nt - k);
-    const long long n_items = per_p * prm.P;
-    if (variant < 2 && ctas > n_items) ctas = (int)n_items;
     if (variant == 2) {
         agp_ozaki_update2_kernel<1><<<ctas, OZ2_THREADS, Oz2<1>::SMEM, s>>>(prm, maps);
-    } else if (variant == 3) {
+    } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(ctas & ~1), 1, 1);
         cfg.blockDim = dim3(OZ2_THREADS, 1, 1);
@@ -856,16 +598,11 @@ void launch_ozaki_update(const OzakiParams& prm_in, const OzakiMaps& maps, int c
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, agp_ozaki_update2_kernel<2>, prm, maps);
-    } else if (variant == 1) agp_ozaki_update_kernel<OZ_NA_S, OZ_NBUF_S, 2><<<ctas, OZ_THREADS, OZ_SMEM_S, s>>>(prm, maps);
-    else agp_ozaki_update_kernel<OZ_NA, OZ_NBUF, 1><<<ctas, OZ_THREADS, OZ_SMEM, s>>>(prm, maps);
+    }
 }
 
 cudaError_t configure_ozaki() {
-    cudaError_t e = cudaFuncSetAttribute(agp_ozaki_update_kernel<OZ_NA, OZ_NBUF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(agp_ozaki_update_kernel<OZ_NA_S, OZ_NBUF_S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_S);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(agp_ozaki_update2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2<1>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(agp_ozaki_update2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2<1>::SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(agp_ozaki_update2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Oz2<2>::SMEM);
 }

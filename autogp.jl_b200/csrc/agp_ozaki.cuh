@@ -4,11 +4,13 @@
 // tcgen05.mma has no f64 kind, so the FP64 tensor path of sm_100a is DMMA (mma.sync m8n8k4) at 64 FMA/clk/SM.  The
 // int8 kind runs at 8192 MAC/clk/SM.  An FP64 product  sum_j L_ij L_kj^T  is rebuilt from exact integer products:
 // every row of L is scaled by a power of two known BEFORE the factorisation (|L_ij| <= sqrt(K_ii) <= 2^e_i), the scaled
-// entry is cut into eight signed 7-bit digits  x = sum_p a_p 2^(-6-7p)  (|a_p| <= 64: 55 bits below the row scale), and
-// the 36 digit-plane products with p + q <= 7 are accumulated EXACTLY in int32, one accumulator per weight
-// g = p + q (8 accumulators x 64 columns = the SM's 512 TMEM columns), over the WHOLE contraction depth.  The eight
-// integer sums are recombined once per output tile in FP64.  Error of the scheme on the benchmark factor: 2.9e-14 of
-// the largest entry for a 1920-deep contraction (plain FP64 accumulation: 1.2e-14; tools/ozaki_accuracy.py).
+// entry is rounded once to 55 bits below that scale and cut into seven balanced base-256 digits
+// x = 2^e sum_p a_p 2^(-7-8p)  (a_p in [-128, 127]: exactly the range of a signed byte), and the 28 digit-plane products
+// with p + q <= 6 are accumulated EXACTLY in int32, one accumulator per weight g = p + q, over the WHOLE contraction
+// depth (|sum| <= 7 depth 2^14 < 2^31 up to depth 18 724).  The integer sums are recombined once per output tile in FP64.
+// Error of the scheme on the benchmark factor (tests/test_ozaki_scheme.py): 4.0e-15 of sqrt(K_ii K_kk) for a 1920-deep
+// contraction — plain FP64 accumulation: 2.8e-15.  (Round 2 started with eight 7-bit digits, 36 products, 2.6e-14:
+// tools/ozaki_accuracy.py; full bytes cost nothing in the int32 sums and save a plane and eight products.)
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -16,7 +18,7 @@
 
 namespace agp {
 
-constexpr int OZ_SLICES = 8;
+constexpr int OZ_SLICES = 7;
 
 struct OzakiMaps {
     CUtensorMap a, b;  // digit planes viewed as one [8 P ld][ld] byte matrix: boxes of 128 bytes x 128 rows (A) / x 64 rows (B), 128-byte swizzle
@@ -46,8 +48,8 @@ void launch_ozaki_rowscale(const double* L, long long mat_stride, int ld, int P,
 void launch_ozaki_slice(const double* L, long long mat_stride, int ld, int nt, int P, const double* rscale, int8_t* S, int c0, int c1, int r0,
                         cudaStream_t s);
 // the contraction over block columns [0, c0) of every lower tile of block columns [c0, c1), subtracted in place
-// variant 0: the product kernel (one CTA per SM); 1: small shared-memory image (experiments)
-void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant = 0);
+// variant 2: one CTA per unit; 3: CTA pairs (cta_group::2)
+void launch_ozaki_update(const OzakiParams& prm, const OzakiMaps& maps, int ctas, cudaStream_t s, int variant = 3);
 bool make_ozaki_maps(int8_t* S, int ld, int P, OzakiMaps* out);
 cudaError_t configure_ozaki();
 

@@ -45,7 +45,7 @@ KERNEL_SOURCES = ("agp_chol_kernel.cu", "agp_chol_diag.cu", "agp_chol_potf2.cu",
 # dense int8 tensor rate measured on this pool (profiles/r02_i8_probe.txt, r02_i8_shape_probe.txt): one M128 N128 K32
 # tcgen05.mma kind::i8 per 64.0 clocks and SM = 8192 MAC/clk/SM = 4117 TOP/s at the clocks of that run
 INT8_PEAK_TOPS = 4117.0
-INT8_PRODUCTS = 36  # digit-plane products per FP64 product (8 planes, p + q <= 7)
+INT8_PRODUCTS = 28  # digit-plane products per FP64 product (7 planes of 8 bits, p + q <= 6)
 
 
 def workload_name(n, P):
@@ -298,7 +298,7 @@ class Bench:
                 "digit_planes_ms": stage_ms[3],
                 "share_of_flops_on_int8": 2.0 * mac / (n ** 3 / 3.0) if n % 128 == 0 else None,
                 "int8_kernel": {"kernel": "agp_ozaki_update2_kernel (tcgen05.mma kind::i8, TMEM accumulators; one CTA per unit below 24 block columns, CTA pairs with cta_group::2 from there on)",
-                                "achieved": int8_tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, 36 digit-plane products per FP64 product)",
+                                "achieved": int8_tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, 28 digit-plane products per FP64 product)",
                                 "frac": None if int8_tops is None else int8_tops / INT8_PEAK_TOPS,
                                 "peak_source": "measured on this pool: tcgen05.mma kind::i8 issue rate with operands resident in shared memory, 8192 MAC/clk/SM "
                                                "at 1965 MHz (profiles/r02_i8_probe.txt); 2 x MEASURED_PEAKS.json's dense bf16 burst figure would be 3326",

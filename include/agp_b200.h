@@ -265,7 +265,7 @@ int64_t agp_queue_build_marginals(int32_t P, int32_t nt, int32_t nt_total, int32
  * the mvnormal of src/Model.jl:136 — is computed by exact int8 digit-plane products on the 5th-generation tensor cores
  * (tcgen05.mma kind::i8, int32 accumulators in TMEM; tcgen05 has no f64 kind), the persistent FP64 kernel then does the
  * contractions inside the super-column, POTF2 and the panel solves.  Rows are scaled by a power of two >= sqrt(K_ii)
- * (an a-priori bound on |L_ij|) and cut into eight signed 7-bit digits; products below 2^-61 of the row scales are
+ * (an a-priori bound on |L_ij|) and cut into seven signed 8-bit digits; products below 2^-62 of the row scales are
  * dropped: the contraction error is of the order of FP64 accumulation (measured: tests/test_gpu_parity.py).
  * mode: -1 = by size (default), 0 = never (every run takes the single-launch FP64 schedule), 1 = whenever the batch has
  * more than `width` block columns.  Environment: AGP_OZAKI, AGP_OZ_W, AGP_OZ_MIN_NT. */
@@ -287,8 +287,8 @@ int64_t agp_queue_build_hybrid(int32_t P, int32_t nt, int32_t width, int32_t gra
                                int32_t* seg_out, int32_t seg_cap);
 
 /* Experiment behind DESIGN.md's co-residency note: the single-launch FP64 step of the resident batch with `ctas_per_sm`
- * CTAs per SM, `reps` int8 update launches over block columns [c0, c0 + 4) on a second stream (variant 0: the product
- * kernel, 1: the small shared-memory image that fits next to one FP64 CTA), alone and at the same time.
+ * CTAs per SM, `reps` int8 update launches over block columns [c0, c0 + 4) on a second stream (variant 2: one CTA per unit,
+ * 3: CTA pairs), alone and at the same time.
  * ms_out[4] = {FP64 alone, int8 alone, FP64 next to int8, int8 next to FP64}. */
 int agp_dev_overlap_probe(agp_handle* h, int32_t ctas_per_sm, int32_t variant, int32_t c0, int32_t reps, float* ms_out);
 

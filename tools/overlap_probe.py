@@ -16,7 +16,7 @@ ts, xs = o.synthetic_series(n)
 parts = [o.synthetic_particle(p, "se*per+lin") for p in range(P)]
 eng.upload([to_agp(nd) for nd, _ in parts], [nz for _, nz in parts], ts, xs)
 ms = (C.c_float * 4)()
-for ctas, variant, reps in [(2, 0, 6), (1, 0, 6), (1, 1, 4), (2, 1, 4)]:
+for ctas, variant, reps in [(2, 3, 6), (1, 3, 6), (1, 2, 6), (2, 2, 6)]:
     rc = eng._lib.agp_dev_overlap_probe(eng._h, ctas, variant, 8, reps, ms)
     print(f"FP64 kernel {ctas} CTA/SM, int8 variant {variant} x {reps} launches: rc={rc}  FP64 alone {ms[0]:.3f} ms, int8 alone {ms[1]:.3f} ms; "
           f"together: FP64 {ms[2]:.3f} ms, int8 {ms[3]:.3f} ms (sum of alone {ms[0] + ms[1]:.3f})", flush=True)

@@ -78,10 +78,10 @@ struct agp_handle {
     // only).  Plain LML runs from `oz_min_nt` block columns on.
     int oz_mode = -1;      // AGP_OZAKI: -1 = by size, 0 = never, 1 = whenever the batch is a plain LML run with >= 2 super-columns
     int oz_width = 0;      // AGP_OZ_W (0 = by size)
-    int oz_min_nt = 14;    // AGP_OZ_MIN_NT (measured, 64 particles, FP64 single launch -> hybrid: n = 1536 3.59 -> 3.61 ms, 1664 4.36 -> 4.30,
-                           // 1792 5.26 -> 5.05, 1920 6.25 -> 5.80, 2048 7.31 -> 6.54)
-    int oz_min_nt_aug = 12;  // AGP_OZ_MIN_NT_AUG: the gradient calls gain earlier (three passes of contractions, the lauum pass all int8): measured
-                             // n = 1280 7.46 -> 7.61 ms, 1536 11.49 -> 10.85, 1792 16.78 -> 14.76, 2048 23.6 -> 19.3 (64 particles)
+    int oz_min_nt = 12;    // AGP_OZ_MIN_NT (measured, 64 particles, FP64 single launch -> hybrid, W = 4: n = 1280 2.36 -> 2.43 ms, 1408 2.93 -> 2.87,
+                           // 1536 3.57 -> 3.44, 1664 4.35 -> 4.09, 2048 7.30 -> 6.17)
+    int oz_min_nt_aug = 8;   // AGP_OZ_MIN_NT_AUG: the gradient calls gain earlier (three passes of contractions, the lauum pass all int8): measured
+                             // n = 1024 4.51 -> 4.22 ms, 1280 7.48 -> 6.84, 1536 11.49 -> 9.69, 2048 23.6 -> 17.3 (64 particles)
     double min_noise = 0.0;  // smallest noise of the resident batch (NaN counts as -1)
     // The appended rows of an identity-augmented batch are scaled by the a-priori bound 1 / sqrt(noise) (agp_ozaki.cuh); a noise
     // far below the smallest eigenvalue the kernel itself provides (a WhiteNoise node with noise ~ 0) makes that bound loose and

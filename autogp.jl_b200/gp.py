@@ -475,7 +475,7 @@ class Engine:
         self._check(self._lib.agp_gram_items(self._h, C.byref(a), C.byref(b)))
         return bool(a.value), int(b.value)
 
-    def set_hybrid(self, mode: int = -1, width: int = 0, min_nt: int = 14) -> None:
+    def set_hybrid(self, mode: int = -1, width: int = 0, min_nt: int = 12) -> None:
         """Hybrid factorisation of plain LML runs (agp_set_hybrid): the long contractions as exact int8 digit-plane
         products on tcgen05, super-columns of `width` block columns (0 = by size); mode -1 = from `min_nt` block columns on, 0 = never,
         1 = whenever the batch has more than `width` block columns."""

@@ -461,6 +461,8 @@ def test_lml_block_append_is_bitwise_the_full_recompute(engine):
     parts = [o.synthetic_particle(p, t) for p, t in zip(range(P), ["se*per+lin", "se+wn", "ge+per*lin", "se*per+lin", "cp(lin,se)", "se*per+lin"])]
     nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
     fresh = agp.Engine(0)
+    fresh.set_hybrid(0)   # the reference run of every prefix on the same FP64 schedule as the continuation (from 12 block columns on a
+                          # from-scratch run would take the hybrid schedule: equal to 1e-11, not bit for bit — tests/test_hybrid_gpu.py)
     engine.upload(nodes, noises, ts, xs)
     with pytest.raises(_lib.AgpError):   # nothing factored yet
         engine.run_append()

@@ -10,6 +10,6 @@ from .model import (  # noqa: F401
     JITTER, PosDefException, log_marginal_likelihood_grads, log_marginal_likelihoods, log_marginal_likelihoods_info,
     mvnormal_logpdf, predictive_logpdfs, transform_param, transform_param_grad, untransform_param,
 )
-from . import rejuvenate, smc  # noqa: F401
+from . import rejuvenate, smc, tree_moves  # noqa: F401
 
 __version__ = "0.1.0"

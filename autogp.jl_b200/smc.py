@@ -215,3 +215,75 @@ def rejuvenate(state: ParticleState, ts, xs, *, n_mcmc: int, n_hmc: int, propose
         for k, v in st.items():
             total[k] = total.get(k, 0) + v
     return total
+
+
+def initialize_particles(n_particles: int, config, seed: int) -> ParticleState:
+    """``Gen.initialize_particle_filter(model, (Float64[], config), observations, n_particles)``
+    (src/inference_smc_anneal_data.jl:183-190): kernels from ``covariance_prior``, noise latents from ``normal(0, 1)``
+    unless ``config.noise`` fixes the noise — then the constrained latent's prior density is every particle's initial
+    log-weight, as ``Gen.generate`` returns it.  No data yet: the empty ``mvnormal`` scores 0.  Particle p draws from
+    the stream (seed, p), whatever rank asks."""
+    from . import model, tree_moves
+
+    nodes, noises = [], []
+    for p in range(n_particles):
+        rng = np.random.default_rng([int(seed), 0x5EED, p])
+        nodes.append(tree_moves.sample_tree_prior(1, config, rng))
+        z = float(rng.standard_normal())
+        noises.append(float(config.noise) if config.noise is not None
+                      else model.transform_param("noise", z) + model.JITTER)
+    state = ParticleState(nodes, noises)
+    if config.noise is not None:
+        z_fixed = model.untransform_param("noise", float(config.noise))     # :186 (no JITTER subtracted there either)
+        state.log_weights[:] = -0.5 * z_fixed * z_fixed - 0.5 * math.log(2.0 * math.pi)
+    return state
+
+
+def run_smc_anneal_data(ts, xs, *, config=None, biased: bool = False, n_particles: int = 4, n_mcmc=10, n_hmc=10,
+                        hmc_config: Optional[dict] = None, permutation: Optional[Sequence[int]] = None,
+                        schedule: Optional[Sequence[int]] = None, adaptive_resampling: bool = True,
+                        adaptive_rejuvenation: bool = False, seed: int = 0, engine: Optional[gp.Engine] = None,
+                        group=None, callback_fn=None) -> ParticleState:
+    """``run_smc_anneal_data`` (src/inference_smc_anneal_data.jl:143-273): SMC over growing data prefixes with the
+    reference's structure proposals (``tree_moves``), every scoring step a batched GPU call — reweight
+    (``smc_step``), resample on the replicated weights (``maybe_resample``; never after the last prefix), rejuvenate
+    in lock step (``rejuvenate``).  ``permutation`` is 0-based.  With ``torch.distributed`` initialised every rank
+    calls this with the same arguments and holds the same state afterwards."""
+    from . import tree_moves
+
+    config = config or tree_moves.GPConfig()
+    ts, xs = np.asarray(ts, dtype=np.float64), np.asarray(xs, dtype=np.float64)
+    n = ts.shape[0]
+    if xs.shape != ts.shape:
+        raise ValueError("ts and xs must have equal length")
+    permutation = np.arange(n) if permutation is None else np.asarray(permutation, dtype=np.int64)
+    if sorted(permutation.tolist()) != list(range(n)):
+        raise ValueError("permutation must be a permutation of 0..n-1")
+    ts, xs = ts[permutation], xs[permutation]
+    schedule = list(range(1, n + 1)) if schedule is None else [int(s) for s in schedule]
+    if not (schedule and 1 <= schedule[0] and schedule[-1] == n and all(b > a for a, b in zip(schedule, schedule[1:]))):
+        raise ValueError("schedule must increase strictly from >= 1 to len(ts)")
+    n_mcmc = [int(n_mcmc)] * len(schedule) if np.isscalar(n_mcmc) else [int(v) for v in n_mcmc]
+    n_hmc = [int(n_hmc)] * len(schedule) if np.isscalar(n_hmc) else [int(v) for v in n_hmc]
+    if len(n_mcmc) != len(schedule) or len(n_hmc) != len(schedule):
+        raise ValueError("n_mcmc / n_hmc: one value, or one per schedule entry")
+    propose = tree_moves.tree_rejuvenation_proposer(config, biased)
+    state = initialize_particles(n_particles, config, seed)
+    if callback_fn:
+        callback_fn(state=state, ts=ts, xs=xs, step=0, rejuvenated=False, resampled=False, stats=None)
+    for i, step in enumerate(schedule):
+        ts_obs, xs_obs = ts[:step], xs[:step]
+        smc_step(state, ts_obs, xs_obs, engine=engine, group=group)
+        resampled = False
+        if step < schedule[-1]:
+            ess_threshold = n_particles / 2 if adaptive_resampling else n_particles
+            resampled = maybe_resample(state, ess_threshold, seed=int(np.random.default_rng([int(seed), 0xE55, i]).integers(2 ** 62)))
+        rejuvenated, stats = False, None
+        if not adaptive_rejuvenation or resampled:
+            rejuvenated = True
+            stats = rejuvenate(state, ts_obs, xs_obs, n_mcmc=n_mcmc[i], n_hmc=n_hmc[i], propose=propose, seed=seed,
+                               engine=engine, group=group, hmc_config=hmc_config, infer_noise=config.noise is None,
+                               round_index=i + 1)
+        if callback_fn:
+            callback_fn(state=state, ts=ts, xs=xs, step=step, rejuvenated=rejuvenated, resampled=resampled, stats=stats)
+    return state

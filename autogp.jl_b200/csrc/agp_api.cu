@@ -1486,9 +1486,27 @@ static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const in
     if (!h) return AGP_ERR_ARG;
     if (P > 0 && (!lml_out || !grad_noise_out || !info_out || !prog_len || !n_params)) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: bad argument");
     size_t total_params = 0;
+    // Kernels of up to 64 nodes and 64 parameters take the hot variant of agp_grad_kernel; a batch with a larger one takes
+    // the big variant (program from global memory, parameters in windows of 64, a tape of AGP_GRAD_TAPE_BIG levels).
+    bool big = false;
+    int max_params = 0;
+    size_t op0 = 0;
     for (int p = 0; p < P && !noise_only; ++p) {
-        if (n_params[p] > agp::AGP_GRAD_MAX_PARAMS || prog_len[p] > 64)
-            return fail(h, AGP_ERR_PROGRAM, "agp_lml_grad_batch: particle " + std::to_string(p) + ": at most 64 nodes and 64 parameters per kernel");
+        if (prog_len[p] < 0 || (prog_len[p] > 0 && !ops)) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: bad program");
+        if (n_params[p] > agp::AGP_GRAD_MAX_PARAMS || prog_len[p] > 64) {
+            big = true;
+            int tape = 0;  // what the forward sweep pushes (agp_eval.cuh: eval_program_grad)
+            for (int q = 0; q < prog_len[p]; ++q) {
+                const int op = ops[op0 + q];
+                tape += op == 3 ? 1 : op == 4 ? 2 : op == 5 ? 3 : op == 7 ? 2 : op == 8 ? 4 : 0;
+            }
+            if (tape > AGP_GRAD_TAPE_BIG)
+                return fail(h, AGP_ERR_PROGRAM, "agp_lml_grad_batch: particle " + std::to_string(p) + ": the kernel needs " + std::to_string(tape) +
+                                                    " tape levels for its gradient, at most " + std::to_string(AGP_GRAD_TAPE_BIG) +
+                                                    " are supported (about 250 nodes)");
+        }
+        op0 += (size_t)prog_len[p];
+        max_params = std::max(max_params, (int)n_params[p]);
         total_params += (size_t)(n_params[p] > 0 ? n_params[p] : 0);
     }
     if (total_params > 0 && !grad_params_out) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: null gradient output");
@@ -1509,7 +1527,7 @@ static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const in
     double* d_gparams = h->d_grad + partial_doubles;
     double* d_gnoise = d_gparams + total_params;
     if (noise_only) agp::launch_noise_grad(h->view, P, h->d_grad, d_gnoise, h->stream);
-    else agp::launch_grad(h->view, P, h->d_param_prefix, h->d_grad, d_gparams, d_gnoise, h->stream);
+    else h->launches += agp::launch_grad(h->view, P, h->d_param_prefix, h->d_grad, d_gparams, d_gnoise, max_params, big, h->stream) - 2;
     h->launches += 2;
     if ((rc = check_launch(h, "grad")) != AGP_OK) return rc;
     if (total_params > 0) AGP_CUDA(h, cudaMemcpyAsync(grad_params_out, d_gparams, total_params * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -501,11 +501,15 @@ __device__ __forceinline__ void eval_entries_grad(const AgpInstr* __restrict__ p
 // Tape traffic for Plus(Times(SE, Periodic), Linear): 6 pushes + 6 pops per entry.
 // ------------------------------------------------------------------------------------------
 constexpr int AGP_GRAD_TAPE = 4 * AGP_GRAD_MAX_NODES;  // a node pushes at most four values
+// The hot variant's tape covers every program of up to AGP_GRAD_MAX_NODES nodes.  Larger kernels (structure learning
+// with max_depth = -1 proposes them now and then) take a second instantiation with a tape of AGP_GRAD_TAPE_BIG levels;
+// the host counts the pushes of every program (agp_grad_tape_need) and picks the variant per batch.
+// (AGP_GRAD_TAPE_BIG: agp_program.h, shared with the host's check)
 
-template <int D, int E, class Acc>
+template <int D, int E, int TAPE, class Acc>
 __device__ __forceinline__ void eval_program_grad(const AgpInstr* __restrict__ prog, int m, const double (&t1)[E], const double (&t2)[E],
                                                   const double (&seed)[E], Acc&& acc) {
-    double tape[AGP_GRAD_TAPE][E];
+    double tape[TAPE][E];
     int tp = 0;
     RegStack<D, E> st;
 #pragma unroll
@@ -756,11 +760,15 @@ __device__ __forceinline__ void eval_program_grad(const AgpInstr* __restrict__ p
 }
 
 // dispatch on the operand-stack depth the program needs, as eval_entries does
-template <int E, class Acc>
+template <int E, int TAPE = AGP_GRAD_TAPE, class Acc>
 __device__ __forceinline__ void eval_entries_grad_tape(const AgpInstr* __restrict__ prog, int m, int need, const double (&t1)[E],
                                                        const double (&t2)[E], const double (&seed)[E], Acc&& acc) {
-    if (need <= 2) eval_program_grad<2, E>(prog, m, t1, t2, seed, acc);
-    else if (need <= 4) eval_program_grad<4, E>(prog, m, t1, t2, seed, acc);
-    else eval_program_grad<AGP_MAX_STACK, E>(prog, m, t1, t2, seed, acc);
+    if (TAPE != AGP_GRAD_TAPE) {  // the big variant: one interpreter copy, the deepest stack
+        eval_program_grad<AGP_MAX_STACK, E, TAPE>(prog, m, t1, t2, seed, acc);
+        return;
+    }
+    if (need <= 2) eval_program_grad<2, E, TAPE>(prog, m, t1, t2, seed, acc);
+    else if (need <= 4) eval_program_grad<4, E, TAPE>(prog, m, t1, t2, seed, acc);
+    else eval_program_grad<AGP_MAX_STACK, E, TAPE>(prog, m, t1, t2, seed, acc);
 }
 }  // namespace agp

@@ -121,8 +121,13 @@ void launch_predict_extract(const BatchView& v, int P, const double* noise_pred,
 // reverse-mode interpreter and keeps per-parameter sums; the CTA reduces them in a fixed order and
 // a second kernel adds the per-CTA partials in a fixed order (bitwise reproducible, no atomics).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __restrict__ param_off, double* __restrict__ partial) {
-    __shared__ AgpInstr prog_s[PROG_SMEM];
+// BIG = false: the hot variant (programs of up to PROG_SMEM nodes cached in shared memory, up to AGP_GRAD_MAX_PARAMS
+// parameters).  BIG = true: any program length (instructions read from global memory), a tape of AGP_GRAD_TAPE_BIG
+// levels, and the parameters [j0, j0 + AGP_GRAD_MAX_PARAMS) of every kernel per launch — the host launches one window
+// after the other; the noise gradient rides in window 0.
+template <bool BIG>
+__global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __restrict__ param_off, double* __restrict__ partial, int j0) {
+    __shared__ AgpInstr prog_s[BIG ? 1 : PROG_SMEM];
 #if AGP_GRAD_ARRAYS
     __shared__ unsigned char opa_s[PROG_SMEM], opb_s[PROG_SMEM];
 #endif
@@ -141,11 +146,12 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
     const double* __restrict__ nal = v.y + (long long)p * ld + lt;  // -alpha
     const int poff = v.prog_off[p];
     const int pm = v.prog_off[p + 1] - poff;
-    {
+    if (!BIG) {
         const double* src = reinterpret_cast<const double*>(v.prog + poff);
         double* dst = reinterpret_cast<double*>(prog_s);
         for (int w = tid; w < pm * AGP_INSTR_DOUBLES; w += FT) dst[w] = src[w];  // host guarantees pm <= PROG_SMEM
     }
+    const AgpInstr* __restrict__ prog_p = BIG ? v.prog + poff : prog_s;
     __syncthreads();
 #if AGP_GRAD_ARRAYS
     if (tid == 0) grad_operands(prog_s, pm, opa_s, opb_s);
@@ -153,7 +159,10 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
 #else
     const int need = v.prog_need[p];
 #endif
-    const int np = param_off[p + 1] - param_off[p];  // host guarantees np <= AGP_GRAD_MAX_PARAMS
+    // parameters of this launch's window; slot np receives the noise gradient (BIG: window 0 only)
+    const int np_all = param_off[p + 1] - param_off[p];  // !BIG: host guarantees np_all <= AGP_GRAD_MAX_PARAMS
+    const int np = BIG ? max(0, min(AGP_GRAD_MAX_PARAMS, np_all - j0)) : np_all;
+    if (BIG && np == 0 && j0 > 0) return;  // this kernel has no parameter in the window
     double g[AGP_GRAD_MAX_PARAMS + 1];
     for (int j = 0; j <= np; ++j) g[j] = 0.0;
     const int c = tid & (UN - 1), rbase = tid >> 7;
@@ -205,7 +214,14 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
 #if AGP_GRAD_ARRAYS
             eval_entries_grad<GE_>(prog_s, pm, opa_s, opb_s, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
 #else
-            eval_entries_grad_tape<GE_>(prog_s, pm, need, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
+            if (BIG) {
+                eval_entries_grad_tape<GE_, AGP_GRAD_TAPE_BIG>(prog_p, pm, need, t1, t2, wgt, [&](int j, double d) {
+                    const unsigned jj = (unsigned)(j - j0);
+                    if (jj < (unsigned)np) g[jj] += d;
+                });
+            } else {
+                eval_entries_grad_tape<GE_>(prog_p, pm, need, t1, t2, wgt, [&](int j, double d) { g[j] += d; });
+            }
 #endif
         }
     }
@@ -222,24 +238,35 @@ __global__ void __launch_bounds__(FT) agp_grad_kernel(BatchView v, const int* __
     }
 }
 
+// window j0 of the parameters (0 for the hot variant); the noise gradient is slot np of window 0
 __global__ void agp_grad_reduce_kernel(const double* __restrict__ partial, int blocks, const int* __restrict__ param_off, double* __restrict__ grad_out,
-                                       double* __restrict__ gnoise_out) {
+                                       double* __restrict__ gnoise_out, int j0) {
     const int p = blockIdx.x, j = threadIdx.x;
-    const int np = param_off[p + 1] - param_off[p];
-    if (j > np) return;
+    const int np = max(0, min(AGP_GRAD_MAX_PARAMS, param_off[p + 1] - param_off[p] - j0));
+    if (j > np || (j == np && j0 > 0)) return;
     double sres = 0.0;
     for (int b = 0; b < blocks; ++b) sres += partial[((long long)p * blocks + b) * (AGP_GRAD_MAX_PARAMS + 1) + j];
-    if (j < np) grad_out[param_off[p] + j] = 0.5 * sres;
+    if (j < np) grad_out[param_off[p] + j0 + j] = 0.5 * sres;
     else gnoise_out[p] = 0.5 * sres;
 }
 
 int grad_blocks_per_particle(const BatchView& v) { return v.nt * (v.nt + 1); }
 
-void launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, cudaStream_t s) {
-    if (P <= 0 || v.nt <= 0) return;
+int launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, int max_params, bool big,
+                cudaStream_t s) {
+    if (P <= 0 || v.nt <= 0) return 0;
     const int blocks = grad_blocks_per_particle(v);
-    agp_grad_kernel<<<dim3(blocks, P), FT, 0, s>>>(v, param_off, partial);
-    agp_grad_reduce_kernel<<<P, AGP_GRAD_MAX_PARAMS + 1, 0, s>>>(partial, blocks, param_off, grad_out, gnoise_out);
+    if (!big) {
+        agp_grad_kernel<false><<<dim3(blocks, P), FT, 0, s>>>(v, param_off, partial, 0);
+        agp_grad_reduce_kernel<<<P, AGP_GRAD_MAX_PARAMS + 1, 0, s>>>(partial, blocks, param_off, grad_out, gnoise_out, 0);
+        return 2;
+    }
+    int launches = 0;
+    for (int j0 = 0; j0 == 0 || j0 < max_params; j0 += AGP_GRAD_MAX_PARAMS, launches += 2) {  // the windows reuse `partial` in stream order
+        agp_grad_kernel<true><<<dim3(blocks, P), FT, 0, s>>>(v, param_off, partial, j0);
+        agp_grad_reduce_kernel<<<P, AGP_GRAD_MAX_PARAMS + 1, 0, s>>>(partial, blocks, param_off, grad_out, gnoise_out, j0);
+    }
+    return launches;
 }
 
 void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s) {

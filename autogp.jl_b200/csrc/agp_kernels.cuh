@@ -80,7 +80,9 @@ void launch_gramfill(const BatchView& v, int P, int row_tile0, cudaStream_t s);
 // dLML/dparams, dLML/dnoise out of the identity-augmented factorisation (agp_lml_grad_batch):
 // partial[P][blocks][AGP_GRAD_MAX_PARAMS + 1] per-CTA sums, then grad_out / gnoise_out
 constexpr int AGP_GRAD_MAX_PARAMS = 64;
-void launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, cudaStream_t s);
+// returns the number of launches; big: a kernel of the batch exceeds the hot variant's limits (agp_fused.cu)
+int launch_grad(const BatchView& v, int P, const int* param_off, double* partial, double* grad_out, double* gnoise_out, int max_params, bool big,
+                cudaStream_t s);
 int grad_blocks_per_particle(const BatchView& v);
 // dLML/dnoise alone out of factorisation + trtri (agp_lml_grad_noise_batch): partial[P][blocks] per-CTA sums
 void launch_noise_grad(const BatchView& v, int P, double* partial, double* gnoise_out, cudaStream_t s);

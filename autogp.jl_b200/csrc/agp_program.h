@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #define AGP_MAX_STACK 8
+#define AGP_GRAD_TAPE_BIG 512  // tape levels of the big variant of the gradient interpreter (agp_eval.cuh)
 
 enum AgpDevOp : int32_t {
     AGP_I_CONST = 0,   // a = value

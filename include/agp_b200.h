@@ -152,7 +152,10 @@ int agp_lml_run_append(agp_handle* h);
  * reverse-mode walk of the kernel program per covariance entry; no n x n gradient leaves the GPU.
  * Gradients are with respect to the parameters as passed (amplitudes, lengthscales, ...); the
  * caller applies the chain rule of Model.transform_param.  info_out[p] != 0: lml and gradients NaN.
- * Limits: 64 nodes and 64 parameters per kernel.  Replaces the resident batch of the handle. */
+ * Kernels of up to 64 nodes and 64 parameters take the tuned path; a batch with a larger kernel (structure
+ * learning with max_depth = -1 proposes them now and then) takes a slower general variant — any number of
+ * parameters, up to about 250 nodes (512 tape levels: SE 1, GammaExponential 2, Periodic 3, Times 2,
+ * ChangePoint 4); beyond that AGP_ERR_PROGRAM.  Replaces the resident batch of the handle. */
 int agp_lml_grad_batch(agp_handle* h, int32_t P, const int32_t* prog_len, const int32_t* ops,
                        const int32_t* param_off, const int32_t* n_params, const double* params,
                        const double* noise, const double* ts, const double* xs, int32_t n,

@@ -819,9 +819,60 @@ def test_lml_gradient_edge_cases(engine):
     lml, grads, gnoise, info = engine.lml_grad_batch([agp.Constant(1.0), agp.SquaredExponential(0.3, 1.0)], [-2.0, 0.1], ts, xs)
     assert info[0] != 0 and np.isnan(lml[0]) and np.all(np.isnan(grads[0])) and np.isnan(gnoise[0])
     assert info[1] == 0 and np.all(np.isfinite(grads[1]))
-    # too many parameters for the gradient path is an error, not a crash
-    big = agp.Constant(1.0)
-    for _ in range(70):
-        big = agp.Plus(big, agp.Constant(0.5))
+    # a kernel beyond the general variant's tape (512 levels; 180 Periodic leaves push 540) is an error, not a crash
+    big = agp.Periodic(0.5, 0.3, 1.0)
+    for _ in range(179):
+        big = agp.Plus(big, agp.Periodic(0.5, 0.3, 0.01))
     with pytest.raises(_lib.AgpError):
         engine.lml_grad_batch([big], [0.1], ts, xs)
+
+
+def test_lml_gradient_of_kernels_beyond_64_nodes_and_64_parameters(engine):
+    """Structure learning with max_depth = -1 proposes large kernels now and then; their gradient takes the general
+    variant of agp_grad_kernel (program from global memory, parameters in windows of 64).  Checked against the
+    finite-difference oracle, against the tuned variant on a small kernel riding in the same batch, and on a chain
+    of 71 Constants whose 71 gradients must all be the same number."""
+    import autogp.jl_b200 as agp
+
+    n = 60
+    ts, xs = o.synthetic_series(n)
+    rng = np.random.default_rng(3)
+
+    def leaf(k):
+        u = lambda lo, hi: float(rng.uniform(lo, hi))
+        return [lambda: o.Linear(u(0.1, 0.9), u(0.1, 0.5), u(0.05, 0.3)), lambda: o.SquaredExponential(u(0.1, 0.6), u(0.05, 0.3)),
+                lambda: o.GammaExponential(u(0.1, 0.6), u(0.6, 1.8), u(0.05, 0.3)), lambda: o.Periodic(u(0.3, 1.2), u(0.1, 0.5), u(0.05, 0.3)),
+                lambda: o.Constant(u(0.05, 0.3))][k % 5]()
+
+    def grow(k0, k1):   # a balanced tree over leaves k0..k1-1 with Plus / Times / ChangePoint alternating by level
+        if k1 - k0 == 1:
+            return leaf(k0)
+        mid = (k0 + k1) // 2
+        left, right = grow(k0, mid), grow(mid, k1)
+        kind = (k1 - k0) % 3
+        return o.Plus(left, right) if kind == 0 else o.Times(left, right) if kind == 1 else o.ChangePoint(left, right, 0.4 + 0.01 * (k0 % 7), 0.05)
+
+    big = grow(0, 48)                                  # 95 nodes, > 64 parameters, operand stack depth 6
+    small = o.synthetic_particle(21, "se*per+lin")[0]
+    assert len(o.unroll(big)) > 64 and len(o.encode_program(big)[2]) > 64
+    nodes, noises = [H.to_agp(big), H.to_agp(small)], [0.07, 0.05]
+    lml, grads, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
+    assert np.all(info == 0)
+    assert H.rel_err(lml, oracle_lmls([(big, 0.07), (small, 0.05)], ts, xs)) <= LML_RTOL_TIGHT
+    g_dn, gn_dn = o.lml_grad_dense_fd(big, 0.07, ts, xs)
+    assert len(grads[0]) == len(g_dn)
+    assert _grad_close(grads[0], g_dn), np.max(np.abs(grads[0] - g_dn))
+    assert abs(gnoise[0] - gn_dn) <= 1e-8 * max(1.0, abs(gn_dn))
+    # the small kernel: same numbers as from the tuned variant (a batch of its own)
+    lml1, grads1, gnoise1, _ = engine.lml_grad_batch(nodes[1:], noises[1:], ts, xs)
+    np.testing.assert_allclose(grads[1], grads1[0], rtol=1e-12, atol=0)
+    assert lml[1] == lml1[0] and abs(gnoise[1] - gnoise1[0]) <= 1e-12 * abs(gnoise1[0])
+    # 71 Constants: dK/dc = ones for every one of them
+    chain = agp.Constant(1.0)
+    for _ in range(70):
+        chain = agp.Plus(chain, agp.Constant(0.5))
+    lml, grads, gnoise, info = engine.lml_grad_batch([chain], [0.1], ts, xs)
+    assert info[0] == 0 and len(grads[0]) == 71
+    np.testing.assert_allclose(grads[0], grads[0][0], rtol=1e-13)
+    g1 = engine.lml_grad_batch([agp.Constant(36.0)], [0.1], ts, xs)[1][0][0]
+    assert grads[0][0] == pytest.approx(g1, rel=1e-10)

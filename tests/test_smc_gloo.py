@@ -148,3 +148,41 @@ def test_two_rank_smc_round_with_rejuvenation_matches_single_process():
             assert got[2] == want[2] and got[3] == want[3]
             assert got[4] == want[4]                                # same accept / reject counts, summed over ranks
     assert sum(r[2] for r in results) == ref_evals
+
+
+# ---- the whole loop (run_smc_anneal_data) with the reference's structure proposals, two ranks against one ----
+def _run_whole_loop(P):
+    from autogp.jl_b200 import smc, tree_moves as tm
+
+    ts, xs = o.synthetic_series(30)
+    state = smc.run_smc_anneal_data(ts, xs, config=tm.GPConfig(max_depth=2), n_particles=P, n_mcmc=2, n_hmc=1,
+                                    schedule=[10, 20, 30], seed=9, engine=H.OracleEngine(),
+                                    hmc_config={"L_param": 2, "L_noise": 2, "n_exit": 1})
+    return [repr(nd) for nd in state.nodes], list(state.noises), state.scores.tolist(), state.log_weights.tolist(), state.log_ml_est
+
+
+def _worker_loop(rank, world, port, P, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank,) + tuple(_run_whole_loop(P)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_run_smc_anneal_data_matches_single_process():
+    P = 5
+    ref = _run_whole_loop(P)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_loop, args=(r, 2, port, P, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for res in results:
+        assert tuple(res[1:]) == tuple(ref)          # prior draws, proposals, decisions: identical on 1 and 2 ranks, bitwise

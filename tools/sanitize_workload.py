@@ -52,6 +52,13 @@ def main():
     _, hgn2, hinfo2 = eng.lml_grad_noise_batch(nodes[:2], noises[:2], ts5[:400], xs5[:400])
     assert np.all(hinfo == 0) and np.all(hinfo2 == 0) and np.all(np.isfinite(hgn)) and np.all(np.isfinite(hgn2))
     eng.set_hybrid(-1)
+    # a kernel beyond 64 nodes / 64 parameters: the general variant of agp_grad_kernel (parameter windows, big tape)
+    big = agp.Periodic(0.5, 0.3, 0.2)
+    for j in range(36):
+        leaf = agp.Periodic(0.5 + 0.01 * j, 0.3, 0.05) if j % 2 else agp.Linear(0.3, 0.1, 0.05)
+        big = agp.Plus(big, leaf) if j % 3 else agp.Times(big, leaf)
+    _, bg, bgn, binfo = eng.lml_grad_batch([big, nodes[0]], [0.1, noises[0]], ts[:150], xs[:150])
+    assert binfo[0] == 0 and len(bg[0]) > 64 and np.all(np.isfinite(bg[0])) and np.all(np.isfinite(bg[1]))
     print(f"sanitize workload ok: {eng.launch_count} launches")
     eng.close()
 

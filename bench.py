@@ -394,6 +394,31 @@ class Bench:
                                                    "exchange = all-gather of the log-weights + D2H + ESS / resample decision (+ re-upload when resampled)"}}
         return result
 
+    # -- the callers of the path: the whole data-annealing SMC loop ------------------------
+    def fit_point(self, n, P, n_mcmc, n_hmc):
+        """smc.run_smc_anneal_data = run_smc_anneal_data of src/inference_smc_anneal_data.jl:143-273 with the reference's
+        tree prior and subtree-replace / detach-attach proposals (tree_moves.py): every reweighting step, MH proposal and
+        leapfrog step of all particles is one batched C-ABI call.  Wall clock of one fit, host work included."""
+        from autogp.jl_b200 import tree_moves
+
+        rng = np.random.default_rng(4)
+        ts = rng.permutation(np.arange(n) / (n - 1))
+        xs = 0.8 * np.sin(2 * np.pi * ts / 0.125) + 0.5 * ts + 0.05 * rng.standard_normal(n)
+        sched = self.smc.linear_schedule(n, 0.10)
+        calls = {"n": 0}
+        t0 = time.perf_counter()
+        state = self.smc.run_smc_anneal_data(ts, xs, config=tree_moves.GPConfig(), n_particles=P, n_mcmc=n_mcmc, n_hmc=n_hmc, schedule=sched,
+                                             seed=0, engine=self.eng,
+                                             callback_fn=lambda **kw: calls.__setitem__("n", calls["n"] + 1))
+        dt = time.perf_counter() - t0
+        w = self.smc.compute_particle_weights(state.log_weights)
+        return {"workload": f"n={n}, {P} particles, {len(sched)} prefixes of linear_schedule(n, .10), n_mcmc={n_mcmc}, n_hmc={n_hmc} (L = 10 + 10 leapfrog steps), "
+                            "prior over kernels = GPConfig defaults (max_depth = -1), synthetic periodic + trend series",
+                "seconds_per_fit": dt, "rounds": calls["n"] - 1, "log_ml_est": float(state.log_ml_est),
+                "posterior_weight_on_periodic_kernels": float(sum(wi for wi, nd in zip(w, state.nodes)
+                                                                  if any(type(a).__name__ == "Periodic" for a in self.agp.unroll(nd)))),
+                "note": "one GPU; includes the host side (proposals, latents, program encoding) and one-time imports"}
+
     def run(self):
         args, torch, dist, eng = self.args, self.torch, self.dist, self.eng
         rank, world = self.rank, self.world
@@ -549,6 +574,8 @@ class Bench:
                 also["n8192"] = self.size_point(8192, P, steps=3, warmup=1)
                 also["grad_n2048"] = self.grad_point(2048, P, reps=3)
                 also["anneal_schedule_n2048"] = self.schedule_point(2048, P, passes=3)
+                if world == 1:
+                    also["structure_learning_n512"] = self.fit_point(512, P, n_mcmc=3, n_hmc=2)
             except Exception as e:  # the headline line must survive a failure of the extras
                 also["error"] = f"{type(e).__name__}: {e}"
             line["also"] = also

@@ -933,7 +933,9 @@ static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->g
 
 // Super-column width: AGP_OZ_W / agp_set_hybrid, or by size (measured, 64 particles: n = 2048: 4 best, 6.72 ms against
 // 6.81 with 3 and 6.98 with 2; n = 4096: 2..4 within 0.5 %; n = 8192: 3 best, 205 ms against 207 / 208 with 2 / 4)
-static int hybrid_width(const agp_handle* h, int nt) { return h->oz_width > 0 ? h->oz_width : (nt >= 48 ? 3 : 4); }
+// by size (tools/width_sweep.py, final int8 kernel): n = 2048: W = 3 6.16, 4 6.16, 2 6.31, 5 6.30 ms; n = 4096: W = 2 29.4, 3 29.7,
+// 4 30.0; n = 8192: W = 2 175.4, 3 177.1, 4 177.6 — the deeper the contractions, the less a launch's fixed costs weigh
+static int hybrid_width(const agp_handle* h, int nt) { return h->oz_width > 0 ? h->oz_width : (nt >= 32 ? 2 : 4); }
 
 // Plain LML run with at least two super-columns: does this handle factor it through the hybrid schedule?
 static bool use_hybrid(const agp_handle* h, int first_row) {

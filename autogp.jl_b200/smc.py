@@ -99,6 +99,10 @@ def all_gather_log_weights(local: "np.ndarray | object", P: int, group=None, dev
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     width = -(-P // world)
+    if device_tensor is None and _device_only_backend(dist, group):
+        # an NCCL-only process group cannot move host tensors: stage the shard on this rank's GPU (the caller has set it
+        # with torch.cuda.set_device, as every NCCL program must)
+        device_tensor = torch.as_tensor(np.asarray(local, dtype=np.float64), device=f"cuda:{torch.cuda.current_device()}")
     if device_tensor is not None:
         src = device_tensor
         buf = torch.full((width,), float("nan"), dtype=torch.float64, device=src.device)
@@ -115,6 +119,13 @@ def all_gather_log_weights(local: "np.ndarray | object", P: int, group=None, dev
         lo, hi = shard_range(P, r, world)
         pieces.append(out[r * width: r * width + (hi - lo)])
     return np.concatenate(pieces)
+
+
+def _device_only_backend(dist, group) -> bool:
+    try:
+        return "gloo" not in str(dist.get_backend(group)).lower() and "nccl" in str(dist.get_backend(group)).lower()
+    except Exception:
+        return False
 
 
 def resample_indices(log_weights: np.ndarray, seed: int) -> np.ndarray:

@@ -62,7 +62,7 @@ struct agp_handle {
 
     // persistent dataflow kernel: work queues per batch shape + dependency counters
     int order = 3;        // queue order variant (AGP_ORDER)
-    int ctas_per_sm = 2;  // AGP_CTAS_PER_SM (diagnostics)
+    int ctas_per_sm = 0;  // AGP_CTAS_PER_SM forces 1 or 2 CTAs of the persistent kernel per SM; 0 = by batch shape (chol_ctas)
     // Plain LML runs evaluate the Gram matrix either by a launch of its own in front of the persistent kernel or as GRAM
     // items of its queue.  Measured (64 particles, profiles/r02_gram_items.txt): items win 5-8 % of the step up to 5 block
     // columns (n <= 640: the factorisation is a dependency chain there and idle CTAs pick the units up), lose 3-7 % from 8
@@ -929,7 +929,23 @@ static bool gram_as_items(const agp_handle* h, int first_row) {
     if (h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.max_prog_len > 64) return false;
     return h->fuse_gram < 0 ? v.nt <= agp_handle::kGramItemsMaxNt : h->fuse_gram != 0;
 }
-static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : h->ctas_per_sm * h->num_sms; }
+// CTAs of the persistent kernel.  Two per SM hide each other's dependency waits and pipeline latencies when there is work for
+// all of them; a small batch is bound by its per-particle chain (POTF2 -> panel -> diagonal tile), and every item of the
+// chain runs faster with the SM to itself.  Measured (tools/ctas_ab.sh, one against two CTAs per SM, plain LML):
+// P = 16: n = 512 -12 %, 1024 -18 %, 1536 -12 %, 2048 -7 %; P = 24: -15 / -15 / . / -2 %; P = 32: -13 / -9 / . / +2.5 %;
+// P = 48: +3 / +4 / . / +7 %; n = 128, P = 64: -17 %; gradient calls (twice the tile rows): P = 16: n = 512 -8 %, 1024 -11 %,
+// 2048 0; P = 32: 0 / +1 / +7 %.  The lock-step rejuvenation loops (rejuvenate.py) call with 10 - 20 active particles.
+static int chol_ctas(const agp_handle* h) {
+    if (h->ctas_per_sm > 0) return h->ctas_per_sm * h->num_sms;
+    const int nt = h->view.nt_total > 0 ? h->view.nt_total : h->view.nt, P = h->P;
+    bool one;
+    if (h->aug_identity) one = P <= 24 - std::max(0, h->view.nt - 8);
+    else if (nt <= 1) one = P <= h->num_sms;
+    else if (nt == 2) one = P <= 64;
+    else one = 2 * P <= 80 - 3 * std::max(0, nt - 8);
+    return (one ? 1 : 2) * h->num_sms;
+}
+static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : chol_ctas(h); }
 
 // Super-column width: AGP_OZ_W / agp_set_hybrid, or by size (measured, 64 particles: n = 2048: 4 best, 6.72 ms against
 // 6.81 with 3 and 6.98 with 2; n = 4096: 2..4 within 0.5 %; n = 8192: 3 best, 205 ms against 207 / 208 with 2 / 4)
@@ -1045,7 +1061,7 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         h->tma_ld = h->ld;
         h->tma_rows = (long long)P * h->ld;
     }
-    agp::launch_chol(v, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
+    agp::launch_chol(v, q, h->tma, chol_ctas(h), h->stream);
     if (kernel_ms) {
         AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         AGP_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -1206,7 +1222,7 @@ static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
         q.items = qu.d_items + 2 * (size_t)qu.seg[s];
         q.n_items = qu.seg[s + 1] - qu.seg[s];
         q.trace = d_trace ? d_trace + 8 * (long long)qu.seg[s] : nullptr;
-        agp::launch_chol(vq, q, h->tma, h->ctas_per_sm * h->num_sms, h->stream);
+        agp::launch_chol(vq, q, h->tma, chol_ctas(h), h->stream);
         h->launches += 1;
         if ((rc = toc(1)) != AGP_OK) return rc;
     }

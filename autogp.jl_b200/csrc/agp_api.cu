@@ -959,7 +959,13 @@ static bool use_hybrid(const agp_handle* h, int first_row) {
     if (h->force_plain || first_row != 0 || h->comp.M != 0 || v.nt <= hybrid_width(h, v.nt)) return false;
     if (h->aug_identity ? (!h->oz_aug || v.nt_total != 2 * v.nt || !(h->min_noise >= agp_handle::kAugMinNoise)) : v.nt_total != v.nt) return false;
     if (h->oz_nomem) return false;
-    const int min_nt = h->aug_identity ? std::min(h->oz_min_nt, h->oz_min_nt_aug) : h->oz_min_nt;
+    // the thresholds are measured at 64 particles; a small batch of plain LML runs leaves the int8 launches too few units per
+    // CTA for their fixed costs (tools/hybrid_small_batch.sh, FP64 schedule against hybrid: P = 8, n = 2048: 1.47 / 1.69 ms,
+    // n = 4096: 8.70 / 6.26; P = 16: n = 1536 1.26 / 1.39, 1792 1.73 / 1.82, 2048 2.30 / 2.30; P = 32: n = 2048 3.95 / 3.64),
+    // so the switch moves up by one block column per 8 particles below 48; the gradient calls win from 8 block columns on
+    // at 16 particles as well (n = 1024: 1.60 / 1.55 ms, 1536: 3.59 / 3.10)
+    const int small_batch = h->aug_identity ? 0 : std::max(0, (48 - h->P + 7) / 8);
+    const int min_nt = (h->aug_identity ? std::min(h->oz_min_nt, h->oz_min_nt_aug) : h->oz_min_nt) + small_batch;
     return h->oz_mode < 0 ? (v.nt >= min_nt && h->fuse_gram != 1) : h->oz_mode != 0;
 }
 

@@ -60,9 +60,15 @@ def test_hybrid_matches_the_fp64_schedule_and_the_oracle(eng, n, width):
 
 
 def test_hybrid_is_chosen_by_size_and_can_be_switched_off(eng):
-    """Default: plain LML runs from 12 block columns on (n >= 1409), the gradient calls from 8 (n >= 897); continuations
-    (set_prefix + run_append) and predictive batches never."""
-    ts, xs, parts, nodes, noises = _batch(2048, 3)
+    """Default: plain LML runs from 12 block columns on (n >= 1409) — one block column later per 8 particles below 48 —, the
+    gradient calls from 8 (n >= 897); continuations (set_prefix + run_append) and predictive batches never."""
+    ts, xs, parts, nodes, noises = _batch(2048, 48)
+    eng.upload(nodes[:3], noises[:3], ts, xs)       # 3 particles: the switch sits at 18 block columns
+    assert not eng.hybrid_info()[0]
+    eng.upload(nodes[:20], noises[:20], ts, xs)     # 20 particles: at 16
+    assert eng.hybrid_info()[0]
+    eng.set_prefix(1900)
+    assert not eng.hybrid_info()[0]
     eng.upload(nodes, noises, ts, xs)
     assert eng.hybrid_info()[0]
     eng.run()

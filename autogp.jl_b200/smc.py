@@ -58,6 +58,18 @@ def linear_schedule(n: int, percent: float) -> List[int]:
     return checkpoints + [n]
 
 
+def _dist():
+    """``torch.distributed`` when this process has a process group, else None.  A process that never imported torch has
+    none, and a single-GPU fit does not pay the import (about 2 s) for finding that out."""
+    import sys
+
+    if "torch" not in sys.modules:
+        return None
+    import torch.distributed as dist
+
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
 def shard_range(P: int, rank: int, world: int):
     """Contiguous block of particles owned by `rank` (sizes differ by at most one)."""
     base, rem = divmod(P, world)
@@ -89,13 +101,13 @@ def all_gather_log_weights(local: "np.ndarray | object", P: int, group=None, dev
     tensors live on the GPU, gloo in the CPU tests); single-process it is the identity.
     Shards may be ragged (P not divisible by the world size): shards are padded to the largest.
     """
-    import torch
-    import torch.distributed as dist
-
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    dist = _dist()
+    if dist is None or dist.get_world_size(group) == 1:
         if device_tensor is not None:
             return device_tensor.detach().cpu().numpy().copy()
         return np.asarray(local, dtype=np.float64).copy()
+    import torch
+
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     width = -(-P // world)
@@ -156,10 +168,9 @@ def smc_step(state: ParticleState, ts, xs, *, engine: Optional[gp.Engine] = None
     """``smc_step!`` (:127-141): re-score every particle on the grown data prefix and add the
     incremental weight ``LML_new - score_old``.  Each rank scores its shard on its own GPU;
     the all-gather replicates the new scores so every rank holds the full weight vector."""
-    import torch.distributed as dist
-
+    dist = _dist()
     P = len(state.nodes)
-    dist_on = dist.is_available() and dist.is_initialized()
+    dist_on = dist is not None
     world = dist.get_world_size(group) if dist_on else 1
     rank = dist.get_rank(group) if dist_on else 0
     lo, hi = shard_range(P, rank, world)
@@ -185,12 +196,11 @@ def rejuvenate(state: ParticleState, ts, xs, *, n_mcmc: int, n_hmc: int, propose
     stream's seed, so a caller that passes the same ``seed`` every round still gets fresh draws.  The rejuvenated kernels are a few hundred
     bytes per particle: one all-gather of them replicates the state for the next resampling step.  MCMC moves leave
     the log-weights alone and replace the trace scores."""
-    import torch.distributed as dist
-
     from . import model, rejuvenate as rj
 
+    dist = _dist()
     P = len(state.nodes)
-    dist_on = dist.is_available() and dist.is_initialized()
+    dist_on = dist is not None
     world = dist.get_world_size(group) if dist_on else 1
     rank = dist.get_rank(group) if dist_on else 0
     lo, hi = shard_range(P, rank, world)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("AGP_LIB") or os.path.join(_HERE, "libagp_b200.so")  #
 
 # every symbol include/agp_b200.h declares
 EXPORTS = (
-    "agp_create", "agp_destroy", "agp_last_error", "agp_version",
+    "agp_create", "agp_destroy", "agp_reserve", "agp_last_error", "agp_version",
     "agp_gram", "agp_gram_device",
     "agp_lml_batch", "agp_lml_upload", "agp_lml_run", "agp_lml_fetch",
     "agp_lml_device_results", "agp_lml_set_prefix",
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.agp_queue_build.restype = C.c_int64
     lib.agp_queue_build_gram.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i32p, C.c_int64]
     lib.agp_queue_build_gram.restype = C.c_int64
+    lib.agp_reserve.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.agp_reserve.restype = C.c_int
     lib.agp_set_hybrid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     lib.agp_set_hybrid.restype = C.c_int
     lib.agp_hybrid_info.argtypes = [vp, i32p, i32p, C.POINTER(C.c_float)]

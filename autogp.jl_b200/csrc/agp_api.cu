@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/agp_b200.h"
+#include <chrono>
 #include "agp_kernels.cuh"
 #include "agp_ozaki.cuh"
 #include "agp_program.h"
@@ -107,13 +108,26 @@ struct agp_handle {
     float hybrid_ms[4] = {0.f, 0.f, 0.f, 0.f};  // last agp_lml_stage_times of a hybrid run: Gram, DMMA segments, int8 updates, digit planes
     struct Queue {
         int4* d_items = nullptr;
+        size_t cap_bytes = 0;  // size of the device buffer (a power of two: evicted buffers are recycled, see queue_buffer)
         int n_items = 0;
         unsigned long long last_use = 0;
         std::vector<int> seg;  // hybrid schedule: first item of every super-column's segment (+ the total at the end)
     };
     unsigned long long queue_clock = 0;
-    static constexpr size_t kMaxQueues = 48;  // least recently used queues beyond this are freed (lock-step loops shrink
-                                              // the batch one particle at a time, data annealing walks through every nt)
+    static constexpr size_t kMaxQueues = 256;  // least recently used queues beyond this are evicted (lock-step loops shrink
+                                               // the batch one particle at a time, data annealing walks through every nt)
+    // Buffers of evicted queues, kept for the next miss: cudaFree / cudaMalloc in the middle of an inference loop were
+    // measured at 50 - 600 ms a piece on a handle that holds gigabytes (profiles/r02_fit_time.txt), so the steady state of
+    // a loop allocates nothing.
+    std::vector<std::pair<int4*, size_t>> spare_queues;
+    static constexpr size_t kMaxSpareQueues = 32;
+    // agp_reserve carves one slab into spare buffers up front (cudaMalloc alone was measured at 20 - 60 ms per queue miss);
+    // chunks of the slab circulate between the cache and the spares and are freed with the slab
+    unsigned char* queue_slab = nullptr;
+    size_t queue_slab_bytes = 0;
+    bool in_slab(const void* p) const {
+        return queue_slab && (const unsigned char*)p >= queue_slab && (const unsigned char*)p < queue_slab + queue_slab_bytes;
+    }
     std::map<std::tuple<int, int, int, int, int>, Queue> queues;  // (P, nt, nt_total, first row tile, nt_stride)
     int* d_sync = nullptr;   size_t cap_sync = 0;
     int* h_sync = nullptr;   // pinned, 2 ints: queue head, error flag
@@ -137,9 +151,30 @@ int fail(agp_handle* h, int code, const std::string& msg) {
         }                                                                                        \
     } while (0)
 
+// AGP_STALL_MS=<ms>: report (stderr) every instrumented section that takes longer — developer diagnostics
+struct StallTimer {
+    const char* what;
+    size_t arg;
+    std::chrono::steady_clock::time_point t0;
+    static double limit_ms() {
+        static const double v = [] { const char* e = getenv("AGP_STALL_MS"); return e ? atof(e) : -1.0; }();
+        return v;
+    }
+    StallTimer(const char* w, size_t a = 0) : what(w), arg(a), t0(std::chrono::steady_clock::now()) {}
+    ~StallTimer() {
+        if (limit_ms() < 0) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > limit_ms()) fprintf(stderr, "[agp stall] %s(%zu): %.1f ms\n", what, arg, ms);
+    }
+};
+
 template <typename T>
 int grow_device(agp_handle* h, T** ptr, size_t* cap, size_t bytes) {
     if (bytes <= *cap) return AGP_OK;
+    StallTimer stall_("grow_device", bytes);
+    // small buffers (counters, partial sums, staging arenas) at least double: a loop whose batches and series grow step by
+    // step would otherwise free and allocate on every step; the big ones (factors, digit planes) are sized exactly
+    if (bytes < ((size_t)256 << 20)) bytes = std::max(bytes, std::min<size_t>(2 * *cap, (size_t)256 << 20));
     if (*ptr) {
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
         AGP_CUDA(h, cudaFree(*ptr));
@@ -158,6 +193,8 @@ int grow_device(agp_handle* h, T** ptr, size_t* cap, size_t bytes) {
 
 int grow_pinned(agp_handle* h, unsigned char** ptr, size_t* cap, size_t bytes) {
     if (bytes <= *cap) return AGP_OK;
+    StallTimer stall_("grow_pinned", bytes);
+    bytes = std::max(bytes, 2 * *cap);
     if (*ptr) {
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
         AGP_CUDA(h, cudaFreeHost(*ptr));
@@ -240,7 +277,11 @@ void agp_destroy(agp_handle* h) {
     cudaFree(h->d_grad);
     cudaFree(h->d_S);
     cudaFree(h->d_rscale);
-    for (auto& kv : h->queues) cudaFree(kv.second.d_items);
+    for (auto& kv : h->queues)
+        if (!h->in_slab(kv.second.d_items)) cudaFree(kv.second.d_items);
+    for (auto& sp : h->spare_queues)
+        if (!h->in_slab(sp.first)) cudaFree(sp.first);
+    cudaFree(h->queue_slab);
     cudaFreeHost(h->h_sync);
     cudaFreeHost(h->h_gin);
     cudaFreeHost(h->h_in);
@@ -448,6 +489,58 @@ static int upload_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const 
     h->n_pred = m;
     h->ld = ld;
     h->uploaded = true;
+    return AGP_OK;
+}
+
+static size_t sync_ints(int P, int nt_stride, bool fused);
+
+int agp_reserve(agp_handle* h, int32_t max_n, int32_t max_pred, int32_t max_batch, int32_t with_gradient) {
+    if (!h || max_n < 0 || max_pred < 0 || max_batch < 0) return AGP_ERR_ARG;
+    if (max_batch > 65535) return fail(h, AGP_ERR_ARG, "agp_reserve: at most 65535 particles per batch");
+    AGP_CUDA(h, cudaSetDevice(h->device));
+    const size_t P = (size_t)max_batch;
+    const size_t ld_obs = align_up((size_t)(max_n > 0 ? max_n : 1), TB);
+    const size_t ld_pred = ld_obs + align_up((size_t)max_pred, TB), ld_aug = with_gradient ? 2 * ld_obs : 0;
+    const size_t ld = std::max(ld_pred, ld_aug);
+    int rc;
+    if ((rc = grow_device(h, &h->d_L, &h->cap_L, std::max<size_t>(16, P * ld * ld * 8))) != AGP_OK) return rc;
+    // work arena of upload_impl: y, z, cum, dinv
+    const size_t work = align_up(2 * P * ld * 8 + P * (ld / TB) * 16, 256) + P * (ld / TB) * 4096 * 8;
+    if ((rc = grow_device(h, &h->d_work, &h->cap_work, work)) != AGP_OK) return rc;
+    const int nt = (int)(ld_obs / TB);
+    if (with_gradient) {  // per-CTA partial sums of agp_grad_kernel + outputs (64 parameters per kernel assumed; grows if there are more)
+        const size_t blocks = (size_t)nt * (nt + 1);
+        if ((rc = grow_device(h, &h->d_grad, &h->cap_grad, (P * blocks * (agp::AGP_GRAD_MAX_PARAMS + 1) + P * (agp::AGP_GRAD_MAX_PARAMS + 1) + 2) * 8)) != AGP_OK) return rc;
+    }
+    {   // dependency counters of the persistent kernel (incl. the flags of Gram items)
+        const size_t nts = ld / TB;
+        if ((rc = grow_device(h, &h->d_sync, &h->cap_sync, sync_ints((int)P, (int)nts, true) * sizeof(int))) != AGP_OK) return rc;
+    }
+    if (!h->queue_slab) {  // spare queue buffers: 8 x 2 MB, 16 x 1 MB, 32 x 512 KB, 32 x 256 KB, 64 x 64 KB, 64 x 16 KB = 61 MB
+        const size_t sizes[6] = {(size_t)2 << 20, (size_t)1 << 20, (size_t)512 << 10, (size_t)256 << 10, (size_t)64 << 10, (size_t)16 << 10};
+        const int counts[6] = {8, 16, 32, 32, 64, 64};
+        size_t total = 0;
+        for (int a = 0; a < 6; ++a) total += sizes[a] * counts[a];
+        if (cudaMalloc(reinterpret_cast<void**>(&h->queue_slab), total) == cudaSuccess) {
+            h->queue_slab_bytes = total;
+            size_t off = 0;
+            for (int a = 0; a < 6; ++a)
+                for (int c = 0; c < counts[a]; ++c, off += sizes[a]) h->spare_queues.emplace_back(reinterpret_cast<int4*>(h->queue_slab + off), sizes[a]);
+        } else {
+            cudaGetLastError();
+            h->queue_slab = nullptr;
+        }
+    }
+    // digit planes and row scales of the hybrid schedule, when a call of this size would take it
+    const int min_nt = with_gradient ? std::min(h->oz_min_nt, h->oz_min_nt_aug) : h->oz_min_nt;
+    if (h->oz_mode != 0 && nt >= min_nt) {
+        const size_t ld_h = with_gradient ? ld_aug : ld_obs;
+        if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld_h * ld_h)) != AGP_OK) {
+            cudaGetLastError();  // the hybrid schedule is optional: the calls fall back to the FP64 schedule when the planes do not fit
+        } else if ((rc = grow_device(h, &h->d_rscale, &h->cap_rscale, P * ld_h * 16)) != AGP_OK) {
+            return rc;
+        }
+    }
     return AGP_OK;
 }
 
@@ -924,6 +1017,52 @@ static void build_queue_inverse(int P, int nt, int nt_stride, int order, std::ve
 
 // Plain LML run (no appended rows, no continuation, every program fits the item's shared-memory cache): may the Gram units
 // ride in the queue, and does this handle want them to for this size?
+// Device buffer for a new queue of `bytes`: the smallest spare that fits, else a fresh allocation rounded up to a power of
+// two (so that it fits most later queues of its size class).
+static int queue_buffer(agp_handle* h, size_t bytes, agp_handle::Queue* qu) {
+    size_t best = h->spare_queues.size();
+    for (size_t a = 0; a < h->spare_queues.size(); ++a)
+        if (h->spare_queues[a].second >= bytes && (best == h->spare_queues.size() || h->spare_queues[a].second < h->spare_queues[best].second)) best = a;
+    if (best < h->spare_queues.size()) {
+        qu->d_items = h->spare_queues[best].first;
+        qu->cap_bytes = h->spare_queues[best].second;
+        h->spare_queues.erase(h->spare_queues.begin() + (long)best);
+        return AGP_OK;
+    }
+    size_t cap = 4096;
+    while (cap < bytes) cap *= 2;
+    StallTimer st_("queue_buffer.cudaMalloc", cap);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu->d_items), cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        qu->d_items = nullptr;
+        return fail(h, AGP_ERR_NOMEM, std::string("work queue allocation failed: ") + cudaGetErrorString(e));
+    }
+    qu->cap_bytes = cap;
+    return AGP_OK;
+}
+// Evict the least recently used queue when the cache is full; its buffer becomes a spare.
+static int evict_queue_if_full(agp_handle* h) {
+    if (h->queues.size() < agp_handle::kMaxQueues) return AGP_OK;
+    auto lru = h->queues.begin();
+    for (auto jt = h->queues.begin(); jt != h->queues.end(); ++jt)
+        if (jt->second.last_use < lru->second.last_use) lru = jt;
+    AGP_CUDA(h, cudaStreamSynchronize(h->stream));  // a launch that reads it may still be in flight
+    h->spare_queues.emplace_back(lru->second.d_items, lru->second.cap_bytes);
+    h->queues.erase(lru);
+    size_t own = 0, small = h->spare_queues.size();  // spares allocated one by one: drop the smallest beyond the limit
+    for (size_t a = 0; a < h->spare_queues.size(); ++a) {
+        if (h->in_slab(h->spare_queues[a].first)) continue;
+        ++own;
+        if (small == h->spare_queues.size() || h->spare_queues[a].second < h->spare_queues[small].second) small = a;
+    }
+    if (own > agp_handle::kMaxSpareQueues) {
+        cudaFree(h->spare_queues[small].first);
+        h->spare_queues.erase(h->spare_queues.begin() + (long)small);
+    }
+    return AGP_OK;
+}
+
 static bool gram_as_items(const agp_handle* h, int first_row) {
     const BatchView& v = h->view;
     if (h->aug_identity || first_row != 0 || v.nt_total != v.nt || h->comp.M != 0 || v.max_prog_len > 64) return false;
@@ -990,22 +1129,11 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         if (fused) fuse_gram_items(P, nt_stride, lead, items);
         agp_handle::Queue qu;
         qu.n_items = (int)(items.size() / 2);
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(h, AGP_ERR_NOMEM, std::string("work queue allocation failed: ") + cudaGetErrorString(e));
-        }
+        int qrc;
+        if ((qrc = evict_queue_if_full(h)) != AGP_OK || (qrc = queue_buffer(h, items.size() * sizeof(int4), &qu)) != AGP_OK) return qrc;
         // pageable source: the copy is staged before the call returns, so `items` may go out of scope
         AGP_CUDA(h, cudaMemcpyAsync(qu.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (h->queues.size() >= agp_handle::kMaxQueues) {
-            auto lru = h->queues.begin();
-            for (auto jt = h->queues.begin(); jt != h->queues.end(); ++jt)
-                if (jt->second.last_use < lru->second.last_use) lru = jt;
-            AGP_CUDA(h, cudaStreamSynchronize(h->stream));  // a launch that reads it may still be in flight
-            cudaFree(lru->second.d_items);
-            h->queues.erase(lru);
-        }
         it = h->queues.emplace(key, qu).first;
     }
     it->second.last_use = ++h->queue_clock;
@@ -1082,6 +1210,7 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
 // Hybrid factorisation: Gram fill, row scales, then per super-column  [digit planes of the previous super-column's
 // panels -> int8 update of this super-column's tiles ->] one launch of the persistent kernel over the segment.
 static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
+    StallTimer st_all_("run_hybrid", (size_t)h->P);
     const BatchView& v = h->view;
     const int P = h->P, nt = v.nt, ld = h->ld;
     const int nt_stride = ld / TB;
@@ -1098,24 +1227,15 @@ static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
     auto key = std::make_tuple(P, nt, nt, -5 - W - (ride ? 1000 : 0) - (aug ? 2000 : 0) - (slice_items ? 4000 : 0) - (lauum ? 8000 : 0), nt_stride);
     auto it = h->queues.find(key);
     if (it == h->queues.end()) {
+        StallTimer st_("run_hybrid.queue_miss", (size_t)h->queues.size());
         std::vector<int4> items;
         agp_handle::Queue qu;
         build_queue_hybrid(P, nt, nt_stride, W, ride ? gram_items_lead(h) : 0, items, qu.seg, aug, slice_items, lauum);
         qu.n_items = (int)(items.size() / 2);
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&qu.d_items), items.size() * sizeof(int4));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(h, AGP_ERR_NOMEM, std::string("work queue allocation failed: ") + cudaGetErrorString(e));
-        }
+        int qrc;
+        if ((qrc = evict_queue_if_full(h)) != AGP_OK || (qrc = queue_buffer(h, items.size() * sizeof(int4), &qu)) != AGP_OK) return qrc;
         AGP_CUDA(h, cudaMemcpyAsync(qu.d_items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         AGP_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (h->queues.size() >= agp_handle::kMaxQueues) {
-            auto lru = h->queues.begin();
-            for (auto jt = h->queues.begin(); jt != h->queues.end(); ++jt)
-                if (jt->second.last_use < lru->second.last_use) lru = jt;
-            cudaFree(lru->second.d_items);
-            h->queues.erase(lru);
-        }
         it = h->queues.emplace(key, qu).first;
     }
     it->second.last_use = ++h->queue_clock;
@@ -1371,7 +1491,10 @@ static int predict_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const
     const size_t mean_bytes = (size_t)P * m * 8, cov_bytes = (size_t)P * m * (marginals ? 1 : m) * 8;
     if ((rc = grow_device(h, &h->d_pred, &h->cap_pred, mean_bytes + cov_bytes + 16)) != AGP_OK) return rc;
     AGP_CUDA(h, cudaMemsetAsync(h->d_res, 0, align_up((size_t)P * 8, 16) + (size_t)P * 4, h->stream));  // info = 0 when nothing is factored
-    if ((rc = run_fused(h)) != AGP_OK) return rc;
+    {
+        StallTimer st_("grad_impl.run_fused", (size_t)P);
+        if ((rc = run_fused(h)) != AGP_OK) return rc;
+    }
     h->n_factored = -1;  // the resident factor belongs to an augmented matrix
     if (m > 0) {
         const double* d_npred = h->view.noise + P;  // noise_pred[P] follows noise[P] in the input arena
@@ -1534,7 +1657,12 @@ static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const in
         total_params += (size_t)(n_params[p] > 0 ? n_params[p] : 0);
     }
     if (total_params > 0 && !grad_params_out) return fail(h, AGP_ERR_ARG, "agp_lml_grad_batch: null gradient output");
-    int rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, nullptr, 0, nullptr, n > 0);
+    StallTimer stall_all_("grad_impl", (size_t)n);
+    int rc;
+    {
+        StallTimer st_("grad_impl.upload", (size_t)P);
+        rc = upload_impl(h, P, prog_len, ops, param_off, n_params, params, noise, ts, xs, n, nullptr, 0, nullptr, n > 0);
+    }
     if (rc != AGP_OK) return rc;
     h->trtri_only = noise_only;
     if (P == 0) return AGP_OK;
@@ -1556,7 +1684,10 @@ static int grad_impl(agp_handle* h, int32_t P, const int32_t* prog_len, const in
     if ((rc = check_launch(h, "grad")) != AGP_OK) return rc;
     if (total_params > 0) AGP_CUDA(h, cudaMemcpyAsync(grad_params_out, d_gparams, total_params * 8, cudaMemcpyDeviceToHost, h->stream));
     AGP_CUDA(h, cudaMemcpyAsync(grad_noise_out, d_gnoise, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
-    rc = agp_lml_fetch(h, lml_out, info_out);  // synchronises
+    {
+        StallTimer st_("grad_impl.fetch", (size_t)P);
+        rc = agp_lml_fetch(h, lml_out, info_out);  // synchronises
+    }
     h->factor_clean = false;
     if (rc != AGP_OK) return rc;
     const double nan = std::nan("");

@@ -221,6 +221,11 @@ class Engine:
             raise _lib.AgpError(rc, self._lib.agp_last_error(self._h).decode())
 
     # ---- site 1 -------------------------------------------------------------------------
+    def reserve(self, max_n: int, max_batch: int, *, max_pred: int = 0, gradient: bool = False) -> None:
+        """Size the large device buffers once (``agp_reserve``): a data-annealing run otherwise re-allocates them every
+        time the series grows."""
+        self._check(self._lib.agp_reserve(self._h, int(max_n), int(max_pred), int(max_batch), 1 if gradient else 0))
+
     def gram(self, node: Node, noise: float, ts, form: int = FORM_VECTORIZED) -> np.ndarray:
         ops, offs, params = encode_program(node)
         ts = np.ascontiguousarray(ts, dtype=np.float64)

@@ -289,6 +289,12 @@ def run_smc_anneal_data(ts, xs, *, config=None, biased: bool = False, n_particle
     if len(n_mcmc) != len(schedule) or len(n_hmc) != len(schedule):
         raise ValueError("n_mcmc / n_hmc: one value, or one per schedule entry")
     propose = tree_moves.tree_rejuvenation_proposer(config, biased)
+    engine = engine or gp.default_engine()
+    if hasattr(engine, "reserve"):
+        # the series grows round by round: size the factor (and the gradient calls' augmented one) once
+        dist = _dist()
+        world = dist.get_world_size(group) if dist is not None else 1
+        engine.reserve(n, -(-n_particles // world), gradient=any(h > 0 for h in n_hmc))
     state = initialize_particles(n_particles, config, seed)
     if callback_fn:
         callback_fn(state=state, ts=ts, xs=xs, step=0, rejuvenated=False, resampled=False, stats=None)

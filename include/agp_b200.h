@@ -69,6 +69,13 @@ enum {
  * or one shared handle for the batched lock-step path. */
 int agp_create(int device, agp_handle** out);
 void agp_destroy(agp_handle* h);
+/* Size the handle's large device buffers once for the biggest call it will see: `max_n` observations (plus
+ * `max_pred` prediction points), `max_batch` particles, `with_gradient` != 0 when agp_lml_grad_batch /
+ * agp_lml_grad_noise_batch will be called at that size (their identity-augmented factor has twice the rows).
+ * Optional: every call grows what it needs, but a data-annealing run (src/inference_smc_anneal_data.jl:206-217) grows the
+ * series round by round, and each growth is a cudaFree + cudaMalloc of gigabytes (20 - 200 ms) in the middle of the loop.
+ * This is the `agp_create(device, max_n, max_batch)` of SURVEY.md §8b as a separate call.  Never shrinks. */
+int agp_reserve(agp_handle* h, int32_t max_n, int32_t max_pred, int32_t max_batch, int32_t with_gradient);
 /* Text of the last error on this handle (valid until the next call on it). */
 const char* agp_last_error(const agp_handle* h);
 /* "major.minor.patch+sm_100a" */

@@ -876,3 +876,29 @@ def test_lml_gradient_of_kernels_beyond_64_nodes_and_64_parameters(engine):
     np.testing.assert_allclose(grads[0], grads[0][0], rtol=1e-13)
     g1 = engine.lml_grad_batch([agp.Constant(36.0)], [0.1], ts, xs)[1][0][0]
     assert grads[0][0] == pytest.approx(g1, rel=1e-10)
+
+
+def test_reserve_sizes_the_buffers_once(engine):
+    """agp_reserve: after reserving for the largest call, growing the series (the data-annealing pattern) re-allocates
+    nothing — the factor's device address stays put — and results are those of an engine that never reserved."""
+    import autogp.jl_b200 as agp
+
+    ts, xs = o.synthetic_series(700)
+    parts = [o.synthetic_particle(40 + p, "se*per+lin") for p in range(3)]
+    nodes, noises = [H.to_agp(nd) for nd, _ in parts], [nz for _, nz in parts]
+    eng = agp.Engine(0)
+    eng.reserve(700, 3, gradient=True)
+    ptrs, out = set(), []
+    for n in (100, 300, 700):
+        lml, info = eng.lml_batch(nodes, noises, ts[:n], xs[:n])
+        ptrs.add(eng.device_results()[0])
+        _, g, gn, ginfo = eng.lml_grad_batch(nodes, noises, ts[:n], xs[:n])
+        assert np.all(info == 0) and np.all(ginfo == 0)
+        out.append((lml, g, gn))
+    for n, (lml, g, gn) in zip((100, 300, 700), out):
+        lml0, _ = engine.lml_batch(nodes, noises, ts[:n], xs[:n])
+        _, g0, gn0, _ = engine.lml_grad_batch(nodes, noises, ts[:n], xs[:n])
+        assert np.array_equal(lml, lml0) and np.array_equal(gn, gn0) and all(np.array_equal(a, b) for a, b in zip(g, g0))
+    with pytest.raises(Exception):
+        eng.reserve(-1, 3)
+    eng.close()

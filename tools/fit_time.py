@@ -50,7 +50,18 @@ class Timed:
             t0 = time.perf_counter()
             out = f(nodes, *args, **kw)
             self.t[name] += time.perf_counter() - t0
-            self.log.append((time.perf_counter() - t0, name, len(nodes), len(args[1])))
+            if os.environ.get("FIT_TIME_CALLS") and time.perf_counter() - t0 > 0.1:   # a stall: is it the input or the moment?
+                again = []
+                for _ in range(2):
+                    t1 = time.perf_counter()
+                    f(nodes, *args, **kw)
+                    again.append(round(1e3 * (time.perf_counter() - t1), 1))
+                info = out[-1]
+                print(f"stall: {name} batch {len(nodes)} n {len(args[1])}: {1e3 * (time.perf_counter() - t0):.0f} ms incl. two repeats of {again} ms; "
+                      f"info != 0 for {int(np.count_nonzero(info))} particles; hybrid {self.eng.hybrid_info()[:2]}", flush=True)
+                import pickle
+                pickle.dump((name, [repr(nd) for nd in nodes], list(args[0]), len(args[1])), open(os.path.join(ROOT, "gpurun_out", f"stall_{len(self.log)}.pkl"), "wb"))
+            self.log.append((time.perf_counter() - t0, name, len(nodes), len(args[1]), max(agp.size(nd) for nd in nodes)))
             self.calls[name] += 1
             self.evals[name] += len(nodes)
             if name == "lml_batch" and len(self.failures) < a.show_failures:
@@ -94,5 +105,4 @@ print("sizes of the final kernels:", sorted(agp.size(nd) for nd in state.nodes))
 for n_obs, info, lml, noise, nd in eng.failures[:a.show_failures]:
     print(f"  unscoreable proposal at n = {n_obs}: info {info} lml {lml} noise {noise:.4g} size {agp.size(nd)}: {nd}")
 if os.environ.get("FIT_TIME_CALLS"):
-    print("slowest calls (ms, call, batch, n):", [(round(1e3 * d, 1), nm, P, n) for d, nm, P, n in sorted(eng.log, reverse=True)[:25]])
-    print("first calls:", [(round(1e3 * d, 1), nm, P, n) for d, nm, P, n in eng.log[:40]])
+    print("slowest calls (ms, call, batch, n, largest kernel):", [(round(1e3 * d, 1), nm, P, n, sz) for d, nm, P, n, sz in sorted(eng.log, reverse=True)[:25]])

@@ -537,6 +537,7 @@ int agp_reserve(agp_handle* h, int32_t max_n, int32_t max_pred, int32_t max_batc
         const size_t ld_h = with_gradient ? ld_aug : ld_obs;
         if ((rc = grow_device(h, &h->d_S, &h->cap_S, (size_t)agp::OZ_SLICES * P * ld_h * ld_h)) != AGP_OK) {
             cudaGetLastError();  // the hybrid schedule is optional: the calls fall back to the FP64 schedule when the planes do not fit
+            h->err.clear();
         } else if ((rc = grow_device(h, &h->d_rscale, &h->cap_rscale, P * ld_h * 16)) != AGP_OK) {
             return rc;
         }

@@ -259,3 +259,50 @@ def test_gpu_structure_learning_finds_the_periodic_structure():
     assert w[has_per].sum() > 0.8
     assert np.median(lml) > np.nanmedian(np.where(prior_info == 0, prior_lml, np.nan)) + 20
     assert math.isfinite(state.log_ml_est)
+
+
+def test_move_edge_cases():
+    rng = np.random.default_rng(0)
+    # max_depth = 1: only leaves exist; detach-attach is impossible (the reference errors) and the mixture never picks it
+    cfg1 = tm.GPConfig(max_depth=1)
+    leaf = tm.sample_tree_prior(1, cfg1, rng)
+    assert isinstance(leaf, gp.LeafNode)
+    with pytest.raises(ValueError):
+        tm.detach_attach_proposal(leaf, rng, cfg1, False)
+    propose = tm.tree_rejuvenation_proposer(cfg1, False)
+    for _ in range(50):
+        new, logr = propose(leaf, rng)
+        assert isinstance(new, gp.LeafNode) and logr == pytest.approx(0.0, abs=1e-12)   # leaf for leaf from the prior: ratio 1
+    # a tree the prior cannot generate (ChangePoint below Plus) can be left but never entered
+    lin, per = gp.Linear(0.3, 0.2, 0.1), gp.Periodic(0.5, 0.3, 0.2)
+    bad = gp.Plus(gp.ChangePoint(lin, per, 0.5, tm.CHANGEPOINT_SCALE), per)
+    assert tm.log_prior_tree(bad, 1, tm.GPConfig()) == -math.inf
+    # no ChangePoints in the configuration: none is ever proposed
+    cfg = tm.GPConfig(changepoints=False)
+    t = tm.sample_tree_prior(1, cfg, rng)
+    for _ in range(300):
+        new, logr = tm.tree_rejuvenation_proposer(cfg, True)(t, rng)
+        assert not any(isinstance(a, gp.ChangePoint) for a in gp.unroll(new))
+        if math.log(rng.random()) < logr:
+            t = new
+    # heap-index helpers
+    tree = gp.Plus(gp.Times(lin, per), per)
+    assert tm.subtree_at(tree, 5) is per and tm.subtree_at(tree, 2).left is lin
+    assert repr(tm.replace_at(tree, 4, per)) == repr(gp.Plus(gp.Times(per, per), per))
+    with pytest.raises(ValueError):
+        tm._path_bits(2, 7)
+
+
+def test_run_smc_anneal_data_with_fixed_noise():
+    """config.noise fixes the observation noise (src/inference_smc_anneal_data.jl:183-187): no noise moves, every
+    particle keeps the value, and the constrained latent's prior density enters every initial log-weight."""
+    from autogp.jl_b200 import smc
+    from helpers import OracleEngineWithNoiseCall
+
+    ts, xs = _series(20)
+    eng = OracleEngineWithNoiseCall()
+    state = smc.run_smc_anneal_data(ts, xs, config=tm.GPConfig(max_depth=2, noise=0.05), n_particles=3, n_mcmc=2, n_hmc=1,
+                                    schedule=[10, 20], seed=2, engine=eng, hmc_config={"L_param": 2, "L_noise": 2})
+    assert state.noises == [0.05] * 3
+    assert not any(kind == "noise" for kind, _ in eng.batches)
+    assert np.all(np.isfinite(state.log_weights)) and np.all(np.isfinite(state.scores))

@@ -641,7 +641,8 @@ struct TileState {
 static void build_queue_order3(int P, int nt, int nt_stride, int late, std::vector<int4>& items) {
     items.clear();
     TileState b(P, nt, nt_stride, &items);
-    const int split_from = 3;
+    int split_from = 3;
+    if (const char* e = getenv("AGP_SPLIT_FROM")) split_from = std::max(2, atoi(e));  // developer A/B
     auto split = [&](int k) { return k >= split_from && k < nt; };
     const int ks = std::max(nt - late, 1);  // first block column of the right-looking phase
     double pos_la = 0.0, pos_diag = 1.0 / 3, pos_potf2 = 0.5;

@@ -74,20 +74,22 @@ def latents(node: gp.Node) -> np.ndarray:
     return np.array([model.untransform_param(f, v) for (f, lat), v in zip(parameter_fields(node), params) if lat])
 
 
-def with_latents(node: gp.Node, z: Sequence[float]) -> gp.Node:
-    params = gp.encode_program(node)[2].copy()
+def with_latents(node: gp.Node, z: Sequence[float], fields=None, params=None) -> gp.Node:
+    """The tree with its latents replaced.  ``fields`` = ``parameter_fields(node)`` and ``params`` = the tree's parameter
+    vector may be passed by a caller that moves the same structure many times (one HMC trajectory = L calls per particle)."""
+    params = (gp.encode_program(node)[2] if params is None else params).copy()
     it = iter(z)
-    for j, (f, lat) in enumerate(parameter_fields(node)):
+    for j, (f, lat) in enumerate(parameter_fields(node) if fields is None else fields):
         if lat:
             params[j] = model.transform_param(f, float(next(it)))
     return with_parameters(node, params)
 
 
-def latent_gradient(node: gp.Node, z: Sequence[float], grad_params: np.ndarray) -> np.ndarray:
+def latent_gradient(node: gp.Node, z: Sequence[float], grad_params: np.ndarray, fields=None) -> np.ndarray:
     """dLML/dz from dLML/dparams (chain rule through ``transform_param``)."""
     it = iter(z)
     out = []
-    for (f, lat), g in zip(parameter_fields(node), grad_params):
+    for (f, lat), g in zip(parameter_fields(node) if fields is None else fields, grad_params):
         if lat:
             out.append(g * model.transform_param_grad(f, float(next(it))))
     return np.array(out)
@@ -129,7 +131,7 @@ class Chains:
         return np.array([noise_of(z) for z in z_noise])
 
 
-def _evaluate(ch: Chains, who, nodes, z_list, z_noise, ts, xs, engine, noise_only: bool = False):
+def _evaluate(ch: Chains, who, nodes, z_list, z_noise, ts, xs, engine, noise_only: bool = False, fields_list=None):
     """LML and latent-space gradients of the given candidate states: one batched call.  ``noise_only``: the cheaper
     ``agp_lml_grad_noise_batch`` (no K^-1, no kernel-tree walk); the parameter gradients come back as None."""
     noises = list(ch.noises_at(who, z_noise))
@@ -141,7 +143,7 @@ def _evaluate(ch: Chains, who, nodes, z_list, z_noise, ts, xs, engine, noise_onl
         gz = [None] * len(nodes)
     else:
         lml, gparams, gnoise, info = engine.lml_grad_batch(nodes, noises, ts, xs)
-        gz = [latent_gradient(nd, z, g) for nd, z, g in zip(nodes, z_list, gparams)]
+        gz = [latent_gradient(nd, z, g, None if fields_list is None else fields_list[a]) for a, (nd, z, g) in enumerate(zip(nodes, z_list, gparams))]
     gzn = np.array([g * model.transform_param_grad("noise", z) for g, z in zip(gnoise, z_noise)])
     ok = np.asarray(info) == 0
     ok &= np.isfinite(lml)
@@ -202,6 +204,9 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
     gzn = ch.grad_zn[active].copy()
     cand_nodes = list(nodes)
     cheap_noise = select == "noise" and hasattr(engine, "lml_grad_noise_batch")
+    # the structure of a particle's tree is fixed along the trajectory: its field list and parameter vector are derived once
+    fields = [parameter_fields(nd) for nd in nodes]
+    params0 = [gp.encode_program(nd)[2] for nd in nodes] if select == "params" else None
     for step in range(L):
         for a in range(A):
             if alive[a]:
@@ -213,7 +218,7 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
             try_nodes = []
             for a in range(A):
                 try:
-                    try_nodes.append(with_latents(nodes[a], zs[a]))
+                    try_nodes.append(with_latents(nodes[a], zs[a], fields[a], params0[a]))
                 except (AssertionError, OverflowError, ValueError):   # e.g. gamma rounded to 0 or out of (0, 2]
                     alive[a] = False
                     zs[a] = z0[a]
@@ -227,7 +232,7 @@ def hmc_lockstep(ch: Chains, active: np.ndarray, ts, xs, *, select: str, L: int,
             zns = np.array([sel[a][0] if alive[a] else zn0[a] for a in range(A)])
         # a noise trajectory needs dLML/dnoise only; its LAST evaluation is a full one so that the cached parameter
         # gradients of an accepted state are current for the parameter move that follows
-        lml, gz, gzn, ok = _evaluate(ch, active, cand_nodes, zs, zns, ts, xs, engine, noise_only=cheap_noise and step < L - 1)
+        lml, gz, gzn, ok = _evaluate(ch, active, cand_nodes, zs, zns, ts, xs, engine, noise_only=cheap_noise and step < L - 1, fields_list=fields)
         newly_dead = alive & ~ok
         ch.stats["not_pd"] += int(newly_dead.sum())
         alive &= ok

@@ -294,7 +294,10 @@ def run_smc_anneal_data(ts, xs, *, config=None, biased: bool = False, n_particle
         # the series grows round by round: size the factor (and the gradient calls' augmented one) once
         dist = _dist()
         world = dist.get_world_size(group) if dist is not None else 1
-        engine.reserve(n, -(-n_particles // world), gradient=any(h > 0 for h in n_hmc))
+        try:
+            engine.reserve(n, -(-n_particles // world), gradient=any(h > 0 for h in n_hmc))
+        except Exception:   # no room for everything at once: the calls size what they need as they go
+            pass
     state = initialize_particles(n_particles, config, seed)
     if callback_fn:
         callback_fn(state=state, ts=ts, xs=xs, step=0, rejuvenated=False, resampled=False, stats=None)

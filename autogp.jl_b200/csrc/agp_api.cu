@@ -1077,6 +1077,8 @@ static bool gram_as_items(const agp_handle* h, int first_row) {
 // P = 48: +3 / +4 / . / +7 %; n = 128, P = 64: -17 %; gradient calls (twice the tile rows): P = 16: n = 512 -8 %, 1024 -11 %,
 // 2048 0; P = 32: 0 / +1 / +7 %.  The lock-step rejuvenation loops (rejuvenate.py) call with 10 - 20 active particles.
 static int chol_ctas(const agp_handle* h) {
+    static const int forced_total = [] { const char* e = getenv("AGP_CTAS"); return e ? atoi(e) : 0; }();  // developer A/B: absolute grid size
+    if (forced_total > 0) return std::min(forced_total, 2 * h->num_sms);
     if (h->ctas_per_sm > 0) return h->ctas_per_sm * h->num_sms;
     const int nt = h->view.nt_total > 0 ? h->view.nt_total : h->view.nt, P = h->P;
     bool one;

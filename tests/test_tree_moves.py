@@ -306,3 +306,26 @@ def test_run_smc_anneal_data_with_fixed_noise():
     assert state.noises == [0.05] * 3
     assert not any(kind == "noise" for kind, _ in eng.batches)
     assert np.all(np.isfinite(state.log_weights)) and np.all(np.isfinite(state.scores))
+
+
+def test_single_process_smc_does_not_import_torch():
+    """A fit without a process group must not pay the torch import (about 2 s): smc.* consult torch.distributed only when
+    torch is already in the process."""
+    import subprocess
+    import sys
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import numpy as np\n"
+        "from autogp.jl_b200 import smc, tree_moves as tm\n"
+        "from helpers import OracleEngineWithNoiseCall\n"
+        "ts = np.linspace(0, 1, 12); xs = np.sin(7 * ts)\n"
+        "st = smc.run_smc_anneal_data(ts, xs, config=tm.GPConfig(max_depth=2), n_particles=2, n_mcmc=1, n_hmc=1, schedule=[6, 12], seed=1,\n"
+        "                             engine=OracleEngineWithNoiseCall(), hmc_config={'L_param': 1, 'L_noise': 1})\n"
+        "assert len(st.nodes) == 2\n"
+        "assert 'torch' not in sys.modules, 'torch was imported'\n"
+        "print('ok')\n") % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -232,7 +232,7 @@ int agp_create(int device, agp_handle** out) {
     agp_handle* h = new agp_handle();
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_fused() != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess || agp::configure_fused() != cudaSuccess || agp::configure_fused_solo() != cudaSuccess ||
         cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaMallocHost(reinterpret_cast<void**>(&h->h_sync), 2 * sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
@@ -1076,6 +1076,9 @@ static bool gram_as_items(const agp_handle* h, int first_row) {
 // P = 16: n = 512 -12 %, 1024 -18 %, 1536 -12 %, 2048 -7 %; P = 24: -15 / -15 / . / -2 %; P = 32: -13 / -9 / . / +2.5 %;
 // P = 48: +3 / +4 / . / +7 %; n = 128, P = 64: -17 %; gradient calls (twice the tile rows): P = 16: n = 512 -8 %, 1024 -11 %,
 // 2048 0; P = 32: 0 / +1 / +7 %.  The lock-step rejuvenation loops (rejuvenate.py) call with 10 - 20 active particles.
+// One CTA per SM runs the kernel's second instantiation (launch bounds (256, 1), no 128-register cap: Makefile RDC_SOLO), another
+// -3.5 .. -9 % on plain LML runs and bitwise the same results; with it: P = 40: n = 512 0.341 -> 0.293 ms, 1024 1.079 -> 1.007;
+// P = 48: 0.356 -> 0.330, 1.185 -> 1.165; n = 2048: P = 24 3.03 -> 2.88, P = 32 3.63 -> 3.59 (two -> one CTA per SM).
 static int chol_ctas(const agp_handle* h) {
     static const int forced_total = [] { const char* e = getenv("AGP_CTAS"); return e ? atoi(e) : 0; }();  // developer A/B: absolute grid size
     if (forced_total > 0) return std::min(forced_total, 2 * h->num_sms);
@@ -1085,10 +1088,17 @@ static int chol_ctas(const agp_handle* h) {
     if (h->aug_identity) one = P <= 24 - std::max(0, h->view.nt - 8);
     else if (nt <= 1) one = P <= h->num_sms;
     else if (nt == 2) one = P <= 64;
-    else one = 2 * P <= 80 - 3 * std::max(0, nt - 8);
+    else one = 2 * P <= 100 - 6 * std::max(0, nt - 8);  // with the uncapped one-CTA instantiation: 48 particles at n <= 1024, 32 at n = 2048 still win
     return (one ? 1 : 2) * h->num_sms;
 }
 static int gram_items_lead(const agp_handle* h) { return h->gram_lead > 0 ? h->gram_lead : chol_ctas(h); }
+// one CTA per SM runs the instantiation compiled for it (no register cap; AGP_CHOL_SOLO=0: the shipped two-CTA build on a smaller grid)
+static void launch_chol_by_grid(const agp_handle* h, const BatchView& v, const agp::SchedView& q) {
+    static const bool solo_ok = [] { const char* e = getenv("AGP_CHOL_SOLO"); return !e || atoi(e) != 0; }();
+    const int ctas = chol_ctas(h);
+    if (solo_ok && ctas <= h->num_sms) agp::launch_chol_solo(v, q, h->tma, ctas, h->stream);
+    else agp::launch_chol(v, q, h->tma, ctas, h->stream);
+}
 
 // Super-column width: AGP_OZ_W / agp_set_hybrid, or by size (measured, 64 particles: n = 2048: 4 best, 6.72 ms against
 // 6.81 with 3 and 6.98 with 2; n = 4096: 2..4 within 0.5 %; n = 8192: 3 best, 205 ms against 207 / 208 with 2 / 4)
@@ -1199,7 +1209,7 @@ static int run_fused(agp_handle* h, long long* d_trace = nullptr, float* kernel_
         h->tma_ld = h->ld;
         h->tma_rows = (long long)P * h->ld;
     }
-    agp::launch_chol(v, q, h->tma, chol_ctas(h), h->stream);
+    launch_chol_by_grid(h, v, q);
     if (kernel_ms) {
         AGP_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         AGP_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -1352,7 +1362,7 @@ static int run_hybrid(agp_handle* h, float* kernel_ms, long long* d_trace) {
         q.items = qu.d_items + 2 * (size_t)qu.seg[s];
         q.n_items = qu.seg[s + 1] - qu.seg[s];
         q.trace = d_trace ? d_trace + 8 * (long long)qu.seg[s] : nullptr;
-        agp::launch_chol(vq, q, h->tma, chol_ctas(h), h->stream);
+        launch_chol_by_grid(h, vq, q);
         h->launches += 1;
         if ((rc = toc(1)) != AGP_OK) return rc;
     }

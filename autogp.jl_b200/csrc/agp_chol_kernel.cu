@@ -306,7 +306,13 @@ __device__ __forceinline__ bool do_update(const BatchView& v, const SchedView& q
 
 }  // namespace
 
-__global__ void __launch_bounds__(FT, 2) agp_chol_kernel(const __grid_constant__ BatchView v, const __grid_constant__ SchedView q, const __grid_constant__ TmaMaps maps) {
+// AGP_CHOL_MIN_CTAS: 2 in the shipped instantiation (two CTAs per SM, 128 registers); the Makefile compiles the kernel's
+// translation units a second time with -DAGP_CHOL_MIN_CTAS=1, no register cap and every external name suffixed _solo — the
+// instantiation small batches run on, one CTA per SM (chol_ctas in agp_api.cu; csrc/experiments/README.md: -3 .. -5 %)
+#ifndef AGP_CHOL_MIN_CTAS
+#define AGP_CHOL_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(FT, AGP_CHOL_MIN_CTAS) agp_chol_kernel(const __grid_constant__ BatchView v, const __grid_constant__ SchedView q, const __grid_constant__ TmaMaps maps) {
     const Smem s = smem_view();
     if (threadIdx.x == 0) {
         // the two TMA descriptors are fetched now, not on the first copy of the first item

@@ -113,6 +113,10 @@ bool make_tma_maps(double* L, int ld, long long rows, TmaMaps* out);
 // One launch = the whole batch: Cholesky + solve + logdet for every particle.
 void launch_chol(const BatchView& v, const SchedView& q, const TmaMaps& maps, int ctas, cudaStream_t s);
 cudaError_t configure_fused();
+#ifndef launch_chol  // the second instantiation (Makefile: RDC_SOLO) for one CTA per SM; inside its own translation units the names above ARE these
+void launch_chol_solo(const BatchView& v, const SchedView& q, const TmaMaps& maps, int ctas, cudaStream_t s);
+cudaError_t configure_fused_solo();
+#endif
 
 // Stand-alone Gram matrix (drop-in for compute_cov_matrix[_vectorized]): column-major, both triangles
 void launch_gram(const AgpInstr* prog, int m, int need, const double* ts, int n, double noise, int form,

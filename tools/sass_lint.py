@@ -26,7 +26,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "autogp.jl_b200", "csrc")
-DEFAULT_OBJS = [os.path.join(CSRC, "agp_chol_kernel.o"), os.path.join(CSRC, "agp_chol_diag.o")]
+DEFAULT_OBJS = [os.path.join(CSRC, f) for f in ("agp_chol_kernel.o", "agp_chol_diag.o", "agp_chol_kernel_solo.o", "agp_chol_diag_solo.o")]
 FUNCS = ("agp_chol_kernel", "do_diag")  # the functions that read TMA-fed operand stages (panel item inlined in the kernel; diagonal-tile item)
 
 
